@@ -1,0 +1,129 @@
+// Error reporting, handle destruction and the device micro-benchmarks of the C ABI.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace carmpc {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return kNumSMsFallback;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+        return kNumSMsFallback;
+    return n;
+}
+
+// ---- micro-benchmarks: dependent-chain-free FMA streams, 8 independent accumulators per thread ----------------
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
+    T acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = T(threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = acc[k] * a + b;
+        }
+    }
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += acc[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = src[i];
+}
+
+template <typename T>
+static int measure_fma(double* value) {
+    const int blocks = sm_count() * 8, threads = 256, iters = 4096;
+    T* out = nullptr;
+    CARMPC_CUDA(cudaMalloc(&out, sizeof(T) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CARMPC_CUDA(cudaEventCreate(&e0));
+    CARMPC_CUDA(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CARMPC_CUDA(cudaEventRecord(e0));
+        fma_peak_kernel<T><<<blocks, threads>>>(out, iters, T(0.999), T(1e-3));
+        CARMPC_CUDA(cudaEventRecord(e1));
+        CARMPC_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        CARMPC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *value = best;
+    return CARMPC_OK;
+}
+
+static int measure_copy(double* value) {
+    const size_t bytes = (size_t)2 << 30;          // 2 GiB each way, far larger than the 126 MB L2
+    double2 *src = nullptr, *dst = nullptr;
+    CARMPC_CUDA(cudaMalloc(&src, bytes));
+    CARMPC_CUDA(cudaMalloc(&dst, bytes));
+    CARMPC_CUDA(cudaMemset(src, 1, bytes));
+    cudaEvent_t e0, e1;
+    CARMPC_CUDA(cudaEventCreate(&e0));
+    CARMPC_CUDA(cudaEventCreate(&e1));
+    double best = 0;
+    const size_t n = bytes / sizeof(double2);
+    for (int rep = 0; rep < 6; ++rep) {
+        CARMPC_CUDA(cudaEventRecord(e0));
+        copy_kernel<<<sm_count() * 16, 256>>>(src, dst, n);
+        CARMPC_CUDA(cudaEventRecord(e1));
+        CARMPC_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        CARMPC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double gbs = 2.0 * bytes / (ms * 1e-3) / 1e9;
+        if (rep > 0 && gbs > best) best = gbs;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(src);
+    cudaFree(dst);
+    *value = best;
+    return CARMPC_OK;
+}
+
+}  // namespace carmpc
+
+extern "C" {
+
+const char* carmpc_last_error(void) { return carmpc::g_error; }
+
+const char* carmpc_version(void) { return "carmpc-b200 0.1 (sm_100a)"; }
+
+void carmpc_destroy(void* handle) {
+    if (handle == nullptr) return;
+    delete static_cast<carmpc::HandleBase*>(handle);
+}
+
+int carmpc_measure_peak(int which, double* h_value) {
+    CARMPC_REQUIRE(h_value != nullptr, "h_value");
+    switch (which) {
+        case 0: return carmpc::measure_fma<float>(h_value);
+        case 1: return carmpc::measure_fma<double>(h_value);
+        case 2: return carmpc::measure_copy(h_value);
+        default: carmpc::set_error("carmpc_measure_peak: which must be 0, 1 or 2"); return CARMPC_ERR_INVALID;
+    }
+}
+
+}  // extern "C"

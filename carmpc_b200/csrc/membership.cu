@@ -1,0 +1,541 @@
+// Terminal-set membership kernels (K1: H-representation, K2: LQR-rollout form) and their C ABI.
+//
+// Reference semantics: lib/terminal_set.py:107-113 tests np.all(A @ point <= b) one grid point at a time in a
+// Python triple loop.  Here one thread evaluates two samples held in registers, the H-rep rows are broadcast from
+// shared memory, the four SoA coordinate arrays are read with 128-bit streaming loads and the result leaves as a
+// warp-ballot bitset (1 bit per sample).  Algorithmic HBM traffic: 4 x 8 B read + 1 bit written = 32.125 B / sample.
+//
+// Arithmetic contract (shared with oracle/carmpc_oracle.c, bit for bit):
+//     r = fma(a3, v, fma(a2, psi, fma(a1, y, a0 * x)));   member &= (r <= b);
+// in IEEE float64, rows in file order.  Mode 1 screens each row in float32 first and only falls back to the
+// float64 expression when the float32 margin is within a rigorous rounding bound of zero, so it returns the same
+// bits while keeping the FP64 pipe (the co-limiter of this kernel on B200) almost idle.
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace carmpc {
+
+constexpr int kMaxRows = 512;
+constexpr int kThreads = 256;
+constexpr int kSamplesPerThread = 2;
+constexpr int kChunk = kThreads * kSamplesPerThread;       // samples per block iteration
+constexpr int kEarlyExitStride = 4;                          // rows between "whole warp already outside" votes
+
+// float32 screen of one row: 4 coefficients, b, and the two constants of the error bound
+struct __align__(16) RowF32 {
+    float a0, a1, a2, a3;
+    float b, bound_coef, bound_const, pad;
+};
+
+struct Polytope : HandleBase {
+    int rows = 0;
+    double* d_rows = nullptr;        // rows x 5 (float64)
+    RowF32* d_rows32 = nullptr;      // rows
+    // staging for the host-buffer path
+    double* d_stage[2] = {nullptr, nullptr};
+    uint32_t* d_stage_bits[2] = {nullptr, nullptr};
+    unsigned long long* d_count = nullptr;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    int64_t stage_samples = 0;
+    ~Polytope() override {
+        cudaFree(d_rows);
+        cudaFree(d_rows32);
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(d_stage[i]);
+            cudaFree(d_stage_bits[i]);
+            if (streams[i]) cudaStreamDestroy(streams[i]);
+        }
+        cudaFree(d_count);
+    }
+};
+
+struct Rollout : HandleBase {
+    int s = 0, rin = 0, k_steps = 0, input_mode = 0;
+    double* d_data = nullptr;        // [Ak 16 | goal 4 | Acon s*4 | bcon s | Ain rin*4 | bin rin]
+    ~Rollout() override { cudaFree(d_data); }
+};
+
+// spread the low 16 bits of v to the even bit positions
+__device__ __forceinline__ uint32_t spread16(uint32_t v) {
+    v &= 0xffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+// Evaluate every row for the two samples of this thread.  Warp-synchronous: all 32 lanes must call it.
+template <int MODE>
+__device__ __forceinline__ void eval_rows(const double* __restrict__ s_rows, const RowF32* __restrict__ s_rows32,
+                                          int rows, const double (&x)[2], const double (&y)[2],
+                                          const double (&p)[2], const double (&v)[2], bool (&in)[2]) {
+    float xf[2], yf[2], pf[2], vf[2], pmax[2];
+    if (MODE == 1) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            xf[k] = (float)x[k];
+            yf[k] = (float)y[k];
+            pf[k] = (float)p[k];
+            vf[k] = (float)v[k];
+            pmax[k] = fmaxf(fmaxf(fabsf(xf[k]), fabsf(yf[k])), fmaxf(fabsf(pf[k]), fabsf(vf[k])));
+        }
+    }
+    for (int r0 = 0; r0 < rows; r0 += kEarlyExitStride) {
+        if (!__any_sync(0xffffffffu, in[0] | in[1])) break;
+        const int r1 = min(r0 + kEarlyExitStride, rows);
+        for (int r = r0; r < r1; ++r) {
+            if (MODE == 1) {
+                const RowF32 q = s_rows32[r];
+                bool ambiguous = false;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float dot = fmaf(q.a3, vf[k], fmaf(q.a2, pf[k], fmaf(q.a1, yf[k], q.a0 * xf[k])));
+                    const float margin = q.b - dot;
+                    const float bound = fmaf(q.bound_coef, pmax[k], q.bound_const);
+                    const bool sure_in = margin > bound;
+                    const bool sure_out = margin < -bound;
+                    ambiguous |= in[k] & !(sure_in | sure_out);
+                    in[k] &= !sure_out;
+                }
+                if (__any_sync(0xffffffffu, ambiguous)) {
+                    // rare: decide this row in float64 for every live sample of the warp (same bits as mode 0)
+                    const double* a = s_rows + 5 * r;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const double rr = fma(a[3], v[k], fma(a[2], p[k], fma(a[1], y[k], a[0] * x[k])));
+                        in[k] &= (rr <= a[4]);
+                    }
+                }
+            } else {
+                const double* a = s_rows + 5 * r;
+                const double a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3], b = a[4];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const double rr = fma(a3, v[k], fma(a2, p[k], fma(a1, y[k], a0 * x[k])));
+                    in[k] &= (rr <= b);
+                }
+            }
+        }
+    }
+}
+
+// write the 64 decisions of a warp (thread t holds samples 2t, 2t+1 of the warp's chunk) as two words
+__device__ __forceinline__ int store_bits(uint32_t* __restrict__ bits, int64_t warp_base, int64_t n, bool in0, bool in1) {
+    const uint32_t even = __ballot_sync(0xffffffffu, in0);
+    const uint32_t odd = __ballot_sync(0xffffffffu, in1);
+    const int lane = threadIdx.x & 31;
+    if (lane < 2) {
+        const uint32_t e = lane ? (even >> 16) : even;
+        const uint32_t o = lane ? (odd >> 16) : odd;
+        const uint32_t word = spread16(e) | (spread16(o) << 1);
+        const int64_t first = warp_base + 32 * lane;
+        if (first < n) bits[first >> 5] = word;
+    }
+    return __popc(even) + __popc(odd);
+}
+
+__device__ __forceinline__ void block_count(int warp_members, unsigned long long* __restrict__ count) {
+    __shared__ int s_partial[kThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_partial[warp] = warp_members;
+    __syncthreads();
+    if (threadIdx.x == 0 && count != nullptr) {
+        int total = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) total += s_partial[w];
+        if (total) atomicAdd(count, (unsigned long long)total);
+    }
+}
+
+__device__ __forceinline__ void stage_rows(const double* __restrict__ g_rows, const RowF32* __restrict__ g_rows32,
+                                           int rows, double* s_rows, RowF32* s_rows32) {
+    for (int i = threadIdx.x; i < rows * 5; i += blockDim.x) s_rows[i] = g_rows[i];
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) s_rows32[i] = g_rows32[i];
+    __syncthreads();
+}
+
+template <int MODE, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+membership_kernel(const double* __restrict__ g_rows, const RowF32* __restrict__ g_rows32, int rows,
+                  const double* __restrict__ gx, const double* __restrict__ gy, const double* __restrict__ gp,
+                  const double* __restrict__ gv, int64_t n, uint32_t* __restrict__ bits,
+                  unsigned long long* __restrict__ count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_rows = reinterpret_cast<double*>(smem_raw);
+    RowF32* s_rows32 = reinterpret_cast<RowF32*>(s_rows + ((rows * 5 + 1) & ~1));
+    stage_rows(g_rows, g_rows32, rows, s_rows, s_rows32);
+
+    int members = 0;
+    const int64_t n_chunks = (n + kChunk - 1) / kChunk;
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int64_t i0 = chunk * kChunk + 2 * (int64_t)threadIdx.x;
+        double x[2], y[2], p[2], v[2];
+        bool in[2];
+        if (VEC && i0 + 1 < n) {
+            const double2 X = ld_stream_f64x2(gx + i0), Y = ld_stream_f64x2(gy + i0);
+            const double2 P = ld_stream_f64x2(gp + i0), V = ld_stream_f64x2(gv + i0);
+            x[0] = X.x; x[1] = X.y; y[0] = Y.x; y[1] = Y.y;
+            p[0] = P.x; p[1] = P.y; v[0] = V.x; v[1] = V.y;
+            in[0] = in[1] = true;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const bool ok = i0 + k < n;
+                const int64_t i = ok ? i0 + k : 0;
+                x[k] = ok ? ld_stream_f64(gx + i) : 0.0;
+                y[k] = ok ? ld_stream_f64(gy + i) : 0.0;
+                p[k] = ok ? ld_stream_f64(gp + i) : 0.0;
+                v[k] = ok ? ld_stream_f64(gv + i) : 0.0;
+                in[k] = ok;
+            }
+        }
+        eval_rows<MODE>(s_rows, s_rows32, rows, x, y, p, v, in);
+        const int64_t warp_base = chunk * kChunk + 64 * (int64_t)(threadIdx.x >> 5);
+        members += store_bits(bits, warp_base, n, in[0], in[1]);
+    }
+    block_count(members, count);
+}
+
+struct GridDesc {
+    int32_t dims[4];
+    int32_t state_of_axis[4];
+    int32_t offset[4];      // start of each axis in the concatenated axes array
+};
+
+// implicit tensor grid: coordinates come from four short axes staged in shared memory, no HBM reads at all
+__global__ void __launch_bounds__(kThreads)
+membership_grid_kernel(const double* __restrict__ g_rows, const RowF32* __restrict__ g_rows32, int rows,
+                       const double* __restrict__ g_axes, GridDesc gd, int64_t n, uint32_t* __restrict__ bits,
+                       unsigned long long* __restrict__ count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_rows = reinterpret_cast<double*>(smem_raw);
+    RowF32* s_rows32 = reinterpret_cast<RowF32*>(s_rows + ((rows * 5 + 1) & ~1));
+    double* s_axes = reinterpret_cast<double*>(s_rows32 + rows);
+    const int axes_len = gd.offset[3] + gd.dims[3];
+    for (int i = threadIdx.x; i < axes_len; i += blockDim.x) s_axes[i] = g_axes[i];
+    stage_rows(g_rows, g_rows32, rows, s_rows, s_rows32);
+
+    int members = 0;
+    const int64_t n_chunks = (n + kChunk - 1) / kChunk;
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int64_t i0 = chunk * kChunk + 2 * (int64_t)threadIdx.x;
+        double c[4][2];
+        bool in[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            in[k] = i0 + k < n;
+            uint64_t rem = in[k] ? (uint64_t)(i0 + k) : 0;
+#pragma unroll
+            for (int ax = 3; ax >= 0; --ax) {
+                const uint32_t d = (uint32_t)gd.dims[ax];
+                const uint64_t qd = rem / d;
+                const uint32_t idx = (uint32_t)(rem - qd * d);
+                rem = qd;
+                const double val = s_axes[gd.offset[ax] + idx];
+                // state_of_axis is a permutation of 0..3
+#pragma unroll
+                for (int st = 0; st < 4; ++st)
+                    if (gd.state_of_axis[ax] == st) c[st][k] = val;
+            }
+        }
+        eval_rows<1>(s_rows, s_rows32, rows, c[0], c[1], c[2], c[3], in);
+        const int64_t warp_base = chunk * kChunk + 64 * (int64_t)(threadIdx.x >> 5);
+        members += store_bits(bits, warp_base, n, in[0], in[1]);
+    }
+    block_count(members, count);
+}
+
+// ---- K2: rollout form --------------------------------------------------------------------------------------------------
+// one sample per thread; e (4 registers) is propagated k_steps times by A_k, rows are broadcast from shared memory.
+__global__ void __launch_bounds__(kThreads)
+rollout_kernel(const double* __restrict__ g_data, int s, int rin, int k_steps, int input_mode,
+               const double* __restrict__ gx, const double* __restrict__ gy, const double* __restrict__ gp,
+               const double* __restrict__ gv, int64_t n, uint32_t* __restrict__ bits,
+               int32_t* __restrict__ first_violation, unsigned long long* __restrict__ count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_data = reinterpret_cast<double*>(smem_raw);
+    const int total = 20 + 5 * s + 5 * rin;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) s_data[i] = g_data[i];
+    __syncthreads();
+    const double* Ak = s_data;
+    const double* goal = s_data + 16;
+    const double* Acon = s_data + 20;
+    const double* bcon = Acon + 4 * s;
+    const double* Ain = bcon + s;
+    const double* bin = Ain + 4 * rin;
+
+    int members = 0;
+    const int64_t n_chunks = (n + kThreads - 1) / kThreads;
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int64_t i = chunk * kThreads + threadIdx.x;
+        const bool valid = i < n;
+        const int64_t j = valid ? i : 0;
+        double e0 = ld_stream_f64(gx + j) - goal[0];
+        double e1 = ld_stream_f64(gy + j) - goal[1];
+        double e2 = ld_stream_f64(gp + j) - goal[2];
+        double e3 = ld_stream_f64(gv + j) - goal[3];
+        bool in = valid;
+        int first = -1;
+        for (int t = 0; t <= k_steps; ++t) {
+            if (!__any_sync(0xffffffffu, in)) break;
+            bool ok = true;
+            for (int r = 0; r < s; ++r) {
+                const double* a = Acon + 4 * r;
+                const double rr = fma(a[3], e3, fma(a[2], e2, fma(a[1], e1, a[0] * e0)));
+                ok &= (rr <= bcon[r]);
+            }
+            if (t == 0 || input_mode == 1) {
+                for (int r = 0; r < rin; ++r) {
+                    const double* a = Ain + 4 * r;
+                    const double rr = fma(a[3], e3, fma(a[2], e2, fma(a[1], e1, a[0] * e0)));
+                    ok &= (rr <= bin[r]);
+                }
+            }
+            if (in && !ok) first = t;
+            in &= ok;
+            const double n0 = fma(Ak[3], e3, fma(Ak[2], e2, fma(Ak[1], e1, Ak[0] * e0)));
+            const double n1 = fma(Ak[7], e3, fma(Ak[6], e2, fma(Ak[5], e1, Ak[4] * e0)));
+            const double n2 = fma(Ak[11], e3, fma(Ak[10], e2, fma(Ak[9], e1, Ak[8] * e0)));
+            const double n3 = fma(Ak[15], e3, fma(Ak[14], e2, fma(Ak[13], e1, Ak[12] * e0)));
+            e0 = n0; e1 = n1; e2 = n2; e3 = n3;
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, in);
+        if ((threadIdx.x & 31) == 0 && i < n) bits[i >> 5] = word;
+        if (first_violation != nullptr && valid) first_violation[i] = first;
+        if ((threadIdx.x & 31) == 0) members += __popc(word);
+    }
+    // members is only non-zero on lane 0 of each warp here
+    __shared__ int s_partial[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) s_partial[threadIdx.x >> 5] = members;
+    __syncthreads();
+    if (threadIdx.x == 0 && count != nullptr) {
+        int total_members = 0;
+        for (int w = 0; w < kThreads / 32; ++w) total_members += s_partial[w];
+        if (total_members) atomicAdd(count, (unsigned long long)total_members);
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------------
+static size_t membership_smem(int rows) { return sizeof(double) * ((rows * 5 + 1) & ~1) + sizeof(RowF32) * rows; }
+
+static int grid_blocks(int64_t n_chunks, int per_sm) {
+    const int64_t cap = (int64_t)sm_count() * per_sm;
+    return (int)(n_chunks < cap ? (n_chunks > 0 ? n_chunks : 1) : cap);
+}
+
+static int launch_membership(Polytope* P, const double* x, const double* y, const double* p, const double* v,
+                             int64_t n, uint32_t* bits, unsigned long long* count, int mode, cudaStream_t st) {
+    if (n == 0) return CARMPC_OK;
+    const size_t smem = membership_smem(P->rows);
+    const int64_t n_chunks = (n + kChunk - 1) / kChunk;
+    const int blocks = grid_blocks(n_chunks, 8);
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+                       reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+#define LAUNCH(M, V)                                                                                        \
+    membership_kernel<M, V><<<blocks, kThreads, smem, st>>>(P->d_rows, P->d_rows32, P->rows, x, y, p, v, n, \
+                                                            bits, count)
+    if (mode == 0) {
+        if (vec) LAUNCH(0, true); else LAUNCH(0, false);
+    } else {
+        if (vec) LAUNCH(1, true); else LAUNCH(1, false);
+    }
+#undef LAUNCH
+    CARMPC_CUDA(cudaGetLastError());
+    return CARMPC_OK;
+}
+
+}  // namespace carmpc
+
+using namespace carmpc;
+
+extern "C" {
+
+int carmpc_polytope_create(const double* h_Ab, int rows, void** handle) {
+    CARMPC_REQUIRE(h_Ab != nullptr && handle != nullptr, "null pointer");
+    CARMPC_REQUIRE(rows >= 0 && rows <= kMaxRows, "rows must be in [0, 512]");
+    Polytope* P = new Polytope();
+    P->kind = kPolytope;
+    P->rows = rows;
+    cudaGetDevice(&P->device);
+    std::vector<RowF32> r32(rows > 0 ? rows : 1);
+    const double gamma = 16.0 * 5.9604644775390625e-08;      // 16 * 2^-24, see eval_rows<1>
+    for (int r = 0; r < rows; ++r) {
+        const double* a = h_Ab + 5 * r;
+        RowF32 q;
+        q.a0 = (float)a[0]; q.a1 = (float)a[1]; q.a2 = (float)a[2]; q.a3 = (float)a[3];
+        q.b = (float)a[4];
+        const double l1 = fabs(a[0]) + fabs(a[1]) + fabs(a[2]) + fabs(a[3]);
+        // round the bound constants up so that the float32 bound dominates the analysed error
+        q.bound_coef = nextafterf((float)(gamma * l1 * 1.0000005), INFINITY);
+        q.bound_const = nextafterf((float)(gamma * fabs(a[4]) * 1.0000005 + 1e-37), INFINITY);
+        q.pad = 0.f;
+        r32[r] = q;
+    }
+    auto fail = [&](int code) { delete P; return code; };
+    if (cudaMalloc(&P->d_rows, sizeof(double) * 5 * (rows > 0 ? rows : 1)) != cudaSuccess ||
+        cudaMalloc(&P->d_rows32, sizeof(RowF32) * (rows > 0 ? rows : 1)) != cudaSuccess) {
+        set_error("carmpc_polytope_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(CARMPC_ERR_CUDA);
+    }
+    if (rows > 0) {
+        if (cudaMemcpy(P->d_rows, h_Ab, sizeof(double) * 5 * rows, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(P->d_rows32, r32.data(), sizeof(RowF32) * rows, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("carmpc_polytope_create: cudaMemcpy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail(CARMPC_ERR_CUDA);
+        }
+    }
+    *handle = P;
+    return CARMPC_OK;
+}
+
+int carmpc_membership_bitset(void* polytope, const double* d_x, const double* d_y, const double* d_psi,
+                             const double* d_v, int64_t n, uint32_t* d_bits, int64_t* d_count, int mode,
+                             void* stream) {
+    Polytope* P = check_handle<Polytope>(polytope, kPolytope);
+    CARMPC_REQUIRE(P != nullptr, "not a polytope handle");
+    CARMPC_REQUIRE(n >= 0, "n");
+    CARMPC_REQUIRE(mode == 0 || mode == 1, "mode must be 0 or 1");
+    if (n == 0) {
+        if (d_count) CARMPC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), (cudaStream_t)stream));
+        return CARMPC_OK;
+    }
+    CARMPC_REQUIRE(d_x && d_y && d_psi && d_v && d_bits, "null device pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_count) CARMPC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+    return launch_membership(P, d_x, d_y, d_psi, d_v, n, d_bits, reinterpret_cast<unsigned long long*>(d_count),
+                             mode, st);
+}
+
+int carmpc_membership_grid(void* polytope, const double* h_axes, const int32_t dims[4],
+                           const int32_t axis_to_state[4], uint32_t* d_bits, int64_t* d_count, void* stream) {
+    Polytope* P = check_handle<Polytope>(polytope, kPolytope);
+    CARMPC_REQUIRE(P != nullptr, "not a polytope handle");
+    CARMPC_REQUIRE(h_axes && dims && axis_to_state && d_bits, "null pointer");
+    GridDesc gd;
+    int64_t n = 1;
+    int off = 0, seen = 0;
+    for (int k = 0; k < 4; ++k) {
+        CARMPC_REQUIRE(dims[k] >= 1 && dims[k] <= 4096, "each axis must have 1..4096 points");
+        CARMPC_REQUIRE(axis_to_state[k] >= 0 && axis_to_state[k] < 4, "axis_to_state entries must be 0..3");
+        seen |= 1 << axis_to_state[k];
+        gd.dims[k] = dims[k];
+        gd.state_of_axis[k] = axis_to_state[k];
+        gd.offset[k] = off;
+        off += dims[k];
+        n *= dims[k];
+    }
+    CARMPC_REQUIRE(seen == 15, "axis_to_state must be a permutation of 0..3");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* d_axes = nullptr;
+    CARMPC_CUDA(cudaMallocAsync(&d_axes, sizeof(double) * off, st));
+    CARMPC_CUDA(cudaMemcpyAsync(d_axes, h_axes, sizeof(double) * off, cudaMemcpyHostToDevice, st));
+    if (d_count) CARMPC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+    const size_t smem = membership_smem(P->rows) + sizeof(double) * off;
+    CARMPC_CUDA(cudaFuncSetAttribute(membership_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t n_chunks = (n + kChunk - 1) / kChunk;
+    membership_grid_kernel<<<grid_blocks(n_chunks, 4), kThreads, smem, st>>>(
+        P->d_rows, P->d_rows32, P->rows, d_axes, gd, n, d_bits, reinterpret_cast<unsigned long long*>(d_count));
+    CARMPC_CUDA(cudaGetLastError());
+    CARMPC_CUDA(cudaFreeAsync(d_axes, st));
+    return CARMPC_OK;
+}
+
+int carmpc_membership_bitset_host(void* polytope, const double* h_x, const double* h_y, const double* h_psi,
+                                  const double* h_v, int64_t n, uint32_t* h_bits, int64_t* h_count, int mode) {
+    Polytope* P = check_handle<Polytope>(polytope, kPolytope);
+    CARMPC_REQUIRE(P != nullptr, "not a polytope handle");
+    CARMPC_REQUIRE(n >= 0, "n");
+    CARMPC_REQUIRE(mode == 0 || mode == 1, "mode must be 0 or 1");
+    if (h_count) *h_count = 0;
+    if (n == 0) return CARMPC_OK;
+    CARMPC_REQUIRE(h_x && h_y && h_psi && h_v && h_bits, "null host pointer");
+    // chunked double-buffered pipeline: H2D of chunk c+1 overlaps the kernel and D2H of chunk c
+    const int64_t chunk = 1 << 23;                  // 8 Mi samples: 256 MiB of coordinates per stage
+    if (P->stage_samples == 0) {
+        for (int i = 0; i < 2; ++i) {
+            CARMPC_CUDA(cudaMalloc(&P->d_stage[i], sizeof(double) * 4 * chunk));
+            CARMPC_CUDA(cudaMalloc(&P->d_stage_bits[i], sizeof(uint32_t) * (chunk / 32)));
+            CARMPC_CUDA(cudaStreamCreateWithFlags(&P->streams[i], cudaStreamNonBlocking));
+        }
+        CARMPC_CUDA(cudaMalloc(&P->d_count, sizeof(unsigned long long)));
+        P->stage_samples = chunk;
+    }
+    CARMPC_CUDA(cudaMemset(P->d_count, 0, sizeof(unsigned long long)));
+    int slot = 0;
+    for (int64_t s = 0; s < n; s += chunk, slot ^= 1) {
+        const int64_t len = (n - s < chunk) ? (n - s) : chunk;
+        cudaStream_t st = P->streams[slot];
+        double* d = P->d_stage[slot];
+        const double* src[4] = {h_x, h_y, h_psi, h_v};
+        for (int a = 0; a < 4; ++a)
+            CARMPC_CUDA(cudaMemcpyAsync(d + a * chunk, src[a] + s, sizeof(double) * len, cudaMemcpyHostToDevice, st));
+        int rc = launch_membership(P, d, d + chunk, d + 2 * chunk, d + 3 * chunk, len, P->d_stage_bits[slot],
+                                   P->d_count, mode, st);
+        if (rc != CARMPC_OK) return rc;
+        CARMPC_CUDA(cudaMemcpyAsync(h_bits + (s >> 5), P->d_stage_bits[slot], sizeof(uint32_t) * ((len + 31) / 32),
+                                    cudaMemcpyDeviceToHost, st));
+    }
+    CARMPC_CUDA(cudaStreamSynchronize(P->streams[0]));
+    CARMPC_CUDA(cudaStreamSynchronize(P->streams[1]));
+    if (h_count) {
+        unsigned long long c = 0;
+        CARMPC_CUDA(cudaMemcpy(&c, P->d_count, sizeof(c), cudaMemcpyDeviceToHost));
+        *h_count = (int64_t)c;
+    }
+    return CARMPC_OK;
+}
+
+int carmpc_rollout_create(const double* h_Ak, const double* h_Acon, const double* h_bcon, int s,
+                          const double* h_Ain, const double* h_bin, int rin, const double* h_goal,
+                          int k_steps, int input_check_mode, void** handle) {
+    CARMPC_REQUIRE(h_Ak && h_goal && handle, "null pointer");
+    CARMPC_REQUIRE(s >= 0 && s <= 256 && rin >= 0 && rin <= 256, "row counts must be in [0, 256]");
+    CARMPC_REQUIRE((s == 0 || (h_Acon && h_bcon)) && (rin == 0 || (h_Ain && h_bin)), "null row pointer");
+    CARMPC_REQUIRE(k_steps >= 0 && k_steps <= 100000, "k_steps");
+    CARMPC_REQUIRE(input_check_mode == 0 || input_check_mode == 1, "input_check_mode must be 0 or 1");
+    std::vector<double> data(20 + 5 * s + 5 * rin);
+    for (int i = 0; i < 16; ++i) data[i] = h_Ak[i];
+    for (int i = 0; i < 4; ++i) data[16 + i] = h_goal[i];
+    double* q = data.data() + 20;
+    for (int i = 0; i < 4 * s; ++i) *q++ = h_Acon[i];
+    for (int i = 0; i < s; ++i) *q++ = h_bcon[i];
+    for (int i = 0; i < 4 * rin; ++i) *q++ = h_Ain[i];
+    for (int i = 0; i < rin; ++i) *q++ = h_bin[i];
+    Rollout* R = new Rollout();
+    R->kind = kRollout;
+    R->s = s; R->rin = rin; R->k_steps = k_steps; R->input_mode = input_check_mode;
+    cudaGetDevice(&R->device);
+    if (cudaMalloc(&R->d_data, sizeof(double) * data.size()) != cudaSuccess ||
+        cudaMemcpy(R->d_data, data.data(), sizeof(double) * data.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("carmpc_rollout_create: %s", cudaGetErrorString(cudaGetLastError()));
+        delete R;
+        return CARMPC_ERR_CUDA;
+    }
+    *handle = R;
+    return CARMPC_OK;
+}
+
+int carmpc_rollout_bitset(void* rollout, const double* d_x, const double* d_y, const double* d_psi,
+                          const double* d_v, int64_t n, uint32_t* d_bits, int32_t* d_first_violation,
+                          int64_t* d_count, void* stream) {
+    Rollout* R = check_handle<Rollout>(rollout, kRollout);
+    CARMPC_REQUIRE(R != nullptr, "not a rollout handle");
+    CARMPC_REQUIRE(n >= 0, "n");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_count) CARMPC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+    if (n == 0) return CARMPC_OK;
+    CARMPC_REQUIRE(d_x && d_y && d_psi && d_v && d_bits, "null device pointer");
+    const size_t smem = sizeof(double) * (20 + 5 * R->s + 5 * R->rin);
+    const int64_t n_chunks = (n + kThreads - 1) / kThreads;
+    rollout_kernel<<<grid_blocks(n_chunks, 8), kThreads, smem, st>>>(
+        R->d_data, R->s, R->rin, R->k_steps, R->input_mode, d_x, d_y, d_psi, d_v, n, d_bits, d_first_violation,
+        reinterpret_cast<unsigned long long*>(d_count));
+    CARMPC_CUDA(cudaGetLastError());
+    return CARMPC_OK;
+}
+
+}  // extern "C"

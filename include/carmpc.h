@@ -1,0 +1,181 @@
+/*
+ * carmpc.h - C ABI of the B200 batch-evaluation library for CarMPC's hot path.
+ *
+ * The reference (ahmad12hamdan99/CarMPC) is pure Python and has no FFI of its own; the entry points
+ * below are what a ctypes binding of its two hot loops replaces:
+ *
+ *   (A) terminal-set membership of a state      lib/terminal_set.py:107-113  (np.all(A @ point <= b))
+ *       and its sampled LQR-rollout form         lib/terminal_set.py:53-59, 198-200
+ *   (B) one condensed MPC QP per initial state  lib/mpc.py:318-335 (state feedback), :456-478 (output
+ *       feedback), built from lib/matrix_gen.py:6-72, closed against lib/simulator.py:51-69 and the
+ *       observer lib/mpc.py:439-448 for Monte-Carlo closed loops.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++ or torch types.
+ *   - Every function returns 0 on success and a negative carmpc_status on failure; nothing throws
+ *     across the ABI.  carmpc_last_error() returns a thread-local message for the last failure.
+ *   - Pointers named d_* are DEVICE pointers owned by the caller; h_* are HOST pointers.
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Handles are opaque, created and destroyed by the library, bound to the CUDA device that was
+ *     current at creation, and may be used from one host thread at a time.
+ *   - Sample grids are structure-of-arrays float64: four arrays x, y, psi, v of n elements.
+ *   - Membership results are bitsets: bit (i & 31) of word (i >> 5) is sample i; the unused high
+ *     bits of the last word are zero.
+ */
+#ifndef CARMPC_H
+#define CARMPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum carmpc_status {
+    CARMPC_OK = 0,
+    CARMPC_ERR_INVALID = -1,   /* bad argument (null pointer, size out of range, bad handle kind) */
+    CARMPC_ERR_CUDA = -2,      /* a CUDA runtime call failed; message has the CUDA error string  */
+    CARMPC_ERR_NUMERIC = -3,   /* host setup failed (matrix not positive definite, ...)          */
+    CARMPC_ERR_UNSUPPORTED = -4
+} carmpc_status;
+
+/* QP status codes written per sample */
+#define CARMPC_QP_SOLVED 0
+#define CARMPC_QP_INFEASIBLE 1 /* primal infeasible: the state is outside the region of attraction; the
+                                  reference raises OutsideTheRegionOfAttractionError (lib/mpc.py:336-338) */
+#define CARMPC_QP_MAX_ITER 2
+
+const char* carmpc_last_error(void);
+const char* carmpc_version(void);
+void carmpc_destroy(void* handle);
+
+/* ------------------------------------------------------------------------------------------------
+ * (A) terminal-set membership
+ * ---------------------------------------------------------------------------------------------- */
+
+/* H-representation {x : A x <= b}.  h_Ab: rows x 5 row-major [a0 a1 a2 a3 | b] - exactly the layout of
+ * terminal_sets/<env>_<goal>.npy (lib/terminal_set.py:206-210, lib/mpc.py:101-102).  rows <= 512. */
+int carmpc_polytope_create(const double* h_Ab, int rows, void** handle);
+
+/* Membership of n samples: bit i = all_r( fma(a3,v, fma(a2,psi, fma(a1,y, a0*x))) <= b ).
+ * Replaces the triple loop lib/terminal_set.py:107-113.
+ *   mode 0: every row evaluated in float64.
+ *   mode 1: float32 screen with a rigorous error bound, float64 re-evaluation of every row whose
+ *           float32 margin is inside the bound.  Same bits as mode 0 by construction.
+ * d_bits: ceil(n/32) words.  d_count (nullable): number of members, int64, overwritten. */
+int carmpc_membership_bitset(void* polytope, const double* d_x, const double* d_y, const double* d_psi,
+                             const double* d_v, int64_t n, uint32_t* d_bits, int64_t* d_count, int mode,
+                             void* stream);
+
+/* The same test on an implicit tensor grid (the reference builds its grid from linspace / arange,
+ * lib/terminal_set.py:96-106): sample i has multi-index (i0, i1, i2, i3) in C order over
+ * (n0, n1, n2, n3) and coordinate axis_k[i_k]; axis_to_state[k] in {0,1,2,3} says which state
+ * component (x, y, psi, v) axis k carries.  h_axes: the four axes concatenated (host). */
+int carmpc_membership_grid(void* polytope, const double* h_axes, const int32_t dims[4],
+                           const int32_t axis_to_state[4], uint32_t* d_bits, int64_t* d_count, void* stream);
+
+/* Host-buffer convenience (end-to-end path): pinned or pageable host SoA arrays in, host bitset out;
+ * the copies are chunked and overlapped with the kernel on internal streams. */
+int carmpc_membership_bitset_host(void* polytope, const double* h_x, const double* h_y, const double* h_psi,
+                                  const double* h_v, int64_t n, uint32_t* h_bits, int64_t* h_count, int mode);
+
+/* LQR-rollout form of the terminal set.  e_0 = p - goal, e_{t+1} = A_k e_t; state rows
+ * Acon e_t <= bcon for t = 0..k_steps; input rows Ain e_t <= bin at t = 0 only
+ * (input_check_mode 0, what lib/terminal_set.py:198-203 does) or at every step (mode 1).
+ * h_Ak: 4x4 row-major; h_Acon: s x 4, h_bcon: s (already shifted to the goal, unit-norm rows as
+ * the reference's polytope construction makes them); h_Ain: rin x 4, h_bin: rin. */
+int carmpc_rollout_create(const double* h_Ak, const double* h_Acon, const double* h_bcon, int s,
+                          const double* h_Ain, const double* h_bin, int rin, const double* h_goal,
+                          int k_steps, int input_check_mode, void** handle);
+
+/* d_first_violation (nullable): int32 per sample, first step t at which a row is violated, -1 if none. */
+int carmpc_rollout_bitset(void* rollout, const double* d_x, const double* d_y, const double* d_psi,
+                          const double* d_v, int64_t n, uint32_t* d_bits, int32_t* d_first_violation,
+                          int64_t* d_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (B) batched condensed MPC QP
+ *
+ *   min_u 1/2 u'Hu + (F (x0 - xref))'u
+ *   s.t.  lo - Gx x0 - Gc c <= G u <= hi - Gx x0 - Gc c      (m general rows, lo = -inf: one-sided)
+ *         lb <= u <= ub                                      (n box rows)
+ *         pre_lo <= Px x0 + Pc c <= pre_hi                   (k rows that do not involve u)
+ *
+ * with x0 (4) the per-sample state, xref (4) the per-batch target (lib/mpc.py:320 / :463) and
+ * c (optional, scalar per sample) a constant-disturbance estimate (lib/mpc.py:637).  H, F, G, Gx are
+ * lib/matrix_gen.py's H, h and the reference's constraint stacks multiplied into S and T
+ * (lib/mpc.py:319-332); see carmpc_b200/condensed.py.
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct carmpc_qp_opts {
+    double rho;            /* ADMM penalty on the scaled problem (default 0.1)                       */
+    double alpha;          /* over-relaxation (default 1.6)                                          */
+    double eps_abs;        /* termination, OSQP-style on unscaled residuals (default 1e-6)           */
+    double eps_rel;        /* (default 1e-6)                                                         */
+    double eps_prim_inf;   /* primal infeasibility certificate tolerance (default 1e-4)              */
+    int32_t max_iter;      /* per sample (default 4000)                                              */
+    int32_t check_every;   /* residual / certificate test cadence in iterations (default 10)         */
+    int32_t scaling_iters; /* Ruiz equilibration passes on the host (default 15; 0 = none)           */
+    int32_t precise;       /* 1: accumulate A'nu and apply K^-1 in float64 (default); 0: float32     */
+} carmpc_qp_opts;
+
+void carmpc_qp_default_opts(carmpc_qp_opts* opts);
+
+/* Host setup: equilibrate, form K = Hs + rho (Gs'Gs + L^2), invert by Cholesky in float64, upload.
+ * Gc / Pc may be NULL (no disturbance term).  n must be even, n <= 160; m <= 1024; k <= 64. */
+int carmpc_qp_create(int n, int m, int k, const double* h_H, const double* h_F, const double* h_G,
+                     const double* h_Gx, const double* h_Gc, const double* h_lo, const double* h_hi,
+                     const double* h_lb, const double* h_ub, const double* h_Px, const double* h_Pc,
+                     const double* h_pre_lo, const double* h_pre_hi, const carmpc_qp_opts* opts,
+                     void** handle);
+
+/* Host-only view of the setup (no CUDA call): scaled matrices exactly as they are uploaded.
+ * which: 0 D(n) 1 Eg(m) 2 Eb(n) 3 c(1) 4 Kinv(n*n) 5 Gs(m*n) 6 lambda(n).  Returns count written. */
+int carmpc_qp_get_setup(void* qp, int which, double* h_out, int capacity);
+
+/* Solve `batch` QPs.  d_x0: SoA, 4 arrays of `batch` float64 (x, y, psi, v).  h_xref: 4 host doubles.
+ * d_c: nullable per-sample disturbance scalar.
+ * Outputs (all device, any may be NULL except d_status):
+ *   d_u0        2 x batch float64 SoA: first input of the optimal sequence (what .step returns)
+ *   d_objective batch float64: 1/2 u'Hu + q'u at the returned point (the reference's `cost`)
+ *   d_status    batch int32 (CARMPC_QP_*)
+ *   d_iters     batch int32
+ *   d_u_full    batch x n float64, row-major per sample (u_horizon of the reference)
+ * d_warm (nullable): batch x (m + n) float32 solver state, read if warm_in != 0, written if warm_out != 0. */
+int carmpc_qp_solve_batch(void* qp, const double* d_x0, const double* h_xref, const double* d_c,
+                          int64_t batch, double* d_u0, double* d_objective, int32_t* d_status,
+                          int32_t* d_iters, double* d_u_full, float* d_warm, int warm_in, int warm_out,
+                          void* stream);
+
+/* Host-buffer convenience: h_x0 is batch x 4 row-major (AoS, as the reference passes states). */
+int carmpc_qp_solve_host(void* qp, const double* h_x0, const double* h_xref, const double* h_c, int64_t batch,
+                         double* h_u0 /* batch x 2 */, double* h_objective, int32_t* h_status,
+                         int32_t* h_iters, double* h_u_full);
+
+/* Sum over the last solve of the per-sample iteration counts and launches issued (for roofline
+ * accounting); both int64. */
+int carmpc_qp_last_stats(void* qp, int64_t* h_total_iters, int64_t* h_launches);
+
+/* ------------------------------------------------------------------------------------------------
+ * Monte-Carlo closed loop against the nonlinear bicycle (lib/simulator.py:51-69), in the order of
+ * examples/run_MPCOutputFB.py:29-41: plant step with the previous input (first [0,0]), observer
+ * update (mode 1, lib/mpc.py:448) or direct state (mode 0), QP, repeat.
+ *   h_A (4x4), h_B (4x2), h_C (3x4), h_L (4x3) row-major; dt, l1 as in the reference (0.2, 3.5).
+ *   d_x_init, d_xhat_init: SoA 4 x runs.  d_final: SoA 4 x runs.  d_fail_step: int32, -1 = none.
+ *   d_traj (nullable): steps x 4 x runs float64.  d_u_log (nullable): steps x 2 x runs.
+ * A run whose QP is infeasible at step t stops there (the reference raises) and keeps its state. */
+int carmpc_closed_loop(void* qp, int mode, const double* h_A, const double* h_B, const double* h_C,
+                       const double* h_L, const double* h_xref, double dt, double l1, int steps, int warm_start,
+                       const double* d_x_init, const double* d_xhat_init, int64_t runs, double* d_final,
+                       int32_t* d_fail_step, double* d_traj, double* d_u_log, int64_t* h_total_iters,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device micro-benchmarks used as roofline denominators that MEASURED_PEAKS.json does not carry.
+ * which: 0 = FP32 FFMA TFLOP/s, 1 = FP64 DFMA TFLOP/s, 2 = HBM copy GB/s (read+write). */
+int carmpc_measure_peak(int which, double* h_value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CARMPC_H */
