@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the CarMPC batch-evaluation hot path on B200 (contract: see the task brief / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Headline line (one JSON object on stdout, rank 0): terminal-set samples/s on BASELINE config 2
+(RoadMultipleCarsEnv H-rep, 100^4 = 10^8-point float64 SoA grid per GPU, resident in HBM).  One "step" = one
+membership pass over the whole grid -> bitset + count.  The same line carries the QP half of the metric under
+``"qp"`` (config 3: 10^6 horizon-20 condensed QPs, RoadOneCarEnv).
+
+``--impl reference`` times the reference's CPU path (its per-point membership test, restated in oracle/ because the
+reference is pure Python with third-party solvers that are not installed) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_SAMPLE = 32.125          # 4 x float64 read + 1 bit written
+TERMINAL_SET = os.path.join(ROOT, "terminal_sets", "RoadMultipleCarsEnv_30_1.5_0_0.npy")
+QP_TERMINAL_SET = os.path.join(ROOT, "terminal_sets", "RoadOneCarEnv_29.9_1.5_0_0.npy")
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int, period_s: float = 0.01):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU legs (the only places that execute oracle/)
+# ------------------------------------------------------------------------------------------------------------
+def _cpu_sample(points: int):
+    """Bounded sample of the config-2 grid: every (10^8 / points)-th grid point, in grid order."""
+    from carmpc_b200.grids import config2_axes, grid_size
+    axes = config2_axes()
+    n = grid_size(axes)
+    idx = np.arange(0, n, n // points, dtype=np.int64)[:points]
+    dims = [len(a) for a in axes]
+    cols, stride = [], n
+    for a, d in zip(axes, dims):
+        stride //= d
+        cols.append(np.ascontiguousarray(a[(idx // stride) % d]))
+    return cols
+
+
+def cpu_membership_rate(min_seconds: float, points: int = 10_000_000, threads: int = 0):
+    """samples/s of the C restatement of lib/terminal_set.py:107-113 on all host threads."""
+    from oracle import c_oracle
+    Ab = np.load(TERMINAL_SET)
+    cols = _cpu_sample(points)
+    threads = threads or c_oracle.max_threads()
+    c_oracle.membership_bits(Ab, *[c[:100000] for c in cols], threads=threads)       # warm-up / build
+    t0 = time.perf_counter()
+    passes = 0
+    while True:
+        c_oracle.membership_bits(Ab, *cols, threads=threads)
+        passes += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds:
+            break
+    return passes * points / dt, threads, f"{passes} passes over a {points}-point strided slice of the 10^8 grid", dt / passes
+
+
+def cpu_pointwise_rate(points: int = 60000):
+    """The reference's literal per-point Python loop (np.all(A @ point <= b)), one core."""
+    from oracle import carmpc_oracle as orc
+    Ab = np.load(TERMINAL_SET)
+    cols = _cpu_sample(points)
+    pts = np.stack(cols, axis=1)
+    t0 = time.perf_counter()
+    orc.membership_pointwise(Ab, pts)
+    return points / (time.perf_counter() - t0)
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    steps, warmup = args.steps, args.warmup
+    per_step_s = 1.0
+    for _ in range(warmup):
+        cpu_membership_rate(0.0, points=2_000_000)
+    rates, step_ms = [], []
+    for _ in range(steps):
+        rate, threads, sample, dt = cpu_membership_rate(per_step_s)
+        rates.append(rate)
+        step_ms.append(dt * 1e3)
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": "terminal-set samples/s", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": float(np.mean(step_ms)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config 2: RoadMultipleCarsEnv terminal set (42 rows) on the 100^4 float64 grid",
+                   "note": "the reference is pure Python (cvxpy/polytope not installed, no build); this arm is the "
+                           "C restatement of lib/terminal_set.py:107-113 in oracle/, all host threads"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
+                         "pointwise_python_samples_per_s": cpu_pointwise_rate()},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+    from carmpc_b200.batch import TerminalSetEvaluator
+    from carmpc_b200.grids import config2_axes, materialise_grid, grid_size
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    Ab = np.load(TERMINAL_SET)
+    ev = TerminalSetEvaluator(Ab)
+    axes = config2_axes()
+    n = grid_size(axes)
+    x, y, psi, v = materialise_grid(axes, device=dev)                 # 3.2 GB of float64 SoA per GPU
+    words = (n + 31) // 32
+    bits = [torch.empty(words, dtype=torch.int32, device=dev) for _ in range(2)]
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    gathered = torch.empty(world * words, dtype=torch.int32, device=dev) if distributed else None
+    launches = 0
+    pending = None
+
+    def step(i):
+        nonlocal launches, pending
+        b = bits[i & 1]
+        ev.contains_bits(x, y, psi, v, mode=args.mode, bits=b, count=count)
+        launches += 1
+        if distributed:
+            if pending is not None:
+                pending.wait()
+            pending = dist.all_gather_into_tensor(gathered, b, async_op=True)     # result gather over NVLink
+
+    for i in range(args.warmup):
+        step(i)
+    if pending is not None:
+        pending.wait()
+        pending = None
+    barrier()
+    launches = 0
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        start.record()
+        for i in range(args.steps):
+            step(i)
+        if pending is not None:
+            pending.wait()
+        stop.record()
+        barrier()
+    ms = start.elapsed_time(stop)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    members = int(count.item())
+
+    # kernel-only timing for the roofline (no gather), same inputs (3.2 GB >> 126 MB L2, so no flush is needed)
+    k_ms = []
+    for i in range(min(args.steps, 50)):
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        ev.contains_bits(x, y, psi, v, mode=args.mode, bits=bits[0], count=count)
+        s1.record()
+        s1.synchronize()
+        k_ms.append(s0.elapsed_time(s1))
+    kernel_ms = float(np.mean(k_ms))
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host SoA in, host bitset out) -----------------
+    e2e = None
+    if not args.skip_e2e:
+        hn = args.e2e_samples
+        host = [torch.empty(hn, dtype=torch.float64, pin_memory=True).copy_(t[:hn]) for t in (x, y, psi, v)]
+        hx, hy, hp, hv = [h.numpy() for h in host]
+        ev.contains_bits_host(hx[:1 << 20], hy[:1 << 20], hp[:1 << 20], hv[:1 << 20], mode=args.mode)   # warm-up
+        ev.contains_bits_host(hx, hy, hp, hv, mode=args.mode)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = args.e2e_steps
+        for _ in range(e2e_steps):
+            hbits, hcount = ev.contains_bits_host(hx, hy, hp, hv, mode=args.mode)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * hn * e2e_steps / float(tt.item()), "unit": "samples/s",
+               "h2d_bytes_per_step": int(hn * 32), "d2h_bytes_per_step": int((hn + 31) // 32 * 4 + 8),
+               "samples_per_step": hn, "steps": e2e_steps,
+               "call": "carmpc_membership_bitset_host (pinned host SoA -> chunked H2D | kernel | D2H pipeline)"}
+
+    qp = None
+    if not args.skip_qp:
+        try:
+            from bench_qp import run_qp_bench
+            qp = run_qp_bench(args, rank, world, dev, barrier)
+        except Exception as exc:                                      # the QP half must never hide the headline
+            qp = {"error": f"{type(exc).__name__}: {exc}"}
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        achieved = n * BYTES_PER_SAMPLE / (kernel_ms * 1e-3) / 1e9
+        cpu = None
+        if world == 1 and not args.skip_cpu:
+            rate, threads, sample, _ = cpu_membership_rate(10.0)
+            cpu = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
+                   "pointwise_python_samples_per_s": cpu_pointwise_rate()}
+        line = {
+            "metric": "terminal-set samples/s", "value": world * n * args.steps / (ms_total * 1e-3),
+            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config 2: RoadMultipleCarsEnv terminal set (42 rows) on the 100^4 = 10^8-point "
+                                   "float64 SoA grid per GPU; one step = one membership pass -> bitset + count",
+                       "samples_per_gpu_per_step": n, "kernel_mode": "fp32 screen + fp64 re-check" if args.mode else "fp64",
+                       "l2": "inputs (3.2 GB) exceed the 126 MB L2; no flush between iterations",
+                       "members": members,
+                       "multi_gpu": "each rank scans its own 10^8 grid; bitsets all-gathered over NCCL, overlapped "
+                                    "with the next step" if distributed else "single GPU"},
+            "clocks": clocks.summary(),
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms,
+                         "kernel": "membership_kernel<mode,VEC>", "bytes_per_sample": BYTES_PER_SAMPLE},
+            "cpu_baseline": cpu,
+            "qp": qp,
+        }
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", type=int, default=1, help="membership kernel: 0 = float64, 1 = float32 screen + float64 re-check")
+    ap.add_argument("--e2e-samples", type=int, default=100_000_000)
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-qp", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--qp-states", type=int, default=1_000_000)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps == 200:
+            args.steps = 10
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py: launch with torch.distributed.run for --gpus > 1")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

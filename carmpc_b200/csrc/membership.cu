@@ -30,31 +30,56 @@ struct __align__(16) RowF32 {
     float b, bound_coef, bound_const, pad;
 };
 
-struct Polytope : HandleBase {
-    int rows = 0;
-    double* d_rows = nullptr;        // rows x 5 (float64)
-    RowF32* d_rows32 = nullptr;      // rows
-    // staging for the host-buffer path
-    double* d_stage[2] = {nullptr, nullptr};
-    uint32_t* d_stage_bits[2] = {nullptr, nullptr};
+// Device staging of the host-buffer entry points: two slots so that the H2D copy of chunk c+1 overlaps the kernel
+// and the D2H copy of chunk c.
+struct HostStage {
+    static constexpr int64_t kChunkSamples = 1 << 23;      // 8 Mi samples: 256 MiB of coordinates per slot
+    double* d_coord[2] = {nullptr, nullptr};
+    uint32_t* d_bits[2] = {nullptr, nullptr};
+    int32_t* d_first[2] = {nullptr, nullptr};
     unsigned long long* d_count = nullptr;
     cudaStream_t streams[2] = {nullptr, nullptr};
-    int64_t stage_samples = 0;
-    ~Polytope() override {
-        cudaFree(d_rows);
-        cudaFree(d_rows32);
+    bool ready = false;
+    int init(bool with_first) {
+        if (!ready) {
+            for (int i = 0; i < 2; ++i) {
+                CARMPC_CUDA(cudaMalloc(&d_coord[i], sizeof(double) * 4 * kChunkSamples));
+                CARMPC_CUDA(cudaMalloc(&d_bits[i], sizeof(uint32_t) * (kChunkSamples / 32)));
+                CARMPC_CUDA(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
+            }
+            CARMPC_CUDA(cudaMalloc(&d_count, sizeof(unsigned long long)));
+            ready = true;
+        }
+        if (with_first && d_first[0] == nullptr)
+            for (int i = 0; i < 2; ++i) CARMPC_CUDA(cudaMalloc(&d_first[i], sizeof(int32_t) * kChunkSamples));
+        return CARMPC_OK;
+    }
+    ~HostStage() {
         for (int i = 0; i < 2; ++i) {
-            cudaFree(d_stage[i]);
-            cudaFree(d_stage_bits[i]);
+            cudaFree(d_coord[i]);
+            cudaFree(d_bits[i]);
+            cudaFree(d_first[i]);
             if (streams[i]) cudaStreamDestroy(streams[i]);
         }
         cudaFree(d_count);
     }
 };
 
+struct Polytope : HandleBase {
+    int rows = 0;
+    double* d_rows = nullptr;        // rows x 5 (float64)
+    RowF32* d_rows32 = nullptr;      // rows
+    HostStage stage;
+    ~Polytope() override {
+        cudaFree(d_rows);
+        cudaFree(d_rows32);
+    }
+};
+
 struct Rollout : HandleBase {
     int s = 0, rin = 0, k_steps = 0, input_mode = 0;
     double* d_data = nullptr;        // [Ak 16 | goal 4 | Acon s*4 | bcon s | Ain rin*4 | bin rin]
+    HostStage stage;
     ~Rollout() override { cudaFree(d_data); }
 };
 
@@ -348,6 +373,51 @@ static int launch_membership(Polytope* P, const double* x, const double* y, cons
     return CARMPC_OK;
 }
 
+static int launch_rollout(Rollout* R, const double* x, const double* y, const double* p, const double* v, int64_t n,
+                          uint32_t* bits, int32_t* first, unsigned long long* count, cudaStream_t st) {
+    if (n == 0) return CARMPC_OK;
+    const size_t smem = sizeof(double) * (20 + 5 * R->s + 5 * R->rin);
+    const int64_t n_chunks = (n + kThreads - 1) / kThreads;
+    rollout_kernel<<<grid_blocks(n_chunks, 8), kThreads, smem, st>>>(R->d_data, R->s, R->rin, R->k_steps, R->input_mode,
+                                                                     x, y, p, v, n, bits, first, count);
+    CARMPC_CUDA(cudaGetLastError());
+    return CARMPC_OK;
+}
+
+// chunked double-buffered host pipeline shared by the two *_host entry points
+template <class Launch>
+static int host_pipeline(HostStage& S, const double* h_x, const double* h_y, const double* h_psi, const double* h_v,
+                         int64_t n, uint32_t* h_bits, int32_t* h_first, int64_t* h_count, Launch launch) {
+    int rc = S.init(h_first != nullptr);
+    if (rc != CARMPC_OK) return rc;
+    const int64_t chunk = HostStage::kChunkSamples;
+    CARMPC_CUDA(cudaMemsetAsync(S.d_count, 0, sizeof(unsigned long long), S.streams[0]));
+    CARMPC_CUDA(cudaStreamSynchronize(S.streams[0]));
+    int slot = 0;
+    for (int64_t s = 0; s < n; s += chunk, slot ^= 1) {
+        const int64_t len = (n - s < chunk) ? (n - s) : chunk;
+        cudaStream_t st = S.streams[slot];
+        double* d = S.d_coord[slot];
+        const double* src[4] = {h_x, h_y, h_psi, h_v};
+        for (int a = 0; a < 4; ++a)
+            CARMPC_CUDA(cudaMemcpyAsync(d + a * chunk, src[a] + s, sizeof(double) * len, cudaMemcpyHostToDevice, st));
+        rc = launch(d, d + chunk, d + 2 * chunk, d + 3 * chunk, len, S.d_bits[slot], S.d_first[slot], S.d_count, st);
+        if (rc != CARMPC_OK) return rc;
+        CARMPC_CUDA(cudaMemcpyAsync(h_bits + (s >> 5), S.d_bits[slot], sizeof(uint32_t) * ((len + 31) / 32),
+                                    cudaMemcpyDeviceToHost, st));
+        if (h_first)
+            CARMPC_CUDA(cudaMemcpyAsync(h_first + s, S.d_first[slot], sizeof(int32_t) * len, cudaMemcpyDeviceToHost, st));
+    }
+    CARMPC_CUDA(cudaStreamSynchronize(S.streams[0]));
+    CARMPC_CUDA(cudaStreamSynchronize(S.streams[1]));
+    if (h_count) {
+        unsigned long long c = 0;
+        CARMPC_CUDA(cudaMemcpy(&c, S.d_count, sizeof(c), cudaMemcpyDeviceToHost));
+        *h_count = (int64_t)c;
+    }
+    return CARMPC_OK;
+}
+
 }  // namespace carmpc
 
 using namespace carmpc;
@@ -453,40 +523,11 @@ int carmpc_membership_bitset_host(void* polytope, const double* h_x, const doubl
     if (h_count) *h_count = 0;
     if (n == 0) return CARMPC_OK;
     CARMPC_REQUIRE(h_x && h_y && h_psi && h_v && h_bits, "null host pointer");
-    // chunked double-buffered pipeline: H2D of chunk c+1 overlaps the kernel and D2H of chunk c
-    const int64_t chunk = 1 << 23;                  // 8 Mi samples: 256 MiB of coordinates per stage
-    if (P->stage_samples == 0) {
-        for (int i = 0; i < 2; ++i) {
-            CARMPC_CUDA(cudaMalloc(&P->d_stage[i], sizeof(double) * 4 * chunk));
-            CARMPC_CUDA(cudaMalloc(&P->d_stage_bits[i], sizeof(uint32_t) * (chunk / 32)));
-            CARMPC_CUDA(cudaStreamCreateWithFlags(&P->streams[i], cudaStreamNonBlocking));
-        }
-        CARMPC_CUDA(cudaMalloc(&P->d_count, sizeof(unsigned long long)));
-        P->stage_samples = chunk;
-    }
-    CARMPC_CUDA(cudaMemset(P->d_count, 0, sizeof(unsigned long long)));
-    int slot = 0;
-    for (int64_t s = 0; s < n; s += chunk, slot ^= 1) {
-        const int64_t len = (n - s < chunk) ? (n - s) : chunk;
-        cudaStream_t st = P->streams[slot];
-        double* d = P->d_stage[slot];
-        const double* src[4] = {h_x, h_y, h_psi, h_v};
-        for (int a = 0; a < 4; ++a)
-            CARMPC_CUDA(cudaMemcpyAsync(d + a * chunk, src[a] + s, sizeof(double) * len, cudaMemcpyHostToDevice, st));
-        int rc = launch_membership(P, d, d + chunk, d + 2 * chunk, d + 3 * chunk, len, P->d_stage_bits[slot],
-                                   P->d_count, mode, st);
-        if (rc != CARMPC_OK) return rc;
-        CARMPC_CUDA(cudaMemcpyAsync(h_bits + (s >> 5), P->d_stage_bits[slot], sizeof(uint32_t) * ((len + 31) / 32),
-                                    cudaMemcpyDeviceToHost, st));
-    }
-    CARMPC_CUDA(cudaStreamSynchronize(P->streams[0]));
-    CARMPC_CUDA(cudaStreamSynchronize(P->streams[1]));
-    if (h_count) {
-        unsigned long long c = 0;
-        CARMPC_CUDA(cudaMemcpy(&c, P->d_count, sizeof(c), cudaMemcpyDeviceToHost));
-        *h_count = (int64_t)c;
-    }
-    return CARMPC_OK;
+    return host_pipeline(P->stage, h_x, h_y, h_psi, h_v, n, h_bits, nullptr, h_count,
+                         [&](const double* x, const double* y, const double* p, const double* v, int64_t len,
+                             uint32_t* bits, int32_t*, unsigned long long* count, cudaStream_t st) {
+                             return launch_membership(P, x, y, p, v, len, bits, count, mode, st);
+                         });
 }
 
 int carmpc_rollout_create(const double* h_Ak, const double* h_Acon, const double* h_bcon, int s,
@@ -529,13 +570,25 @@ int carmpc_rollout_bitset(void* rollout, const double* d_x, const double* d_y, c
     if (d_count) CARMPC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
     if (n == 0) return CARMPC_OK;
     CARMPC_REQUIRE(d_x && d_y && d_psi && d_v && d_bits, "null device pointer");
-    const size_t smem = sizeof(double) * (20 + 5 * R->s + 5 * R->rin);
-    const int64_t n_chunks = (n + kThreads - 1) / kThreads;
-    rollout_kernel<<<grid_blocks(n_chunks, 8), kThreads, smem, st>>>(
-        R->d_data, R->s, R->rin, R->k_steps, R->input_mode, d_x, d_y, d_psi, d_v, n, d_bits, d_first_violation,
-        reinterpret_cast<unsigned long long*>(d_count));
-    CARMPC_CUDA(cudaGetLastError());
-    return CARMPC_OK;
+    return launch_rollout(R, d_x, d_y, d_psi, d_v, n, d_bits, d_first_violation,
+                          reinterpret_cast<unsigned long long*>(d_count), st);
+}
+
+int carmpc_rollout_bitset_host(void* rollout, const double* h_x, const double* h_y, const double* h_psi,
+                               const double* h_v, int64_t n, uint32_t* h_bits, int32_t* h_first_violation,
+                               int64_t* h_count) {
+    Rollout* R = check_handle<Rollout>(rollout, kRollout);
+    CARMPC_REQUIRE(R != nullptr, "not a rollout handle");
+    CARMPC_REQUIRE(n >= 0, "n");
+    if (h_count) *h_count = 0;
+    if (n == 0) return CARMPC_OK;
+    CARMPC_REQUIRE(h_x && h_y && h_psi && h_v && h_bits, "null host pointer");
+    return host_pipeline(R->stage, h_x, h_y, h_psi, h_v, n, h_bits, h_first_violation, h_count,
+                         [&](const double* x, const double* y, const double* p, const double* v, int64_t len,
+                             uint32_t* bits, int32_t* first, unsigned long long* count, cudaStream_t st) {
+                             return launch_rollout(R, x, y, p, v, len, bits, h_first_violation ? first : nullptr, count,
+                                                   st);
+                         });
 }
 
 }  // extern "C"

@@ -93,6 +93,11 @@ int carmpc_rollout_bitset(void* rollout, const double* d_x, const double* d_y, c
                           const double* d_v, int64_t n, uint32_t* d_bits, int32_t* d_first_violation,
                           int64_t* d_count, void* stream);
 
+/* Host-buffer form of the rollout test (same chunked, overlapped pipeline as the H-rep one). */
+int carmpc_rollout_bitset_host(void* rollout, const double* h_x, const double* h_y, const double* h_psi,
+                               const double* h_v, int64_t n, uint32_t* h_bits, int32_t* h_first_violation,
+                               int64_t* h_count);
+
 /* ------------------------------------------------------------------------------------------------
  * (B) batched condensed MPC QP
  *

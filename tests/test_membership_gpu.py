@@ -1,0 +1,213 @@
+"""Parity of the CUDA terminal-set kernels against the oracle, through the C ABI (needs a B200).
+
+Bit-exact: the C oracle evaluates the same fma chain in IEEE float64, so bitsets are compared with ==.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, FIXTURES, K_STAR, golden, make_env
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "the GPU tests need a CUDA device"
+    return torch
+
+
+def _dev(torch, *arrays):
+    return [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda() for a in arrays]
+
+
+def _bits_np(bits_tensor):
+    return bits_tensor.cpu().numpy().view(np.uint32)
+
+
+def test_config1_grid_known_answer(torch_cuda):
+    """lib/terminal_set.py:96-113 on RoadOneCarEnv goal (29.9, 1.5, 0, 0): 434 members, [49, 70, 84, 91, 91, 49]."""
+    from carmpc_b200.batch import TerminalSetEvaluator, unpack_bits
+    from carmpc_b200.lib.terminal_set import grid_points, grid_membership
+    g = golden("grid_config1.npz")
+    env = make_env("RoadOneCarEnv", [29.9, 1.5, 0, 0])
+    Ab = np.load(os.path.join(GOLDEN, "terminal_sets", "RoadOneCarEnv_29.9_1.5_0_0.npy"))
+    x, y, psi, v = grid_points(env)
+    ev = TerminalSetEvaluator(Ab)
+    want = g["member"].reshape(-1)
+    for mode in (0, 1):
+        bits, count = ev.contains_bits(*_dev(torch_cuda, x, y, psi, v), mode=mode)
+        got = unpack_bits(_bits_np(bits), len(x))
+        np.testing.assert_array_equal(got, want)
+        assert int(count.item()) == 434
+        assert list(got.reshape(6, -1).sum(1)) == [49, 70, 84, 91, 91, 49]
+    # the drop-in entry point the reference's visualise_set would call
+    pts, member = grid_membership(Ab[:, :4], Ab[:, 4], env)
+    np.testing.assert_array_equal(member, want)
+    assert pts.shape == (60000, 4)
+    # implicit grid: axes (v, y, x) with psi a single-point axis
+    xs = np.linspace(4.9, 54.9, 100)
+    ys = np.linspace(-23.5, 26.5, 100)
+    bits, count = ev.contains_grid_bits([np.arange(6.0), ys, xs, [0.0]], axis_to_state=(3, 1, 0, 2))
+    np.testing.assert_array_equal(unpack_bits(_bits_np(bits), 60000), want)
+    assert int(count.item()) == 434
+
+
+@pytest.mark.parametrize("file", sorted(FIXTURES))
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 511, 513, 100_003, 1_000_000])
+def test_membership_bit_exact_vs_oracle(torch_cuda, file, n):
+    from carmpc_b200.batch import TerminalSetEvaluator
+    from oracle import c_oracle
+    Ab = np.load(os.path.join(GOLDEN, "terminal_sets", file))
+    rng = np.random.default_rng(n)
+    goal = np.array(FIXTURES[file][1], dtype=float)
+    p = goal + rng.uniform(-1, 1, size=(n, 4)) * np.array([12.0, 2.5, 0.45, 3.2])
+    p[: n // 4] = goal + rng.uniform(-1, 1, size=(n // 4, 4)) * np.array([30.0, 6.0, 1.0, 8.0])
+    want_bits, want_cnt = c_oracle.membership_bits(Ab, *p.T)
+    ev = TerminalSetEvaluator(Ab)
+    x, y, psi, v = _dev(torch_cuda, *p.T)
+    for mode in (0, 1):
+        bits, count = ev.contains_bits(x, y, psi, v, mode=mode)
+        np.testing.assert_array_equal(_bits_np(bits), want_bits)
+        assert int(count.item()) == want_cnt
+
+
+def test_membership_edge_cases(torch_cuda):
+    from carmpc_b200.batch import TerminalSetEvaluator
+    from carmpc_b200._capi import CarmpcError
+    from oracle import c_oracle
+    torch = torch_cuda
+    Ab = np.load(os.path.join(GOLDEN, "terminal_sets", "RoadMultipleCarsEnv_30_1.5_0_0.npy"))
+    ev = TerminalSetEvaluator(Ab)
+    # empty input
+    e = torch.empty(0, dtype=torch.float64, device="cuda")
+    bits, count = ev.contains_bits(e, e, e, e)
+    assert bits.numel() == 0 and int(count.item()) == 0
+    # unaligned views (odd element offset -> scalar-load path), ragged tail
+    rng = np.random.default_rng(5)
+    p = np.array([30, 1.5, 0, 0]) + rng.uniform(-1, 1, size=(4099, 4)) * np.array([10.0, 2.0, 0.4, 3.0])
+    big = [torch.from_numpy(np.concatenate(([0.0], c))).cuda() for c in p.T]
+    views = [b[1:] for b in big]
+    want_bits, want_cnt = c_oracle.membership_bits(Ab, *p.T)
+    bits, count = ev.contains_bits(*views, mode=1)
+    np.testing.assert_array_equal(_bits_np(bits), want_bits)
+    # exact ties on a facet: v = 5 with '<='
+    tie = np.array([[30.0, 1.5, 0.0, 5.0], [30.0, 1.5, 0.0, np.nextafter(5.0, 6.0)]])
+    bits, count = ev.contains_bits(*_dev(torch, *tie.T), mode=1)
+    want_bits, _ = c_oracle.membership_bits(Ab, *tie.T)
+    np.testing.assert_array_equal(_bits_np(bits), want_bits)
+    # empty polytope: everything is inside
+    ev0 = TerminalSetEvaluator(np.zeros((0, 5)))
+    bits, count = ev0.contains_bits(*_dev(torch, *p.T))
+    assert int(count.item()) == len(p)
+    # argument errors surface as exceptions with the library's message
+    with pytest.raises(ValueError):
+        ev.contains_bits(views[0].float(), views[1], views[2], views[3])
+    with pytest.raises(CarmpcError):
+        ev.contains_bits(*views, mode=7)
+    # NaN coordinates are never members (NaN <= b is false)
+    nanp = np.array([[np.nan, 1.5, 0.0, 1.0], [30.0, 1.5, 0.0, 0.0]])
+    bits, count = ev.contains_bits(*_dev(torch, *nanp.T), mode=1)
+    assert int(count.item()) == 1 and int(_bits_np(bits)[0]) == 2
+
+
+@pytest.mark.parametrize("file", sorted(FIXTURES))
+def test_rollout_bit_exact_vs_oracle_and_equals_hrep(torch_cuda, file):
+    from carmpc_b200.batch import RolloutEvaluator, TerminalSetEvaluator, unpack_bits
+    from oracle import c_oracle, carmpc_oracle as orc
+    env_name, goal = FIXTURES[file]
+    env = make_env(env_name, goal)
+    k = K_STAR[env_name]
+    n = 300_007
+    rng = np.random.default_rng(7)
+    g = np.array(goal, dtype=float)
+    p = g + rng.uniform(-1, 1, size=(n, 4)) * np.array([12.0, 2.5, 0.45, 3.0])
+    for every in (False, True):
+        ev = RolloutEvaluator.from_env(env, k, input_every_step=every)
+        want_bits, want_first, want_cnt = c_oracle.rollout_bits(ev.A_k, ev.A_con, ev.b_con, ev.A_in, ev.b_in, g, k,
+                                                                int(every), *p.T)
+        bits, count, first = ev.contains_bits(*_dev(torch_cuda, *p.T), want_first_violation=True)
+        np.testing.assert_array_equal(_bits_np(bits), want_bits)
+        np.testing.assert_array_equal(first.cpu().numpy(), want_first)
+        assert int(count.item()) == want_cnt
+    # the oracle's setup and the product's are the same numbers
+    Ak, K, Ac, bc, Ai, bi = orc.rollout_setup(env_name, goal)
+    ev = RolloutEvaluator.from_env(env, k)
+    np.testing.assert_allclose(ev.A_k, Ak, atol=1e-13)
+    np.testing.assert_allclose(ev.A_con, Ac, atol=1e-13)
+    np.testing.assert_allclose(ev.b_con, bc, atol=1e-12)
+    np.testing.assert_allclose(ev.A_in, Ai, atol=1e-12)
+    # rollout form == shipped H-rep outside the 1e-6 boundary band, band enumerated
+    Ab = np.load(os.path.join(GOLDEN, "terminal_sets", file))
+    bits_r, _ = ev.contains_bits(*_dev(torch_cuda, *p.T))
+    bits_h, _ = TerminalSetEvaluator(Ab).contains_bits(*_dev(torch_cuda, *p.T))
+    diff = unpack_bits(_bits_np(bits_r), n) != unpack_bits(_bits_np(bits_h), n)
+    _, margin_h = orc.membership(Ab, *p.T)
+    _, _, margin_r = orc.rollout_membership(env_name, goal, k, *p.T)
+    band = (np.abs(margin_h) <= 1e-6) | (np.abs(margin_r) <= 1e-6)
+    assert not (diff & ~band).any(), f"{(diff & ~band).sum()} disagreements outside the boundary band"
+
+
+def test_host_pipeline_multi_chunk(torch_cuda):
+    """Host-buffer entry points: > 1 pipeline chunk (8 Mi samples), ragged tail, same bits as the device path."""
+    from carmpc_b200.batch import TerminalSetEvaluator, RolloutEvaluator
+    from oracle import c_oracle
+    Ab = np.load(os.path.join(GOLDEN, "terminal_sets", "RoadMultipleCarsEnv_30_1.5_0_0.npy"))
+    n = (1 << 23) * 2 + 12_345
+    rng = np.random.default_rng(11)
+    p = np.array([30, 1.5, 0, 0]) + rng.uniform(-1, 1, size=(n, 4)) * np.array([10.0, 2.0, 0.4, 3.0])
+    cols = [np.ascontiguousarray(c) for c in p.T]
+    want_bits, want_cnt = c_oracle.membership_bits(Ab, *cols)
+    ev = TerminalSetEvaluator(Ab)
+    for mode in (0, 1):
+        bits, cnt = ev.contains_bits_host(*cols, mode=mode)
+        np.testing.assert_array_equal(bits, want_bits)
+        assert cnt == want_cnt
+    env = make_env("RoadMultipleCarsEnv")
+    rv = RolloutEvaluator.from_env(env, 16)
+    m = 3_000_001
+    want_bits, want_first, want_cnt = c_oracle.rollout_bits(rv.A_k, rv.A_con, rv.b_con, rv.A_in, rv.b_in, rv.goal, 16, 0,
+                                                            *[c[:m] for c in cols])
+    bits, cnt, first = rv.contains_bits_host(*[c[:m] for c in cols], want_first_violation=True)
+    np.testing.assert_array_equal(bits, want_bits)
+    np.testing.assert_array_equal(first, want_first)
+    assert cnt == want_cnt
+
+
+def test_config2_full_grid_properties(torch_cuda):
+    """BASELINE config 2: RoadMultipleCarsEnv on the 100^4 = 10^8 grid.  The oracle cannot scan 10^8 points in
+    seconds, so: (i) the implicit-grid kernel and the explicit SoA kernel give the same bitset and count,
+    (ii) a 2 % strided sample is bit-exact against the C oracle, (iii) the count is the sum of shard counts."""
+    torch = torch_cuda
+    from carmpc_b200.batch import TerminalSetEvaluator, unpack_bits
+    from carmpc_b200.grids import config2_axes, materialise_grid
+    from oracle import c_oracle
+    Ab = np.load(os.path.join(GOLDEN, "terminal_sets", "RoadMultipleCarsEnv_30_1.5_0_0.npy"))
+    ev = TerminalSetEvaluator(Ab)
+    axes = config2_axes()
+    x, y, psi, v = materialise_grid(axes, device="cuda")
+    n = x.numel()
+    assert n == 10 ** 8
+    bits, count = ev.contains_bits(x, y, psi, v, mode=1)
+    bits0, count0 = ev.contains_bits(x, y, psi, v, mode=0)
+    assert torch.equal(bits, bits0) and int(count.item()) == int(count0.item())
+    gbits, gcount = ev.contains_grid_bits(axes)
+    assert torch.equal(bits, gbits) and int(count.item()) == int(gcount.item())
+    frac = int(count.item()) / n
+    assert 0.001 < frac < 0.2
+    # strided sample against the oracle
+    idx = torch.arange(0, n, 47, device="cuda")
+    sx, sy, sp, sv = [t[idx].cpu().numpy() for t in (x, y, psi, v)]
+    want_bits, _ = c_oracle.membership_bits(Ab, sx, sy, sp, sv)
+    got = unpack_bits(_bits_np(bits), n)[idx.cpu().numpy()]
+    np.testing.assert_array_equal(got, c_oracle.unpack_bits(want_bits, len(sx)))
+    # shard additivity (the multi-GPU partition: contiguous ranges, multiples of 32)
+    total = 0
+    for r in range(8):
+        lo, hi = r * (n // 8), (r + 1) * (n // 8)
+        b, c = ev.contains_bits(x[lo:hi], y[lo:hi], psi[lo:hi], v[lo:hi])
+        assert torch.equal(b, bits[lo // 32: hi // 32])
+        total += int(c.item())
+    assert total == int(count.item())

@@ -109,6 +109,7 @@ class DeviceModel:
         status[~pre_ok] = 1
         iters = np.zeros(Bn, dtype=np.int32)
         xout = np.zeros((Bn, n), dtype=f)
+        self.w_out = np.zeros((Bn, m + n), dtype=f)        # final w (scaled), kept for polish experiments
         live = pre_ok.copy()
         for it in range(1, max_iter + 1):
             xt = (t @ KinvT).astype(f)                                      # Kinv symmetric
@@ -149,12 +150,15 @@ class DeviceModel:
                 status[newly & ~solved] = 1
                 iters[newly] = it
                 xout[newly] = xt[newly]
+                self.w_out[newly] = np.hstack((wg, wb))[newly]
                 live &= ~newly
                 if verbose and it % (check_every * 10) == 0:
                     print(it, live.sum())
                 if not live.any():
                     break
         xout[live] = xt[live]
+        self.w_out[live] = np.hstack((wg, wb))[live]
+        self.lo_out, self.hi_out = np.hstack((lo, np.broadcast_to(lbs, (Bn, n)))), np.hstack((hi, np.broadcast_to(ubs, (Bn, n))))
         iters[live] = max_iter
         u = xout.astype(float) * self.D[None, :]
         return u, status, iters
