@@ -322,6 +322,11 @@ def main():
     ap.add_argument("--skip-qp", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--qp-states", type=int, default=1_000_000)
+    ap.add_argument("--qp-steps", type=int, default=5)
+    ap.add_argument("--skip-sweep", action="store_true")
+    ap.add_argument("--skip-closed-loop", action="store_true")
+    ap.add_argument("--cl-runs", type=int, default=100_000)
+    ap.add_argument("--cl-steps", type=int, default=200)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -1,0 +1,175 @@
+"""QP half of bench.py: BASELINE configs 3 (10^6 horizon-20 QPs), 5 (horizon sweep) and 4 (Monte-Carlo closed loop).
+
+Imported by bench.py; returns a dict that goes under ``"qp"`` in the JSON line.  The CPU leg (numpy float64
+OSQP-style ADMM of oracle/, the restatement of what cvxpy's default solver does for lib/mpc.py:334-335) is the only
+place oracle/ is executed, as the baseline being timed.
+"""
+from __future__ import annotations
+
+import io
+import contextlib
+import os
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _controller(env_name, goal, N, cls="MPCStateFB", **kw):
+    from carmpc_b200.lib import environments, mpc, terminal_set as ts
+    from carmpc_b200.lib.configuration import DT_CONTROL, LINEARIZE_STATE, LINEARIZE_INPUT
+    env = getattr(environments, env_name)()
+    if goal is not None:
+        env.set_goal(goal)
+    ts.TERMINAL_SET_DIR = os.path.join(ROOT, "terminal_sets")
+    with contextlib.redirect_stdout(io.StringIO()):
+        return getattr(mpc, cls)(dt=DT_CONTROL, N=N, lin_state=LINEARIZE_STATE, lin_input=LINEARIZE_INPUT, env=env, **kw)
+
+
+def cpu_qp_rate(n_states: int = 1500, seed: int = 0):
+    """QPs/s of the numpy float64 ADMM oracle at cvxpy's default OSQP tolerances (eps 1e-5), config-3 states."""
+    from oracle import carmpc_oracle as orc
+    from carmpc_b200.grids import config3_axes, grid_size
+    Ab = np.load(os.path.join(ROOT, "terminal_sets", "RoadOneCarEnv_29.9_1.5_0_0.npy"))
+    oq = orc.CondensedQP("RoadOneCarEnv", 20, Ab)
+    axes = config3_axes()
+    n = grid_size(axes)
+    idx = np.random.default_rng(seed).choice(n, n_states, replace=False)
+    dims = [len(a) for a in axes]
+    cols, stride = [], n
+    for a, d in zip(axes, dims):
+        stride //= d
+        cols.append(a[(idx // stride) % d])
+    x0 = np.stack(cols, axis=1)
+    t0 = time.perf_counter()
+    u, y, st, iters = orc.qp_solve_admm(oq, x0, np.array([29.9, 1.5, 0, 0]), eps=1e-5, eps_inf=1e-4, max_iter=4000,
+                                        return_iters=True)
+    dt = time.perf_counter() - t0
+    return {"value": n_states / dt, "unit": "QPs/s", "cores": int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)),
+            "kind": "port", "sample": f"{n_states} random states of the config-3 grid, numpy float64 ADMM (OSQP iteration, "
+            f"eps 1e-5, rho 30 unscaled), {dt:.1f} s", "mean_iters": float(iters.mean()),
+            "feasible_frac": float((st == 0).mean())}
+
+
+def _time_solves(bq, x0, steps, warmup, torch):
+    for _ in range(warmup):
+        out = bq.solve(x0)
+    torch.cuda.synchronize()
+    t_iters, launches = 0, 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = bq.solve(x0)
+        it, la = bq.last_stats()
+        t_iters += it
+        launches += la
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / steps, t_iters / steps, launches, out
+
+
+def run_qp_bench(args, rank, world, dev, barrier):
+    import torch
+    import torch.distributed as dist
+    from carmpc_b200.batch import BatchQP, measure_peak
+    from carmpc_b200.grids import config3_axes, materialise_grid
+
+    B = args.qp_states
+    axes = config3_axes()
+    x0_full = torch.stack(materialise_grid(axes, device=dev)).contiguous()          # (4, 10^6)
+    x0 = x0_full[:, :B].contiguous() if B < x0_full.shape[1] else x0_full
+    B = x0.shape[1]
+    steps, warmup = args.qp_steps, 3
+
+    c20 = _controller("RoadOneCarEnv", [29.9, 1.5, 0, 0], 20)
+    bq = BatchQP.from_controller(c20)
+    tiling = bq.tiling()
+    barrier()
+    ms, iters, launches, out = _time_solves(bq, x0, steps, warmup, torch)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    status = out["status"]
+    res = {
+        "metric": "horizon-20 QPs/s", "value": world * B / (ms_max * 1e-3), "unit": "QPs/s", "ms_per_step": ms_max,
+        "steps": steps, "warmup": warmup,
+        "config": {"workload": "config 3: RoadOneCarEnv goal (29.9, 1.5, 0, 0), N = 20, 100x100x10x10 grid of initial "
+                               "states, one condensed QP each, cold start", "states_per_gpu": B,
+                   "tolerance": "ADMM float32 to 1e-3 (active set) + float64 polish with KKT check"},
+        "feasible_frac": float((status == 0).float().mean().item()),
+        "max_iter_count": int((status == 2).sum().item()),
+        "mean_admm_iters": iters / B, "gpu_launches": launches, "tiling": tiling,
+    }
+    if rank == 0:
+        fp32_peak = measure_peak("fp32")
+        flops_exec = iters * tiling["flop_per_iter"]
+        flops_dense = iters * tiling["flop_per_iter_dense"]
+        res["roofline"] = {"bound": "fp32-ffma", "achieved": flops_exec / (ms * 1e-3) / 1e12, "peak": fp32_peak,
+                           "unit": "TFLOP/s", "frac": flops_exec / (ms * 1e-3) / 1e12 / fp32_peak,
+                           "peak_source": "measured live (carmpc_measure_peak fp32 FFMA)",
+                           "flop_per_iter_executed": tiling["flop_per_iter"],
+                           "flop_per_iter_dense": tiling["flop_per_iter_dense"],
+                           "dense_equivalent_tflops": flops_dense / (ms * 1e-3) / 1e12,
+                           "note": "whole solve (ADMM + polish) time; executed flops exclude structural zeros"}
+    # end to end through the host entry point (numpy AoS states in, numpy results out)
+    xh = np.ascontiguousarray(x0.cpu().numpy().T)
+    bq.solve_host(xh[:1000])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_steps = 2
+    for _ in range(e2e_steps):
+        r = bq.solve_host(xh)
+    dt = (time.perf_counter() - t0) / e2e_steps
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    res["e2e"] = {"value": world * B / float(tt.item()), "unit": "QPs/s", "h2d_bytes_per_step": B * 32,
+                  "d2h_bytes_per_step": B * (16 + 8 + 4 + 4), "call": "carmpc_qp_solve_host"}
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        res["cpu_baseline"] = cpu_qp_rate()
+
+    # ---- config 5: horizon sweep ----------------------------------------------------------------------------
+    if not args.skip_sweep:
+        sweep = {}
+        for N in (10, 20, 40, 80):
+            cN = c20 if N == 20 else _controller("RoadOneCarEnv", [29.9, 1.5, 0, 0], N)
+            bN = bq if N == 20 else BatchQP.from_controller(cN)
+            bN.solve(x0[:, :4096].contiguous())
+            ms_n, it_n, _, o = _time_solves(bN, x0, 1, 0, torch)
+            tl = bN.tiling()
+            sweep[str(N)] = {"qps": B / (ms_n * 1e-3), "ms": ms_n, "mean_iters": it_n / B,
+                             "feasible_frac": float((o["status"] == 0).float().mean().item()),
+                             "max_iter_count": int((o["status"] == 2).sum().item()),
+                             "executed_tflops": it_n * tl["flop_per_iter"] / (ms_n * 1e-3) / 1e12,
+                             "samples_per_lane": tl["samples_per_lane"], "matrices_in_smem": tl["matrices_in_smem"]}
+        res["horizon_sweep"] = sweep
+
+    # ---- config 4: output-feedback Monte-Carlo closed loop --------------------------------------------------------
+    if not args.skip_closed_loop:
+        from oracle_free_constants import C_OUT, L_OBS
+        ofb = _controller("RoadEnv", None, 20)
+        bl = BatchQP.from_controller(ofb)
+        R, T = args.cl_runs, args.cl_steps
+        g = torch.Generator(device="cpu").manual_seed(0)
+        lo = torch.tensor([0.0, -2.5, -0.2, 0.0], dtype=torch.float64)
+        hi = torch.tensor([10.0, 2.5, 0.2, 3.0], dtype=torch.float64)
+        x_init = (lo[:, None] + (hi - lo)[:, None] * torch.rand((4, R), generator=g, dtype=torch.float64)).to(dev).contiguous()
+        bl.closed_loop(x_init[:, :1024].contiguous(), 5, ofb.A, ofb.B, C=C_OUT, L=L_OBS)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        o = bl.closed_loop(x_init, T, ofb.A, ofb.B, C=C_OUT, L=L_OBS)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        fail = o["fail_step"]
+        final = o["final"]
+        goal = torch.tensor([30.0, 1.5, 0.0, 0.0], dtype=torch.float64, device=dev)
+        ok = fail < 0
+        reached = ((final - goal[:, None]).abs() <= 0.1).all(0) & ok
+        res["closed_loop"] = {"workload": f"config 4: RoadEnv output-feedback MPC, {R} runs x {T} steps vs nonlinear bicycle",
+                              "closed_loop_steps_per_s": float(ok.sum().item()) * T / dt, "runs_per_s": R / dt,
+                              "seconds": dt, "never_infeasible_frac": float(ok.float().mean().item()),
+                              "reached_goal_frac": float(reached.float().mean().item()),
+                              "mean_admm_iters_per_qp": o["total_iters"] / max(1.0, float(ok.sum().item()) * T)}
+    return res

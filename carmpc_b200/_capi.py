@@ -21,8 +21,7 @@ class QPOpts(ctypes.Structure):
     _fields_ = [("rho", ctypes.c_double), ("alpha", ctypes.c_double), ("eps_abs", ctypes.c_double),
                 ("eps_rel", ctypes.c_double), ("eps_prim_inf", ctypes.c_double),
                 ("max_iter", ctypes.c_int32), ("check_every", ctypes.c_int32),
-                ("scaling_iters", ctypes.c_int32), ("precise", ctypes.c_int32),
-                ("polish", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("scaling_iters", ctypes.c_int32), ("polish", ctypes.c_int32)]
 
 
 _vp, _dp, _i64, _i32 = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int

@@ -193,3 +193,144 @@ def measure_peak(which: str) -> float:
     val = ctypes.c_double(0.0)
     check(_capi.load().carmpc_measure_peak(idx, ctypes.byref(val)))
     return float(val.value)
+
+
+# ----------------------------------------------------------------------------------------------------
+# batched condensed MPC QP
+# ----------------------------------------------------------------------------------------------------
+@dataclass
+class QPResult:
+    """Per-sample results of a batched solve, in the layouts the reference uses for one sample."""
+    u0: np.ndarray              # (B, 2)   first input of the optimal sequence (what ``.step`` returns)
+    objective: np.ndarray       # (B,)     1/2 u'Hu + q'u  (the reference's ``cost``); +inf when infeasible
+    status: np.ndarray          # (B,)     0 solved, 1 infeasible (outside the region of attraction), 2 max_iter
+    iters: np.ndarray           # (B,)     ADMM iterations spent
+    u_full: Optional[np.ndarray] = None     # (B, 2N)
+
+
+class BatchQP(_Handle):
+    """One condensed MPC QP per initial state, all on the GPU (``carmpc_qp_*``)."""
+
+    def __init__(self, pq, **opts):
+        super().__init__()
+        self.pq = pq
+        self.n, self.m = pq.n, pq.m
+        o = _capi.QPOpts()
+        self._lib.carmpc_qp_default_opts(ctypes.byref(o))
+        for k, v in opts.items():
+            if not hasattr(o, k):
+                raise TypeError(f"unknown QP option {k!r}")
+            setattr(o, k, v)
+        self.opts = o
+        arrs = [_f64(pq.H), _f64(pq.F), _f64(pq.G), _f64(pq.Gx), _f64(pq.Gc), _f64(pq.lo), _f64(pq.hi), _f64(pq.lb),
+                _f64(pq.ub), _f64(pq.Px), _f64(pq.Pc), _f64(pq.pre_lo), _f64(pq.pre_hi)]
+        self._keep = arrs
+        check(self._lib.carmpc_qp_create(pq.n, pq.m, len(pq.pre_hi), *[_capi.ptr(a) if a.size else None for a in arrs],
+                                         ctypes.byref(o), ctypes.byref(self._h)))
+
+    @classmethod
+    def from_controller(cls, controller, **opts) -> "BatchQP":
+        """Condense an ``lib.mpc.MPC`` controller (its enabled constraint blocks, goal, horizon)."""
+        from .condensed import build_parametric_qp
+        return cls(build_parametric_qp(controller), **opts)
+
+    # ---- introspection --------------------------------------------------------------------------
+    def setup(self, which: int) -> np.ndarray:
+        """Host view of the solver setup (see ``carmpc_qp_get_setup``)."""
+        cnt = self._lib.carmpc_qp_get_setup(self._h, which, None, 0)
+        if cnt < 0:
+            check(cnt)
+        out = np.zeros(cnt)
+        got = self._lib.carmpc_qp_get_setup(self._h, which, _capi.ptr(out), cnt)
+        if got < 0:
+            check(got)
+        return out
+
+    def tiling(self) -> dict:
+        t = self.setup(7)
+        keys = ("samples_per_lane", "groups_a", "groups_b", "matrices_in_smem", "smem_bytes", "flop_per_iter",
+                "flop_per_iter_dense", "k_total", "padded_rows", "padded_vars")
+        return dict(zip(keys, t))
+
+    def last_stats(self):
+        """(sum of ADMM iterations over the samples of the last solve, kernel launches issued)."""
+        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        check(self._lib.carmpc_qp_last_stats(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return int(a.value), int(b.value)
+
+    # ---- device tensors ---------------------------------------------------------------------------
+    def solve(self, x0, x_ref=None, c=None, want_u_full: bool = False, warm=None, warm_in: bool = False,
+              warm_out: bool = False, stream=None) -> dict:
+        """``x0``: (4, B) float64 CUDA tensor (SoA).  Returns a dict of CUDA tensors: ``u0`` (2, B), ``objective``
+        (B,), ``status`` (B,) int32, ``iters`` (B,) int32 and optionally ``u_full`` (B, 2N)."""
+        torch = _torch()
+        if not (x0.is_cuda and x0.dtype == torch.float64 and x0.dim() == 2 and x0.shape[0] == 4 and x0.is_contiguous()):
+            raise ValueError("x0 must be a contiguous (4, B) float64 CUDA tensor")
+        B = x0.shape[1]
+        dev = x0.device
+        xref = _f64(self.pq.goal if x_ref is None else x_ref)
+        out = {"u0": torch.empty((2, B), dtype=torch.float64, device=dev),
+               "objective": torch.empty(B, dtype=torch.float64, device=dev),
+               "status": torch.empty(B, dtype=torch.int32, device=dev),
+               "iters": torch.empty(B, dtype=torch.int32, device=dev)}
+        if want_u_full:
+            out["u_full"] = torch.empty((B, self.n), dtype=torch.float64, device=dev)
+        if warm is not None and not (warm.is_cuda and warm.dtype == torch.float32 and warm.numel() == B * (self.m + self.n)):
+            raise ValueError("warm must be a float32 CUDA tensor of B * (m + n) elements")
+        check(self._lib.carmpc_qp_solve_batch(
+            self._h, x0.data_ptr(), _capi.ptr(xref), c.data_ptr() if c is not None else None, B,
+            out["u0"].data_ptr(), out["objective"].data_ptr(), out["status"].data_ptr(), out["iters"].data_ptr(),
+            out["u_full"].data_ptr() if want_u_full else None, warm.data_ptr() if warm is not None else None,
+            int(warm_in), int(warm_out), _stream_ptr(stream)))
+        return out
+
+    # ---- host arrays ---------------------------------------------------------------------------------
+    def solve_host(self, x0, x_ref=None, want_u_full: bool = False, c=None) -> QPResult:
+        """``x0``: (B, 4) numpy states, as the reference passes them to ``.step`` one at a time."""
+        x0 = _f64(np.atleast_2d(x0))
+        if x0.shape[1] != 4:
+            raise ValueError("x0 must be (B, 4)")
+        B = len(x0)
+        xref = _f64(self.pq.goal if x_ref is None else x_ref)
+        res = QPResult(u0=np.zeros((B, 2)), objective=np.zeros(B), status=np.zeros(B, dtype=np.int32),
+                       iters=np.zeros(B, dtype=np.int32), u_full=np.zeros((B, self.n)) if want_u_full else None)
+        cc = _f64(c) if c is not None else None
+        check(self._lib.carmpc_qp_solve_host(self._h, _capi.ptr(x0), _capi.ptr(xref), _capi.ptr(cc), B,
+                                             _capi.ptr(res.u0), _capi.ptr(res.objective), _capi.ptr(res.status),
+                                             _capi.ptr(res.iters), _capi.ptr(res.u_full)))
+        return res
+
+    # ---- Monte-Carlo closed loop ------------------------------------------------------------------------
+    def closed_loop(self, x_init, steps: int, A, B, x_ref=None, C=None, L=None, xhat_init=None, dt: float = 0.2,
+                    l1: float = 3.5, warm_start: bool = True, want_traj: bool = False, want_inputs: bool = False,
+                    stream=None) -> dict:
+        """Runs ``steps`` closed-loop steps for every column of ``x_init`` ((4, R) float64 CUDA tensor) against the
+        nonlinear bicycle.  Output feedback when ``C`` and ``L`` are given (observer started at ``xhat_init`` or the
+        true state), state feedback otherwise.  Returns ``final`` (4, R), ``fail_step`` (R,) int32 (-1: never
+        infeasible), optionally ``traj`` (steps, 4, R) and ``inputs`` (steps, 2, R), and ``total_iters``."""
+        torch = _torch()
+        if not (x_init.is_cuda and x_init.dtype == torch.float64 and x_init.dim() == 2 and x_init.shape[0] == 4
+                and x_init.is_contiguous()):
+            raise ValueError("x_init must be a contiguous (4, R) float64 CUDA tensor")
+        R = x_init.shape[1]
+        dev = x_init.device
+        mode = 1 if C is not None else 0
+        xref = _f64(self.pq.goal if x_ref is None else x_ref)
+        A_, B_ = _f64(A), _f64(B)
+        C_ = _f64(C) if C is not None else None
+        L_ = _f64(L) if L is not None else None
+        out = {"final": torch.empty((4, R), dtype=torch.float64, device=dev),
+               "fail_step": torch.empty(R, dtype=torch.int32, device=dev)}
+        if want_traj:
+            out["traj"] = torch.empty((steps, 4, R), dtype=torch.float64, device=dev)
+        if want_inputs:
+            out["inputs"] = torch.empty((steps, 2, R), dtype=torch.float64, device=dev)
+        total = ctypes.c_int64(0)
+        check(self._lib.carmpc_closed_loop(
+            self._h, mode, _capi.ptr(A_), _capi.ptr(B_), _capi.ptr(C_), _capi.ptr(L_), _capi.ptr(xref), float(dt),
+            float(l1), int(steps), int(warm_start), x_init.data_ptr(),
+            xhat_init.data_ptr() if xhat_init is not None else None, R, out["final"].data_ptr(),
+            out["fail_step"].data_ptr(), out["traj"].data_ptr() if want_traj else None,
+            out["inputs"].data_ptr() if want_inputs else None, ctypes.byref(total), _stream_ptr(stream)))
+        out["total_iters"] = int(total.value)
+        return out

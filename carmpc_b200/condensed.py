@@ -39,7 +39,9 @@ class ParametricQP:
     hi: np.ndarray         # (m,)
     lb: np.ndarray         # (n,)  -inf when the input box is disabled
     ub: np.ndarray         # (n,)
+    Gc: np.ndarray         # (m,)  shift per unit of the scalar disturbance estimate (zeros without one)
     Px: np.ndarray         # (k, 4)
+    Pc: np.ndarray         # (k,)
     pre_lo: np.ndarray     # (k,)
     pre_hi: np.ndarray     # (k,)
     goal: np.ndarray       # (4,)  default x_ref
@@ -109,13 +111,19 @@ def build_parametric_qp(controller, merge_rows: bool = True) -> ParametricQP:
         rows_b = np.zeros(0)
     G_all = rows_x @ S
     Gx_all = rows_x @ T
-
-    if merge_rows:
-        M, lo, hi, src_hi, src_lo = _merge_opposites(np.hstack((G_all, Gx_all)), rows_b)
+    # constant-disturbance controllers predict x_ = T x0 + S u + ABd d (lib/mpc.py:631-637): one more column
+    if hasattr(controller, "disturbance_response"):
+        Gc_all = rows_x @ controller.disturbance_response()
     else:
-        M, lo, hi = np.hstack((G_all, Gx_all)), np.full(len(rows_b), -np.inf), rows_b.copy()
+        Gc_all = np.zeros(len(rows_b))
+
+    stacked = np.hstack((G_all, Gx_all, Gc_all[:, None]))
+    if merge_rows:
+        M, lo, hi, src_hi, src_lo = _merge_opposites(stacked, rows_b)
+    else:
+        M, lo, hi = stacked, np.full(len(rows_b), -np.inf), rows_b.copy()
         src_hi, src_lo = np.arange(len(rows_b)), np.full(len(rows_b), -1)
-    G, Gx = M[:, :n], M[:, n:]
+    G, Gx, Gc = M[:, :n], M[:, n:n + 4], M[:, n + 4]
     param_only = ~np.any(G != 0.0, axis=1)
 
     if controller.input_constraint_bool:
@@ -128,6 +136,7 @@ def build_parametric_qp(controller, merge_rows: bool = True) -> ParametricQP:
     return ParametricQP(
         N=N, H=np.array(controller.H, dtype=float), F=np.array(controller.h, dtype=float),
         G=np.ascontiguousarray(G[keep]), Gx=np.ascontiguousarray(Gx[keep]), lo=lo[keep], hi=hi[keep],
-        lb=lb, ub=ub, Px=np.ascontiguousarray(Gx[param_only]), pre_lo=lo[param_only], pre_hi=hi[param_only],
+        Gc=np.ascontiguousarray(Gc[keep]), lb=lb, ub=ub, Px=np.ascontiguousarray(Gx[param_only]),
+        Pc=np.ascontiguousarray(Gc[param_only]), pre_lo=lo[param_only], pre_hi=hi[param_only],
         goal=np.array(controller.goal, dtype=float), T=T, S=S, rows_x=rows_x, rows_b=rows_b,
         src_hi=src_hi[keep], src_lo=src_lo[keep])

@@ -1,0 +1,285 @@
+// C ABI of the batched QP solver (include/carmpc.h, part B): handle creation (host setup + upload), the two-pass
+// ADMM -> polish orchestration, host-buffer convenience entry point and statistics.
+#include <string.h>
+
+#include <algorithm>
+
+#include "qp_internal.cuh"
+
+namespace carmpc {
+
+namespace {
+
+template <class T>
+int upload(QPHandle* q, const std::vector<T>& v, const T** dst) {
+    void* d = nullptr;
+    const size_t bytes = sizeof(T) * std::max<size_t>(v.size(), 1);
+    CARMPC_CUDA(cudaMalloc(&d, bytes));
+    q->allocations.push_back(d);
+    if (!v.empty()) CARMPC_CUDA(cudaMemcpy(d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+    *dst = static_cast<const T*>(d);
+    return CARMPC_OK;
+}
+
+}  // namespace
+
+QPHandle::~QPHandle() {
+    for (void* p : allocations) cudaFree(p);
+    cudaFree(ws_sign); cudaFree(ws_u); cudaFree(ws_status); cudaFree(ws_iters); cudaFree(ws_failed);
+    cudaFree(ws_counters); cudaFree(ws_total_iters); cudaFree(ws_polished);
+}
+
+int QPHandle::ensure_workspace(int64_t batch) {
+    if (ws_counters == nullptr) {
+        CARMPC_CUDA(cudaMalloc(&ws_counters, sizeof(int) * 8));
+        CARMPC_CUDA(cudaMalloc(&ws_total_iters, sizeof(unsigned long long)));
+    }
+    if (batch <= ws_batch) return CARMPC_OK;
+    cudaFree(ws_sign); cudaFree(ws_u); cudaFree(ws_status); cudaFree(ws_iters); cudaFree(ws_failed); cudaFree(ws_polished);
+    ws_sign = nullptr; ws_u = nullptr; ws_status = nullptr; ws_iters = nullptr; ws_failed = nullptr; ws_polished = nullptr;
+    ws_batch = 0;
+    CARMPC_CUDA(cudaMalloc(&ws_sign, (size_t)batch * admm.mt));
+    CARMPC_CUDA(cudaMalloc(&ws_u, sizeof(float) * (size_t)batch * admm.n));
+    CARMPC_CUDA(cudaMalloc(&ws_status, sizeof(int) * (size_t)batch));
+    CARMPC_CUDA(cudaMalloc(&ws_iters, sizeof(int) * (size_t)batch));
+    CARMPC_CUDA(cudaMalloc(&ws_failed, sizeof(int) * (size_t)batch));
+    CARMPC_CUDA(cudaMalloc(&ws_polished, (size_t)batch));
+    ws_batch = batch;
+    return CARMPC_OK;
+}
+
+int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, const double* d_c, const int* d_idx,
+                    int64_t count, double* d_u0, double* d_objective, int32_t* d_status, int32_t* d_iters,
+                    double* d_u_full, float* d_warm, int warm_in, int warm_out, cudaStream_t st) {
+    // `stride` is the number of samples the per-sample arrays are sized for; `count` the number solved now
+    // (all of them, or those listed in d_idx).
+    if (host_only) { set_error("carmpc_qp: this handle was created without a CUDA device; there is no CPU solver"); return CARMPC_ERR_CUDA; }
+    int rc = ensure_workspace(stride);
+    if (rc != CARMPC_OK) return rc;
+    last_launches = 0;
+    last_second_pass = 0;
+    CARMPC_CUDA(cudaMemsetAsync(ws_counters, 0, sizeof(int) * 8, st));
+    CARMPC_CUDA(cudaMemsetAsync(ws_total_iters, 0, sizeof(unsigned long long), st));
+    int* status = d_status ? d_status : ws_status;
+    int* iters = d_iters ? d_iters : ws_iters;
+
+    AdmmBatch ab;
+    memset(&ab, 0, sizeof(ab));
+    ab.x0 = d_x0; ab.stride = stride; ab.cdist = d_c;
+    for (int c = 0; c < 4; ++c) ab.xref[c] = xref[c];
+    ab.idx_list = d_idx; ab.count = (int)count; ab.next = ws_counters + 0;
+    ab.sign = ws_sign; ab.u_admm = ws_u; ab.status = status; ab.iters = iters;
+    ab.warm = d_warm; ab.warm_in = d_warm ? warm_in : 0; ab.warm_out = d_warm ? warm_out : 0;
+    ab.total_iters = ws_total_iters; ab.eps_scale = 1.f; ab.max_iter = host.opts.max_iter; ab.iters_accumulate = 0;
+    rc = admm_launch(this, ab, st);
+    if (rc != CARMPC_OK) return rc;
+    ++last_launches;
+
+    PolishBatch pb;
+    memset(&pb, 0, sizeof(pb));
+    pb.x0 = d_x0; pb.stride = stride; pb.cdist = d_c;
+    for (int c = 0; c < 4; ++c) pb.xref[c] = xref[c];
+    pb.idx_list = d_idx; pb.count = (int)count; pb.sign = ws_sign; pb.u_admm = ws_u; pb.status = status;
+    pb.u0 = d_u0; pb.objective = d_objective; pb.u_full = d_u_full; pb.polished = ws_polished;
+    pb.n_failed = ws_counters + 1; pb.failed_list = ws_failed;
+    pb.rounds = host.opts.polish ? -1 : 0;
+    pb.final_pass = host.opts.polish ? 0 : 1;
+    rc = polish_launch(this, pb, st);
+    if (rc != CARMPC_OK) return rc;
+    ++last_launches;
+
+    int n_failed = 0;
+    if (host.opts.polish) {
+        CARMPC_CUDA(cudaMemcpyAsync(&n_failed, ws_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CARMPC_CUDA(cudaStreamSynchronize(st));
+    }
+    if (n_failed > 0) {
+        // second pass on the samples whose active set the polish could not certify: tighter ADMM, then accept
+        last_second_pass = n_failed;
+        ab.idx_list = ws_failed; ab.count = n_failed; ab.next = ws_counters + 2; ab.eps_scale = 0.01f;
+        ab.warm_in = 0; ab.iters_accumulate = 1;
+        rc = admm_launch(this, ab, st);
+        if (rc != CARMPC_OK) return rc;
+        pb.idx_list = ws_failed; pb.count = n_failed; pb.n_failed = ws_counters + 3; pb.final_pass = 1;
+        rc = polish_launch(this, pb, st);
+        if (rc != CARMPC_OK) return rc;
+        last_launches += 2;
+    }
+    unsigned long long total = 0;
+    CARMPC_CUDA(cudaMemcpyAsync(&total, ws_total_iters, sizeof(total), cudaMemcpyDeviceToHost, st));
+    CARMPC_CUDA(cudaStreamSynchronize(st));
+    last_total_iters = (int64_t)total;
+    return CARMPC_OK;
+}
+
+}  // namespace carmpc
+
+using namespace carmpc;
+
+extern "C" {
+
+void carmpc_qp_default_opts(carmpc_qp_opts* o) {
+    if (!o) return;
+    o->rho = 0.1; o->alpha = 1.6; o->eps_abs = 1e-3; o->eps_rel = 1e-3; o->eps_prim_inf = 1e-4;
+    o->max_iter = 4000; o->check_every = 10; o->scaling_iters = 15; o->polish = 1;
+}
+
+int carmpc_qp_create(int n, int m, int k, const double* h_H, const double* h_F, const double* h_G, const double* h_Gx,
+                     const double* h_Gc, const double* h_lo, const double* h_hi, const double* h_lb,
+                     const double* h_ub, const double* h_Px, const double* h_Pc, const double* h_pre_lo,
+                     const double* h_pre_hi, const carmpc_qp_opts* opts, void** handle) {
+    CARMPC_REQUIRE(handle != nullptr, "handle");
+    CARMPC_REQUIRE(n >= 1 && n <= kMaxN, "n must be in [1, 160]");
+    CARMPC_REQUIRE(m >= 0 && m <= 1024, "m must be in [0, 1024]");
+    CARMPC_REQUIRE(k >= 0 && k <= 64, "k must be in [0, 64]");
+    CARMPC_REQUIRE(h_H && h_F && h_lb && h_ub, "null matrix pointer");
+    CARMPC_REQUIRE(m == 0 || (h_G && h_Gx && h_lo && h_hi), "null constraint pointer");
+    CARMPC_REQUIRE(k == 0 || (h_Px && h_pre_lo && h_pre_hi), "null pre-check pointer");
+    carmpc_qp_opts o;
+    carmpc_qp_default_opts(&o);
+    if (opts) o = *opts;
+    CARMPC_REQUIRE(o.rho > 0 && o.alpha > 0 && o.alpha < 2, "rho > 0, 0 < alpha < 2");
+    CARMPC_REQUIRE(o.check_every >= 1 && o.max_iter >= o.check_every, "check_every >= 1, max_iter >= check_every");
+    CARMPC_REQUIRE(o.scaling_iters >= 0 && o.scaling_iters <= 100, "scaling_iters");
+    QPHandle* q = new QPHandle();
+    q->kind = kQP;
+    cudaGetDevice(&q->device);
+    q->sm = sm_count();
+    int rc = qp_host_setup(n, m, k, h_H, h_F, h_G, h_Gx, h_Gc, h_lo, h_hi, h_lb, h_ub, h_Px, h_Pc, h_pre_lo, h_pre_hi, o,
+                           &q->host);
+    if (rc != CARMPC_OK) { delete q; return rc; }
+    QPHost& h = q->host;
+    q->admm = h.geo;
+    AdmmTables& a = q->admm;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        // no CUDA device: keep the host-side setup inspectable (carmpc_qp_get_setup); every solve fails loudly
+        cudaGetLastError();
+        q->host_only = true;
+        *handle = q;
+        return CARMPC_OK;
+    }
+#define UP(vec, field) do { rc = upload(q, h.vec, &a.field); if (rc != CARMPC_OK) { delete q; return rc; } } while (0)
+    UP(P, P); UP(Gs, Gs); UP(GsT, GsT); UP(his, his); UP(Gxs, Gxs); UP(Gcs, Gcs); UP(width, width); UP(Einv_g, Einv_g);
+    UP(vpos, vpos); UP(row_id, row_id); UP(lam, lam); UP(lbs, lbs); UP(ubs, ubs); UP(Einv_b, Einv_b); UP(Dinv, Dinv);
+    UP(Dsc, Dsc); UP(KF, KF); UP(var_id, var_id); UP(segA, segA); UP(segB, segB); UP(Px, Px); UP(Pc, Pc);
+    UP(pre_lo, pre_lo); UP(pre_hi, pre_hi);
+#undef UP
+    PolishTables& p = q->polish;
+    p.n = n; p.m = m; p.mt = m + n;
+#define UP(vec, field) do { rc = upload(q, h.vec, &p.field); if (rc != CARMPC_OK) { delete q; return rc; } } while (0)
+    UP(H, H); UP(Hinv, Hinv); UP(F, F); UP(GT, GT); UP(AH, AH); UP(AHA, AHA); UP(Gx, Gx); UP(Gc, Gc); UP(hi, hi); UP(lo, lo);
+#undef UP
+    *handle = q;
+    return CARMPC_OK;
+}
+
+int carmpc_qp_get_setup(void* qp, int which, double* h_out, int capacity) {
+    QPHandle* q = check_handle<QPHandle>(qp, kQP);
+    CARMPC_REQUIRE(q != nullptr, "not a QP handle");
+    const QPHost& h = q->host;
+    std::vector<double> tmp;
+    const std::vector<double>* src = nullptr;
+    switch (which) {
+        case 0: src = &h.D; break;
+        case 1: src = &h.Eg; break;
+        case 2: src = &h.Eb; break;
+        case 3: tmp = {h.cscale}; src = &tmp; break;
+        case 4: src = &h.Kinv; break;
+        case 5: src = &h.Gs64; break;
+        case 6: tmp.resize(h.n); for (int j = 0; j < h.n; ++j) tmp[j] = h.Eb[j] * h.D[j]; src = &tmp; break;
+        case 7: tmp = {(double)h.samples_per_lane, (double)h.ga_per_warp, (double)h.gb_per_warp, (double)h.mats_in_smem,
+                       (double)h.smem_bytes, h.flops_per_iter, h.flops_per_iter_dense, (double)h.geo.ktot,
+                       (double)h.geo.m_phys, (double)h.geo.nA_rows}; src = &tmp; break;
+        // padded device images, as float64 (tests re-run the kernel's arithmetic on the host from these)
+        case 10: tmp.assign(h.P.begin(), h.P.end()); src = &tmp; break;
+        case 11: tmp.assign(h.Gs.begin(), h.Gs.end()); src = &tmp; break;
+        case 12: tmp.assign(h.GsT.begin(), h.GsT.end()); src = &tmp; break;
+        case 13: src = &h.his; break;
+        case 14: src = &h.Gxs; break;
+        case 15: tmp.assign(h.width.begin(), h.width.end()); src = &tmp; break;
+        case 16: tmp.assign(h.vpos.begin(), h.vpos.end()); src = &tmp; break;
+        case 17: tmp.assign(h.row_id.begin(), h.row_id.end()); src = &tmp; break;
+        case 18: tmp.assign(h.lam.begin(), h.lam.end()); src = &tmp; break;
+        case 19: tmp.assign(h.lbs.begin(), h.lbs.end()); src = &tmp; break;
+        case 20: tmp.assign(h.ubs.begin(), h.ubs.end()); src = &tmp; break;
+        case 21: src = &h.KF; break;
+        case 22: tmp.assign(h.var_id.begin(), h.var_id.end()); src = &tmp; break;
+        case 23: for (const int4& s4 : h.segA) { tmp.push_back(s4.x); tmp.push_back(s4.y); tmp.push_back(s4.z); tmp.push_back(s4.w); } src = &tmp; break;
+        case 24: for (const int2& s2 : h.segB) { tmp.push_back(s2.x); tmp.push_back(s2.y); } src = &tmp; break;
+        case 25: tmp.assign(h.Dsc.begin(), h.Dsc.end()); src = &tmp; break;
+        case 26: tmp = {(double)h.geo.n, (double)h.geo.m, (double)h.geo.nA_rows, (double)h.geo.m_phys, (double)h.geo.npad4,
+                        (double)h.geo.mv4, (double)h.geo.ktot, (double)h.geo.nGA, (double)h.geo.nGB}; src = &tmp; break;
+        default: set_error("carmpc_qp_get_setup: unknown selector %d", which); return CARMPC_ERR_INVALID;
+    }
+    const int cnt = (int)src->size();
+    if (h_out) {
+        CARMPC_REQUIRE(capacity >= cnt, "capacity too small");
+        memcpy(h_out, src->data(), sizeof(double) * cnt);
+    }
+    return cnt;
+}
+
+int carmpc_qp_solve_batch(void* qp, const double* d_x0, const double* h_xref, const double* d_c, int64_t batch,
+                          double* d_u0, double* d_objective, int32_t* d_status, int32_t* d_iters, double* d_u_full,
+                          float* d_warm, int warm_in, int warm_out, void* stream) {
+    QPHandle* q = check_handle<QPHandle>(qp, kQP);
+    CARMPC_REQUIRE(q != nullptr, "not a QP handle");
+    CARMPC_REQUIRE(batch >= 0 && batch < (int64_t)1 << 31, "batch");
+    CARMPC_REQUIRE(h_xref != nullptr, "h_xref");
+    if (batch == 0) { q->last_total_iters = 0; q->last_launches = 0; return CARMPC_OK; }
+    CARMPC_REQUIRE(d_x0 && d_status, "d_x0 and d_status are required");
+    return q->solve(d_x0, batch, h_xref, d_c, nullptr, batch, d_u0, d_objective, d_status, d_iters, d_u_full, d_warm,
+                    warm_in, warm_out, (cudaStream_t)stream);
+}
+
+int carmpc_qp_solve_host(void* qp, const double* h_x0, const double* h_xref, const double* h_c, int64_t batch,
+                         double* h_u0, double* h_objective, int32_t* h_status, int32_t* h_iters, double* h_u_full) {
+    QPHandle* q = check_handle<QPHandle>(qp, kQP);
+    CARMPC_REQUIRE(q != nullptr, "not a QP handle");
+    CARMPC_REQUIRE(batch >= 0 && batch < (int64_t)1 << 31, "batch");
+    if (batch == 0) return CARMPC_OK;
+    CARMPC_REQUIRE(h_x0 && h_xref && h_status, "null host pointer");
+    const int n = q->host.n;
+    // AoS (batch x 4, as the reference passes states) -> SoA on the way in; results back in the reference's layouts
+    std::vector<double> soa((size_t)4 * batch);
+    for (int64_t i = 0; i < batch; ++i)
+        for (int c = 0; c < 4; ++c) soa[(size_t)c * batch + i] = h_x0[i * 4 + c];
+    double *d_x0 = nullptr, *d_c = nullptr, *d_u0 = nullptr, *d_obj = nullptr, *d_full = nullptr;
+    int32_t *d_status = nullptr, *d_iters = nullptr;
+    int rc = CARMPC_OK;
+    auto cleanup = [&]() { cudaFree(d_x0); cudaFree(d_c); cudaFree(d_u0); cudaFree(d_obj); cudaFree(d_full); cudaFree(d_status); cudaFree(d_iters); };
+#define TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(e__)); cleanup(); return CARMPC_ERR_CUDA; } } while (0)
+    TRY(cudaMalloc(&d_x0, sizeof(double) * 4 * batch));
+    TRY(cudaMalloc(&d_u0, sizeof(double) * 2 * batch));
+    TRY(cudaMalloc(&d_obj, sizeof(double) * batch));
+    TRY(cudaMalloc(&d_status, sizeof(int32_t) * batch));
+    TRY(cudaMalloc(&d_iters, sizeof(int32_t) * batch));
+    if (h_c) { TRY(cudaMalloc(&d_c, sizeof(double) * batch)); TRY(cudaMemcpy(d_c, h_c, sizeof(double) * batch, cudaMemcpyHostToDevice)); }
+    if (h_u_full) TRY(cudaMalloc(&d_full, sizeof(double) * (size_t)n * batch));
+    TRY(cudaMemcpy(d_x0, soa.data(), sizeof(double) * 4 * batch, cudaMemcpyHostToDevice));
+    rc = q->solve(d_x0, batch, h_xref, d_c, nullptr, batch, d_u0, d_obj, d_status, d_iters, d_full, nullptr, 0, 0, nullptr);
+    if (rc != CARMPC_OK) { cleanup(); return rc; }
+    if (h_u0) {
+        std::vector<double> u0((size_t)2 * batch);
+        TRY(cudaMemcpy(u0.data(), d_u0, sizeof(double) * 2 * batch, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < batch; ++i) { h_u0[2 * i] = u0[i]; h_u0[2 * i + 1] = u0[batch + i]; }
+    }
+    if (h_objective) TRY(cudaMemcpy(h_objective, d_obj, sizeof(double) * batch, cudaMemcpyDeviceToHost));
+    TRY(cudaMemcpy(h_status, d_status, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost));
+    if (h_iters) TRY(cudaMemcpy(h_iters, d_iters, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost));
+    if (h_u_full) TRY(cudaMemcpy(h_u_full, d_full, sizeof(double) * (size_t)n * batch, cudaMemcpyDeviceToHost));
+#undef TRY
+    cleanup();
+    return CARMPC_OK;
+}
+
+int carmpc_qp_last_stats(void* qp, int64_t* h_total_iters, int64_t* h_launches) {
+    QPHandle* q = check_handle<QPHandle>(qp, kQP);
+    CARMPC_REQUIRE(q != nullptr, "not a QP handle");
+    if (h_total_iters) *h_total_iters = q->last_total_iters;
+    if (h_launches) *h_launches = q->last_launches;
+    return CARMPC_OK;
+}
+
+}  // extern "C"

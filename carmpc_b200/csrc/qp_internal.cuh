@@ -1,0 +1,190 @@
+// Internal layout of the batched condensed-QP solver (shared by qp_setup.cu, qp_admm.cu, qp_polish.cu, qp_api.cu and
+// closed_loop.cu).  Nothing here is part of the C ABI.
+//
+// Problem (include/carmpc.h):   min 1/2 u'Hu + (F (x0 - xref))'u
+//                               lo - Gx x0 - Gc c <= G u <= hi - Gx x0 - Gc c ,   lb <= u <= ub
+// One instance per initial state x0; H, F, G, Gx and the bounds are shared by the whole batch, which is what
+// makes the ADMM linear operator one dense matrix applied to a (variables x samples) tile.
+//
+// Device algorithm (two kernels per pass):
+//   1. admm_kernel   float32 OSQP-style ADMM on the Ruiz-equilibrated problem, in the single-vector form
+//                        c = clip(w) ; x~ = P (2c - w) + x~0 ; z = A_s x~ ; w += alpha (z - c)
+//                    with P = rho K^-1 A_s' precomputed on the host (K = H_s + rho A_s'A_s is shared).  It only has
+//                    to identify the active set / prove infeasibility.
+//   2. polish_kernel float64 active-set solve through the Schur complement  (A_act H^-1 A_act') lambda = ... with
+//                    the shared H^-1, A H^-1, A H^-1 A' precomputed; verifies primal feasibility and multiplier
+//                    signs (a KKT certificate), repairs the set a few times, and produces u to ~1e-10.
+#pragma once
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace carmpc {
+
+constexpr int kRA = 5;            // rows of x~ per thread tile in stage A
+constexpr int kRB = 7;            // constraint rows per thread tile in stage B
+constexpr int kAdmmWarps = 8;
+constexpr int kAdmmThreads = kAdmmWarps * 32;
+constexpr int kMaxN = 160;        // variables (2 x horizon 80)
+constexpr int kMaxM = 392;        // general rows (8 warps x 7 groups x 7 rows)
+constexpr int kPolishMaxActive = 64;
+
+enum SlotState : int { kSlotIdle = -1, kSlotRunning = 0, kSlotSolved = 1, kSlotInfeasible = 2, kSlotMaxIter = 3,
+                       kSlotPreInfeasible = 4 };
+
+// status codes between the kernels (the ABI codes are CARMPC_QP_*)
+constexpr int kStatusNeedsMoreAdmm = 3;      // polish could not certify: re-run ADMM tighter
+
+struct AdmmTables {
+    // matrices (float32)
+    const float* P;        // [nA_rows][ktot]      rho K^-1 [Gs' | diag(lam)], columns in V order
+    const float* Gs;       // [m_phys][npad4]      scaled general rows, physical (owner) order, permuted variables
+    const float* GsT;      // [nA_rows][mv4]       Gs', columns in V order (certificate pass)
+    // per physical general row
+    const double* his;     // [m_phys]   Eg * hi        (pad rows: 3e38)
+    const double* Gxs;     // [m_phys][4]
+    const double* Gcs;     // [m_phys]
+    const float* width;    // [m_phys]   Eg * (hi - lo), +inf for one-sided and pad rows
+    const float* Einv_g;   // [m_phys]   1 / Eg         (pad rows: 0)
+    const int* vpos;       // [m_phys]   row of V this constraint row writes
+    const int* row_id;     // [m_phys]   logical row index, -1 for pad rows
+    // per permuted variable
+    const float* lam;      // [nA_rows]  Eb * D (scaled box row), 0 for pad
+    const float* lbs;      // [nA_rows]
+    const float* ubs;      // [nA_rows]
+    const float* Einv_b;   // [nA_rows]
+    const float* Dinv;     // [nA_rows]
+    const float* Dsc;      // [nA_rows]  D (u = D x~)
+    const double* KF;      // [nA_rows][4]   x~0 = KF (x0 - xref)
+    const int* var_id;     // [nA_rows]  logical variable index, -1 for pad
+    // per group of rows
+    const int4* segA;      // [nA_rows / kRA]   V ranges (general beg, end, box beg, end), multiples of 4
+    const int2* segB;      // [m_phys / kRB]    x~ range (beg, end), multiples of 4
+    // rows that do not depend on u: pre_lo <= Px x0 + Pc c <= pre_hi
+    const double* Px;
+    const double* Pc;
+    const double* pre_lo;
+    const double* pre_hi;
+    int kpre;
+    int n, m, mt;                          // logical sizes, mt = m + n
+    int nA_rows, m_phys, npad4, mv4, ktot; // padded sizes
+    int nGA, nGB;                          // number of row groups in stage A / B
+    float rho, alpha, eps_abs, eps_rel, eps_inf;
+    int check_every;
+};
+
+struct AdmmBatch {
+    const double* x0;        // SoA: x0[c * stride + sample]
+    int64_t stride;
+    const double* cdist;     // nullable, per sample
+    double xref[4];
+    const int* idx_list;     // nullable: sample = idx_list[q]
+    int count;               // number of queue entries
+    int* next;               // global work counter (zeroed before launch)
+    int8_t* sign;            // [batch][mt]   +1 upper active, -1 lower active
+    float* u_admm;           // [batch][n]    unscaled iterate (fallback when the polish cannot certify)
+    int* status;
+    int* iters;
+    float* warm;             // nullable, [batch][mt] scaled w
+    int warm_in, warm_out;
+    unsigned long long* total_iters;
+    float eps_scale;
+    int max_iter;
+    int iters_accumulate;    // second pass: add to the iteration count of the first
+};
+
+struct PolishTables {
+    const double* H;         // [n][n]
+    const double* Hinv;      // [n][n]
+    const double* F;         // [n][4]
+    const double* GT;        // [n][m]      G transposed (coalesced row sweeps)
+    const double* AH;        // [mt][n]     [G; I] H^-1
+    const double* AHA;       // [mt][mt]    [G; I] H^-1 [G; I]'
+    const double* Gx;        // [m][4]
+    const double* Gc;        // [m]
+    const double* hi;        // [mt]  (general rows then box)
+    const double* lo;        // [mt]
+    int n, m, mt;
+};
+
+struct PolishBatch {
+    const double* x0;
+    int64_t stride;
+    const double* cdist;
+    double xref[4];
+    const int* idx_list;
+    int count;
+    const int8_t* sign;
+    const float* u_admm;
+    int* status;             // in: 0 / 2 from ADMM -> out: 0 solved (polished or accepted), 3 needs more ADMM
+    double* u0;              // SoA 2 x stride (nullable)
+    double* objective;       // nullable
+    double* u_full;          // [batch][n] nullable
+    int8_t* polished;        // nullable
+    int* n_failed;           // device counter of samples set to kStatusNeedsMoreAdmm
+    int* failed_list;        // their indices
+    int final_pass;          // 1: accept the ADMM iterate when the polish cannot certify
+    int rounds;              // repair rounds (-1: default; 0: no polish, pass the ADMM iterate through)
+};
+
+// Host-side setup product (qp_setup.cu)
+struct QPHost {
+    int n = 0, m = 0, kpre = 0;
+    carmpc_qp_opts opts;
+    // scaling (logical order)
+    std::vector<double> D, Eg, Eb, Kinv, Gs64;
+    double cscale = 1.0;
+    // padded device images
+    AdmmTables geo;          // sizes only (pointers filled by the handle)
+    std::vector<float> P, Gs, GsT, width, Einv_g, lam, lbs, ubs, Einv_b, Dinv, Dsc;
+    std::vector<double> his, Gxs, Gcs, KF, Px, Pc, pre_lo, pre_hi;
+    std::vector<int> vpos, row_id, var_id;
+    std::vector<int4> segA;
+    std::vector<int2> segB;
+    // polish (logical order, unscaled)
+    std::vector<double> H, Hinv, F, G, GT, AH, AHA, Gx, Gc, hi, lo;
+    int ga_per_warp = 0, gb_per_warp = 0, samples_per_lane = 0;
+    bool mats_in_smem = false;
+    size_t smem_bytes = 0;
+    double flops_per_iter = 0;      // executed FFMA * 2 per sample-iteration (structure-aware)
+    double flops_per_iter_dense = 0;
+};
+
+int qp_host_setup(int n, int m, int k, const double* H, const double* F, const double* G, const double* Gx,
+                  const double* Gc, const double* lo, const double* hi, const double* lb, const double* ub,
+                  const double* Px, const double* Pc, const double* pre_lo, const double* pre_hi,
+                  const carmpc_qp_opts& opts, QPHost* out);
+
+struct QPHandle;
+int admm_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st);
+int polish_launch(QPHandle* q, const PolishBatch& b, cudaStream_t st);
+size_t admm_smem_bytes(const QPHost& h, int samples_per_lane, bool mats_in_smem);
+
+struct QPHandle : HandleBase {
+    QPHost host;
+    AdmmTables admm;
+    PolishTables polish;
+    std::vector<void*> allocations;
+    // per-batch workspace (grown on demand)
+    int64_t ws_batch = 0;
+    int8_t* ws_sign = nullptr;
+    float* ws_u = nullptr;
+    int* ws_status = nullptr;
+    int* ws_iters = nullptr;
+    int* ws_failed = nullptr;
+    int* ws_counters = nullptr;                  // [0] work counter, [1] n_failed
+    unsigned long long* ws_total_iters = nullptr;
+    int8_t* ws_polished = nullptr;
+    int64_t last_total_iters = 0, last_launches = 0, last_second_pass = 0;
+    int sm = 148;
+    bool host_only = false;
+    ~QPHandle() override;
+    int ensure_workspace(int64_t batch);
+    // full solve on device buffers (all pointers device; any output may be null except status)
+    int solve(const double* d_x0, int64_t stride, const double* xref, const double* d_c, const int* d_idx, int64_t count,
+              double* d_u0, double* d_objective, int32_t* d_status, int32_t* d_iters, double* d_u_full, float* d_warm,
+              int warm_in, int warm_out, cudaStream_t st);
+};
+
+}  // namespace carmpc

@@ -381,9 +381,8 @@ class MPCOutputFBWithDisturbance(MPC):
         x_ref, u_ref = np.array([30, 1.5, 0, 0]), np.zeros(2)
         self.x_estimate = x0
         self.d_estimate = d0
-        offset = self.disturbance_response() * self.d_estimate
         res = self.batch_solver().solve_host(x0[None, :], x_ref=x_ref, want_u_full=True,
-                                             state_offset=offset[None, :])
+                                             c=np.array([float(self.d_estimate)]))
         if res.status[0] == 1:
             raise OutsideTheRegionOfAttractionError
         if res.status[0] != 0:

@@ -115,19 +115,21 @@ int carmpc_rollout_bitset_host(void* rollout, const double* h_x, const double* h
 typedef struct carmpc_qp_opts {
     double rho;            /* ADMM penalty on the scaled problem (default 0.1)                       */
     double alpha;          /* over-relaxation (default 1.6)                                          */
-    double eps_abs;        /* termination, OSQP-style on unscaled residuals (default 1e-6)           */
-    double eps_rel;        /* (default 1e-6)                                                         */
+    double eps_abs;        /* ADMM stop: fixed-point residual, unscaled, abs + rel (default 1e-3;    */
+    double eps_rel;        /*   the float64 polish, not this tolerance, sets the final accuracy)     */
     double eps_prim_inf;   /* primal infeasibility certificate tolerance (default 1e-4)              */
     int32_t max_iter;      /* per sample (default 4000)                                              */
     int32_t check_every;   /* residual / certificate test cadence in iterations (default 10)         */
     int32_t scaling_iters; /* Ruiz equilibration passes on the host (default 15; 0 = none)           */
-    int32_t precise;       /* 1: accumulate A'nu and apply K^-1 in float64 (default); 0: float32     */
+    int32_t polish;        /* 1 (default): float64 active-set polish with a KKT check after the      */
+                           /*   float32 ADMM; 0: return the raw ADMM iterate                         */
 } carmpc_qp_opts;
 
 void carmpc_qp_default_opts(carmpc_qp_opts* opts);
 
-/* Host setup: equilibrate, form K = Hs + rho (Gs'Gs + L^2), invert by Cholesky in float64, upload.
- * Gc / Pc may be NULL (no disturbance term).  n must be even, n <= 160; m <= 1024; k <= 64. */
+/* Host setup: equilibrate, form K = Hs + rho (Gs'Gs + L^2), invert by Cholesky in float64, analyse the structure
+ * (independent chains, causal rows), build the polish matrices, upload.
+ * Gc / Pc may be NULL (no disturbance term).  n <= 160; at most 392 general rows with a finite bound; k <= 64. */
 int carmpc_qp_create(int n, int m, int k, const double* h_H, const double* h_F, const double* h_G,
                      const double* h_Gx, const double* h_Gc, const double* h_lo, const double* h_hi,
                      const double* h_lb, const double* h_ub, const double* h_Px, const double* h_Pc,
@@ -135,7 +137,14 @@ int carmpc_qp_create(int n, int m, int k, const double* h_H, const double* h_F, 
                      void** handle);
 
 /* Host-only view of the setup (no CUDA call): scaled matrices exactly as they are uploaded.
- * which: 0 D(n) 1 Eg(m) 2 Eb(n) 3 c(1) 4 Kinv(n*n) 5 Gs(m*n) 6 lambda(n).  Returns count written. */
+ * which: 0 D(n) 1 Eg(m) 2 Eb(n) 3 c(1) 4 Kinv(n*n) 5 Gs(m*n) 6 lambda(n)
+ *        7 tiling: [samples per lane, stage-A groups per warp, stage-B groups per warp, matrices in shared memory,
+ *                   shared bytes, executed flop per sample-iteration, dense flop per sample-iteration, K, padded rows,
+ *                   padded variables].
+ *        10..26 the padded, permuted float32 device images as float64 (P, Gs, Gs', bounds, tiling tables; see
+ *        qp_api.cu) - used by the tests to re-run the kernel's arithmetic on the host.
+ * Returns the count (written when h_out != NULL).  A handle created on a machine without a CUDA device keeps this
+ * view working; its solve calls return CARMPC_ERR_CUDA. */
 int carmpc_qp_get_setup(void* qp, int which, double* h_out, int capacity);
 
 /* Solve `batch` QPs.  d_x0: SoA, 4 arrays of `batch` float64 (x, y, psi, v).  h_xref: 4 host doubles.
@@ -146,7 +155,8 @@ int carmpc_qp_get_setup(void* qp, int which, double* h_out, int capacity);
  *   d_status    batch int32 (CARMPC_QP_*)
  *   d_iters     batch int32
  *   d_u_full    batch x n float64, row-major per sample (u_horizon of the reference)
- * d_warm (nullable): batch x (m + n) float32 solver state, read if warm_in != 0, written if warm_out != 0. */
+ * d_warm (nullable): batch x (m + n) float32 solver state, read if warm_in != 0, written if warm_out != 0.
+ * The call synchronises `stream` (it reads back how many samples need the second, tighter pass). */
 int carmpc_qp_solve_batch(void* qp, const double* d_x0, const double* h_xref, const double* d_c,
                           int64_t batch, double* d_u0, double* d_objective, int32_t* d_status,
                           int32_t* d_iters, double* d_u_full, float* d_warm, int warm_in, int warm_out,

@@ -1,0 +1,245 @@
+"""Parity of the batched QP path (CUDA ADMM + float64 polish, through the C ABI) against the CPU oracle.
+
+Tolerances are BASELINE.json's: first inputs within 1e-4 absolute, objectives within 1e-5 relative, feasibility flags
+identical (states whose exact feasibility slack is within 1e-6 of zero are enumerated, not compared).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, make_env, make_controller
+
+pytestmark = pytest.mark.gpu
+
+U_TOL = 1e-4
+OBJ_RTOL = 1e-5
+FIXTURE = {"RoadOneCarEnv": "RoadOneCarEnv_29.9_1.5_0_0.npy", "RoadMultipleCarsEnv": "RoadMultipleCarsEnv_30_1.5_0_0.npy",
+           "RoadEnv": "RoadEnv_30_1.5_0_0.npy"}
+GOAL = {"RoadOneCarEnv": [29.9, 1.5, 0, 0], "RoadMultipleCarsEnv": None, "RoadEnv": None}
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "the GPU tests need a CUDA device"
+    return torch
+
+
+def _setup(env_name, N, **opts):
+    from carmpc_b200.batch import BatchQP
+    from oracle import carmpc_oracle as orc
+    c = make_controller(make_env(env_name, GOAL[env_name]), N)
+    bq = BatchQP.from_controller(c, **opts)
+    Ab = np.load(os.path.join(GOLDEN, "terminal_sets", FIXTURE[env_name]))
+    return c, bq, orc.CondensedQP(env_name, N, Ab)
+
+
+def _states(c, n, seed, spread=(12.0, 1.4, 0.25, 2.5)):
+    rng = np.random.default_rng(seed)
+    g = np.array(c.goal, dtype=float)
+    return g + rng.uniform(-1, 1, size=(n, 4)) * np.array(spread)
+
+
+def _compare(res, x0, oq, goal, min_feasible=5):
+    from oracle import carmpc_oracle as orc
+    ue, obje, ste, polished, slack = orc.qp_solve_exact(oq, x0, goal)
+    band = np.abs(slack) <= 1e-6
+    status = np.where(res.status == 0, 0, 1)
+    assert not (res.status == 2).any(), f"{(res.status == 2).sum()} samples hit max_iter"
+    np.testing.assert_array_equal(status[~band], ste[~band])
+    ok = (ste == 0) & ~band & polished
+    assert ok.sum() >= min_feasible
+    du = np.abs(res.u0[ok] - ue[ok, :2]).max()
+    assert du <= U_TOL, f"first input differs by {du}"
+    rel = np.abs(res.objective[ok] - obje[ok]) / np.maximum(1.0, np.abs(obje[ok]))
+    assert rel.max() <= OBJ_RTOL, f"objective differs by {rel.max()} (relative)"
+    if res.u_full is not None:
+        assert np.abs(res.u_full[ok] - ue[ok]).max() <= U_TOL
+    bad = ste == 1
+    assert np.all(np.isinf(res.objective[bad & ~band])) and np.all(np.isnan(res.u0[bad & ~band]))
+    return int(band.sum()), float(du), float(rel.max())
+
+
+@pytest.mark.parametrize("env_name,N,n_states", [("RoadOneCarEnv", 20, 400), ("RoadEnv", 20, 200), ("RoadMultipleCarsEnv", 20, 200),
+                                                 ("RoadOneCarEnv", 10, 200), ("RoadOneCarEnv", 5, 100), ("RoadOneCarEnv", 1, 100),
+                                                 ("RoadOneCarEnv", 40, 120), ("RoadMultipleCarsEnv", 40, 60),
+                                                 ("RoadOneCarEnv", 80, 60), ("RoadEnv", 80, 40)])
+def test_qp_solutions_match_exact_oracle(torch_cuda, env_name, N, n_states):
+    c, bq, oq = _setup(env_name, N)
+    x0 = _states(c, n_states, seed=N)
+    res = bq.solve_host(x0, want_u_full=True)
+    n_band, du, rel = _compare(res, x0, oq, np.array(c.goal, dtype=float))
+    assert n_band <= 3
+    total_iters, launches = bq.last_stats()
+    assert launches >= 2 and total_iters == int(res.iters.sum())
+
+
+def test_known_answer_single_qp(torch_cuda):
+    """a state with saturated acceleration; the solution must satisfy the KKT conditions of the reference's
+    QP (lib/mpc.py:321-332) built from the reference-identical matrices."""
+    c, bq, oq = _setup("RoadOneCarEnv", 20)
+    x0 = np.array([[12.0, 0.4, 0.05, 2.0]])
+    res = bq.solve_host(x0, want_u_full=True)
+    assert res.status[0] == 0
+    u = res.u_full[0]
+    assert abs(u[0] - 2.0) < 1e-9                              # a(0) at its bound
+    ub = oq.rhs(x0)[0]
+    assert (oq.G @ u - ub).max() <= 1e-8
+    grad = oq.H @ u + oq.lin(x0, c.goal)[0]
+    act = np.flatnonzero(oq.G @ u - ub > -1e-7)
+    lam, *_ = np.linalg.lstsq(oq.G[act].T, -grad, rcond=None)
+    assert np.abs(oq.G[act].T @ lam + grad).max() < 1e-6 and lam.min() > -1e-7
+
+
+def test_device_and_host_entry_points_agree_and_are_deterministic(torch_cuda):
+    torch = torch_cuda
+    c, bq, oq = _setup("RoadOneCarEnv", 20)
+    for B in (1, 2, 127, 129, 1000):
+        x0 = _states(c, B, seed=B)
+        host = bq.solve_host(x0, want_u_full=True)
+        dev = bq.solve(torch.from_numpy(np.ascontiguousarray(x0.T)).cuda(), want_u_full=True)
+        np.testing.assert_array_equal(dev["status"].cpu().numpy(), host.status)
+        np.testing.assert_array_equal(dev["iters"].cpu().numpy(), host.iters)
+        np.testing.assert_array_equal(dev["u0"].cpu().numpy().T, host.u0)
+        np.testing.assert_array_equal(dev["objective"].cpu().numpy(), host.objective)
+        np.testing.assert_array_equal(dev["u_full"].cpu().numpy(), host.u_full)
+    # empty batch
+    dev = bq.solve(torch.empty((4, 0), dtype=torch.float64, device="cuda"))
+    assert dev["status"].numel() == 0
+
+
+def test_infeasible_and_degenerate_inputs(torch_cuda):
+    c, bq, oq = _setup("RoadOneCarEnv", 20)
+    g = np.array(c.goal, dtype=float)
+    x0 = np.array([
+        g,                                   # at the goal: u = 0, nothing active
+        [31.0, 1.5, 0.0, 0.0],               # behind the obstacle line x <= 30: infeasible through the u-free rows
+        [5.0, 1.5, 0.0, 5.0],                # feasible far away
+        [29.0, 1.5, 0.0, 5.0],               # too fast, too close: infeasible
+        [np.nan, 0.0, 0.0, 0.0],             # NaN state: infeasible, never a crash
+        [10.0, 2.99, 0.39, 3.0],             # heading into the road edge
+    ])
+    res = bq.solve_host(x0, want_u_full=True)
+    assert res.status[0] == 0 and np.abs(res.u_full[0]).max() < 1e-9 and abs(res.objective[0]) < 1e-9
+    assert res.status[1] == 1 and res.status[3] == 1 and res.status[4] == 1
+    assert res.status[2] == 0
+    from oracle import carmpc_oracle as orc
+    ue, obje, ste, polished, slack = orc.qp_solve_exact(oq, x0[[0, 1, 2, 3, 5]], g)
+    np.testing.assert_array_equal(np.where(res.status[[0, 1, 2, 3, 5]] == 0, 0, 1), ste)
+
+
+def test_raw_admm_mode_is_close_but_polish_is_what_meets_the_tolerance(torch_cuda):
+    """polish=0 returns the float32 ADMM iterate (OSQP-like accuracy); with eps 1e-5 it is within ~1e-3 of the exact
+    solution, which is why the default path polishes in float64."""
+    from oracle import carmpc_oracle as orc
+    c, bq, oq = _setup("RoadOneCarEnv", 20, polish=0, eps_abs=1e-5, eps_rel=1e-5)
+    x0 = _states(c, 200, seed=3)
+    res = bq.solve_host(x0)
+    ue, obje, ste, polished, slack = orc.qp_solve_exact(oq, x0, np.array(c.goal, dtype=float))
+    ok = (ste == 0) & (res.status == 0)
+    assert ok.sum() > 50
+    assert np.abs(res.u0[ok] - ue[ok, :2]).max() < 5e-3
+
+
+def test_controller_step_is_a_drop_in(torch_cuda):
+    """MPCStateFB.step / MPCOutputFB.step keep the reference's contract (lib/mpc.py:312-349, :450-492): return u(0),
+    set the side-effect attributes, raise OutsideTheRegionOfAttractionError when infeasible."""
+    from carmpc_b200.lib.mpc import OutsideTheRegionOfAttractionError
+    from oracle import carmpc_oracle as orc
+    c, bq, oq = _setup("RoadOneCarEnv", 20)
+    g = np.array(c.goal, dtype=float)
+    x0 = np.array([12.0, 0.4, 0.05, 2.0])
+    u0 = c.step(x0)
+    ue, obje, *_ = orc.qp_solve_exact(oq, x0[None, :], g)
+    assert u0.shape == (2,) and np.abs(u0 - ue[0, :2]).max() <= U_TOL
+    assert c.x_horizon.shape == (21, 4) and c.u_horizon.shape == (20, 2)
+    np.testing.assert_allclose(c.x_horizon[0], x0, atol=1e-12)
+    xs = (c.T @ x0 + c.S @ ue[0]).reshape(-1, 4)
+    np.testing.assert_allclose(c.x_horizon, xs, atol=1e-3)
+    assert abs(c.cost - obje[0]) <= OBJ_RTOL * abs(obje[0])
+    assert abs(c.terminal_cost - xs[-1] @ c.P @ xs[-1]) <= 1e-2 * abs(c.terminal_cost)     # absolute x(N): reference quirk
+    with pytest.raises(OutsideTheRegionOfAttractionError):
+        c.step(np.array([29.0, 1.5, 0.0, 5.0]))
+    # output feedback: observer update, then the same QP on the estimate
+    ofb = make_controller(make_env("RoadEnv"), 20, cls="MPCOutputFB", init_state=[5, -1.5, 0, 0])
+    y = np.array([5.1, -1.45, 0.4])
+    xhat = ofb.luenberger_observer(y)
+    u = ofb.step(y)
+    np.testing.assert_allclose(ofb.x_estimate, xhat, atol=1e-14)
+    Ab = np.load(os.path.join(GOLDEN, "terminal_sets", FIXTURE["RoadEnv"]))
+    oq2 = orc.CondensedQP("RoadEnv", 20, Ab)
+    ue2, *_ = orc.qp_solve_exact(oq2, xhat[None, :], np.array([30, 1.5, 0, 0.0]))
+    assert np.abs(u - ue2[0, :2]).max() <= U_TOL
+    np.testing.assert_array_equal(ofb.previous_u, u)
+
+
+def test_closed_loop_matches_oracle(torch_cuda):
+    """BASELINE config 4 in miniature: output-feedback runs against the nonlinear bicycle, order of
+    examples/run_MPCOutputFB.py:29-41.  The oracle steps the same loop with exact QP solutions."""
+    torch = torch_cuda
+    from oracle import carmpc_oracle as orc
+    c, bq, oq = _setup("RoadEnv", 20)
+    g = np.array(c.goal, dtype=float)
+    rng = np.random.default_rng(0)
+    R, steps = 12, 25
+    x_init = rng.uniform([0, -2.5, -0.2, 0], [10, 2.5, 0.2, 3], size=(R, 4))
+
+    def exact(x):
+        u, obj, st, *_ = orc.qp_solve_exact(oq, x, g)
+        return u[:, :2], st
+
+    for output_feedback in (True, False):
+        want_x, want_fail, want_traj = orc.closed_loop(oq, x_init, g, steps, output_feedback, exact)
+        out = bq.closed_loop(torch.from_numpy(np.ascontiguousarray(x_init.T)).cuda(), steps, c.A, c.B,
+                             C=orc.C_OUT if output_feedback else None, L=orc.L_OBS if output_feedback else None,
+                             want_traj=True, want_inputs=True)
+        fail = out["fail_step"].cpu().numpy()
+        np.testing.assert_array_equal(fail, want_fail)
+        traj = out["traj"].cpu().numpy().transpose(0, 2, 1)                   # (steps, R, 4)
+        alive = want_fail < 0
+        assert alive.sum() >= R // 2
+        assert np.abs(traj[:, alive] - want_traj[:, alive]).max() <= 1e-6
+        np.testing.assert_allclose(out["final"].cpu().numpy().T[alive], want_x[alive], atol=1e-6)
+        assert out["total_iters"] > 0
+
+
+def test_config3_full_grid_properties(torch_cuda):
+    """BASELINE config 3: 10^6 initial states on the RoadOneCarEnv grid, one horizon-20 QP each.  The oracle cannot
+    solve 10^6 QPs in seconds, so: every solved sample is polished (KKT-certified in float64 on the device),
+    a strided sample of 600 is compared with the exact oracle, feasibility is monotone along rays towards the goal
+    (convexity of the feasible set), and a second solve is bit-identical (idempotence)."""
+    torch = torch_cuda
+    from carmpc_b200.grids import config3_axes, materialise_grid
+    c, bq, oq = _setup("RoadOneCarEnv", 20)
+    axes = config3_axes()
+    x0 = torch.stack(materialise_grid(axes, device="cuda")).contiguous()          # (4, 10^6)
+    n = x0.shape[1]
+    assert n == 10 ** 6
+    out = bq.solve(x0)
+    status = out["status"].cpu().numpy()
+    assert (status == 2).sum() == 0
+    frac = (status == 0).mean()
+    assert 0.3 < frac < 0.95
+    out2 = bq.solve(x0)
+    assert torch.equal(out["status"], out2["status"]) and torch.equal(out["iters"], out2["iters"])
+    assert torch.equal(out["u0"].nan_to_num(7.0), out2["u0"].nan_to_num(7.0))
+    idx = np.arange(0, n, n // 600)[:600]
+    from oracle import carmpc_oracle as orc
+    xs = x0[:, torch.from_numpy(idx).cuda()].cpu().numpy().T
+    ue, obje, ste, polished, slack = orc.qp_solve_exact(oq, xs, np.array(c.goal, dtype=float))
+    band = np.abs(slack) <= 1e-6
+    np.testing.assert_array_equal(np.where(status[idx] == 0, 0, 1)[~band], ste[~band])
+    ok = (ste == 0) & ~band & polished
+    u0 = out["u0"].cpu().numpy().T[idx]
+    assert np.abs(u0[ok] - ue[ok, :2]).max() <= U_TOL
+    obj = out["objective"].cpu().numpy()[idx]
+    assert (np.abs(obj[ok] - obje[ok]) / np.maximum(1, np.abs(obje[ok]))).max() <= OBJ_RTOL
+    # convexity of the feasible set: the midpoint of two feasible states is feasible
+    feas = np.flatnonzero(status == 0)
+    rng = np.random.default_rng(0)
+    a, b = rng.choice(feas, 4000), rng.choice(feas, 4000)
+    xa = x0[:, torch.from_numpy(a).cuda()]
+    xb = x0[:, torch.from_numpy(b).cuda()]
+    mid = bq.solve((0.5 * (xa + xb)).contiguous())
+    assert int((mid["status"] != 0).sum()) == 0

@@ -1,0 +1,104 @@
+"""Host-side setup of the batched QP solver, checked on the CPU: scaling and KKT inverse against the numpy model,
+and the padded / permuted kernel tables by re-running the kernel's arithmetic (tests/admm_emulation.py) and
+comparing with the exact oracle.  No GPU: the handle is created host-only and refuses to solve."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, make_env, make_controller
+from admm_emulation import KernelTables, emulate, polish_reference
+
+
+def _bq(env_name, goal, N, **opts):
+    from carmpc_b200.batch import BatchQP
+    c = make_controller(make_env(env_name, goal), N)
+    return c, BatchQP.from_controller(c, **opts)
+
+
+@pytest.mark.parametrize("env_name,goal,N", [("RoadOneCarEnv", [29.9, 1.5, 0, 0], 20), ("RoadMultipleCarsEnv", None, 10),
+                                             ("RoadEnv", None, 40)])
+def test_scaling_and_kkt_inverse_match_numpy_model(env_name, goal, N):
+    from tools.admm_model import DeviceModel
+    c, bq = _bq(env_name, goal, N)
+    dm = DeviceModel(bq.pq, rho=0.1, scaling_iters=15)
+    np.testing.assert_allclose(bq.setup(0), dm.D, rtol=1e-12)
+    np.testing.assert_allclose(bq.setup(1), dm.Eg, rtol=1e-12)
+    np.testing.assert_allclose(bq.setup(2), dm.Eb, rtol=1e-12)
+    np.testing.assert_allclose(bq.setup(3)[0], dm.c, rtol=1e-12)
+    n = bq.n
+    np.testing.assert_allclose(bq.setup(4).reshape(n, n), dm.Kinv64, rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(bq.setup(5).reshape(bq.m, n), dm.Gs64, rtol=1e-12, atol=1e-12)   # noise entries are dropped
+
+
+@pytest.mark.parametrize("env_name,goal,N,spl", [("RoadOneCarEnv", [29.9, 1.5, 0, 0], 20, 4), ("RoadOneCarEnv", [29.9, 1.5, 0, 0], 10, 4),
+                                                 ("RoadMultipleCarsEnv", None, 20, 4), ("RoadEnv", None, 40, 2),
+                                                 ("RoadOneCarEnv", [29.9, 1.5, 0, 0], 80, 1), ("RoadEnv", None, 1, 4)])
+def test_tiling_class_and_structure(env_name, goal, N, spl):
+    c, bq = _bq(env_name, goal, N)
+    t = bq.tiling()
+    assert t["samples_per_lane"] == spl
+    assert t["smem_bytes"] <= 227 * 1024
+    T = KernelTables(bq)
+    # every live row and every variable appears exactly once
+    assert sorted(T.row_id[T.row_id >= 0]) == list(range(bq.m))
+    assert sorted(T.var_id[T.var_id >= 0]) == list(range(bq.n))
+    assert len(set(T.vpos[T.row_id >= 0])) == bq.m
+    # structure is exploited: the decoupled environments do at most ~half of the dense work
+    if env_name != "RoadMultipleCarsEnv" and N >= 10:
+        assert t["flop_per_iter"] < 0.6 * t["flop_per_iter_dense"]
+    # the K ranges cover every non-zero of the padded matrices
+    for ga in range(T.nGA):
+        rows = T.P[ga * 5:(ga + 1) * 5]
+        mask = np.zeros(T.ktot, dtype=bool)
+        mask[T.segA[ga, 0]:T.segA[ga, 1]] = True
+        mask[T.segA[ga, 2]:T.segA[ga, 3]] = True
+        assert not np.any(rows[:, ~mask] != 0)
+        assert not np.any(T.GsT[ga * 5:(ga + 1) * 5][:, ~mask[:T.mv4]] != 0)
+    for g in range(T.nGB):
+        rows = T.Gs[g * 7:(g + 1) * 7]
+        mask = np.zeros(T.npad4, dtype=bool)
+        mask[T.segB[g, 0]:T.segB[g, 1]] = True
+        assert not np.any(rows[:, ~mask] != 0)
+
+
+@pytest.mark.parametrize("env_name,goal,N", [("RoadOneCarEnv", [29.9, 1.5, 0, 0], 20), ("RoadMultipleCarsEnv", None, 20),
+                                             ("RoadEnv", None, 10)])
+def test_emulated_kernel_plus_polish_reproduces_exact_solution(env_name, goal, N):
+    """The kernel's arithmetic (from the exported tables) identifies the active set; the polish then matches the
+    exact oracle to 1e-7 (north_star tolerance: 1e-4 on inputs, 1e-5 relative on objectives)."""
+    from oracle import carmpc_oracle as orc
+    c, bq = _bq(env_name, goal, N)
+    pq = bq.pq
+    fixture = {"RoadOneCarEnv": "RoadOneCarEnv_29.9_1.5_0_0.npy", "RoadMultipleCarsEnv": "RoadMultipleCarsEnv_30_1.5_0_0.npy",
+               "RoadEnv": "RoadEnv_30_1.5_0_0.npy"}[env_name]
+    Ab = np.load(os.path.join(GOLDEN, "terminal_sets", fixture))
+    oq = orc.CondensedQP(env_name, N, Ab)
+    g = np.array(c.goal, dtype=float)
+    rng = np.random.default_rng(4)
+    x0 = g + rng.uniform(-1, 1, size=(40, 4)) * np.array([12.0, 1.2, 0.2, 2.0])
+    ue, obje, ste, polished, slack = orc.qp_solve_exact(oq, x0, g)
+    feas = np.flatnonzero(ste == 0)
+    assert len(feas) >= 10
+    T = KernelTables(bq)
+    u, sign = emulate(T, x0[feas], g, iters=150)
+    assert np.abs(u - ue[feas]).max() < 0.05                 # float32 ADMM after 150 iterations: close, not exact
+    n_cert = 0
+    for k, i in enumerate(feas):
+        up, ok = polish_reference(pq, x0[i], g, sign[k])
+        if ok:
+            n_cert += 1
+            np.testing.assert_allclose(up, ue[i], rtol=0, atol=1e-7)
+            obj = 0.5 * up @ pq.H @ up + (pq.F @ (x0[i] - g)) @ up
+            assert abs(obj - obje[i]) <= 1e-8 * max(1.0, abs(obje[i]))
+    assert n_cert >= len(feas) - 1
+
+
+def test_host_only_handle_refuses_to_solve():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from carmpc_b200._capi import CarmpcError
+    c, bq = _bq("RoadEnv", None, 5)
+    with pytest.raises(CarmpcError):
+        bq.solve_host(np.array([[10.0, 0.0, 0.0, 1.0]]))
