@@ -148,7 +148,7 @@ def run_qp_bench(args, rank, world, dev, barrier):
 
     # ---- config 4: output-feedback Monte-Carlo closed loop --------------------------------------------------------
     if not args.skip_closed_loop:
-        from oracle_free_constants import C_OUT, L_OBS
+        from carmpc_b200.lib.mpc import _C_XYV as C_OUT, _L_OBSERVER as L_OBS
         ofb = _controller("RoadEnv", None, 20)
         bl = BatchQP.from_controller(ofb)
         R, T = args.cl_runs, args.cl_steps
