@@ -195,6 +195,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     words = (n + 31) // 32
     bits = [torch.empty(words, dtype=torch.int32, device=dev) for _ in range(2)]
     count = torch.zeros(1, dtype=torch.int64, device=dev)
+    from carmpc_b200.sharding import gather_bitset
     gathered = torch.empty(world * words, dtype=torch.int32, device=dev) if distributed else None
     launches = 0
     pending = None
@@ -207,7 +208,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         if distributed:
             if pending is not None:
                 pending.wait()
-            pending = dist.all_gather_into_tensor(gathered, b, async_op=True)     # result gather over NVLink
+            # result gather over NVLink (the job's sample set is world x 10^8; this rank owns one contiguous range)
+            pending, _ = gather_bitset(b, world * n, async_op=True, out=gathered)
 
     for i in range(args.warmup):
         step(i)

@@ -165,7 +165,6 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
     float wB[GB][kRB][S];          // general rows owned by this thread
     float wA[GA][kRA][S];          // box rows (one per variable) owned by this thread
     float x0t[GA][kRA][S];         // x~0 = -K^-1 q of the slot's sample
-    float xt[GA][kRA][S];          // last x~
 #pragma unroll
     for (int g = 0; g < GB; ++g)
 #pragma unroll
@@ -177,7 +176,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
 #pragma unroll
         for (int r = 0; r < kRA; ++r)
 #pragma unroll
-            for (int s = 0; s < S; ++s) { wA[g][r][s] = 0.f; x0t[g][r][s] = 0.f; xt[g][r][s] = 0.f; }
+            for (int s = 0; s < S; ++s) { wA[g][r][s] = 0.f; x0t[g][r][s] = 0.f; }
     __syncthreads();
 
     const float eps_abs = T.eps_abs * Bq.eps_scale, eps_rel = T.eps_rel * Bq.eps_scale;
@@ -186,6 +185,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
     auto iteration = [&](auto check_tag) {
         constexpr bool CHECK = decltype(check_tag)::value;
         // ---------------- stage A: x~ = P V + x~0 ----------------
+        float xt[GA][kRA][S];
 #pragma unroll
         for (int g = 0; g < GA; ++g) {
             const int pg = g * kAdmmWarps + warp;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
                             if (ub == INFINITY) e = fminf(e, 0.f);
                             if (lb == -INFINITY) e = fmaxf(e, 0.f);
                             egA[g][r][s] = e;
-                            if (einv > 0.f) p_ndy[s] = fmaxf(p_ndy[s], fabsf(e) / einv);
+                            p_ndy[s] = fmaxf(p_ndy[s], fabsf(e) * T.Esc_b[j]);
                             p_sup[s] += e > 0.f ? ub * e : (e < 0.f ? lb * e : 0.f);
                         }
                     }
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
                         float e = (w1 - c1) - (w0 - c0);
                         if (wd == INFINITY) e = fmaxf(e, 0.f);
                         o.v[s] = e;                         // V carries delta-y for the certificate product
-                        if (einv > 0.f) p_ndy[s] = fmaxf(p_ndy[s], fabsf(e) / einv);
+                        p_ndy[s] = fmaxf(p_ndy[s], fabsf(e) * T.Esc_g[i]);
                         p_sup[s] += e > 0.f ? h * e : (e < 0.f ? lo * e : 0.f);
                     }
                 }
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
                     if (fin[s] < 0) continue;
                     const float w = wA[g][r][s];
                     Bq.sign[(size_t)fin[s] * T.mt + T.m + vid] = (int8_t)((w > ub) - (w < lb));
-                    Bq.u_admm[(size_t)fin[s] * T.n + vid] = d * xt[g][r][s];
+                    Bq.u_admm[(size_t)fin[s] * T.n + vid] = d * sm.Xt[j * Bt + s0 + s];
                     if (Bq.warm_out) Bq.warm[(size_t)fin[s] * T.mt + T.m + vid] = w;
                 }
             }
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
 
 template <int S, int GA, int GB>
 int launch_variant(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
-    const size_t smem = q->host.smem_bytes;
+    const size_t smem = admm_smem_bytes(q->host, S, q->host.mats_in_smem);
     const int64_t tiles = (b.count + 32 * S - 1) / (32 * S);
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, q->sm));
     if (q->host.mats_in_smem) {
@@ -559,10 +559,19 @@ int launch_variant(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
 
 int admm_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
     if (b.count <= 0) return CARMPC_OK;
-    switch (q->host.samples_per_lane) {
-        case 4: return launch_variant<4, 1, 2>(q, b, st);
-        case 2: return launch_variant<2, 2, 4>(q, b, st);
-        case 1: return launch_variant<1, 4, 7>(q, b, st);
+    // Samples per lane: the size class fixes the maximum (registers / shared memory); a batch too small to give every
+    // SM a full tile runs narrower tiles, whose iterations are proportionally shorter.
+    const int smax = q->host.samples_per_lane;
+    int S = 1;
+    while (S * 2 <= smax && (int64_t)b.count >= (int64_t)32 * (S * 2) * q->sm) S *= 2;
+    const int key = q->host.ga_per_warp * 100 + q->host.gb_per_warp * 10 + S;
+    switch (key) {
+        case 124: return launch_variant<4, 1, 2>(q, b, st);
+        case 122: return launch_variant<2, 1, 2>(q, b, st);
+        case 121: return launch_variant<1, 1, 2>(q, b, st);
+        case 242: return launch_variant<2, 2, 4>(q, b, st);
+        case 241: return launch_variant<1, 2, 4>(q, b, st);
+        case 471: return launch_variant<1, 4, 7>(q, b, st);
     }
     set_error("admm_launch: no kernel variant for this problem size");
     return CARMPC_ERR_UNSUPPORTED;

@@ -26,7 +26,7 @@ int upload(QPHandle* q, const std::vector<T>& v, const T** dst) {
 QPHandle::~QPHandle() {
     for (void* p : allocations) cudaFree(p);
     cudaFree(ws_sign); cudaFree(ws_u); cudaFree(ws_status); cudaFree(ws_iters); cudaFree(ws_failed);
-    cudaFree(ws_counters); cudaFree(ws_total_iters); cudaFree(ws_polished);
+    cudaFree(ws_counters); cudaFree(ws_total_iters); cudaFree(ws_polished); cudaFree(ws_warm);
 }
 
 int QPHandle::ensure_workspace(int64_t batch) {
@@ -36,6 +36,7 @@ int QPHandle::ensure_workspace(int64_t batch) {
     }
     if (batch <= ws_batch) return CARMPC_OK;
     cudaFree(ws_sign); cudaFree(ws_u); cudaFree(ws_status); cudaFree(ws_iters); cudaFree(ws_failed); cudaFree(ws_polished);
+    cudaFree(ws_warm); ws_warm = nullptr;
     ws_sign = nullptr; ws_u = nullptr; ws_status = nullptr; ws_iters = nullptr; ws_failed = nullptr; ws_polished = nullptr;
     ws_batch = 0;
     CARMPC_CUDA(cudaMalloc(&ws_sign, (size_t)batch * admm.mt));
@@ -44,6 +45,7 @@ int QPHandle::ensure_workspace(int64_t batch) {
     CARMPC_CUDA(cudaMalloc(&ws_iters, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_failed, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_polished, (size_t)batch));
+    CARMPC_CUDA(cudaMalloc(&ws_warm, sizeof(float) * (size_t)batch * admm.mt));
     ws_batch = batch;
     return CARMPC_OK;
 }
@@ -69,7 +71,8 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
     for (int c = 0; c < 4; ++c) ab.xref[c] = xref[c];
     ab.idx_list = d_idx; ab.count = (int)count; ab.next = ws_counters + 0;
     ab.sign = ws_sign; ab.u_admm = ws_u; ab.status = status; ab.iters = iters;
-    ab.warm = d_warm; ab.warm_in = d_warm ? warm_in : 0; ab.warm_out = d_warm ? warm_out : 0;
+    // the ADMM state of every sample is kept (caller's buffer or the workspace): the second pass resumes from it
+    ab.warm = d_warm ? d_warm : ws_warm; ab.warm_in = d_warm ? warm_in : 0; ab.warm_out = 1;
     ab.total_iters = ws_total_iters; ab.eps_scale = 1.f; ab.max_iter = host.opts.max_iter; ab.iters_accumulate = 0;
     rc = admm_launch(this, ab, st);
     if (rc != CARMPC_OK) return rc;
@@ -97,7 +100,7 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
         // second pass on the samples whose active set the polish could not certify: tighter ADMM, then accept
         last_second_pass = n_failed;
         ab.idx_list = ws_failed; ab.count = n_failed; ab.next = ws_counters + 2; ab.eps_scale = 0.01f;
-        ab.warm_in = 0; ab.iters_accumulate = 1;
+        ab.warm_in = 1; ab.iters_accumulate = 1;
         rc = admm_launch(this, ab, st);
         if (rc != CARMPC_OK) return rc;
         pb.idx_list = ws_failed; pb.count = n_failed; pb.n_failed = ws_counters + 3; pb.final_pass = 1;
@@ -160,7 +163,7 @@ int carmpc_qp_create(int n, int m, int k, const double* h_H, const double* h_F, 
         return CARMPC_OK;
     }
 #define UP(vec, field) do { rc = upload(q, h.vec, &a.field); if (rc != CARMPC_OK) { delete q; return rc; } } while (0)
-    UP(P, P); UP(Gs, Gs); UP(GsT, GsT); UP(his, his); UP(Gxs, Gxs); UP(Gcs, Gcs); UP(width, width); UP(Einv_g, Einv_g);
+    UP(P, P); UP(Gs, Gs); UP(GsT, GsT); UP(his, his); UP(Gxs, Gxs); UP(Gcs, Gcs); UP(width, width); UP(Einv_g, Einv_g); UP(Esc_g, Esc_g); UP(Esc_b, Esc_b);
     UP(vpos, vpos); UP(row_id, row_id); UP(lam, lam); UP(lbs, lbs); UP(ubs, ubs); UP(Einv_b, Einv_b); UP(Dinv, Dinv);
     UP(Dsc, Dsc); UP(KF, KF); UP(var_id, var_id); UP(segA, segA); UP(segB, segB); UP(Px, Px); UP(Pc, Pc);
     UP(pre_lo, pre_lo); UP(pre_hi, pre_hi);
@@ -168,7 +171,7 @@ int carmpc_qp_create(int n, int m, int k, const double* h_H, const double* h_F, 
     PolishTables& p = q->polish;
     p.n = n; p.m = m; p.mt = m + n;
 #define UP(vec, field) do { rc = upload(q, h.vec, &p.field); if (rc != CARMPC_OK) { delete q; return rc; } } while (0)
-    UP(H, H); UP(Hinv, Hinv); UP(F, F); UP(GT, GT); UP(AH, AH); UP(AHA, AHA); UP(Gx, Gx); UP(Gc, Gc); UP(hi, hi); UP(lo, lo);
+    UP(H, H); UP(Hinv, Hinv); UP(F, F); UP(Uu, Uu); UP(AUu, AUu); UP(AH, AH); UP(AHA, AHA); UP(Gx, Gx); UP(Gc, Gc); UP(hi, hi); UP(lo, lo);
 #undef UP
     *handle = q;
     return CARMPC_OK;

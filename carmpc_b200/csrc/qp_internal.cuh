@@ -47,6 +47,7 @@ struct AdmmTables {
     const double* Gcs;     // [m_phys]
     const float* width;    // [m_phys]   Eg * (hi - lo), +inf for one-sided and pad rows
     const float* Einv_g;   // [m_phys]   1 / Eg         (pad rows: 0)
+    const float* Esc_g;    // [m_phys]   Eg             (pad rows: 0)
     const int* vpos;       // [m_phys]   row of V this constraint row writes
     const int* row_id;     // [m_phys]   logical row index, -1 for pad rows
     // per permuted variable
@@ -54,6 +55,7 @@ struct AdmmTables {
     const float* lbs;      // [nA_rows]
     const float* ubs;      // [nA_rows]
     const float* Einv_b;   // [nA_rows]
+    const float* Esc_b;    // [nA_rows]  Eb
     const float* Dinv;     // [nA_rows]
     const float* Dsc;      // [nA_rows]  D (u = D x~)
     const double* KF;      // [nA_rows][4]   x~0 = KF (x0 - xref)
@@ -98,7 +100,8 @@ struct PolishTables {
     const double* H;         // [n][n]
     const double* Hinv;      // [n][n]
     const double* F;         // [n][4]
-    const double* GT;        // [n][m]      G transposed (coalesced row sweeps)
+    const double* Uu;        // [n][4]      u_unc = Uu (x0 - xref),  Uu = -H^-1 F
+    const double* AUu;       // [mt][4]     [G; I] Uu
     const double* AH;        // [mt][n]     [G; I] H^-1
     const double* AHA;       // [mt][mt]    [G; I] H^-1 [G; I]'
     const double* Gx;        // [m][4]
@@ -137,13 +140,13 @@ struct QPHost {
     double cscale = 1.0;
     // padded device images
     AdmmTables geo;          // sizes only (pointers filled by the handle)
-    std::vector<float> P, Gs, GsT, width, Einv_g, lam, lbs, ubs, Einv_b, Dinv, Dsc;
+    std::vector<float> P, Gs, GsT, width, Einv_g, Esc_g, lam, lbs, ubs, Einv_b, Esc_b, Dinv, Dsc;
     std::vector<double> his, Gxs, Gcs, KF, Px, Pc, pre_lo, pre_hi;
     std::vector<int> vpos, row_id, var_id;
     std::vector<int4> segA;
     std::vector<int2> segB;
     // polish (logical order, unscaled)
-    std::vector<double> H, Hinv, F, G, GT, AH, AHA, Gx, Gc, hi, lo;
+    std::vector<double> H, Hinv, F, G, Uu, AUu, AH, AHA, Gx, Gc, hi, lo;
     int ga_per_warp = 0, gb_per_warp = 0, samples_per_lane = 0;
     bool mats_in_smem = false;
     size_t smem_bytes = 0;
@@ -176,6 +179,7 @@ struct QPHandle : HandleBase {
     int* ws_counters = nullptr;                  // [0] work counter, [1] n_failed
     unsigned long long* ws_total_iters = nullptr;
     int8_t* ws_polished = nullptr;
+    float* ws_warm = nullptr;                    // ADMM state of every sample (warm start of the second pass)
     int64_t last_total_iters = 0, last_launches = 0, last_second_pass = 0;
     int sm = 148;
     bool host_only = false;

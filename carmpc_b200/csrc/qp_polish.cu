@@ -16,7 +16,8 @@ namespace carmpc {
 
 namespace {
 
-constexpr int kPolishRounds = 8;
+constexpr int kPolishRounds = 10;
+constexpr int kPolishThreads = 128;
 constexpr double kFeasTol = 1e-8;
 constexpr double kSignTol = 1e-9;
 
@@ -32,7 +33,7 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 
 struct PolishSmemLayout {
-    int na_max, ldm;
+    int na_max;
     size_t per_warp;
 };
 
@@ -41,38 +42,40 @@ __host__ __device__ inline PolishSmemLayout polish_layout(int n, int mt) {
     L.na_max = n + 8 < kPolishMaxActive ? n + 8 : kPolishMaxActive;
     if (L.na_max > mt) L.na_max = mt;
     if (L.na_max < 1) L.na_max = 1;
-    L.ldm = L.na_max | 1;                                    // odd leading dimension: conflict-free column walks
     size_t d = 0;
-    d += 3 * (size_t)n;                                      // q, u_unc, u
-    d += 3 * (size_t)mt;                                     // Au_unc, hi, lo
-    d += (size_t)L.na_max * L.ldm;                           // M
+    d += 2 * (size_t)n;                                      // u_unc, u
+    d += 3 * (size_t)mt;                                     // A u_unc, hi, lo
+    d += (size_t)L.na_max * (L.na_max + 1) / 2;              // M, packed lower triangle
     d += 3 * (size_t)L.na_max;                               // rhs / lambda, b, diag0
     size_t bytes = d * sizeof(double);
     bytes += sizeof(int) * (size_t)L.na_max;                 // act
+    bytes += sizeof(int) * 16;                               // rows added by the repair, newest first
     bytes += (size_t)((mt + 15) & ~15);                      // sgn
     L.per_warp = (bytes + 15) & ~size_t(15);
     return L;
 }
 
-__global__ void __launch_bounds__(256) polish_kernel(const PolishTables T, const PolishBatch B, int warps_per_cta) {
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }     // j <= i
+
+__global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTables T, const PolishBatch B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (warp >= warps_per_cta) return;
+    constexpr int warps_per_cta = kPolishThreads / 32;
     const int n = T.n, m = T.m, mt = T.mt;
     const PolishSmemLayout L = polish_layout(n, mt);
     unsigned char* base = smem_raw + (size_t)warp * L.per_warp;
-    double* q = reinterpret_cast<double*>(base);
-    double* uunc = q + n;
+    double* uunc = reinterpret_cast<double*>(base);
     double* u = uunc + n;
     double* Auu = u + n;
     double* hi = Auu + mt;
     double* lo = hi + mt;
     double* M = lo + mt;
-    double* rhs = M + (size_t)L.na_max * L.ldm;
+    double* rhs = M + (size_t)L.na_max * (L.na_max + 1) / 2;
     double* bact = rhs + L.na_max;
     double* diag0 = bact + L.na_max;
     int* act = reinterpret_cast<int*>(diag0 + L.na_max);
-    signed char* sgn = reinterpret_cast<signed char*>(act + L.na_max);
+    int* added = act + L.na_max;
+    signed char* sgn = reinterpret_cast<signed char*>(added + 16);
     const double NaN = __longlong_as_double(0x7ff8000000000000ll);
 
     const int gw = blockIdx.x * warps_per_cta + warp, nw = gridDim.x * warps_per_cta;
@@ -93,11 +96,14 @@ __global__ void __launch_bounds__(256) polish_kernel(const PolishTables T, const
 #pragma unroll
         for (int c = 0; c < 4; ++c) { x0[c] = B.x0[(size_t)c * B.stride + sample]; dx[c] = x0[c] - B.xref[c]; }
         const double cd = B.cdist ? B.cdist[sample] : 0.0;
+        // everything unconstrained is linear in dx:  u_unc = -H^-1 F dx = Uu dx ,  A u_unc = (A Uu) dx
         for (int j = lane; j < n; j += 32) {
-            const double* f = T.F + (size_t)j * 4;
-            q[j] = f[0] * dx[0] + f[1] * dx[1] + f[2] * dx[2] + f[3] * dx[3];
+            const double* w = T.Uu + (size_t)j * 4;
+            uunc[j] = w[0] * dx[0] + w[1] * dx[1] + w[2] * dx[2] + w[3] * dx[3];
         }
         for (int i = lane; i < mt; i += 32) {
+            const double* w = T.AUu + (size_t)i * 4;
+            Auu[i] = w[0] * dx[0] + w[1] * dx[1] + w[2] * dx[2] + w[3] * dx[3];
             double shift = 0.0;
             if (i < m) {
                 const double* gx = T.Gx + (size_t)i * 4;
@@ -107,33 +113,24 @@ __global__ void __launch_bounds__(256) polish_kernel(const PolishTables T, const
             lo[i] = T.lo[i] - shift;
             sgn[i] = B.sign[(size_t)sample * mt + i];
         }
-        __syncwarp();
-        for (int j = lane; j < n; j += 32) {                 // u_unc = -H^-1 q
-            double s = 0;                                     // Hinv is symmetric: walk it column-wise (coalesced)
-            for (int k = 0; k < n; ++k) s += T.Hinv[(size_t)k * n + j] * q[k];
-            uunc[j] = -s;
-        }
-        __syncwarp();
-        for (int i = lane; i < mt; i += 32) {                // A u_unc
-            double s;
-            if (i < m) {
-                s = 0;
-                for (int k = 0; k < n; ++k) s += T.GT[(size_t)k * m + i] * uunc[k];
-            } else {
-                s = uunc[i - m];
-            }
-            Auu[i] = s;
-        }
+        int n_added = 0;
         __syncwarp();
 
         bool certified = false;
+        int na = 0;
         const int max_rounds = B.rounds < 0 ? kPolishRounds : B.rounds;
         for (int round = 0; round < max_rounds && !certified; ++round) {
-            // ---- compact the active set ----
-            int na = 0;
+            // ---- active list: rows added by the repair first (newest first: they keep their pivot when the set is
+            //      linearly dependent, and an older guess gets the zero multiplier), then the ADMM guess by index ----
+            na = 0;
+            for (int a = 0; a < n_added; ++a) {
+                const int i = added[a];
+                if (sgn[i] != 0) { if (lane == 0 && na < L.na_max) act[na] = i; ++na; }
+            }
             for (int i0 = 0; i0 < mt; i0 += 32) {
                 const int i = i0 + lane;
-                const bool on = i < mt && sgn[i] != 0;
+                bool on = i < mt && sgn[i] != 0;
+                if (on) for (int a = 0; a < n_added; ++a) on = on && added[a] != i;
                 const unsigned mask = __ballot_sync(0xffffffffu, on);
                 const int p = na + __popc(mask & ((1u << lane) - 1u));
                 if (on && p < L.na_max) act[p] = i;
@@ -141,10 +138,15 @@ __global__ void __launch_bounds__(256) polish_kernel(const PolishTables T, const
             }
             if (na > L.na_max) break;
             __syncwarp();
-            // ---- M = AHA[act, act], rhs = A_act u_unc - b_act ----
-            for (int e = lane; e < na * na; e += 32) {
-                const int a = e / na, b = e - a * na;
-                M[a * L.ldm + b] = T.AHA[(size_t)act[a] * mt + act[b]];
+            // ---- M = AHA[act, act] (lower triangle), rhs = A_act u_unc - b_act ----
+            for (int e = lane; e < na * (na + 1) / 2; e += 32) {
+                int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+                while (tri(a + 1, 0) <= e) ++a;
+                while (tri(a, 0) > e) --a;
+                const int b = e - tri(a, 0);
+                double v = T.AHA[(size_t)act[a] * mt + act[b]];
+                if (a == b) { diag0[a] = v; v += 1e-13 * v; }
+                M[e] = v;
             }
             for (int a = lane; a < na; a += 32) {
                 const int i = act[a];
@@ -152,56 +154,68 @@ __global__ void __launch_bounds__(256) polish_kernel(const PolishTables T, const
                 rhs[a] = Auu[i] - bact[a];
             }
             __syncwarp();
-            for (int a = lane; a < na; a += 32) { diag0[a] = M[a * L.ldm + a]; M[a * L.ldm + a] += 1e-13 * diag0[a]; }
-            __syncwarp();
-            // ---- Cholesky with pivot skipping (dependent active rows get lambda = 0) ----
+            // ---- Cholesky with pivot skipping (a row that depends on earlier ones gets lambda = 0) ----
             for (int j = 0; j < na; ++j) {
-                const double d = M[j * L.ldm + j];
+                const double d = M[tri(j, j)];
                 const bool skip = !(d > 1e-11 * diag0[j]);
                 const double piv = skip ? 1.0 : sqrt(d);
                 __syncwarp();
-                if (lane == 0) M[j * L.ldm + j] = skip ? 0.0 : piv;      // 0 on the diagonal marks a skipped pivot
-                for (int i = j + 1 + lane; i < na; i += 32) M[i * L.ldm + j] = skip ? 0.0 : M[i * L.ldm + j] / piv;
+                if (lane == 0) M[tri(j, j)] = skip ? 0.0 : piv;           // 0 on the diagonal marks a skipped pivot
+                for (int i = j + 1 + lane; i < na; i += 32) M[tri(i, j)] = skip ? 0.0 : M[tri(i, j)] / piv;
                 __syncwarp();
                 if (!skip)
                     for (int i = j + 1 + lane; i < na; i += 32) {
-                        const double lij = M[i * L.ldm + j];
-                        for (int k = j + 1; k <= i; ++k) M[i * L.ldm + k] -= lij * M[k * L.ldm + j];
+                        const double lij = M[tri(i, j)];
+                        for (int k = j + 1; k <= i; ++k) M[tri(i, k)] -= lij * M[tri(k, j)];
                     }
                 __syncwarp();
             }
             // ---- L y = rhs, L' lambda = y ----
             for (int j = 0; j < na; ++j) {
-                const double d = M[j * L.ldm + j];
+                const double d = M[tri(j, j)];
                 const double y = d > 0.0 ? rhs[j] / d : 0.0;
                 __syncwarp();
                 if (lane == 0) rhs[j] = y;
-                for (int i = j + 1 + lane; i < na; i += 32) rhs[i] -= M[i * L.ldm + j] * y;
+                for (int i = j + 1 + lane; i < na; i += 32) rhs[i] -= M[tri(i, j)] * y;
                 __syncwarp();
             }
             for (int j = na - 1; j >= 0; --j) {
-                const double d = M[j * L.ldm + j];
+                const double d = M[tri(j, j)];
                 const double x = d > 0.0 ? rhs[j] / d : 0.0;
                 __syncwarp();
                 if (lane == 0) rhs[j] = x;
-                for (int i = lane; i < j; i += 32) rhs[i] -= M[j * L.ldm + i] * x;
+                for (int i = lane; i < j; i += 32) rhs[i] -= M[tri(j, i)] * x;
                 __syncwarp();
             }
             // rhs now holds lambda (signed: positive pushes against an upper bound)
             // ---- u = u_unc - (AH)'_act lambda ----
             for (int j = lane; j < n; j += 32) {
-                double s = uunc[j];
-                for (int a = 0; a < na; ++a) s -= T.AH[(size_t)act[a] * n + j] * rhs[a];
-                u[j] = s;
+                double s0 = uunc[j], s1 = 0.0;
+                int a = 0;
+                for (; a + 1 < na; a += 2) {
+                    s0 -= T.AH[(size_t)act[a] * n + j] * rhs[a];
+                    s1 -= T.AH[(size_t)act[a + 1] * n + j] * rhs[a + 1];
+                }
+                if (a < na) s0 -= T.AH[(size_t)act[a] * n + j] * rhs[a];
+                u[j] = s0 + s1;
             }
-            // ---- KKT check ----
+            // ---- KKT check: every row within its bounds, multiplier signs right ----
             double worst = 0.0;
             int worst_i = -1, worst_sign = 0;
             for (int i = lane; i < mt; i += 32) {
-                if (isinf(hi[i]) && isinf(lo[i])) continue;
-                double s = Auu[i];
-                for (int a = 0; a < na; ++a) s -= T.AHA[(size_t)act[a] * mt + i] * rhs[a];
-                const double vu = s - hi[i], vl = lo[i] - s;
+                const double h = hi[i], l = lo[i];
+                if (isinf(h) && isinf(l)) continue;
+                double s0 = Auu[i], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                int a = 0;
+                for (; a + 3 < na; a += 4) {
+                    s0 -= T.AHA[(size_t)act[a] * mt + i] * rhs[a];
+                    s1 -= T.AHA[(size_t)act[a + 1] * mt + i] * rhs[a + 1];
+                    s2 -= T.AHA[(size_t)act[a + 2] * mt + i] * rhs[a + 2];
+                    s3 -= T.AHA[(size_t)act[a + 3] * mt + i] * rhs[a + 3];
+                }
+                for (; a < na; ++a) s0 -= T.AHA[(size_t)act[a] * mt + i] * rhs[a];
+                const double s = (s0 + s1) + (s2 + s3);
+                const double vu = s - h, vl = l - s;
                 const double v = fmax(vu, vl);
                 if (v > worst) { worst = v; worst_i = i; worst_sign = vu >= vl ? 1 : -1; }
             }
@@ -224,10 +238,24 @@ __global__ void __launch_bounds__(256) polish_kernel(const PolishTables T, const
             n_bad = __reduce_add_sync(0xffffffffu, n_bad);
             __syncwarp();
             if (add_i < 0 && n_bad == 0) { certified = true; break; }
-            if (add_i >= 0 && lane == 0) sgn[add_i] = (signed char)add_sign;
+            if (add_i >= 0) {
+                int k = 0;
+                for (int a = 0; a < n_added; ++a) if (added[a] != add_i) ++k;
+                __syncwarp();
+                if (lane == 0) {
+                    sgn[add_i] = (signed char)add_sign;
+                    int w = 0;                                         // move / insert add_i at the front
+                    for (int a = 0; a < n_added; ++a) if (added[a] != add_i) added[w++] = added[a];
+                    const int keep = w < 15 ? w : 15;
+                    for (int a = keep; a > 0; --a) added[a] = added[a - 1];
+                    added[0] = add_i;
+                }
+                n_added = (k < 15 ? k : 15) + 1;
+            }
             __syncwarp();
         }
 
+        double obj;
         if (!certified) {
             if (!B.final_pass) {
                 if (lane == 0) {
@@ -237,17 +265,29 @@ __global__ void __launch_bounds__(256) polish_kernel(const PolishTables T, const
                 }
                 continue;
             }
+            // accept the float32 ADMM iterate: objective 1/2 u'Hu + q'u evaluated directly
             for (int j = lane; j < n; j += 32) u[j] = (double)B.u_admm[(size_t)sample * n + j];
             __syncwarp();
+            double part = 0.0;
+            for (int j = lane; j < n; j += 32) {
+                const double* f = T.F + (size_t)j * 4;
+                const double qj = f[0] * dx[0] + f[1] * dx[1] + f[2] * dx[2] + f[3] * dx[3];
+                double s = 0;                                     // H is symmetric: column walk is coalesced
+                for (int k = 0; k < n; ++k) s += T.H[(size_t)k * n + j] * u[k];
+                part += u[j] * (0.5 * s + qj);
+            }
+            obj = warp_sum(part);
+        } else {
+            // at a KKT point  H u + q + A_act' lambda = 0  and  A_act u = b_act  (rows with a skipped pivot have
+            // lambda = 0), hence  1/2 u'Hu + q'u = 1/2 (q'u - lambda'b_act)
+            double part = 0.0;
+            for (int j = lane; j < n; j += 32) {
+                const double* f = T.F + (size_t)j * 4;
+                part += (f[0] * dx[0] + f[1] * dx[1] + f[2] * dx[2] + f[3] * dx[3]) * u[j];
+            }
+            for (int a = lane; a < na; a += 32) part -= rhs[a] * bact[a];
+            obj = 0.5 * warp_sum(part);
         }
-        // ---- outputs: u(0), objective 1/2 u'Hu + q'u, full sequence ----
-        double part = 0.0;
-        for (int j = lane; j < n; j += 32) {
-            double s = 0;                                     // H is symmetric
-            for (int k = 0; k < n; ++k) s += T.H[(size_t)k * n + j] * u[k];
-            part += u[j] * (0.5 * s + q[j]);
-        }
-        const double obj = warp_sum(part);
         if (lane == 0) {
             if (B.u0) { B.u0[sample] = u[0]; B.u0[B.stride + sample] = n > 1 ? u[1] : 0.0; }
             if (B.objective) B.objective[sample] = obj;
@@ -263,13 +303,15 @@ __global__ void __launch_bounds__(256) polish_kernel(const PolishTables T, const
 int polish_launch(QPHandle* qh, const PolishBatch& b, cudaStream_t st) {
     if (b.count <= 0) return CARMPC_OK;
     const PolishSmemLayout L = polish_layout(qh->polish.n, qh->polish.mt);
-    int warps = (int)std::min<size_t>(8, (size_t)(200 * 1024) / L.per_warp);
-    if (warps < 1) { set_error("polish: shared-memory budget exceeded"); return CARMPC_ERR_UNSUPPORTED; }
+    constexpr int warps = kPolishThreads / 32;
     const size_t smem = L.per_warp * warps;
+    if (smem > (size_t)227 * 1024) { set_error("polish: shared-memory budget exceeded"); return CARMPC_ERR_UNSUPPORTED; }
     CARMPC_CUDA(cudaFuncSetAttribute(polish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)std::min<size_t>(8, (size_t)(220 * 1024) / smem);
+    if (per_sm < 1) per_sm = 1;
     const int64_t need = (b.count + warps - 1) / warps;
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)qh->sm * 4));
-    polish_kernel<<<blocks, 256, smem, st>>>(qh->polish, b, warps);
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)qh->sm * per_sm));
+    polish_kernel<<<blocks, kPolishThreads, smem, st>>>(qh->polish, b);
     CARMPC_CUDA(cudaGetLastError());
     return CARMPC_OK;
 }

@@ -295,6 +295,7 @@ int qp_host_setup(int n, int m_in, int kpre, const double* H_in, const double* F
     q.Gcs.assign(g.m_phys, 0.0);
     q.width.assign(g.m_phys, INFINITY);
     q.Einv_g.assign(g.m_phys, 0.f);
+    q.Esc_g.assign(g.m_phys, 0.f);
     q.vpos.assign(g.m_phys, 0);
     q.row_id.assign(g.m_phys, -1);
     q.segB.assign(g.nGB, make_int2(0, 0));
@@ -315,6 +316,7 @@ int qp_host_setup(int n, int m_in, int kpre, const double* H_in, const double* F
             q.Gcs[pi] = Eg[i] * q.Gc[i];
             q.width[pi] = isinf(q.lo[i]) ? INFINITY : (float)(Eg[i] * (q.hi[i] - q.lo[i]));
             q.Einv_g[pi] = (float)(1.0 / Eg[i]);
+            q.Esc_g[pi] = (float)Eg[i];
             q.vpos[pi] = vpos_of[i];
             q.row_id[pi] = i;
             b = std::min(b, row_beg[i]); e = std::max(e, row_end[i]);
@@ -326,7 +328,7 @@ int qp_host_setup(int n, int m_in, int kpre, const double* H_in, const double* F
 
     // variables
     q.lam.assign(g.nA_rows, 0.f); q.lbs.assign(g.nA_rows, -INFINITY); q.ubs.assign(g.nA_rows, INFINITY);
-    q.Einv_b.assign(g.nA_rows, 0.f); q.Dinv.assign(g.nA_rows, 0.f); q.Dsc.assign(g.nA_rows, 0.f);
+    q.Einv_b.assign(g.nA_rows, 0.f); q.Esc_b.assign(g.nA_rows, 0.f); q.Dinv.assign(g.nA_rows, 0.f); q.Dsc.assign(g.nA_rows, 0.f);
     q.KF.assign((size_t)g.nA_rows * 4, 0.0);
     q.var_id.assign(g.nA_rows, -1);
     for (int p = 0; p < n; ++p) {
@@ -335,6 +337,7 @@ int qp_host_setup(int n, int m_in, int kpre, const double* H_in, const double* F
         q.lbs[p] = isinf(lb_in[j]) ? -INFINITY : (float)(Eb[j] * lb_in[j]);
         q.ubs[p] = isinf(ub_in[j]) ? INFINITY : (float)(Eb[j] * ub_in[j]);
         q.Einv_b[p] = (float)(1.0 / Eb[j]);
+        q.Esc_b[p] = (float)Eb[j];
         q.Dinv[p] = (float)(1.0 / D[j]);
         q.Dsc[p] = (float)D[j];
         q.var_id[p] = j;
@@ -420,9 +423,21 @@ int qp_host_setup(int n, int m_in, int kpre, const double* H_in, const double* F
     }
     for (int i = 0; i < m; ++i)
         if (!live[i]) { q.hi[i] = INFINITY; q.lo[i] = -INFINITY; }
-    q.GT.assign((size_t)n * m, 0.0);
-    for (int i = 0; i < m; ++i)
-        for (int j = 0; j < n; ++j) q.GT[(size_t)j * m + i] = q.G[(size_t)i * n + j];
+    q.Uu.assign((size_t)n * 4, 0.0);
+    for (int j = 0; j < n; ++j)
+        for (int c = 0; c < 4; ++c) {
+            double s = 0;
+            for (int k = 0; k < n; ++k) s += q.Hinv[(size_t)j * n + k] * q.F[(size_t)k * 4 + c];
+            q.Uu[(size_t)j * 4 + c] = -s;
+        }
+    q.AUu.assign((size_t)mt * 4, 0.0);
+    for (int i = 0; i < mt; ++i)
+        for (int c = 0; c < 4; ++c) {
+            double s = 0;
+            if (i < m) { if (live[i]) for (int k = 0; k < n; ++k) s += q.G[(size_t)i * n + k] * q.Uu[(size_t)k * 4 + c]; }
+            else s = q.Uu[(size_t)(i - m) * 4 + c];
+            q.AUu[(size_t)i * 4 + c] = s;
+        }
 
     q.mats_in_smem = admm_smem_bytes(q, S, true) <= (size_t)220 * 1024;
     q.smem_bytes = admm_smem_bytes(q, S, q.mats_in_smem);
