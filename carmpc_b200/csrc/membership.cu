@@ -7,11 +7,18 @@
 //
 // Arithmetic contract (shared with oracle/carmpc_oracle.c, bit for bit):
 //     r = fma(a3, v, fma(a2, psi, fma(a1, y, a0 * x)));   member &= (r <= b);
-// in IEEE float64, rows in file order.  Mode 1 screens each row in float32 first and only falls back to the
-// float64 expression when the float32 margin is within a rigorous rounding bound of zero, so it returns the same
-// bits while keeping the FP64 pipe (the co-limiter of this kernel on B200) almost idle.
+// in IEEE float64.  Rows are sorted on the host, fewest non-zero coefficients first (for the sets of this model those
+// are the axis-aligned bounds on psi, v and y, which reject most samples), so that the whole-warp early exit fires
+// soon; the conjunction over rows does not depend on their order.  (A per-pattern specialisation that skipped zero
+// coefficients was measured slower than the dense chain: its dispatch cost more issue slots than the FMAs it saved.)
+//
+// Mode 1 (default) decides almost every sample on the FP32 pipe: it tracks  min_r (b_r - a_r . p)  in float32 (four
+// FFMA plus one FMNMX per row) and compares it with a rigorous bound beta(p) on the total rounding error
+// of that float32 evaluation; only samples with |min margin| <= beta are re-evaluated in float64 (same bits as mode 0
+// by construction).  The FP64 pipe, the co-limiter of mode 0 on B200, stays idle.
 #include <math.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -20,14 +27,19 @@ namespace carmpc {
 
 constexpr int kMaxRows = 512;
 constexpr int kThreads = 256;
-constexpr int kSamplesPerThread = 2;
-constexpr int kChunk = kThreads * kSamplesPerThread;       // samples per block iteration
-constexpr int kEarlyExitStride = 4;                          // rows between "whole warp already outside" votes
+constexpr int kNS = 4;                                      // samples per thread
+constexpr int kChunk = kThreads * kNS;                     // samples per block iteration
+constexpr int kMaxClasses = 16;
 
-// float32 screen of one row: 4 coefficients, b, and the two constants of the error bound
+// float32 image of one row: negated coefficients and b, so that  margin = fma(-a3, v, ... fma(-a0, x, b))
 struct __align__(16) RowF32 {
-    float a0, a1, a2, a3;
-    float b, bound_coef, bound_const, pad;
+    float na0, na1, na2, na3;
+    float b, pad0, pad1, pad2;
+};
+
+// rows [beg, end) share one sparsity pattern (bit k set: coefficient k is non-zero)
+struct RowClass {
+    int pattern, beg, end, pad;
 };
 
 // Device staging of the host-buffer entry points: two slots so that the H2D copy of chunk c+1 overlaps the kernel
@@ -67,8 +79,11 @@ struct HostStage {
 
 struct Polytope : HandleBase {
     int rows = 0;
-    double* d_rows = nullptr;        // rows x 5 (float64)
+    double* d_rows = nullptr;        // rows x 5 (float64), sorted by sparsity pattern
     RowF32* d_rows32 = nullptr;      // rows
+    RowClass classes[kMaxClasses];
+    int n_classes = 0;
+    float beta0 = 0.f, beta1 = 0.f;  // |float32 margin - exact margin| <= beta0 + beta1 * max|coordinate|
     HostStage stage;
     ~Polytope() override {
         cudaFree(d_rows);
@@ -83,84 +98,95 @@ struct Rollout : HandleBase {
     ~Rollout() override { cudaFree(d_data); }
 };
 
-// spread the low 16 bits of v to the even bit positions
-__device__ __forceinline__ uint32_t spread16(uint32_t v) {
-    v &= 0xffffu;
-    v = (v | (v << 8)) & 0x00ff00ffu;
-    v = (v | (v << 4)) & 0x0f0f0f0fu;
-    v = (v | (v << 2)) & 0x33333333u;
-    v = (v | (v << 1)) & 0x55555555u;
+// spread the 8 bits of a byte to every fourth bit position (bit j -> bit 4 j)
+__device__ __forceinline__ uint32_t spread8x4(uint32_t v) {
+    v &= 0xffu;
+    v = (v | (v << 12)) & 0x000f000fu;
+    v = (v | (v << 6)) & 0x03030303u;
+    v = (v | (v << 3)) & 0x11111111u;
     return v;
 }
 
-// Evaluate every row for the two samples of this thread.  Warp-synchronous: all 32 lanes must call it.
-template <int MODE>
-__device__ __forceinline__ void eval_rows(const double* __restrict__ s_rows, const RowF32* __restrict__ s_rows32,
-                                          int rows, const double (&x)[2], const double (&y)[2],
-                                          const double (&p)[2], const double (&v)[2], bool (&in)[2]) {
-    float xf[2], yf[2], pf[2], vf[2], pmax[2];
-    if (MODE == 1) {
+struct ScreenConst {         // float32 error-bound constants of the polytope
+    float beta0, beta1;
+};
+
+constexpr int kExit64 = 4;       // rows between "whole warp already outside" votes, float64 path
+constexpr int kRowBlock = 8;     // ... float32 screen (the float32 row image is padded to a multiple of it)
+
+// float64 decision of the NS samples of this thread: the contract chain, every row, rows in host-sorted order
+__device__ __forceinline__ void decide64(const double* __restrict__ s_rows, int rows, const double (&x)[kNS],
+                                         const double (&y)[kNS], const double (&p)[kNS], const double (&v)[kNS],
+                                         bool (&in)[kNS]) {
+    for (int r0 = 0; r0 < rows; r0 += kExit64) {
+        bool any = false;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            xf[k] = (float)x[k];
-            yf[k] = (float)y[k];
-            pf[k] = (float)p[k];
-            vf[k] = (float)v[k];
-            pmax[k] = fmaxf(fmaxf(fabsf(xf[k]), fabsf(yf[k])), fmaxf(fabsf(pf[k]), fabsf(vf[k])));
-        }
-    }
-    for (int r0 = 0; r0 < rows; r0 += kEarlyExitStride) {
-        if (!__any_sync(0xffffffffu, in[0] | in[1])) break;
-        const int r1 = min(r0 + kEarlyExitStride, rows);
+        for (int k = 0; k < kNS; ++k) any |= in[k];
+        if (!__any_sync(0xffffffffu, any)) break;
+        const int r1 = min(r0 + kExit64, rows);
         for (int r = r0; r < r1; ++r) {
-            if (MODE == 1) {
-                const RowF32 q = s_rows32[r];
-                bool ambiguous = false;
+            const double* a = s_rows + 5 * r;
+            const double a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3], b = a[4];
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const float dot = fmaf(q.a3, vf[k], fmaf(q.a2, pf[k], fmaf(q.a1, yf[k], q.a0 * xf[k])));
-                    const float margin = q.b - dot;
-                    const float bound = fmaf(q.bound_coef, pmax[k], q.bound_const);
-                    const bool sure_in = margin > bound;
-                    const bool sure_out = margin < -bound;
-                    ambiguous |= in[k] & !(sure_in | sure_out);
-                    in[k] &= !sure_out;
-                }
-                if (__any_sync(0xffffffffu, ambiguous)) {
-                    // rare: decide this row in float64 for every live sample of the warp (same bits as mode 0)
-                    const double* a = s_rows + 5 * r;
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const double rr = fma(a[3], v[k], fma(a[2], p[k], fma(a[1], y[k], a[0] * x[k])));
-                        in[k] &= (rr <= a[4]);
-                    }
-                }
-            } else {
-                const double* a = s_rows + 5 * r;
-                const double a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3], b = a[4];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const double rr = fma(a3, v[k], fma(a2, p[k], fma(a1, y[k], a0 * x[k])));
-                    in[k] &= (rr <= b);
-                }
-            }
+            for (int k = 0; k < kNS; ++k) in[k] &= (fma(a3, v[k], fma(a2, p[k], fma(a1, y[k], a0 * x[k]))) <= b);
         }
     }
 }
 
-// write the 64 decisions of a warp (thread t holds samples 2t, 2t+1 of the warp's chunk) as two words
-__device__ __forceinline__ int store_bits(uint32_t* __restrict__ bits, int64_t warp_base, int64_t n, bool in0, bool in1) {
-    const uint32_t even = __ballot_sync(0xffffffffu, in0);
-    const uint32_t odd = __ballot_sync(0xffffffffu, in1);
+// float32 screen: in[k] becomes "surely inside"; returns through amb[k] the samples only the float64 chain can decide
+__device__ __forceinline__ void screen32(const RowF32* __restrict__ s_rows32, int rows_padded, const ScreenConst sc,
+                                         const float (&xf)[kNS], const float (&yf)[kNS], const float (&pf)[kNS],
+                                         const float (&vf)[kNS], bool (&in)[kNS], bool (&amb)[kNS]) {
+    float nbeta[kNS], mmin[kNS];
+#pragma unroll
+    for (int k = 0; k < kNS; ++k) {
+        // |x| + |y| + |psi| + |v| >= max |coordinate|, and (unlike fmaxf) it propagates NaN / inf into the bound,
+        // which then fails both "surely in" and "surely out": such samples are decided by the float64 chain
+        const float psum = (fabsf(xf[k]) + fabsf(yf[k])) + (fabsf(pf[k]) + fabsf(vf[k]));
+        nbeta[k] = -fmaf(sc.beta1, psum, sc.beta0);
+        mmin[k] = in[k] ? INFINITY : -INFINITY;              // padding lanes count as "already outside"
+    }
+    for (int r0 = 0; r0 < rows_padded; r0 += kRowBlock) {
+        bool all_out = true;
+#pragma unroll
+        for (int k = 0; k < kNS; ++k) all_out &= mmin[k] < nbeta[k];
+        if (__all_sync(0xffffffffu, all_out)) break;          // every sample of the warp already surely outside
+#pragma unroll
+        for (int r = 0; r < kRowBlock; ++r) {
+            const RowF32 q = s_rows32[r0 + r];
+#pragma unroll
+            for (int k = 0; k < kNS; ++k) {
+                const float m = fmaf(q.na3, vf[k], fmaf(q.na2, pf[k], fmaf(q.na1, yf[k], fmaf(q.na0, xf[k], q.b))));
+                mmin[k] = fminf(mmin[k], m);                  // a NaN margin is ignored here; NaN inputs are caught by the bound
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kNS; ++k) {
+        const bool sure_in = mmin[k] > -nbeta[k], sure_out = mmin[k] < nbeta[k];
+        amb[k] = in[k] && !sure_in && !sure_out;
+        in[k] = in[k] && sure_in;
+    }
+}
+
+// write the 128 decisions of a warp (lane t holds samples 4t .. 4t+3 of the warp's chunk) as four words
+__device__ __forceinline__ int store_bits(uint32_t* __restrict__ bits, int64_t warp_base, int64_t n, const bool (&in)[kNS]) {
+    uint32_t bal[kNS];
+    int members = 0;
+#pragma unroll
+    for (int k = 0; k < kNS; ++k) {
+        bal[k] = __ballot_sync(0xffffffffu, in[k]);
+        members += __popc(bal[k]);
+    }
     const int lane = threadIdx.x & 31;
-    if (lane < 2) {
-        const uint32_t e = lane ? (even >> 16) : even;
-        const uint32_t o = lane ? (odd >> 16) : odd;
-        const uint32_t word = spread16(e) | (spread16(o) << 1);
+    if (lane < 4) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int k = 0; k < kNS; ++k) word |= spread8x4(bal[k] >> (8 * lane)) << k;
         const int64_t first = warp_base + 32 * lane;
         if (first < n) bits[first >> 5] = word;
     }
-    return __popc(even) + __popc(odd);
+    return members;
 }
 
 __device__ __forceinline__ void block_count(int warp_members, unsigned long long* __restrict__ count) {
@@ -177,50 +203,71 @@ __device__ __forceinline__ void block_count(int warp_members, unsigned long long
 }
 
 __device__ __forceinline__ void stage_rows(const double* __restrict__ g_rows, const RowF32* __restrict__ g_rows32,
-                                           int rows, double* s_rows, RowF32* s_rows32) {
+                                           int rows, int rows_padded, double* s_rows, RowF32* s_rows32) {
     for (int i = threadIdx.x; i < rows * 5; i += blockDim.x) s_rows[i] = g_rows[i];
-    for (int i = threadIdx.x; i < rows; i += blockDim.x) s_rows32[i] = g_rows32[i];
+    for (int i = threadIdx.x; i < rows_padded; i += blockDim.x) s_rows32[i] = g_rows32[i];
     __syncthreads();
+}
+
+// four consecutive samples of one coordinate array (two 128-bit streaming loads when aligned and in range)
+template <bool VEC>
+__device__ __forceinline__ void load4(const double* __restrict__ g, int64_t i0, int64_t n, double (&out)[kNS]) {
+    if (VEC && i0 + 3 < n) {
+        const double2 a = ld_stream_f64x2(g + i0), b = ld_stream_f64x2(g + i0 + 2);
+        out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kNS; ++k) out[k] = i0 + k < n ? ld_stream_f64(g + i0 + k) : 0.0;
+    }
 }
 
 template <int MODE, bool VEC>
 __global__ void __launch_bounds__(kThreads)
-membership_kernel(const double* __restrict__ g_rows, const RowF32* __restrict__ g_rows32, int rows,
-                  const double* __restrict__ gx, const double* __restrict__ gy, const double* __restrict__ gp,
-                  const double* __restrict__ gv, int64_t n, uint32_t* __restrict__ bits,
-                  unsigned long long* __restrict__ count) {
+membership_kernel(const double* __restrict__ g_rows, const RowF32* __restrict__ g_rows32, int rows, int rows_padded,
+                  const ScreenConst sc, const double* __restrict__ gx, const double* __restrict__ gy,
+                  const double* __restrict__ gp, const double* __restrict__ gv, int64_t n,
+                  uint32_t* __restrict__ bits, unsigned long long* __restrict__ count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_rows = reinterpret_cast<double*>(smem_raw);
     RowF32* s_rows32 = reinterpret_cast<RowF32*>(s_rows + ((rows * 5 + 1) & ~1));
-    stage_rows(g_rows, g_rows32, rows, s_rows, s_rows32);
+    stage_rows(g_rows, g_rows32, rows, rows_padded, s_rows, s_rows32);
 
     int members = 0;
     const int64_t n_chunks = (n + kChunk - 1) / kChunk;
     for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        const int64_t i0 = chunk * kChunk + 2 * (int64_t)threadIdx.x;
-        double x[2], y[2], p[2], v[2];
-        bool in[2];
-        if (VEC && i0 + 1 < n) {
-            const double2 X = ld_stream_f64x2(gx + i0), Y = ld_stream_f64x2(gy + i0);
-            const double2 P = ld_stream_f64x2(gp + i0), V = ld_stream_f64x2(gv + i0);
-            x[0] = X.x; x[1] = X.y; y[0] = Y.x; y[1] = Y.y;
-            p[0] = P.x; p[1] = P.y; v[0] = V.x; v[1] = V.y;
-            in[0] = in[1] = true;
-        } else {
+        const int64_t i0 = chunk * kChunk + kNS * (int64_t)threadIdx.x;
+        bool in[kNS];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const bool ok = i0 + k < n;
-                const int64_t i = ok ? i0 + k : 0;
-                x[k] = ok ? ld_stream_f64(gx + i) : 0.0;
-                y[k] = ok ? ld_stream_f64(gy + i) : 0.0;
-                p[k] = ok ? ld_stream_f64(gp + i) : 0.0;
-                v[k] = ok ? ld_stream_f64(gv + i) : 0.0;
-                in[k] = ok;
+        for (int k = 0; k < kNS; ++k) in[k] = i0 + k < n;
+        if (MODE == 0) {
+            double x[kNS], y[kNS], p[kNS], v[kNS];
+            load4<VEC>(gx, i0, n, x); load4<VEC>(gy, i0, n, y); load4<VEC>(gp, i0, n, p); load4<VEC>(gv, i0, n, v);
+            decide64(s_rows, rows, x, y, p, v, in);
+        } else {
+            float xf[kNS], yf[kNS], pf[kNS], vf[kNS];
+            {
+                double x[kNS], y[kNS], p[kNS], v[kNS];
+                load4<VEC>(gx, i0, n, x); load4<VEC>(gy, i0, n, y); load4<VEC>(gp, i0, n, p); load4<VEC>(gv, i0, n, v);
+#pragma unroll
+                for (int k = 0; k < kNS; ++k) { xf[k] = (float)x[k]; yf[k] = (float)y[k]; pf[k] = (float)p[k]; vf[k] = (float)v[k]; }
+            }
+            bool amb[kNS];
+            screen32(s_rows32, rows_padded, sc, xf, yf, pf, vf, in, amb);
+            bool any_amb = false;
+#pragma unroll
+            for (int k = 0; k < kNS; ++k) any_amb |= amb[k];
+            if (__any_sync(0xffffffffu, any_amb)) {
+                // rare (|margin| <= beta, ~1e-5 relative, or a non-finite coordinate): the float64 coordinates are
+                // read again (L2) and the float64 chain decides, exactly as in mode 0
+                double x[kNS], y[kNS], p[kNS], v[kNS];
+                load4<VEC>(gx, i0, n, x); load4<VEC>(gy, i0, n, y); load4<VEC>(gp, i0, n, p); load4<VEC>(gv, i0, n, v);
+                decide64(s_rows, rows, x, y, p, v, amb);
+#pragma unroll
+                for (int k = 0; k < kNS; ++k) in[k] |= amb[k];
             }
         }
-        eval_rows<MODE>(s_rows, s_rows32, rows, x, y, p, v, in);
-        const int64_t warp_base = chunk * kChunk + 64 * (int64_t)(threadIdx.x >> 5);
-        members += store_bits(bits, warp_base, n, in[0], in[1]);
+        const int64_t warp_base = chunk * kChunk + 32 * kNS * (int64_t)(threadIdx.x >> 5);
+        members += store_bits(bits, warp_base, n, in);
     }
     block_count(members, count);
 }
@@ -233,25 +280,25 @@ struct GridDesc {
 
 // implicit tensor grid: coordinates come from four short axes staged in shared memory, no HBM reads at all
 __global__ void __launch_bounds__(kThreads)
-membership_grid_kernel(const double* __restrict__ g_rows, const RowF32* __restrict__ g_rows32, int rows,
-                       const double* __restrict__ g_axes, GridDesc gd, int64_t n, uint32_t* __restrict__ bits,
-                       unsigned long long* __restrict__ count) {
+membership_grid_kernel(const double* __restrict__ g_rows, const RowF32* __restrict__ g_rows32, int rows, int rows_padded,
+                       const ScreenConst sc, const double* __restrict__ g_axes, GridDesc gd, int64_t n,
+                       uint32_t* __restrict__ bits, unsigned long long* __restrict__ count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_rows = reinterpret_cast<double*>(smem_raw);
     RowF32* s_rows32 = reinterpret_cast<RowF32*>(s_rows + ((rows * 5 + 1) & ~1));
-    double* s_axes = reinterpret_cast<double*>(s_rows32 + rows);
+    double* s_axes = reinterpret_cast<double*>(s_rows32 + rows_padded);
     const int axes_len = gd.offset[3] + gd.dims[3];
     for (int i = threadIdx.x; i < axes_len; i += blockDim.x) s_axes[i] = g_axes[i];
-    stage_rows(g_rows, g_rows32, rows, s_rows, s_rows32);
+    stage_rows(g_rows, g_rows32, rows, rows_padded, s_rows, s_rows32);
 
     int members = 0;
     const int64_t n_chunks = (n + kChunk - 1) / kChunk;
     for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        const int64_t i0 = chunk * kChunk + 2 * (int64_t)threadIdx.x;
-        double c[4][2];
-        bool in[2];
+        const int64_t i0 = chunk * kChunk + kNS * (int64_t)threadIdx.x;
+        double c[4][kNS];
+        bool in[kNS];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < kNS; ++k) {
             in[k] = i0 + k < n;
             uint64_t rem = in[k] ? (uint64_t)(i0 + k) : 0;
 #pragma unroll
@@ -267,9 +314,21 @@ membership_grid_kernel(const double* __restrict__ g_rows, const RowF32* __restri
                     if (gd.state_of_axis[ax] == st) c[st][k] = val;
             }
         }
-        eval_rows<1>(s_rows, s_rows32, rows, c[0], c[1], c[2], c[3], in);
-        const int64_t warp_base = chunk * kChunk + 64 * (int64_t)(threadIdx.x >> 5);
-        members += store_bits(bits, warp_base, n, in[0], in[1]);
+        float xf[kNS], yf[kNS], pf[kNS], vf[kNS];
+#pragma unroll
+        for (int k = 0; k < kNS; ++k) { xf[k] = (float)c[0][k]; yf[k] = (float)c[1][k]; pf[k] = (float)c[2][k]; vf[k] = (float)c[3][k]; }
+        bool amb[kNS];
+        screen32(s_rows32, rows_padded, sc, xf, yf, pf, vf, in, amb);
+        bool any_amb = false;
+#pragma unroll
+        for (int k = 0; k < kNS; ++k) any_amb |= amb[k];
+        if (__any_sync(0xffffffffu, any_amb)) {
+            decide64(s_rows, rows, c[0], c[1], c[2], c[3], amb);
+#pragma unroll
+            for (int k = 0; k < kNS; ++k) in[k] |= amb[k];
+        }
+        const int64_t warp_base = chunk * kChunk + 32 * kNS * (int64_t)(threadIdx.x >> 5);
+        members += store_bits(bits, warp_base, n, in);
     }
     block_count(members, count);
 }
@@ -345,11 +404,19 @@ rollout_kernel(const double* __restrict__ g_data, int s, int rin, int k_steps, i
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------------
-static size_t membership_smem(int rows) { return sizeof(double) * ((rows * 5 + 1) & ~1) + sizeof(RowF32) * rows; }
+static int pad_rows(int rows) { return (rows + 7) & ~7; }
+static size_t membership_smem(int rows) { return sizeof(double) * ((rows * 5 + 1) & ~1) + sizeof(RowF32) * pad_rows(rows); }
 
 static int grid_blocks(int64_t n_chunks, int per_sm) {
     const int64_t cap = (int64_t)sm_count() * per_sm;
     return (int)(n_chunks < cap ? (n_chunks > 0 ? n_chunks : 1) : cap);
+}
+
+static ScreenConst class_table(const Polytope* P) {
+    ScreenConst sc;
+    sc.beta0 = P->beta0;
+    sc.beta1 = P->beta1;
+    return sc;
 }
 
 static int launch_membership(Polytope* P, const double* x, const double* y, const double* p, const double* v,
@@ -357,12 +424,17 @@ static int launch_membership(Polytope* P, const double* x, const double* y, cons
     if (n == 0) return CARMPC_OK;
     const size_t smem = membership_smem(P->rows);
     const int64_t n_chunks = (n + kChunk - 1) / kChunk;
-    const int blocks = grid_blocks(n_chunks, 8);
     const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
                        reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
-#define LAUNCH(M, V)                                                                                        \
-    membership_kernel<M, V><<<blocks, kThreads, smem, st>>>(P->d_rows, P->d_rows32, P->rows, x, y, p, v, n, \
-                                                            bits, count)
+    // persistent grid: exactly the number of CTAs that are resident at once (a multiple of the SM count)
+#define LAUNCH(M, V)                                                                                              \
+    do {                                                                                                          \
+        int per_sm = 0;                                                                                           \
+        CARMPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, membership_kernel<M, V>, kThreads, smem)); \
+        const int blocks = grid_blocks(n_chunks, per_sm > 0 ? per_sm : 1);                                        \
+        membership_kernel<M, V><<<blocks, kThreads, smem, st>>>(P->d_rows, P->d_rows32, P->rows, pad_rows(P->rows),    \
+                                                                class_table(P), x, y, p, v, n, bits, count);     \
+    } while (0)
     if (mode == 0) {
         if (vec) LAUNCH(0, true); else LAUNCH(0, false);
     } else {
@@ -431,29 +503,65 @@ int carmpc_polytope_create(const double* h_Ab, int rows, void** handle) {
     P->kind = kPolytope;
     P->rows = rows;
     cudaGetDevice(&P->device);
-    std::vector<RowF32> r32(rows > 0 ? rows : 1);
-    const double gamma = 16.0 * 5.9604644775390625e-08;      // 16 * 2^-24, see eval_rows<1>
+    // sort the rows by sparsity pattern: fewest non-zeros first (cheapest, and for these sets the axis-aligned
+    // bounds that reject most samples), stable within a pattern
+    std::vector<int> order(rows), pat(rows);
     for (int r = 0; r < rows; ++r) {
-        const double* a = h_Ab + 5 * r;
-        RowF32 q;
-        q.a0 = (float)a[0]; q.a1 = (float)a[1]; q.a2 = (float)a[2]; q.a3 = (float)a[3];
-        q.b = (float)a[4];
-        const double l1 = fabs(a[0]) + fabs(a[1]) + fabs(a[2]) + fabs(a[3]);
-        // round the bound constants up so that the float32 bound dominates the analysed error
-        q.bound_coef = nextafterf((float)(gamma * l1 * 1.0000005), INFINITY);
-        q.bound_const = nextafterf((float)(gamma * fabs(a[4]) * 1.0000005 + 1e-37), INFINITY);
-        q.pad = 0.f;
-        r32[r] = q;
+        order[r] = r;
+        int m = 0;
+        for (int k = 0; k < 4; ++k) {
+            if (isnan(h_Ab[5 * r + k]) || isinf(h_Ab[5 * r + k])) { delete P; set_error("carmpc_polytope_create: non-finite coefficient in row %d", r); return CARMPC_ERR_INVALID; }
+            if (h_Ab[5 * r + k] != 0.0) m |= 1 << k;
+        }
+        pat[r] = m;
     }
+    auto popc = [](int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1); };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (popc(pat[a]) != popc(pat[b])) return popc(pat[a]) < popc(pat[b]);
+        return pat[a] < pat[b];
+    });
+    std::vector<double> sorted(5 * (rows > 0 ? rows : 1), 0.0);
+    std::vector<RowF32> r32(pad_rows(rows) > 0 ? pad_rows(rows) : 8);
+    for (RowF32& q : r32) { q.na0 = q.na1 = q.na2 = q.na3 = 0.f; q.b = INFINITY; q.pad0 = q.pad1 = q.pad2 = 0.f; }
+    double l1max = 0.0, bmax = 0.0;
+    P->n_classes = 0;
+    for (int i = 0; i < rows; ++i) {
+        const double* a = h_Ab + 5 * order[i];
+        for (int k = 0; k < 5; ++k) sorted[5 * i + k] = a[k];
+        RowF32 q;
+        q.na0 = (float)-a[0]; q.na1 = (float)-a[1]; q.na2 = (float)-a[2]; q.na3 = (float)-a[3];
+        q.b = (float)a[4];
+        q.pad0 = q.pad1 = q.pad2 = 0.f;
+        r32[i] = q;
+        l1max = std::max(l1max, fabs(a[0]) + fabs(a[1]) + fabs(a[2]) + fabs(a[3]));
+        if (!isinf(a[4])) bmax = std::max(bmax, fabs(a[4]));
+        const int m = pat[order[i]];
+        if (P->n_classes == 0 || P->classes[P->n_classes - 1].pattern != m) {
+            P->classes[P->n_classes].pattern = m;
+            P->classes[P->n_classes].beg = i;
+            P->classes[P->n_classes].pad = 0;
+            ++P->n_classes;
+        }
+        P->classes[P->n_classes - 1].end = i + 1;
+    }
+    // Rounding-error bound of the float32 margin  fma(-a3, v, fma(-a2, psi, fma(-a1, y, fma(-a0, x, b))))  against the
+    // exact  b - a . p :  each input is rounded once (relative 2^-24), each of the <= 4 fmas rounds once, so
+    // |error| <= (4 + 2 + 1) 2^-24 (|b| + sum |a_k| |p_k|) (1 + O(2^-24)); the float64 chain's own error (2^-51 of the
+    // same magnitude) and overflow to inf (coordinates above 1e30 give an inf bound) are covered by using 8 and
+    // rounding the two constants up.
+    const double u8 = 8.0 * 5.9604644775390625e-08;
+    P->beta0 = nextafterf((float)(u8 * bmax * 1.000001 + 1e-37), INFINITY);
+    P->beta1 = nextafterf((float)(u8 * l1max * 1.000001 + 1e-37), INFINITY);
+    h_Ab = sorted.data();
     auto fail = [&](int code) { delete P; return code; };
     if (cudaMalloc(&P->d_rows, sizeof(double) * 5 * (rows > 0 ? rows : 1)) != cudaSuccess ||
-        cudaMalloc(&P->d_rows32, sizeof(RowF32) * (rows > 0 ? rows : 1)) != cudaSuccess) {
+        cudaMalloc(&P->d_rows32, sizeof(RowF32) * r32.size()) != cudaSuccess) {
         set_error("carmpc_polytope_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(CARMPC_ERR_CUDA);
     }
     if (rows > 0) {
         if (cudaMemcpy(P->d_rows, h_Ab, sizeof(double) * 5 * rows, cudaMemcpyHostToDevice) != cudaSuccess ||
-            cudaMemcpy(P->d_rows32, r32.data(), sizeof(RowF32) * rows, cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaMemcpy(P->d_rows32, r32.data(), sizeof(RowF32) * r32.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
             set_error("carmpc_polytope_create: cudaMemcpy failed: %s", cudaGetErrorString(cudaGetLastError()));
             return fail(CARMPC_ERR_CUDA);
         }
@@ -508,7 +616,8 @@ int carmpc_membership_grid(void* polytope, const double* h_axes, const int32_t d
     CARMPC_CUDA(cudaFuncSetAttribute(membership_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_chunks = (n + kChunk - 1) / kChunk;
     membership_grid_kernel<<<grid_blocks(n_chunks, 4), kThreads, smem, st>>>(
-        P->d_rows, P->d_rows32, P->rows, d_axes, gd, n, d_bits, reinterpret_cast<unsigned long long*>(d_count));
+        P->d_rows, P->d_rows32, P->rows, pad_rows(P->rows), class_table(P), d_axes, gd, n, d_bits,
+        reinterpret_cast<unsigned long long*>(d_count));
     CARMPC_CUDA(cudaGetLastError());
     CARMPC_CUDA(cudaFreeAsync(d_axes, st));
     return CARMPC_OK;
