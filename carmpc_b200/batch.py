@@ -188,8 +188,9 @@ class RolloutEvaluator(_Handle):
 
 
 def measure_peak(which: str) -> float:
-    """Device micro-benchmarks: 'fp32' / 'fp64' FMA TFLOP/s, 'hbm' copy GB/s (read + write)."""
-    idx = {"fp32": 0, "fp64": 1, "hbm": 2}[which]
+    """Device micro-benchmarks: 'fp32' / 'fp64' FMA TFLOP/s (uniform multiplier), 'hbm' copy GB/s (read + write),
+    'fp32_tile' TFLOP/s of a shared-memory-fed 8 x 8 register-tile product (both multiplicands in vector registers)."""
+    idx = {"fp32": 0, "fp64": 1, "hbm": 2, "fp32_tile": 3}[which]
     val = ctypes.c_double(0.0)
     check(_capi.load().carmpc_measure_peak(idx, ctypes.byref(val)))
     return float(val.value)

@@ -18,7 +18,7 @@ LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcarmpc_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O2,-Wall", "-shared", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC,-O2,-Wall", "-Xptxas", "-v"]
 
 
 def _nvcc() -> str:
@@ -46,15 +46,39 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = _nvcc()
+    headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(os.path.dirname(HERE), "include", "*.h"))
+    newest_header = max(os.path.getmtime(h) for h in headers)
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.isfile(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), newest_header):
+            return obj, "", 0
+        proc = subprocess.run([nvcc] + NVCC_FLAGS + ["-c", "-o", obj, src], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True)
+        return obj, proc.stdout, proc.returncode
+
+    # one nvcc per translation unit, in parallel (qp_admm.cu alone is minutes of ptxas time)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, min(len(sources()), os.cpu_count() or 1))) as pool:
+        results = list(pool.map(compile_one, sources()))
+    log = "".join(out for _, out, _ in results)
+    failed = [obj for obj, _, rc in results if rc != 0]
+    if verbose or failed:
+        print(log, file=sys.stderr)
+    if failed:
+        raise RuntimeError("nvcc failed building " + ", ".join(os.path.basename(f) for f in failed) + " (output above)")
     tmp = LIB_PATH + ".tmp"
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", tmp] + sources()
-    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if verbose or proc.returncode != 0:
-        print(proc.stdout, file=sys.stderr)
+    proc = subprocess.run([nvcc, "-shared", "-o", tmp] + [obj for obj, _, _ in results], stdout=subprocess.PIPE,
+                          stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed building libcarmpc_b200.so (output above)")
-    with open(os.path.join(LIB_DIR, "ptxas.log"), "w") as f:
-        f.write(proc.stdout)
+        print(proc.stdout, file=sys.stderr)
+        raise RuntimeError("linking libcarmpc_b200.so failed (output above)")
+    if log.strip():
+        with open(os.path.join(LIB_DIR, "ptxas.log"), "w") as f:
+            f.write(log)
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 

@@ -41,6 +41,71 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Register-tiled outer-product loop fed from shared memory (8 x 8 accumulators, one broadcast 128-bit and one
+// per-lane 128-bit load pair per 64 FFMA): the practical FFMA ceiling of a shared-memory tile product, where both
+// multiplicands are vector registers (unlike fma_peak_kernel, whose multiplier is a uniform register).
+__global__ void __launch_bounds__(256) tile_peak_kernel(float* out, int iters) {
+    __shared__ __align__(16) float sa[64 * 8];
+    __shared__ __align__(16) float sb[4 * 2048];
+    for (int i = threadIdx.x; i < 64 * 8; i += 256) sa[i] = 1.0f + 1e-6f * i;
+    for (int i = threadIdx.x; i < 4 * 2048; i += 256) sb[i] = 1.0f - 1e-6f * (i & 1023);
+    __syncthreads();
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const int lane8 = threadIdx.x * 8;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 4
+        for (int k = 0; k < 64; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(sa + k * 8);
+            const float4 a1 = *reinterpret_cast<const float4*>(sa + k * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(sb + (((k & 3) * 2048 + lane8) & (4 * 2048 - 1)));
+            const float4 b1 = *reinterpret_cast<const float4*>(sb + (((k & 3) * 2048 + lane8 + 4) & (4 * 2048 - 1)));
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += acc[i][j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+static int measure_tile(double* value) {
+    const int blocks = sm_count() * 2, threads = 256, iters = 256;
+    float* out = nullptr;
+    CARMPC_CUDA(cudaMalloc(&out, sizeof(float) * blocks * threads));
+    CARMPC_CUDA(cudaFuncSetAttribute(tile_peak_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    cudaEvent_t e0, e1;
+    CARMPC_CUDA(cudaEventCreate(&e0));
+    CARMPC_CUDA(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CARMPC_CUDA(cudaEventRecord(e0));
+        tile_peak_kernel<<<blocks, threads>>>(out, iters);
+        CARMPC_CUDA(cudaEventRecord(e1));
+        CARMPC_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        CARMPC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * 64.0 * iters * (double)blocks * threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *value = best;
+    return CARMPC_OK;
+}
+
 __global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -122,7 +187,8 @@ int carmpc_measure_peak(int which, double* h_value) {
         case 0: return carmpc::measure_fma<float>(h_value);
         case 1: return carmpc::measure_fma<double>(h_value);
         case 2: return carmpc::measure_copy(h_value);
-        default: carmpc::set_error("carmpc_measure_peak: which must be 0, 1 or 2"); return CARMPC_ERR_INVALID;
+        case 3: return carmpc::measure_tile(h_value);
+        default: carmpc::set_error("carmpc_measure_peak: which must be 0..3"); return CARMPC_ERR_INVALID;
     }
 }
 

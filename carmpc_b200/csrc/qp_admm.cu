@@ -14,6 +14,7 @@
 // slots are refilled from a global queue at every convergence check: a finished sample leaves its slot, writes its
 // active-set signs / iterate / status, and the next queued sample takes the slot over (state reset in registers).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <type_traits>
@@ -81,7 +82,9 @@ __device__ __forceinline__ void atomic_max_pos(unsigned* addr, float v) {      /
 
 struct Smem {
     float *V, *Xt, *HI, *Pm, *Gm, *width, *lam, *lbs, *ubs;
-    int* vpos;
+    float *einv_g, *esc_g, *einv_b, *esc_b, *dinv, *dsc;     // per-row / per-variable scales (checks, outputs)
+    double *his, *gxs, *gcs, *kf;                             // slot (re)initialisation tables
+    int *vpos, *row_id, *var_id;
     int4* segA;
     int2* segB;
     double* x0;          // [5][Bt]  x, y, psi, v, c
@@ -91,13 +94,17 @@ struct Smem {
     int* misc;           // [0] n_free, [1] base
 };
 
-template <int S, bool MATS>
+template <int S, int H, bool MATS>
 __device__ __forceinline__ Smem carve(unsigned char* raw, const AdmmTables& T) {
-    constexpr int Bt = 32 * S;
+    constexpr int Bt = 32 * S * H;
     Smem s;
     size_t off = 0;
     auto take = [&](size_t bytes) { unsigned char* p = raw + off; off += (bytes + 15) & ~size_t(15); return p; };
     s.x0 = reinterpret_cast<double*>(take(sizeof(double) * 5 * Bt));
+    s.his = reinterpret_cast<double*>(take(sizeof(double) * T.m_phys));
+    s.gxs = reinterpret_cast<double*>(take(sizeof(double) * 4 * T.m_phys));
+    s.gcs = reinterpret_cast<double*>(take(sizeof(double) * T.m_phys));
+    s.kf = reinterpret_cast<double*>(take(sizeof(double) * 4 * T.nA_rows));
     s.V = reinterpret_cast<float*>(take(sizeof(float) * (size_t)T.ktot * Bt));
     s.Xt = reinterpret_cast<float*>(take(sizeof(float) * (size_t)T.npad4 * Bt));
     s.HI = reinterpret_cast<float*>(take(sizeof(float) * (size_t)T.m_phys * Bt));
@@ -111,7 +118,15 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, const AdmmTables& T) {
     s.lam = reinterpret_cast<float*>(take(sizeof(float) * T.nA_rows));
     s.lbs = reinterpret_cast<float*>(take(sizeof(float) * T.nA_rows));
     s.ubs = reinterpret_cast<float*>(take(sizeof(float) * T.nA_rows));
+    s.einv_g = reinterpret_cast<float*>(take(sizeof(float) * T.m_phys));
+    s.esc_g = reinterpret_cast<float*>(take(sizeof(float) * T.m_phys));
+    s.einv_b = reinterpret_cast<float*>(take(sizeof(float) * T.nA_rows));
+    s.esc_b = reinterpret_cast<float*>(take(sizeof(float) * T.nA_rows));
+    s.dinv = reinterpret_cast<float*>(take(sizeof(float) * T.nA_rows));
+    s.dsc = reinterpret_cast<float*>(take(sizeof(float) * T.nA_rows));
     s.vpos = reinterpret_cast<int*>(take(sizeof(int) * T.m_phys));
+    s.row_id = reinterpret_cast<int*>(take(sizeof(int) * T.m_phys));
+    s.var_id = reinterpret_cast<int*>(take(sizeof(int) * T.nA_rows));
     s.segA = reinterpret_cast<int4*>(take(sizeof(int4) * T.nGA));
     s.segB = reinterpret_cast<int2*>(take(sizeof(int2) * T.nGB));
     s.slot_sample = reinterpret_cast<int*>(take(sizeof(int) * Bt));
@@ -128,33 +143,49 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, const AdmmTables& T) {
     return s;
 }
 
-template <int S, int GA, int GB, bool MATS>
-__global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables T, const AdmmBatch Bq) {
-    constexpr int Bt = 32 * S;
+// S samples per lane, H sample-halves: 8 H warps; warp w owns row groups (w & 7) of the samples of half (w >> 3).
+// More warps per scheduler (H = 2) hide shared-memory latency better; fewer (H = 1, larger S) reuse each matrix
+// fragment over more samples.
+template <int S, int H, int GA, int GB, bool MATS>
+__global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTables T, const AdmmBatch Bq) {
+    constexpr int Bt = 32 * S * H;
+    constexpr int NT = kAdmmThreads * H;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem sm = carve<S, MATS>(smem_raw, T);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int s0 = lane * S;
+    const Smem sm = carve<S, H, MATS>(smem_raw, T);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = (tid >> 5) & (kAdmmWarps - 1);            // row-group owner index
+    const int s0 = (tid >> 8) * 32 * S + lane * S;             // first slot of this lane
     const float* __restrict__ Pm = MATS ? sm.Pm : T.P;
     const float* __restrict__ Gm = MATS ? sm.Gm : T.Gs;
     const float alpha = T.alpha;
 
     // ---- one-time staging ------------------------------------------------------------------------------------------------
-    for (int i = tid; i < T.ktot * Bt; i += kAdmmThreads) sm.V[i] = 0.f;
-    for (int i = tid; i < T.npad4 * Bt; i += kAdmmThreads) sm.Xt[i] = 0.f;
-    for (int i = tid; i < T.m_phys * Bt; i += kAdmmThreads) sm.HI[i] = 3.0e38f;
+    for (int i = tid; i < T.ktot * Bt; i += NT) sm.V[i] = 0.f;
+    for (int i = tid; i < T.npad4 * Bt; i += NT) sm.Xt[i] = 0.f;
+    for (int i = tid; i < T.m_phys * Bt; i += NT) sm.HI[i] = 3.0e38f;
     if (MATS) {
         const float4* src = reinterpret_cast<const float4*>(T.P);
         float4* dst = reinterpret_cast<float4*>(sm.Pm);
-        for (int i = tid; i < T.nA_rows * T.ktot / 4; i += kAdmmThreads) dst[i] = src[i];
+        for (int i = tid; i < T.nA_rows * T.ktot / 4; i += NT) dst[i] = src[i];
         src = reinterpret_cast<const float4*>(T.Gs);
         dst = reinterpret_cast<float4*>(sm.Gm);
-        for (int i = tid; i < T.m_phys * T.npad4 / 4; i += kAdmmThreads) dst[i] = src[i];
+        for (int i = tid; i < T.m_phys * T.npad4 / 4; i += NT) dst[i] = src[i];
     }
-    for (int i = tid; i < T.m_phys; i += kAdmmThreads) { sm.width[i] = T.width[i]; sm.vpos[i] = T.vpos[i]; }
-    for (int i = tid; i < T.nA_rows; i += kAdmmThreads) { sm.lam[i] = T.lam[i]; sm.lbs[i] = T.lbs[i]; sm.ubs[i] = T.ubs[i]; }
-    for (int i = tid; i < T.nGA; i += kAdmmThreads) sm.segA[i] = T.segA[i];
-    for (int i = tid; i < T.nGB; i += kAdmmThreads) sm.segB[i] = T.segB[i];
+    for (int i = tid; i < T.m_phys; i += NT) {
+        sm.width[i] = T.width[i]; sm.vpos[i] = T.vpos[i]; sm.row_id[i] = T.row_id[i];
+        sm.einv_g[i] = T.Einv_g[i]; sm.esc_g[i] = T.Esc_g[i];
+        sm.his[i] = T.his[i]; sm.gcs[i] = T.Gcs[i];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sm.gxs[i * 4 + c] = T.Gxs[i * 4 + c];
+    }
+    for (int i = tid; i < T.nA_rows; i += NT) {
+        sm.lam[i] = T.lam[i]; sm.lbs[i] = T.lbs[i]; sm.ubs[i] = T.ubs[i]; sm.var_id[i] = T.var_id[i];
+        sm.einv_b[i] = T.Einv_b[i]; sm.esc_b[i] = T.Esc_b[i]; sm.dinv[i] = T.Dinv[i]; sm.dsc[i] = T.Dsc[i];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sm.kf[i * 4 + c] = T.KF[i * 4 + c];
+    }
+    for (int i = tid; i < T.nGA; i += NT) sm.segA[i] = T.segA[i];
+    for (int i = tid; i < T.nGB; i += NT) sm.segB[i] = T.segB[i];
     if (tid < Bt) {
         sm.slot_sample[tid] = -1; sm.slot_state[tid] = kSlotIdle; sm.slot_iter[tid] = 0; sm.slot_init[tid] = 0;
         sm.red_res[tid] = 0; sm.red_nrm[tid] = 0; sm.red_ndy[tid] = 0; sm.red_t3[tid] = 0; sm.red_sup[tid] = 0.f;
@@ -235,14 +266,14 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
                         wA[g][r][s] = w1;
                         o.v[s] = 2.f * c1 - w1;
                         if (CHECK) {
-                            const float einv = T.Einv_b[j];
+                            const float einv = sm.einv_b[j];
                             p_res[s] = fmaxf(p_res[s], fmaxf(fabsf(z - c1), fabsf(c1 - c0)) * einv);
                             p_nrm[s] = fmaxf(p_nrm[s], fmaxf(fabsf(z), fabsf(c1)) * einv);
                             float e = (w1 - c1) - (w0 - c0);
                             if (ub == INFINITY) e = fminf(e, 0.f);
                             if (lb == -INFINITY) e = fmaxf(e, 0.f);
                             egA[g][r][s] = e;
-                            p_ndy[s] = fmaxf(p_ndy[s], fabsf(e) * T.Esc_b[j]);
+                            p_ndy[s] = fmaxf(p_ndy[s], fabsf(e) * sm.esc_b[j]);
                             p_sup[s] += e > 0.f ? ub * e : (e < 0.f ? lb * e : 0.f);
                         }
                     }
@@ -280,13 +311,13 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
                     if (!CHECK) {
                         o.v[s] = 2.f * c1 - w1;
                     } else {
-                        const float einv = T.Einv_g[i];
+                        const float einv = sm.einv_g[i];
                         p_res[s] = fmaxf(p_res[s], fmaxf(fabsf(z - c1), fabsf(c1 - c0)) * einv);
                         p_nrm[s] = fmaxf(p_nrm[s], fmaxf(fabsf(z), fabsf(c1)) * einv);
                         float e = (w1 - c1) - (w0 - c0);
                         if (wd == INFINITY) e = fmaxf(e, 0.f);
                         o.v[s] = e;                         // V carries delta-y for the certificate product
-                        p_ndy[s] = fmaxf(p_ndy[s], fabsf(e) * T.Esc_g[i]);
+                        p_ndy[s] = fmaxf(p_ndy[s], fabsf(e) * sm.esc_g[i]);
                         p_sup[s] += e > 0.f ? h * e : (e < 0.f ? lo * e : 0.f);
                     }
                 }
@@ -321,7 +352,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
                     tile_product<kRA, S, false>(acc, T.GsT + (size_t)(pg * kRA) * T.mv4, T.mv4, sm.V, Bt, s0, sg.x, sg.y);
 #pragma unroll
                     for (int r = 0; r < kRA; ++r) {
-                        const float dinv = T.Dinv[pg * kRA + r];
+                        const float dinv = sm.dinv[pg * kRA + r];
 #pragma unroll
                         for (int s = 0; s < S; ++s) t3[s] = fmaxf(t3[s], fabsf(acc[r][s]) * dinv);
                     }
@@ -359,13 +390,17 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
 #pragma unroll
         for (int s = 0; s < S; ++s) { const int st = sm.slot_state[s0 + s]; fin[s] = st > 0 ? sm.slot_sample[s0 + s] : -1; }
         // outputs of the finished samples, by the owners of the rows
+        bool any_fin = false;
+#pragma unroll
+        for (int s = 0; s < S; ++s) any_fin |= fin[s] >= 0;
+        if (any_fin) {
 #pragma unroll
         for (int g = 0; g < GB; ++g) {
             const int pg = g * kAdmmWarps + warp;
 #pragma unroll
             for (int r = 0; r < kRB; ++r) {
                 const int i = pg * kRB + r;
-                const int rid = T.row_id[i];
+                const int rid = sm.row_id[i];
                 if (rid < 0) continue;
                 const float wd = sm.width[i];
 #pragma unroll
@@ -384,9 +419,9 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
 #pragma unroll
             for (int r = 0; r < kRA; ++r) {
                 const int j = pg * kRA + r;
-                const int vid = T.var_id[j];
+                const int vid = sm.var_id[j];
                 if (vid < 0) continue;
-                const float lb = sm.lbs[j], ub = sm.ubs[j], d = T.Dsc[j];
+                const float lb = sm.lbs[j], ub = sm.ubs[j], d = sm.dsc[j];
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     if (fin[s] < 0) continue;
@@ -396,6 +431,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
                     if (Bq.warm_out) Bq.warm[(size_t)fin[s] * T.mt + T.m + vid] = w;
                 }
             }
+        }
         }
         if (tid < Bt) {
             const int st = sm.slot_state[tid];
@@ -466,7 +502,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
 #pragma unroll
                 for (int r = 0; r < kRB; ++r) {
                     const int i = pg * kRB + r;
-                    const int rid = T.row_id[i];
+                    const int rid = sm.row_id[i];
                     const float wd = sm.width[i];
                     const int vp = sm.vpos[i];
 #pragma unroll
@@ -474,9 +510,9 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
                         if (!ini[s]) continue;
                         float h = 3.0e38f, w = 0.f;
                         if (ini[s] == 1 && rid >= 0) {
-                            const double* gx = T.Gxs + (size_t)i * 4;
-                            h = (float)(T.his[i] - gx[0] * xs[s][0] - gx[1] * xs[s][1] - gx[2] * xs[s][2] - gx[3] * xs[s][3] -
-                                        T.Gcs[i] * cd[s]);
+                            const double* gx = sm.gxs + i * 4;
+                            h = (float)(sm.his[i] - gx[0] * xs[s][0] - gx[1] * xs[s][1] - gx[2] * xs[s][2] - gx[3] * xs[s][3] -
+                                        sm.gcs[i] * cd[s]);
                             if (Bq.warm_in) w = Bq.warm[(size_t)smp[s] * T.mt + rid];
                         }
                         sm.HI[i * Bt + s0 + s] = h;
@@ -492,14 +528,14 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
 #pragma unroll
                 for (int r = 0; r < kRA; ++r) {
                     const int j = pg * kRA + r;
-                    const int vid = T.var_id[j];
+                    const int vid = sm.var_id[j];
                     const float lb = sm.lbs[j], ub = sm.ubs[j];
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
                         if (!ini[s]) continue;
                         float w = 0.f, x0v = 0.f;
                         if (ini[s] == 1 && vid >= 0) {
-                            const double* kf = T.KF + (size_t)j * 4;
+                            const double* kf = sm.kf + j * 4;
                             x0v = (float)(kf[0] * dx[s][0] + kf[1] * dx[s][1] + kf[2] * dx[s][2] + kf[3] * dx[s][3]);
                             if (Bq.warm_in) w = Bq.warm[(size_t)smp[s] * T.mt + T.m + vid];
                         }
@@ -539,17 +575,17 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) admm_kernel(const AdmmTables 
     }
 }
 
-template <int S, int GA, int GB>
+template <int S, int H, int GA, int GB>
 int launch_variant(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
-    const size_t smem = admm_smem_bytes(q->host, S, q->host.mats_in_smem);
-    const int64_t tiles = (b.count + 32 * S - 1) / (32 * S);
+    const size_t smem = admm_smem_bytes(q->host, S * H, q->host.mats_in_smem);
+    const int64_t tiles = (b.count + 32 * S * H - 1) / (32 * S * H);
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, q->sm));
     if (q->host.mats_in_smem) {
-        CARMPC_CUDA(cudaFuncSetAttribute(admm_kernel<S, GA, GB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        admm_kernel<S, GA, GB, true><<<blocks, kAdmmThreads, smem, st>>>(q->admm, b);
+        CARMPC_CUDA(cudaFuncSetAttribute(admm_kernel<S, H, GA, GB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        admm_kernel<S, H, GA, GB, true><<<blocks, kAdmmThreads * H, smem, st>>>(q->admm, b);
     } else {
-        CARMPC_CUDA(cudaFuncSetAttribute(admm_kernel<S, GA, GB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        admm_kernel<S, GA, GB, false><<<blocks, kAdmmThreads, smem, st>>>(q->admm, b);
+        CARMPC_CUDA(cudaFuncSetAttribute(admm_kernel<S, H, GA, GB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        admm_kernel<S, H, GA, GB, false><<<blocks, kAdmmThreads * H, smem, st>>>(q->admm, b);
     }
     CARMPC_CUDA(cudaGetLastError());
     return CARMPC_OK;
@@ -559,19 +595,20 @@ int launch_variant(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
 
 int admm_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
     if (b.count <= 0) return CARMPC_OK;
-    // Samples per lane: the size class fixes the maximum (registers / shared memory); a batch too small to give every
+    // Samples per tile: the size class fixes the maximum (registers / shared memory); a batch too small to give every
     // SM a full tile runs narrower tiles, whose iterations are proportionally shorter.
     const int smax = q->host.samples_per_lane;
     int S = 1;
     while (S * 2 <= smax && (int64_t)b.count >= (int64_t)32 * (S * 2) * q->sm) S *= 2;
+    static const int variant = getenv("CARMPC_ADMM_WIDE") ? atoi(getenv("CARMPC_ADMM_WIDE")) : 0;   // development knob
     const int key = q->host.ga_per_warp * 100 + q->host.gb_per_warp * 10 + S;
     switch (key) {
-        case 124: return launch_variant<4, 1, 2>(q, b, st);
-        case 122: return launch_variant<2, 1, 2>(q, b, st);
-        case 121: return launch_variant<1, 1, 2>(q, b, st);
-        case 242: return launch_variant<2, 2, 4>(q, b, st);
-        case 241: return launch_variant<1, 2, 4>(q, b, st);
-        case 471: return launch_variant<1, 4, 7>(q, b, st);
+        case 124: return variant == 1 ? launch_variant<4, 1, 1, 2>(q, b, st) : launch_variant<2, 2, 1, 2>(q, b, st);
+        case 122: return launch_variant<2, 1, 1, 2>(q, b, st);
+        case 121: return launch_variant<1, 1, 1, 2>(q, b, st);
+        case 242: return variant == 1 ? launch_variant<2, 1, 2, 4>(q, b, st) : launch_variant<1, 2, 2, 4>(q, b, st);
+        case 241: return launch_variant<1, 1, 2, 4>(q, b, st);
+        case 471: return launch_variant<1, 1, 4, 7>(q, b, st);
     }
     set_error("admm_launch: no kernel variant for this problem size");
     return CARMPC_ERR_UNSUPPORTED;

@@ -154,37 +154,39 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
                 rhs[a] = Auu[i] - bact[a];
             }
             __syncwarp();
-            // ---- Cholesky with pivot skipping (a row that depends on earlier ones gets lambda = 0) ----
+            // ---- Cholesky with pivot skipping (a row that depends on earlier ones gets lambda = 0).  diag0[j] is
+            //      overwritten by 1 / L_jj (0 for a skipped pivot) so that the solves below are division-free ----
             for (int j = 0; j < na; ++j) {
-                const double d = M[tri(j, j)];
+                const int tj = tri(j, 0);
+                const double d = M[tj + j];
                 const bool skip = !(d > 1e-11 * diag0[j]);
-                const double piv = skip ? 1.0 : sqrt(d);
+                const double rinv = skip ? 0.0 : rsqrt(d);                // every lane computes the same value
                 __syncwarp();
-                if (lane == 0) M[tri(j, j)] = skip ? 0.0 : piv;           // 0 on the diagonal marks a skipped pivot
-                for (int i = j + 1 + lane; i < na; i += 32) M[tri(i, j)] = skip ? 0.0 : M[tri(i, j)] / piv;
+                if (lane == 0) diag0[j] = rinv;
+                for (int i = j + 1 + lane; i < na; i += 32) M[tri(i, 0) + j] *= rinv;      // L_ij (0 when skipped)
                 __syncwarp();
                 if (!skip)
                     for (int i = j + 1 + lane; i < na; i += 32) {
-                        const double lij = M[tri(i, j)];
-                        for (int k = j + 1; k <= i; ++k) M[tri(i, k)] -= lij * M[tri(k, j)];
+                        const int ti = tri(i, 0);
+                        const double lij = M[ti + j];
+                        for (int k = j + 1; k <= i; ++k) M[ti + k] -= lij * M[tri(k, 0) + j];
                     }
                 __syncwarp();
             }
             // ---- L y = rhs, L' lambda = y ----
             for (int j = 0; j < na; ++j) {
-                const double d = M[tri(j, j)];
-                const double y = d > 0.0 ? rhs[j] / d : 0.0;
+                const double y = rhs[j] * diag0[j];
                 __syncwarp();
                 if (lane == 0) rhs[j] = y;
-                for (int i = j + 1 + lane; i < na; i += 32) rhs[i] -= M[tri(i, j)] * y;
+                for (int i = j + 1 + lane; i < na; i += 32) rhs[i] -= M[tri(i, 0) + j] * y;
                 __syncwarp();
             }
             for (int j = na - 1; j >= 0; --j) {
-                const double d = M[tri(j, j)];
-                const double x = d > 0.0 ? rhs[j] / d : 0.0;
+                const double x = rhs[j] * diag0[j];
+                const int tj = tri(j, 0);
                 __syncwarp();
                 if (lane == 0) rhs[j] = x;
-                for (int i = lane; i < j; i += 32) rhs[i] -= M[tri(j, i)] * x;
+                for (int i = lane; i < j; i += 32) rhs[i] -= M[tj + i] * x;
                 __syncwarp();
             }
             // rhs now holds lambda (signed: positive pushes against an upper bound)

@@ -118,7 +118,10 @@ size_t admm_smem_bytes(const QPHost& h, int S, bool mats) {
     b += sizeof(float) * (size_t)g.m_phys * Bt;          // hi
     if (mats) b += sizeof(float) * ((size_t)g.nA_rows * g.ktot + (size_t)g.m_phys * g.npad4);
     b += sizeof(float) * ((size_t)g.m_phys + 3 * (size_t)g.nA_rows);     // width, lam, lbs, ubs
-    b += sizeof(int) * (size_t)g.m_phys;                 // vpos
+    b += sizeof(int) * (2 * (size_t)g.m_phys + (size_t)g.nA_rows);          // vpos, row_id, var_id
+    b += sizeof(float) * (2 * (size_t)g.m_phys + 4 * (size_t)g.nA_rows);     // scales for checks / outputs
+    b += sizeof(double) * (6 * (size_t)g.m_phys + 4 * (size_t)g.nA_rows);    // his, Gxs, Gcs, KF
+    b += 16 * 20;                                        // alignment slack of the carve-up
     b += sizeof(int4) * (size_t)g.nGA + sizeof(int2) * (size_t)g.nGB;
     b += (sizeof(double) * 5 + sizeof(int) * 5 + sizeof(float) * 5) * (size_t)Bt;   // per-slot state
     b += 256;
@@ -439,7 +442,7 @@ int qp_host_setup(int n, int m_in, int kpre, const double* H_in, const double* F
             q.AUu[(size_t)i * 4 + c] = s;
         }
 
-    q.mats_in_smem = admm_smem_bytes(q, S, true) <= (size_t)220 * 1024;
+    q.mats_in_smem = admm_smem_bytes(q, S, true) <= (size_t)226 * 1024;
     q.smem_bytes = admm_smem_bytes(q, S, q.mats_in_smem);
     if (q.smem_bytes > (size_t)227 * 1024) { set_error("carmpc_qp_create: shared-memory budget exceeded"); return CARMPC_ERR_UNSUPPORTED; }
     return CARMPC_OK;

@@ -113,8 +113,8 @@ int carmpc_rollout_bitset_host(void* rollout, const double* h_x, const double* h
  * ---------------------------------------------------------------------------------------------- */
 
 typedef struct carmpc_qp_opts {
-    double rho;            /* ADMM penalty on the scaled problem (default 0.1)                       */
-    double alpha;          /* over-relaxation (default 1.6)                                          */
+    double rho;            /* ADMM penalty on the scaled problem (default 0.2)                       */
+    double alpha;          /* over-relaxation (default 1.8)                                          */
     double eps_abs;        /* ADMM stop: fixed-point residual, unscaled, abs + rel (default 1e-3;    */
     double eps_rel;        /*   the float64 polish, not this tolerance, sets the final accuracy)     */
     double eps_prim_inf;   /* primal infeasibility certificate tolerance (default 1e-4)              */
@@ -187,7 +187,8 @@ int carmpc_closed_loop(void* qp, int mode, const double* h_A, const double* h_B,
 
 /* ------------------------------------------------------------------------------------------------
  * Device micro-benchmarks used as roofline denominators that MEASURED_PEAKS.json does not carry.
- * which: 0 = FP32 FFMA TFLOP/s, 1 = FP64 DFMA TFLOP/s, 2 = HBM copy GB/s (read+write). */
+ * which: 0 = FP32 FFMA TFLOP/s (uniform multiplier), 1 = FP64 DFMA TFLOP/s, 2 = HBM copy GB/s (read+write),
+ *        3 = FP32 TFLOP/s of a shared-memory-fed 8x8 register-tile product (the practical ceiling of a tile loop). */
 int carmpc_measure_peak(int which, double* h_value);
 
 #ifdef __cplusplus

@@ -20,7 +20,7 @@ def _bq(env_name, goal, N, **opts):
                                              ("RoadEnv", None, 40)])
 def test_scaling_and_kkt_inverse_match_numpy_model(env_name, goal, N):
     from tools.admm_model import DeviceModel
-    c, bq = _bq(env_name, goal, N)
+    c, bq = _bq(env_name, goal, N, rho=0.1)
     dm = DeviceModel(bq.pq, rho=0.1, scaling_iters=15)
     np.testing.assert_allclose(bq.setup(0), dm.D, rtol=1e-12)
     np.testing.assert_allclose(bq.setup(1), dm.Eg, rtol=1e-12)
