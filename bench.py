@@ -268,6 +268,23 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                "samples_per_step": hn, "steps": e2e_steps,
                "call": "carmpc_membership_bitset_host (pinned host SoA -> chunked H2D | kernel | D2H pipeline)"}
 
+    # the same grid through the implicit-grid entry point: host axes in (3.2 KB), host bitset out (12.5 MB)
+    e2e_grid = None
+    if not args.skip_e2e:
+        gbits = torch.empty(words, dtype=torch.int32, device=dev)
+        hbits = torch.empty(words, dtype=torch.int32, pin_memory=True)
+        ev.contains_grid_bits(axes, bits=gbits, count=count)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            ev.contains_grid_bits(axes, bits=gbits, count=count)
+            hbits.copy_(gbits, non_blocking=True)
+            torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 10
+        e2e_grid = {"value": world * n / dt, "unit": "samples/s", "h2d_bytes_per_step": int(sum(len(a) for a in axes) * 8),
+                    "d2h_bytes_per_step": int(words * 4 + 8),
+                    "call": "carmpc_membership_grid (axes on the host, coordinates generated in-kernel) + D2H of the bitset"}
+
     qp = None
     if not args.skip_qp:
         try:
@@ -298,6 +315,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                     "with the next step" if distributed else "single GPU"},
             "clocks": clocks.summary(),
             "e2e": e2e,
+            "e2e_grid": e2e_grid,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms,

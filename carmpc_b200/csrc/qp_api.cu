@@ -123,7 +123,7 @@ extern "C" {
 
 void carmpc_qp_default_opts(carmpc_qp_opts* o) {
     if (!o) return;
-    o->rho = 0.2; o->alpha = 1.8; o->eps_abs = 1e-3; o->eps_rel = 1e-3; o->eps_prim_inf = 1e-4;
+    o->rho = 0.0; o->alpha = 1.8; o->eps_abs = 1e-3; o->eps_rel = 1e-3; o->eps_prim_inf = 1e-4;
     o->max_iter = 4000; o->check_every = 10; o->scaling_iters = 15; o->polish = 1;
 }
 
@@ -141,7 +141,13 @@ int carmpc_qp_create(int n, int m, int k, const double* h_H, const double* h_F, 
     carmpc_qp_opts o;
     carmpc_qp_default_opts(&o);
     if (opts) o = *opts;
-    CARMPC_REQUIRE(o.rho > 0 && o.alpha > 0 && o.alpha < 2, "rho > 0, 0 < alpha < 2");
+    if (o.rho <= 0) {
+        // automatic penalty: the best fixed rho on the scaled problem falls with the horizon (measured on the
+        // region-of-attraction grid: 0.4 / 0.2 / 0.05 / 0.025 for n = 20 / 40 / 80 / 160 variables)
+        o.rho = 320.0 / ((double)n * n);
+        o.rho = o.rho > 0.4 ? 0.4 : (o.rho < 0.02 ? 0.02 : o.rho);
+    }
+    CARMPC_REQUIRE(o.alpha > 0 && o.alpha < 2, "0 < alpha < 2");
     CARMPC_REQUIRE(o.check_every >= 1 && o.max_iter >= o.check_every, "check_every >= 1, max_iter >= check_every");
     CARMPC_REQUIRE(o.scaling_iters >= 0 && o.scaling_iters <= 100, "scaling_iters");
     QPHandle* q = new QPHandle();

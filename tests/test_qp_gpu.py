@@ -243,3 +243,77 @@ def test_config3_full_grid_properties(torch_cuda):
     xb = x0[:, torch.from_numpy(b).cuda()]
     mid = bq.solve((0.5 * (xa + xb)).contiguous())
     assert int((mid["status"] != 0).sum()) == 0
+
+
+def test_disturbance_controller_shifts_the_constraints(torch_cuda):
+    """MPCOutputFBWithDisturbance (lib/mpc.py:495-667, experimental in the reference): the scalar disturbance estimate
+    enters the prediction as x_ = T x0 + S u + ABd d, i.e. a per-sample shift of the constraint right-hand sides.
+    Checked against the exact oracle on the shifted problem."""
+    from oracle import carmpc_oracle as orc
+    from carmpc_b200.batch import BatchQP
+    env = make_env("RoadEnv")
+    ctl = make_controller(env, 20, cls="MPCOutputFBWithDisturbance", init_state=[20, 0.5, 0, 2])
+    bq = BatchQP.from_controller(ctl)
+    Ab = np.load(os.path.join(GOLDEN, "terminal_sets", FIXTURE["RoadEnv"]))
+    oq = orc.CondensedQP("RoadEnv", 20, Ab)
+    ABd = ctl.disturbance_response()
+    x_ref = np.array([30, 1.5, 0, 0.0])
+    rng = np.random.default_rng(8)
+    x0 = x_ref + rng.uniform(-1, 1, size=(60, 4)) * np.array([10.0, 1.0, 0.2, 2.0])
+    d = rng.uniform(-0.02, 0.02, size=60)
+    res = bq.solve_host(x0, x_ref=x_ref, want_u_full=True, c=d)
+    # oracle: same QP with the bounds shifted by rows_x @ ABd * d  (one-sided form: G u <= w - Gx x0 - Gd d)
+    rows = np.vstack((orc.terminal_constraint(Ab, 20)[0], np.zeros((80, 84)), orc.state_constraint("RoadEnv", 20)[0]))
+    Gd = rows @ ABd
+    n_ok = 0
+    for i in range(len(x0)):
+        class Shifted(orc.CondensedQP):
+            pass
+        q = Shifted("RoadEnv", 20, Ab)
+        q.w = q.w - Gd * d[i]
+        ue, obje, ste, pol, slack = orc.qp_solve_exact(q, x0[i:i + 1], x_ref)
+        if abs(slack[0]) <= 1e-6:
+            continue
+        assert (res.status[i] == 0) == (ste[0] == 0)
+        if ste[0] == 0 and pol[0]:
+            n_ok += 1
+            assert np.abs(res.u_full[i] - ue[0]).max() <= U_TOL
+            assert abs(res.objective[i] - obje[0]) <= OBJ_RTOL * max(1.0, abs(obje[0]))
+    assert n_ok >= 10
+    # and the drop-in step() runs end to end (observer with disturbance state, then the QP)
+    u = ctl.step(np.array([20.3, 0.52, 2.0]))
+    assert u.shape == (2,) and np.all(np.isfinite(u))
+
+
+def test_config4_monte_carlo_properties(torch_cuda):
+    """BASELINE config 4 at full size: 10^5 output-feedback closed loops x 200 steps against the nonlinear bicycle.
+    Too large for the oracle; properties instead: bit-identical when repeated, a run that never failed ends at the
+    goal, a failed run keeps the state it had when its QP became infeasible, inputs within the actuator box."""
+    torch = torch_cuda
+    from carmpc_b200.batch import BatchQP
+    from carmpc_b200.lib.mpc import _C_XYV, _L_OBSERVER
+    ctl = make_controller(make_env("RoadEnv"), 20)
+    bq = BatchQP.from_controller(ctl)
+    R, T = 100_000, 200
+    g = torch.Generator(device="cpu").manual_seed(0)
+    lo = torch.tensor([0.0, -2.5, -0.2, 0.0], dtype=torch.float64)
+    hi = torch.tensor([10.0, 2.5, 0.2, 3.0], dtype=torch.float64)
+    x_init = (lo[:, None] + (hi - lo)[:, None] * torch.rand((4, R), generator=g, dtype=torch.float64)).cuda().contiguous()
+    a = bq.closed_loop(x_init, T, ctl.A, ctl.B, C=_C_XYV, L=_L_OBSERVER)
+    b = bq.closed_loop(x_init, T, ctl.A, ctl.B, C=_C_XYV, L=_L_OBSERVER)
+    assert torch.equal(a["fail_step"], b["fail_step"]) and torch.equal(a["final"], b["final"])
+    fail = a["fail_step"]
+    ok = fail < 0
+    assert 0.05 < ok.float().mean().item() < 0.95
+    goal = torch.tensor([30.0, 1.5, 0.0, 0.0], dtype=torch.float64, device="cuda")
+    err = (a["final"] - goal[:, None]).abs()
+    assert (err[:, ok].max(dim=1).values <= torch.tensor([0.1, 0.05, 0.05, 0.1], dtype=torch.float64, device="cuda")).all()
+    # a short rerun with logs: inputs respect the input box, failed runs freeze
+    small = bq.closed_loop(x_init[:, :2000].contiguous(), 60, ctl.A, ctl.B, C=_C_XYV, L=_L_OBSERVER, want_traj=True,
+                           want_inputs=True)
+    u = small["inputs"]
+    assert (u[:, 0].abs() <= 2.0 + 1e-9).all() and (u[:, 1].abs() <= np.pi / 8 + 1e-9).all()
+    f = small["fail_step"].cpu().numpy()
+    traj = small["traj"].cpu().numpy()
+    for r in np.flatnonzero(f >= 0)[:50]:
+        assert np.array_equal(traj[f[r]:, :, r], np.repeat(traj[f[r]:f[r] + 1, :, r], 60 - f[r], axis=0))

@@ -12,19 +12,16 @@ from carmpc_b200.batch import BatchQP
 from carmpc_b200.grids import config3_axes, materialise_grid
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 x0 = torch.stack(materialise_grid(config3_axes(), device="cuda")).contiguous()
+if B < x0.shape[1]:
+    x0 = x0[:, torch.arange(0, x0.shape[1], x0.shape[1] // B, device="cuda")[:B]].contiguous()
 c = _controller("RoadOneCarEnv", [29.9, 1.5, 0, 0], N)
 ref = None
 grid = []
-for rho in (0.05, 0.1, 0.2, 0.4):
+for rho in (0.025, 0.05, 0.1, 0.2, 0.4):
     for alpha in (1.6, 1.8):
         grid.append(dict(rho=rho, alpha=alpha))
-for eps in (3e-3, 1e-2):
-    grid.append(dict(eps_abs=eps, eps_rel=eps))
-for ce in (5, 20):
-    grid.append(dict(check_every=ce))
-grid.append(dict(scaling_iters=0))
-grid.append(dict(scaling_iters=30))
 for opts in [dict()] + grid:
     bq = BatchQP.from_controller(c, **opts)
     bq.solve(x0)
