@@ -89,8 +89,8 @@ struct Smem {
     int2* segB;
     double* x0;          // [5][Bt]  x, y, psi, v, c
     int *slot_sample, *slot_state, *slot_iter, *slot_init, *slot_pos;
-    unsigned *red_res, *red_nrm, *red_ndy, *red_t3;
-    float* red_sup;
+    unsigned *red_res, *red_nrm;
+    float *red_sup, *red_abs;
     int* misc;           // [0] n_free, [1] base
 };
 
@@ -136,9 +136,8 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, const AdmmTables& T) {
     s.slot_pos = reinterpret_cast<int*>(take(sizeof(int) * Bt));
     s.red_res = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * Bt));
     s.red_nrm = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * Bt));
-    s.red_ndy = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * Bt));
-    s.red_t3 = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * Bt));
     s.red_sup = reinterpret_cast<float*>(take(sizeof(float) * Bt));
+    s.red_abs = reinterpret_cast<float*>(take(sizeof(float) * Bt));
     s.misc = reinterpret_cast<int*>(take(sizeof(int) * 4));
     return s;
 }
@@ -188,7 +187,7 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
     for (int i = tid; i < T.nGB; i += NT) sm.segB[i] = T.segB[i];
     if (tid < Bt) {
         sm.slot_sample[tid] = -1; sm.slot_state[tid] = kSlotIdle; sm.slot_iter[tid] = 0; sm.slot_init[tid] = 0;
-        sm.red_res[tid] = 0; sm.red_nrm[tid] = 0; sm.red_ndy[tid] = 0; sm.red_t3[tid] = 0; sm.red_sup[tid] = 0.f;
+        sm.red_res[tid] = 0; sm.red_nrm[tid] = 0; sm.red_sup[tid] = 0.f; sm.red_abs[tid] = 0.f;
     }
     if (tid == 0) { sm.misc[0] = 0; sm.misc[1] = 0; }
 
@@ -240,11 +239,10 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
             }
         }
         __syncthreads();                                   // x~ complete; every read of V is done
-        float p_res[S], p_nrm[S], p_ndy[S], p_sup[S];
-        float egA[GA][kRA][S];
+        float p_res[S], p_nrm[S], p_abs[S], p_sup[S];
         if (CHECK) {
 #pragma unroll
-            for (int s = 0; s < S; ++s) { p_res[s] = 0.f; p_nrm[s] = 0.f; p_ndy[s] = 0.f; p_sup[s] = 0.f; }
+            for (int s = 0; s < S; ++s) { p_res[s] = 0.f; p_nrm[s] = 0.f; p_abs[s] = 0.f; p_sup[s] = 0.f; }
         }
         // ---------------- box rows: z = lam x~ ----------------
 #pragma unroll
@@ -269,12 +267,6 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
                             const float einv = sm.einv_b[j];
                             p_res[s] = fmaxf(p_res[s], fmaxf(fabsf(z - c1), fabsf(c1 - c0)) * einv);
                             p_nrm[s] = fmaxf(p_nrm[s], fmaxf(fabsf(z), fabsf(c1)) * einv);
-                            float e = (w1 - c1) - (w0 - c0);
-                            if (ub == INFINITY) e = fminf(e, 0.f);
-                            if (lb == -INFINITY) e = fmaxf(e, 0.f);
-                            egA[g][r][s] = e;
-                            p_ndy[s] = fmaxf(p_ndy[s], fabsf(e) * sm.esc_b[j]);
-                            p_sup[s] += e > 0.f ? ub * e : (e < 0.f ? lb * e : 0.f);
                         }
                     }
                     o.st(sm.V + (T.mv4 + j) * Bt + s0);
@@ -317,8 +309,9 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
                         float e = (w1 - c1) - (w0 - c0);
                         if (wd == INFINITY) e = fmaxf(e, 0.f);
                         o.v[s] = e;                         // V carries delta-y for the certificate product
-                        p_ndy[s] = fmaxf(p_ndy[s], fabsf(e) * sm.esc_g[i]);
-                        p_sup[s] += e > 0.f ? h * e : (e < 0.f ? lo * e : 0.f);
+                        const float term = e > 0.f ? h * e : (e < 0.f ? lo * e : 0.f);
+                        p_sup[s] += term;
+                        p_abs[s] += fabsf(term);
                     }
                 }
                 if (vp >= 0) o.st(sm.V + vp * Bt + s0);
@@ -329,16 +322,19 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
             for (int s = 0; s < S; ++s) {
                 atomic_max_pos(sm.red_res + s0 + s, p_res[s]);
                 atomic_max_pos(sm.red_nrm + s0 + s, p_nrm[s]);
-                atomic_max_pos(sm.red_ndy + s0 + s, p_ndy[s]);
+                atomicAdd(sm.red_abs + s0 + s, p_abs[s]);
                 atomicAdd(sm.red_sup + s0 + s, p_sup[s]);
             }
         }
         __syncthreads();                                   // V (or delta-y) complete
         if (CHECK) {
-            // ---------------- certificate: || A_s' dy ||_inf, unscaled ----------------
-            float t3[S];
+            // ---------------- infeasibility certificate (Farkas, with the box rows absorbing the residual) ----------------
+            // y_g = delta-y of the general rows (in V).  Every variable has a finite box, so the multipliers of the box rows
+            // can be chosen as y_b = -(Gs' y_g) / lam, which makes A_s' y = 0 exactly; the problem is infeasible iff the
+            // support function  hi' y_g+ + lo' y_g- + ub' y_b+ + lb' y_b-  is negative.  No tolerance on ||A' y|| is needed,
+            // which certifies barely infeasible states long before OSQP's test (||A' dy|| <= eps ||dy||) would.
 #pragma unroll
-            for (int s = 0; s < S; ++s) t3[s] = 0.f;
+            for (int s = 0; s < S; ++s) { p_sup[s] = 0.f; p_abs[s] = 0.f; }
 #pragma unroll
             for (int g = 0; g < GA; ++g) {
                 const int pg = g * kAdmmWarps + warp;
@@ -348,18 +344,28 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
 #pragma unroll
                     for (int r = 0; r < kRA; ++r)
 #pragma unroll
-                        for (int s = 0; s < S; ++s) acc[r][s] = sm.lam[pg * kRA + r] * egA[g][r][s];
+                        for (int s = 0; s < S; ++s) acc[r][s] = 0.f;
                     tile_product<kRA, S, false>(acc, T.GsT + (size_t)(pg * kRA) * T.mv4, T.mv4, sm.V, Bt, s0, sg.x, sg.y);
 #pragma unroll
                     for (int r = 0; r < kRA; ++r) {
-                        const float dinv = sm.dinv[pg * kRA + r];
+                        const int j = pg * kRA + r;
+                        const float lam = sm.lam[j], lb = sm.lbs[j], ub = sm.ubs[j];
+                        const float rl = lam > 0.f ? -1.f / lam : 0.f;            // pad variables: Gs' column is zero
 #pragma unroll
-                        for (int s = 0; s < S; ++s) t3[s] = fmaxf(t3[s], fabsf(acc[r][s]) * dinv);
+                        for (int s = 0; s < S; ++s) {
+                            const float yb = acc[r][s] * rl;
+                            const float term = yb > 0.f ? ub * yb : (yb < 0.f ? lb * yb : 0.f);   // +inf when that side is unbounded
+                            p_sup[s] += term;
+                            p_abs[s] += fabsf(term);
+                        }
                     }
                 }
             }
 #pragma unroll
-            for (int s = 0; s < S; ++s) atomic_max_pos(sm.red_t3 + s0 + s, t3[s]);
+            for (int s = 0; s < S; ++s) {
+                atomicAdd(sm.red_abs + s0 + s, p_abs[s]);
+                atomicAdd(sm.red_sup + s0 + s, p_sup[s]);
+            }
             __syncthreads();                               // delta-y fully consumed
             // restore V = 2 clip(w) - w for the general rows
 #pragma unroll
@@ -478,7 +484,7 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
                 }
             }
             sm.slot_init[tid] = init;
-            sm.red_res[tid] = 0; sm.red_nrm[tid] = 0; sm.red_ndy[tid] = 0; sm.red_t3[tid] = 0; sm.red_sup[tid] = 0.f;
+            sm.red_res[tid] = 0; sm.red_nrm[tid] = 0; sm.red_sup[tid] = 0.f; sm.red_abs[tid] = 0.f;
         }
         __syncthreads();
         // (re)initialise the registers / tiles of the slots that changed hands
@@ -561,12 +567,12 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
                 const int it = sm.slot_iter[tid] + T.check_every;
                 sm.slot_iter[tid] = it;
                 const float res = __uint_as_float(sm.red_res[tid]), nrm = __uint_as_float(sm.red_nrm[tid]);
-                const float ndy = __uint_as_float(sm.red_ndy[tid]), t3 = __uint_as_float(sm.red_t3[tid]);
-                const float sup = sm.red_sup[tid];
+                const float sup = sm.red_sup[tid], sabs = sm.red_abs[tid];
                 int ns = kSlotRunning;
                 if (st == kSlotPreInfeasible) ns = kSlotInfeasible;
+                // the margin eps_inf * sum |terms| dominates the float32 rounding of the sums (~1e-5 of it) and of the bounds
+                else if (sabs > 0.f && sup <= -T.eps_inf * sabs) ns = kSlotInfeasible;
                 else if (res <= eps_abs + eps_rel * nrm) ns = kSlotSolved;
-                else if (ndy > 0.f && t3 <= T.eps_inf * ndy && sup <= -T.eps_inf * ndy) ns = kSlotInfeasible;
                 else if (it >= Bq.max_iter || !(res == res)) ns = kSlotMaxIter;
                 sm.slot_state[tid] = ns;
             }
