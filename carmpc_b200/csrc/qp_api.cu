@@ -26,7 +26,7 @@ int upload(QPHandle* q, const std::vector<T>& v, const T** dst) {
 QPHandle::~QPHandle() {
     for (void* p : allocations) cudaFree(p);
     cudaFree(ws_sign); cudaFree(ws_u); cudaFree(ws_status); cudaFree(ws_iters); cudaFree(ws_failed);
-    cudaFree(ws_counters); cudaFree(ws_total_iters); cudaFree(ws_polished); cudaFree(ws_warm);
+    cudaFree(ws_counters); cudaFree(ws_total_iters); cudaFree(ws_polished); cudaFree(ws_warm); cudaFree(ws_overflow);
 }
 
 int QPHandle::ensure_workspace(int64_t batch) {
@@ -37,6 +37,7 @@ int QPHandle::ensure_workspace(int64_t batch) {
     if (batch <= ws_batch) return CARMPC_OK;
     cudaFree(ws_sign); cudaFree(ws_u); cudaFree(ws_status); cudaFree(ws_iters); cudaFree(ws_failed); cudaFree(ws_polished);
     cudaFree(ws_warm); ws_warm = nullptr;
+    cudaFree(ws_overflow); ws_overflow = nullptr;
     ws_sign = nullptr; ws_u = nullptr; ws_status = nullptr; ws_iters = nullptr; ws_failed = nullptr; ws_polished = nullptr;
     ws_batch = 0;
     CARMPC_CUDA(cudaMalloc(&ws_sign, (size_t)batch * admm.mt));
@@ -44,6 +45,7 @@ int QPHandle::ensure_workspace(int64_t batch) {
     CARMPC_CUDA(cudaMalloc(&ws_status, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_iters, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_failed, sizeof(int) * (size_t)batch));
+    CARMPC_CUDA(cudaMalloc(&ws_overflow, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_polished, (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_warm, sizeof(float) * (size_t)batch * admm.mt));
     ws_batch = batch;

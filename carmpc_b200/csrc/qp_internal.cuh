@@ -129,6 +129,9 @@ struct PolishBatch {
     int* failed_list;        // their indices
     int final_pass;          // 1: accept the ADMM iterate when the polish cannot certify
     int rounds;              // repair rounds (-1: default; 0: no polish, pass the ADMM iterate through)
+    int na_cap;              // active rows this launch has shared memory for
+    int* overflow_list;      // samples with more (nullable: they count as not certified)
+    int* n_overflow;
 };
 
 // Host-side setup product (qp_setup.cu)
@@ -176,6 +179,7 @@ struct QPHandle : HandleBase {
     int* ws_status = nullptr;
     int* ws_iters = nullptr;
     int* ws_failed = nullptr;
+    int* ws_overflow = nullptr;
     int* ws_counters = nullptr;                  // [0] work counter, [1] n_failed
     unsigned long long* ws_total_iters = nullptr;
     int8_t* ws_polished = nullptr;

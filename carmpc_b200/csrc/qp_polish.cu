@@ -37,14 +37,14 @@ struct PolishSmemLayout {
     size_t per_warp;
 };
 
-__host__ __device__ inline PolishSmemLayout polish_layout(int n, int mt) {
+__host__ __device__ inline PolishSmemLayout polish_layout(int n, int mt, int na_cap) {
     PolishSmemLayout L;
-    L.na_max = n + 8 < kPolishMaxActive ? n + 8 : kPolishMaxActive;
+    L.na_max = na_cap;
     if (L.na_max > mt) L.na_max = mt;
     if (L.na_max < 1) L.na_max = 1;
     size_t d = 0;
     d += 2 * (size_t)n;                                      // u_unc, u
-    d += 3 * (size_t)mt;                                     // A u_unc, hi, lo
+    d += 2 * (size_t)mt;                                     // A u_unc, per-row bound shift
     d += (size_t)L.na_max * (L.na_max + 1) / 2;              // M, packed lower triangle
     d += 3 * (size_t)L.na_max;                               // rhs / lambda, b, diag0
     size_t bytes = d * sizeof(double);
@@ -62,14 +62,13 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int warps_per_cta = kPolishThreads / 32;
     const int n = T.n, m = T.m, mt = T.mt;
-    const PolishSmemLayout L = polish_layout(n, mt);
+    const PolishSmemLayout L = polish_layout(n, mt, B.na_cap);
     unsigned char* base = smem_raw + (size_t)warp * L.per_warp;
     double* uunc = reinterpret_cast<double*>(base);
     double* u = uunc + n;
     double* Auu = u + n;
-    double* hi = Auu + mt;
-    double* lo = hi + mt;
-    double* M = lo + mt;
+    double* shf = Auu + mt;
+    double* M = shf + mt;
     double* rhs = M + (size_t)L.na_max * (L.na_max + 1) / 2;
     double* bact = rhs + L.na_max;
     double* diag0 = bact + L.na_max;
@@ -109,14 +108,13 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
                 const double* gx = T.Gx + (size_t)i * 4;
                 shift = gx[0] * x0[0] + gx[1] * x0[1] + gx[2] * x0[2] + gx[3] * x0[3] + T.Gc[i] * cd;
             }
-            hi[i] = T.hi[i] - shift;
-            lo[i] = T.lo[i] - shift;
+            shf[i] = shift;
             sgn[i] = B.sign[(size_t)sample * mt + i];
         }
         int n_added = 0;
         __syncwarp();
 
-        bool certified = false;
+        bool certified = false, overflow = false;
         int na = 0;
         const int max_rounds = B.rounds < 0 ? kPolishRounds : B.rounds;
         for (int round = 0; round < max_rounds && !certified; ++round) {
@@ -136,7 +134,7 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
                 if (on && p < L.na_max) act[p] = i;
                 na += __popc(mask);
             }
-            if (na > L.na_max) break;
+            if (na > L.na_max) { overflow = true; break; }
             __syncwarp();
             // ---- M = AHA[act, act] (lower triangle), rhs = A_act u_unc - b_act ----
             for (int e = lane; e < na * (na + 1) / 2; e += 32) {
@@ -150,7 +148,7 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
             }
             for (int a = lane; a < na; a += 32) {
                 const int i = act[a];
-                bact[a] = sgn[i] > 0 ? hi[i] : lo[i];
+                bact[a] = (sgn[i] > 0 ? T.hi[i] : T.lo[i]) - shf[i];
                 rhs[a] = Auu[i] - bact[a];
             }
             __syncwarp();
@@ -205,7 +203,7 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
             double worst = 0.0;
             int worst_i = -1, worst_sign = 0;
             for (int i = lane; i < mt; i += 32) {
-                const double h = hi[i], l = lo[i];
+                const double h = T.hi[i] - shf[i], l = T.lo[i] - shf[i];
                 if (isinf(h) && isinf(l)) continue;
                 double s0 = Auu[i], s1 = 0.0, s2 = 0.0, s3 = 0.0;
                 int a = 0;
@@ -258,6 +256,11 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
         }
 
         double obj;
+        if (!certified && overflow && B.overflow_list != nullptr) {
+            // more active rows than this launch's shared-memory budget: retried by a launch with the full-size layout
+            if (lane == 0) B.overflow_list[atomicAdd(B.n_overflow, 1)] = sample;
+            continue;
+        }
         if (!certified) {
             if (!B.final_pass) {
                 if (lane == 0) {
@@ -302,20 +305,45 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
 
 }  // namespace
 
-int polish_launch(QPHandle* qh, const PolishBatch& b, cudaStream_t st) {
-    if (b.count <= 0) return CARMPC_OK;
-    const PolishSmemLayout L = polish_layout(qh->polish.n, qh->polish.mt);
+static int polish_launch_cap(QPHandle* qh, const PolishBatch& b, cudaStream_t st) {
+    const PolishSmemLayout L = polish_layout(qh->polish.n, qh->polish.mt, b.na_cap);
     constexpr int warps = kPolishThreads / 32;
     const size_t smem = L.per_warp * warps;
     if (smem > (size_t)227 * 1024) { set_error("polish: shared-memory budget exceeded"); return CARMPC_ERR_UNSUPPORTED; }
     CARMPC_CUDA(cudaFuncSetAttribute(polish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = (int)std::min<size_t>(8, (size_t)(220 * 1024) / smem);
+    int per_sm = 0;
+    CARMPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, polish_kernel, kPolishThreads, smem));
     if (per_sm < 1) per_sm = 1;
     const int64_t need = (b.count + warps - 1) / warps;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)qh->sm * per_sm));
     polish_kernel<<<blocks, kPolishThreads, smem, st>>>(qh->polish, b);
     CARMPC_CUDA(cudaGetLastError());
     return CARMPC_OK;
+}
+
+// Two launches: a small active-set budget (32 rows: 8 KB of shared memory per warp, 28 warps per SM) covers almost
+// every sample; the few with more active rows are listed and redone with the full-size layout.
+int polish_launch(QPHandle* qh, const PolishBatch& b_in, cudaStream_t st) {
+    if (b_in.count <= 0) return CARMPC_OK;
+    const int n = qh->polish.n, mt = qh->polish.mt;
+    const int full = std::min(mt, std::min(kPolishMaxActive, n + 8));
+    PolishBatch b = b_in;
+    if (full <= 32 || qh->ws_overflow == nullptr) {
+        b.na_cap = full; b.overflow_list = nullptr; b.n_overflow = nullptr;
+        return polish_launch_cap(qh, b, st);
+    }
+    CARMPC_CUDA(cudaMemsetAsync(qh->ws_counters + 4, 0, sizeof(int), st));
+    b.na_cap = 32; b.overflow_list = qh->ws_overflow; b.n_overflow = qh->ws_counters + 4;
+    int rc = polish_launch_cap(qh, b, st);
+    if (rc != CARMPC_OK) return rc;
+    int n_over = 0;
+    CARMPC_CUDA(cudaMemcpyAsync(&n_over, qh->ws_counters + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CARMPC_CUDA(cudaStreamSynchronize(st));
+    if (n_over > 0) {
+        b.na_cap = full; b.idx_list = qh->ws_overflow; b.count = n_over; b.overflow_list = nullptr; b.n_overflow = nullptr;
+        rc = polish_launch_cap(qh, b, st);
+    }
+    return rc;
 }
 
 }  // namespace carmpc
