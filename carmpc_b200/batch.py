@@ -114,8 +114,7 @@ class TerminalSetEvaluator(_Handle):
         if count is None:
             count = torch.empty(1, dtype=torch.int64, device="cuda")
         check(self._lib.carmpc_membership_grid(self._h, _capi.ptr(cat), dims, a2s, bits.data_ptr(), count.data_ptr(),
-                                               _stream_ptr(stream)))
-        torch.cuda.current_stream().synchronize()      # `cat` is pageable host memory read by an async copy
+                                               _stream_ptr(stream)))     # the axes are copied before the call returns
         return bits, count
 
     # ---- host arrays in, host results out ---------------------------------------------------------

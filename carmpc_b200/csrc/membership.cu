@@ -78,9 +78,13 @@ struct Polytope : HandleBase {
     RowF32* d_rows32 = nullptr;      // rows
     float beta0 = 0.f, beta1 = 0.f;  // |float32 margin - exact margin| <= beta0 + beta1 * max|coordinate|
     HostStage stage;
+    double* d_axes = nullptr;        // grid axes of carmpc_membership_grid (4 x 4096 doubles at most)
+    double* h_axes = nullptr;        // pinned staging copy
     ~Polytope() override {
         cudaFree(d_rows);
         cudaFree(d_rows32);
+        cudaFree(d_axes);
+        cudaFreeHost(h_axes);
     }
 };
 
@@ -748,9 +752,14 @@ int carmpc_membership_grid(void* polytope, const double* h_axes, const int32_t d
     }
     CARMPC_REQUIRE(seen == 15, "axis_to_state must be a permutation of 0..3");
     cudaStream_t st = (cudaStream_t)stream;
-    double* d_axes = nullptr;
-    CARMPC_CUDA(cudaMallocAsync(&d_axes, sizeof(double) * off, st));
-    CARMPC_CUDA(cudaMemcpyAsync(d_axes, h_axes, sizeof(double) * off, cudaMemcpyHostToDevice, st));
+    if (P->d_axes == nullptr) {
+        CARMPC_CUDA(cudaMalloc(&P->d_axes, sizeof(double) * 4 * 4096));
+        CARMPC_CUDA(cudaMallocHost(&P->h_axes, sizeof(double) * 4 * 4096));
+    }
+    CARMPC_CUDA(cudaStreamSynchronize(st));            // the staging copy of a previous call must have been consumed
+    for (int i = 0; i < off; ++i) P->h_axes[i] = h_axes[i];
+    double* d_axes = P->d_axes;
+    CARMPC_CUDA(cudaMemcpyAsync(d_axes, P->h_axes, sizeof(double) * off, cudaMemcpyHostToDevice, st));
     if (d_count) CARMPC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
     const size_t smem = membership_smem(P->rows) + sizeof(double) * off;
     CARMPC_CUDA(cudaFuncSetAttribute(membership_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -759,7 +768,6 @@ int carmpc_membership_grid(void* polytope, const double* h_axes, const int32_t d
         P->d_rows, P->d_rows32, P->rows, pad_rows(P->rows), screen_const(P), d_axes, gd, n, d_bits,
         reinterpret_cast<unsigned long long*>(d_count));
     CARMPC_CUDA(cudaGetLastError());
-    CARMPC_CUDA(cudaFreeAsync(d_axes, st));
     return CARMPC_OK;
 }
 

@@ -125,7 +125,7 @@ extern "C" {
 
 void carmpc_qp_default_opts(carmpc_qp_opts* o) {
     if (!o) return;
-    o->rho = 0.0; o->alpha = 1.8; o->eps_abs = 1e-3; o->eps_rel = 1e-3; o->eps_prim_inf = 1e-4;
+    o->rho = 0.0; o->alpha = 1.8; o->eps_abs = 3e-3; o->eps_rel = 3e-3; o->eps_prim_inf = 1e-4;
     o->max_iter = 4000; o->check_every = 10; o->scaling_iters = 15; o->polish = 1;
 }
 

@@ -115,7 +115,7 @@ int carmpc_rollout_bitset_host(void* rollout, const double* h_x, const double* h
 typedef struct carmpc_qp_opts {
     double rho;            /* ADMM penalty on the scaled problem; <= 0 (default): 320 / n^2 in [0.02, 0.4] */
     double alpha;          /* over-relaxation (default 1.8)                                          */
-    double eps_abs;        /* ADMM stop: fixed-point residual, unscaled, abs + rel (default 1e-3;    */
+    double eps_abs;        /* ADMM stop: fixed-point residual, unscaled, abs + rel (default 3e-3;    */
     double eps_rel;        /*   the float64 polish, not this tolerance, sets the final accuracy)     */
     double eps_prim_inf;   /* primal infeasibility certificate tolerance (default 1e-4)              */
     int32_t max_iter;      /* per sample (default 4000)                                              */

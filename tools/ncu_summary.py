@@ -1,0 +1,24 @@
+"""Text summary of an .ncu-rep (selected raw metrics of the first profiled launch): python tools/ncu_summary.py rep"""
+import csv, io, subprocess, sys
+rep = sys.argv[1]
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr, units, r = rows[0], rows[1], rows[2]
+keys = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "gpu__time_duration.sum", "sm__cycles_elapsed.max", "smsp__cycles_active.avg",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct",
+        "lts__t_sector_hit_rate.pct"]
+keys += [k for k in hdr if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio")]
+for k in keys:
+    if k in hdr:
+        i = hdr.index(k)
+        print(f"{k} = {r[i]} {units[i]}")
