@@ -33,6 +33,7 @@ SIGNATURES = {
     "carmpc_destroy": (None, [_vp]),
     "carmpc_polytope_create": (_i32, [_dp, _i32, ctypes.POINTER(_vp)]),
     "carmpc_membership_bitset": (_i32, [_vp, _dp, _dp, _dp, _dp, _i64, _vp, _vp, _i32, _vp]),
+    "carmpc_polytope_tune": (_i32, [_vp, _dp, _dp, _dp, _dp, _i64, _vp]),
     "carmpc_membership_grid": (_i32, [_vp, _dp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                       _vp, _vp, _vp]),
     "carmpc_membership_bitset_host": (_i32, [_vp, _dp, _dp, _dp, _dp, _i64, _vp, ctypes.POINTER(_i64), _i32]),

@@ -100,6 +100,13 @@ class TerminalSetEvaluator(_Handle):
                                                  n, bits.data_ptr(), count.data_ptr(), mode, _stream_ptr(stream)))
         return bits, count
 
+    def tune(self, x, y, psi, v, stream=None) -> None:
+        """Adapt the row order to where these samples lie (done automatically on the first call with >= 2^20 samples);
+        membership results never depend on it."""
+        n = _check_soa(x, y, psi, v)
+        check(self._lib.carmpc_polytope_tune(self._h, x.data_ptr(), y.data_ptr(), psi.data_ptr(), v.data_ptr(), n,
+                                             _stream_ptr(stream)))
+
     def contains_grid_bits(self, axes, axis_to_state=(0, 1, 2, 3), bits=None, count=None, stream=None):
         """Membership on the implicit tensor grid ``axes[0] x axes[1] x axes[2] x axes[3]`` (C order); axis k carries
         state component ``axis_to_state[k]``.  No coordinate array is materialised."""

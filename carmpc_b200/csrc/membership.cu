@@ -78,6 +78,8 @@ struct Polytope : HandleBase {
     RowF32* d_rows32 = nullptr;      // rows
     float beta0 = 0.f, beta1 = 0.f;  // |float32 margin - exact margin| <= beta0 + beta1 * max|coordinate|
     HostStage stage;
+    std::vector<double> h_rows;      // rows x 5 in device order (host copy, for re-ordering)
+    bool tuned = false;              // row order already adapted to a sample set
     double* d_axes = nullptr;        // grid axes of carmpc_membership_grid (4 x 4096 doubles at most)
     double* h_axes = nullptr;        // pinned staging copy
     ~Polytope() override {
@@ -642,6 +644,92 @@ static int host_pipeline(HostStage& S, const double* h_x, const double* h_y, con
     return CARMPC_OK;
 }
 
+// ---- profile-guided row order ------------------------------------------------------------------------------------------
+// The conjunction over rows does not depend on their order, but the cost does: a warp stops as soon as every one of
+// its samples is rejected.  Which rows reject most depends on where the samples lie, so the first large call runs a
+// pilot over a strided subsample (every row in float64, one 64-bit "violated rows" mask per sample) and the host
+// orders the rows greedily: first the row that rejects most samples, then the row that rejects most of the samples
+// still alive, and so on.  Results are bit-identical for any order.
+__global__ void __launch_bounds__(256)
+pilot_kernel(const double* __restrict__ g_rows, int rows, const double* __restrict__ gx, const double* __restrict__ gy,
+             const double* __restrict__ gp, const double* __restrict__ gv, int64_t n, int64_t stride, int n_sub,
+             unsigned long long* __restrict__ masks) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_sub) return;
+    const int64_t i = (int64_t)k * stride;
+    if (i >= n) { masks[k] = 0ull; return; }
+    const double x = gx[i], y = gy[i], p = gp[i], v = gv[i];
+    unsigned long long m = 0ull;
+    for (int r = 0; r < rows; ++r) {
+        const double* a = g_rows + 5 * r;
+        const double lhs = fma(a[3], v, fma(a[2], p, fma(a[1], y, a[0] * x)));
+        if (!(lhs <= a[4])) m |= 1ull << r;
+    }
+    masks[k] = m;
+}
+
+static int upload_rows(Polytope* P, cudaStream_t st) {
+    const int rows = P->rows;
+    std::vector<RowF32> r32(pad_rows(rows) > 0 ? pad_rows(rows) : 8);
+    for (RowF32& q : r32) { q.na0 = q.na1 = q.na2 = q.na3 = 0.f; q.b = INFINITY; q.pad0 = q.pad1 = q.pad2 = 0.f; }
+    for (int i = 0; i < rows; ++i) {
+        const double* a = P->h_rows.data() + 5 * i;
+        RowF32 q;
+        q.na0 = (float)-a[0]; q.na1 = (float)-a[1]; q.na2 = (float)-a[2]; q.na3 = (float)-a[3];
+        q.b = (float)a[4];
+        q.pad0 = q.pad1 = q.pad2 = 0.f;
+        r32[i] = q;
+    }
+    if (rows > 0) CARMPC_CUDA(cudaMemcpyAsync(P->d_rows, P->h_rows.data(), sizeof(double) * 5 * rows, cudaMemcpyHostToDevice, st));
+    CARMPC_CUDA(cudaMemcpyAsync(P->d_rows32, r32.data(), sizeof(RowF32) * r32.size(), cudaMemcpyHostToDevice, st));
+    CARMPC_CUDA(cudaStreamSynchronize(st));            // r32 / h_rows are pageable host memory
+    return CARMPC_OK;
+}
+
+static int tune_row_order(Polytope* P, const double* x, const double* y, const double* p, const double* v, int64_t n,
+                          cudaStream_t st) {
+    const int rows = P->rows;
+    P->tuned = true;
+    if (rows < 2 || rows > 64 || n < 1024) return CARMPC_OK;
+    const int n_sub = (int)std::min<int64_t>(1 << 16, n);
+    const int64_t stride = n / n_sub;
+    unsigned long long* d_masks = nullptr;
+    CARMPC_CUDA(cudaMalloc(&d_masks, sizeof(unsigned long long) * n_sub));
+    pilot_kernel<<<(n_sub + 255) / 256, 256, 0, st>>>(P->d_rows, rows, x, y, p, v, n, stride, n_sub, d_masks);
+    std::vector<unsigned long long> masks(n_sub);
+    cudaError_t err = cudaMemcpyAsync(masks.data(), d_masks, sizeof(unsigned long long) * n_sub, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    cudaFree(d_masks);
+    CARMPC_CUDA(err);
+    // greedy cover
+    std::vector<unsigned long long> alive;
+    alive.reserve(n_sub);
+    for (unsigned long long m : masks) if (m) alive.push_back(m);
+    std::vector<int> order;
+    std::vector<char> used(rows, 0);
+    while (!alive.empty() && (int)order.size() < rows) {
+        int cnt[64] = {0};
+        for (unsigned long long m : alive)
+            for (unsigned long long t = m; t; t &= t - 1) ++cnt[__builtin_ctzll(t)];
+        int best = -1;
+        for (int r = 0; r < rows; ++r) if (!used[r] && (best < 0 || cnt[r] > cnt[best])) best = r;
+        if (best < 0 || cnt[best] == 0) break;
+        used[best] = 1;
+        order.push_back(best);
+        size_t w = 0;
+        for (unsigned long long m : alive) if (!((m >> best) & 1ull)) alive[w++] = m;
+        alive.resize(w);
+    }
+    for (int r = 0; r < rows; ++r) if (!used[r]) order.push_back(r);       // the rest keeps its relative order
+    std::vector<double> sorted(5 * rows);
+    for (int i = 0; i < rows; ++i)
+        for (int k = 0; k < 5; ++k) sorted[5 * i + k] = P->h_rows[5 * order[i] + k];
+    P->h_rows.swap(sorted);
+    return upload_rows(P, st);
+}
+
+static const bool g_auto_tune = getenv("CARMPC_NO_TUNE") == nullptr;       // development knob
+
 }  // namespace carmpc
 
 using namespace carmpc;
@@ -696,6 +784,7 @@ int carmpc_polytope_create(const double* h_Ab, int rows, void** handle) {
     const double u8 = 8.0 * 5.9604644775390625e-08;
     P->beta0 = nextafterf((float)(u8 * bmax * 1.000001 + 1e-37), INFINITY);
     P->beta1 = nextafterf((float)(u8 * l1max * 1.000001 + 1e-37), INFINITY);
+    P->h_rows = sorted;
     h_Ab = sorted.data();
     auto fail = [&](int code) { delete P; return code; };
     if (cudaMalloc(&P->d_rows, sizeof(double) * 5 * (rows > 0 ? rows : 1)) != cudaSuccess ||
@@ -727,9 +816,23 @@ int carmpc_membership_bitset(void* polytope, const double* d_x, const double* d_
     }
     CARMPC_REQUIRE(d_x && d_y && d_psi && d_v && d_bits, "null device pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    if (!P->tuned && g_auto_tune && n >= ((int64_t)1 << 20)) {
+        const int rc = tune_row_order(P, d_x, d_y, d_psi, d_v, n, st);
+        if (rc != CARMPC_OK) return rc;
+    }
     if (d_count) CARMPC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
     return launch_membership(P, d_x, d_y, d_psi, d_v, n, d_bits, reinterpret_cast<unsigned long long*>(d_count),
                              mode, st);
+}
+
+int carmpc_polytope_tune(void* polytope, const double* d_x, const double* d_y, const double* d_psi, const double* d_v,
+                         int64_t n, void* stream) {
+    Polytope* P = check_handle<Polytope>(polytope, kPolytope);
+    CARMPC_REQUIRE(P != nullptr, "not a polytope handle");
+    CARMPC_REQUIRE(n >= 0, "n");
+    if (n == 0) return CARMPC_OK;
+    CARMPC_REQUIRE(d_x && d_y && d_psi && d_v, "null device pointer");
+    return tune_row_order(P, d_x, d_y, d_psi, d_v, n, (cudaStream_t)stream);
 }
 
 int carmpc_membership_grid(void* polytope, const double* h_axes, const int32_t dims[4],

@@ -67,6 +67,12 @@ int carmpc_membership_bitset(void* polytope, const double* d_x, const double* d_
                              const double* d_v, int64_t n, uint32_t* d_bits, int64_t* d_count, int mode,
                              void* stream);
 
+/* Profile-guided row order: evaluates a strided subsample of the given samples and re-orders the rows so that the
+ * ones that reject most samples come first (whole-warp early exit).  Results never depend on the order.
+ * carmpc_membership_bitset does this by itself on its first call with n >= 2^20. */
+int carmpc_polytope_tune(void* polytope, const double* d_x, const double* d_y, const double* d_psi, const double* d_v,
+                         int64_t n, void* stream);
+
 /* The same test on an implicit tensor grid (the reference builds its grid from linspace / arange,
  * lib/terminal_set.py:96-106): sample i has multi-index (i0, i1, i2, i3) in C order over
  * (n0, n1, n2, n3) and coordinate axis_k[i_k]; axis_to_state[k] in {0,1,2,3} says which state

@@ -211,3 +211,36 @@ def test_config2_full_grid_properties(torch_cuda):
         assert torch.equal(b, bits[lo // 32: hi // 32])
         total += int(c.item())
     assert total == int(count.item())
+
+
+def test_profile_guided_row_order_never_changes_results(torch_cuda):
+    """The library re-orders the H-rep rows after a pilot over the samples (rows that reject most first).  The
+    conjunction over rows is order-independent: bitsets stay bit-exact against the oracle, before and after tuning,
+    on the tuning distribution and on a different one, and for a set with more than 64 rows (tuning skipped)."""
+    from carmpc_b200.batch import TerminalSetEvaluator
+    from oracle import c_oracle
+    Ab = np.load(os.path.join(GOLDEN, "terminal_sets", "RoadMultipleCarsEnv_30_1.5_0_0.npy"))
+    rng = np.random.default_rng(21)
+    n = 1_200_000
+    goal = np.array([30, 1.5, 0, 0.0])
+    p1 = goal + rng.uniform(-1, 1, size=(n, 4)) * np.array([25.0, 5.0, 0.8, 6.0])       # mostly outside
+    p2 = goal + rng.uniform(-1, 1, size=(n, 4)) * np.array([3.0, 0.5, 0.1, 1.0])        # mostly inside
+    ev = TerminalSetEvaluator(Ab)
+    for p in (p2[:5000], p1, p2, p1[:777]):        # small call (no tuning yet), large call (tunes), other distribution
+        want_bits, want_cnt = c_oracle.membership_bits(Ab, *p.T)
+        for mode in (1, 0):
+            bits, count = ev.contains_bits(*_dev(torch_cuda, *p.T), mode=mode)
+            np.testing.assert_array_equal(_bits_np(bits), want_bits)
+            assert int(count.item()) == want_cnt
+    ev.tune(*_dev(torch_cuda, *p2.T))               # explicit re-tune on the other distribution
+    want_bits, want_cnt = c_oracle.membership_bits(Ab, *p1.T)
+    bits, count = ev.contains_bits(*_dev(torch_cuda, *p1.T))
+    np.testing.assert_array_equal(_bits_np(bits), want_bits)
+    # > 64 rows: tuning is skipped, results still exact
+    big = np.vstack([Ab, Ab + np.array([0, 0, 0, 0, 0.5])])
+    assert len(big) > 64
+    evb = TerminalSetEvaluator(big)
+    want_bits, want_cnt = c_oracle.membership_bits(big, *p1.T)
+    bits, count = evb.contains_bits(*_dev(torch_cuda, *p1.T))
+    np.testing.assert_array_equal(_bits_np(bits), want_bits)
+    assert int(count.item()) == want_cnt
