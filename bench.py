@@ -296,7 +296,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     if rank == 0:
         peak, peak_src = _peaks()
-        achieved = n * BYTES_PER_SAMPLE / (kernel_ms * 1e-3) / 1e9
+        # at N = 1 a step is exactly one launch of the kernel: its average duration over the timed region (back-to-back
+        # launches, CUDA events on the launching stream); with the gather in the step (N > 1) the isolated timing is used
+        launch_ms = ms / args.steps if not distributed else kernel_ms
+        achieved = n * BYTES_PER_SAMPLE / (launch_ms * 1e-3) / 1e9
         cpu = None
         if world == 1 and not args.skip_cpu:
             rate, threads, sample, _ = cpu_membership_rate(10.0)
@@ -319,8 +322,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "e2e_grid": e2e_grid,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms,
-                         "kernel": "membership_kernel<mode,VEC>", "bytes_per_sample": BYTES_PER_SAMPLE},
+                         "traffic": 3.2125e9, "traffic_source": "ncu --set full: dram__bytes_read.sum 3.200 GB + "
+                         "dram__bytes_write.sum 12.5 MB per launch (profiles/r01_final_membership_tma_ncu_full.txt)",
+                         "peak_source": peak_src, "launch_ms": launch_ms, "isolated_launch_ms": kernel_ms,
+                         "kernel": "membership_tma_kernel<1>" if args.mode == 1 else "membership_kernel<0,true>",
+                         "bytes_per_sample": BYTES_PER_SAMPLE, "algorithmic_bytes_per_launch": n * BYTES_PER_SAMPLE},
             "cpu_baseline": cpu,
             "qp": qp,
         }
