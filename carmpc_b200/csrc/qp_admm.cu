@@ -227,8 +227,10 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
 #pragma unroll
                     for (int s = 0; s < S; ++s) acc[r][s] = x0t[g][r][s];
                 const float* Mrow = Pm + (size_t)(pg * kRA) * T.ktot;
-                tile_product<kRA, S, MATS>(acc, Mrow, T.ktot, sm.V, Bt, s0, sg.x, sg.y);
-                tile_product<kRA, S, MATS>(acc, Mrow, T.ktot, sm.V, Bt, s0, sg.z, sg.w);
+                if (!(Bq.debug_flags & 1)) {
+                    tile_product<kRA, S, MATS>(acc, Mrow, T.ktot, sm.V, Bt, s0, sg.x, sg.y);
+                    tile_product<kRA, S, MATS>(acc, Mrow, T.ktot, sm.V, Bt, s0, sg.z, sg.w);
+                }
 #pragma unroll
                 for (int r = 0; r < kRA; ++r) {
                     Vec<S> o;
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
 #pragma unroll
         for (int g = 0; g < GA; ++g) {
             const int pg = g * kAdmmWarps + warp;
-            if (pg < T.nGA) {
+            if (pg < T.nGA && !(Bq.debug_flags & 2)) {
 #pragma unroll
                 for (int r = 0; r < kRA; ++r) {
                     const int j = pg * kRA + r;
@@ -283,7 +285,9 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
             for (int r = 0; r < kRB; ++r)
 #pragma unroll
                 for (int s = 0; s < S; ++s) acc[r][s] = 0.f;
-            tile_product<kRB, S, MATS>(acc, Gm + (size_t)(pg * kRB) * T.npad4, T.npad4, sm.Xt, Bt, s0, sg.x, sg.y);
+            if (!(Bq.debug_flags & 1))
+                tile_product<kRB, S, MATS>(acc, Gm + (size_t)(pg * kRB) * T.npad4, T.npad4, sm.Xt, Bt, s0, sg.x, sg.y);
+            if (Bq.debug_flags & 2) continue;
 #pragma unroll
             for (int r = 0; r < kRB; ++r) {
                 const int i = pg * kRB + r;
@@ -433,7 +437,7 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
                     if (fin[s] < 0) continue;
                     const float w = wA[g][r][s];
                     Bq.sign[(size_t)fin[s] * T.mt + T.m + vid] = (int8_t)((w > ub) - (w < lb));
-                    Bq.u_admm[(size_t)fin[s] * T.n + vid] = d * sm.Xt[j * Bt + s0 + s];
+                    if (Bq.write_u) Bq.u_admm[(size_t)fin[s] * T.n + vid] = d * sm.Xt[j * Bt + s0 + s];
                     if (Bq.warm_out) Bq.warm[(size_t)fin[s] * T.mt + T.m + vid] = w;
                 }
             }
@@ -607,6 +611,8 @@ int admm_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
     int S = 1;
     while (S * 2 <= smax && (int64_t)b.count >= (int64_t)32 * (S * 2) * q->sm) S *= 2;
     static const int variant = getenv("CARMPC_ADMM_WIDE") ? atoi(getenv("CARMPC_ADMM_WIDE")) : 0;   // development knob
+    static const int debug_flags = getenv("CARMPC_ADMM_DEBUG") ? atoi(getenv("CARMPC_ADMM_DEBUG")) : 0;
+    if (debug_flags) const_cast<AdmmBatch&>(b).debug_flags = debug_flags;
     const int key = q->host.ga_per_warp * 100 + q->host.gb_per_warp * 10 + S;
     switch (key) {
         case 124: return variant == 1 ? launch_variant<4, 1, 1, 2>(q, b, st) : launch_variant<2, 2, 1, 2>(q, b, st);

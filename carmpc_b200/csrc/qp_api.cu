@@ -76,6 +76,7 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
     // the ADMM state of every sample is kept (caller's buffer or the workspace): the second pass resumes from it
     ab.warm = d_warm ? d_warm : ws_warm; ab.warm_in = d_warm ? warm_in : 0; ab.warm_out = 1;
     ab.total_iters = ws_total_iters; ab.eps_scale = 1.f; ab.max_iter = host.opts.max_iter; ab.iters_accumulate = 0;
+    ab.write_u = host.opts.polish ? 0 : 1;        // with the polish on, only the final pass may fall back to the iterate
     rc = admm_launch(this, ab, st);
     if (rc != CARMPC_OK) return rc;
     ++last_launches;
@@ -102,7 +103,7 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
         // second pass on the samples whose active set the polish could not certify: tighter ADMM, then accept
         last_second_pass = n_failed;
         ab.idx_list = ws_failed; ab.count = n_failed; ab.next = ws_counters + 2; ab.eps_scale = 0.01f;
-        ab.warm_in = 1; ab.iters_accumulate = 1;
+        ab.warm_in = 1; ab.iters_accumulate = 1; ab.write_u = 1;
         rc = admm_launch(this, ab, st);
         if (rc != CARMPC_OK) return rc;
         pb.idx_list = ws_failed; pb.count = n_failed; pb.n_failed = ws_counters + 3; pb.final_pass = 1;

@@ -1,16 +1,22 @@
-"""Nonlinear kinematic-bicycle plant.
+"""Nonlinear kinematic-bicycle plant (single run, host side).
 
-Mirror of the reference's ``lib/simulator.py`` (``CarTrailerDimension`` :5-13, ``CarSimulator``
-:16-118): forward-Euler step of [x, y, psi, v] under [a, delta_f], input assertion / clipping,
-output y = C x (+ Cd d).  This class is the single-run host object; the batched Monte-Carlo closed
-loop integrates the same equations on the GPU (``csrc/closed_loop.cu``).
+Drop-in for the reference's ``lib/simulator.py`` (``CarTrailerDimension`` :5-13, ``CarSimulator`` :16-118):
+same constructor, attributes and methods; ``step`` advances ``[x, y, psi, v]`` by one forward-Euler
+step under ``[a, delta_f]``, after asserting (or, with ``clip=True``, clipping) the input against the
+actuator limits, and refreshes ``output = C x (+ Cd d)``.  The batched Monte-Carlo closed loop
+integrates the very same update on the GPU (``csrc/closed_loop.cu``, ``loop_advance_kernel``).
 """
-from typing import Union
+from __future__ import annotations
+
+from typing import Sequence, Union
 
 import numpy as np
 
+ArrayLike = Union[np.ndarray, Sequence[float]]
+
 
 class CarTrailerDimension:
+    """Geometry in metres (only ``l1``, the wheelbase, enters the dynamics)."""
     l1 = 3.5
     l2 = 4
     l12 = 1
@@ -21,64 +27,68 @@ class CarTrailerDimension:
     triangle_length = 2
 
 
+def bicycle_rate(state: ArrayLike, control_input: ArrayLike, wheelbase: float) -> np.ndarray:
+    """Time derivative of ``[x, y, psi, v]``: ``[v cos psi, v sin psi, v / l1 * tan delta_f, a]``."""
+    heading, speed = state[2], state[3]
+    accel, steer = control_input
+    return np.array([speed * np.cos(heading), speed * np.sin(heading), speed / wheelbase * np.tan(steer), accel])
+
+
 class CarSimulator:
-    def __init__(self, dt: float = 0.01, clip: bool = False, C: np.ndarray = None,
-                 Cd: np.ndarray = None) -> None:
-        self.time = 0
-        self.l1 = CarTrailerDimension.l1
-        self.l2 = CarTrailerDimension.l2
-        self.l12 = CarTrailerDimension.l12
-        self.state = np.zeros(4)                       # [x, y, psi, v]
-        self.dt = dt
-        self.clip = clip
+    #: slack the reference grants on top of the nominal actuator limits (2 m/s^2, pi/4 rad)
+    INPUT_MARGIN = 0.05
+
+    def __init__(self, dt: float = 0.01, clip: bool = False, C: np.ndarray = None, Cd: np.ndarray = None) -> None:
+        dims = CarTrailerDimension
+        self.l1, self.l2, self.l12 = dims.l1, dims.l2, dims.l12
+        self.dt, self.clip, self.time = dt, clip, 0
+        self.state = np.zeros(4)
         self.C = np.eye(4) if C is None else C
         assert self.C.shape[1] == 4, \
-            f"The length of the second dimension (currently {self.C.shape[1]}) of C should be equal to the state length (4)."
-        self.output = self.C @ self.state
+            f"C maps the 4 states to the outputs, so it needs 4 columns; it has {self.C.shape[1]}."
         self.Cd = Cd
+        self.output = self.C @ self.state
+        # state ranges (informational, as in the reference: never enforced)
         self.x_lower, self.x_upper = -np.inf, np.inf
         self.y_lower, self.y_upper = -np.inf, np.inf
         self.psi_lower, self.psi_upper = -np.pi, np.pi
         self.v_lower, self.v_upper = -10, 10
-        # input limits, with the reference's 0.05 margin
-        self.delta_lower, self.delta_upper = -np.pi / 4 - 0.05, np.pi / 4 + 0.05
-        self.acc_lower, self.acc_upper = -2 - 0.05, 2 + 0.05
+        # actuator limits
+        self.acc_upper = 2 + self.INPUT_MARGIN
+        self.acc_lower = -self.acc_upper
+        self.delta_upper = np.pi / 4 + self.INPUT_MARGIN
+        self.delta_lower = -self.delta_upper
 
-    def reset(self, state: Union[np.ndarray, list] = np.zeros(5)) -> None:
+    # ------------------------------------------------------------------------------------------
+    def reset(self, state: ArrayLike = np.zeros(5)) -> None:
         assert np.array(state).shape == (4,), \
-            f"The state should have shape (4,), but has shape{np.array(state).shape}"
+            f"A state is [x, y, psi, v]; got an array of shape {np.array(state).shape}."
         self.state = state
 
-    def dynamics_continuous(self, state: np.ndarray, control_input: Union[np.ndarray, list]) -> np.ndarray:
-        """One explicit-Euler step of the continuous bicycle model (reference :51-69)."""
+    def dynamics_continuous(self, state: np.ndarray, control_input: ArrayLike) -> np.ndarray:
+        """The state one Euler step later: ``rate * dt + state`` (reference :51-69)."""
         assert np.array(control_input).shape == (2,), \
-            f"The input should have shape (2,), but has shape{np.array(control_input).shape}"
-        _, _, psi, v = state
-        a, delta_f = control_input
-        rate = np.array([v * np.cos(psi), v * np.sin(psi), v / self.l1 * np.tan(delta_f), a])
-        return rate * self.dt + state
+            f"An input is [a, delta_f]; got an array of shape {np.array(control_input).shape}."
+        return bicycle_rate(state, control_input, self.l1) * self.dt + state
 
-    def get_log(self, control_input: Union[np.ndarray, list]) -> dict[str, np.ndarray]:
-        a, delta_f = control_input
-        return {'car': self.state, 'inputs': np.array([a, delta_f])}
+    def get_log(self, control_input: ArrayLike) -> dict:
+        return {'car': self.state, 'inputs': np.array([control_input[0], control_input[1]])}
 
-    def check_input(self, control_input: Union[np.ndarray, list]) -> Union[np.ndarray, list]:
-        """Assert (or clip, if ``clip``) the input against the actuator limits (reference :83-97).
-
-        As in the reference, the clipped value is returned but ``step`` ignores the return value.
-        """
-        a, delta_f = control_input
+    def check_input(self, control_input: ArrayLike) -> ArrayLike:
+        """Clip (``clip=True``) or assert the input against ``[acc_lower, acc_upper] x [delta_lower, delta_upper]``.
+        Like the reference (:83-97) the possibly clipped value is returned, and ``step`` does not use it."""
+        low = np.array([self.acc_lower, self.delta_lower])
+        high = np.array([self.acc_upper, self.delta_upper])
         if self.clip:
-            control_input = np.clip(control_input, [self.acc_lower, self.delta_lower],
-                                    [self.acc_upper, self.delta_upper])
-        else:
-            assert np.all([a, -a] <= [self.acc_upper, -self.acc_lower]), \
-                f"Acceleration should be between [{self.acc_lower, self.acc_upper}], but is {a}."
-            assert np.all([delta_f, -delta_f] <= [self.delta_upper, -self.delta_lower]), \
-                f"Steering angle should be between [{self.delta_lower:.3f}, {self.delta_upper:.3f}], but is {delta_f}."
+            return np.clip(control_input, low, high)
+        accel, steer = control_input
+        assert low[0] <= accel <= high[0], \
+            f"Acceleration {accel} is outside [{self.acc_lower}, {self.acc_upper}]."
+        assert low[1] <= steer <= high[1], \
+            f"Steering angle {steer} is outside [{self.delta_lower:.3f}, {self.delta_upper:.3f}]."
         return control_input
 
-    def step(self, control_input: Union[np.ndarray, list], d: float = None) -> dict[str, np.ndarray]:
+    def step(self, control_input: ArrayLike, d: float = None) -> dict:
         self.check_input(control_input)
         self.state = self.dynamics_continuous(self.state, control_input)
         self.output = self.C @ self.state
