@@ -180,6 +180,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
     if distributed and not dist.is_initialized():
+        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -209,7 +210,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             if pending is not None:
                 pending.wait()
             # result gather over NVLink (the job's sample set is world x 10^8; this rank owns one contiguous range)
-            pending, _ = gather_bitset(b, world * n, async_op=True, out=gathered)
+            pending, _ = gather_bitset(b, world * n, async_op=True, out=gathered, dst=0)
 
     for i in range(args.warmup):
         step(i)
@@ -315,7 +316,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "samples_per_gpu_per_step": n, "kernel_mode": "fp32 screen + fp64 re-check" if args.mode else "fp64",
                        "l2": "inputs (3.2 GB) exceed the 126 MB L2; no flush between iterations",
                        "members": members,
-                       "multi_gpu": "each rank scans its own 10^8 grid; bitsets all-gathered over NCCL, overlapped "
+                       "multi_gpu": "each rank scans its own 10^8 grid; bitsets gathered to rank 0 over NCCL, overlapped "
                                     "with the next step" if distributed else "single GPU"},
             "clocks": clocks.summary(),
             "e2e": e2e,

@@ -30,12 +30,13 @@ def padded_shard_len(n: int, world: int, align: int = 32) -> int:
     return -(-per // align) * align
 
 
-def gather_bitset(local_bits, n: int, async_op: bool = False, out=None):
-    """All-gather the per-rank bitset words of an n-sample set sharded with ``shard_range(n, rank, world)``.
+def gather_bitset(local_bits, n: int, async_op: bool = False, out=None, dst: Optional[int] = None):
+    """Gather the per-rank bitset words of an n-sample set sharded with ``shard_range(n, rank, world)``.
 
-    ``local_bits``: int32 tensor with the words of this rank's range (ceil(len / 32) words).  Returns the full
-    bitset (ceil(n / 32) int32 words) on every rank - or ``(handle, finish)`` when ``async_op`` - where ``finish()``
-    trims the padding."""
+    ``local_bits``: int32 tensor with the words of this rank's range (ceil(len / 32) words).  With ``dst=None`` every
+    rank receives the full bitset (all-gather); with ``dst=r`` only rank r does (gather: 1/world of the traffic per
+    sender).  Returns the full bitset (ceil(n / 32) int32 words; ``None`` on the ranks that do not receive) - or
+    ``(handle, finish)`` when ``async_op`` - where ``finish()`` trims the padding."""
     import torch
     dist = _dist()
     rank, world = world_info()
@@ -48,12 +49,18 @@ def gather_bitset(local_bits, n: int, async_op: bool = False, out=None):
     if send.numel() != per_words:                       # last ranks own fewer (or zero) words: pad with zeros
         send = torch.zeros(per_words, dtype=local_bits.dtype, device=local_bits.device)
         send[:local_bits.numel()] = local_bits
-    if out is None:
-        out = torch.empty(world * per_words, dtype=local_bits.dtype, device=local_bits.device)
-    handle = dist.all_gather_into_tensor(out, send, async_op=async_op)
+    if dst is None:
+        if out is None:
+            out = torch.empty(world * per_words, dtype=local_bits.dtype, device=local_bits.device)
+        handle = dist.all_gather_into_tensor(out, send, async_op=async_op)
+    else:
+        if rank == dst and out is None:
+            out = torch.empty(world * per_words, dtype=local_bits.dtype, device=local_bits.device)
+        parts = list(out.view(world, per_words).unbind(0)) if rank == dst else None
+        handle = dist.gather(send, parts, dst=dst, async_op=async_op)
 
     def finish():
-        return out[:words_total]
+        return out[:words_total] if out is not None and (dst is None or rank == dst) else None
 
     return (handle, finish) if async_op else finish()
 

@@ -55,6 +55,12 @@ def _worker(rank, world, port, n, tmp):
         want_bits, want_cnt = c_oracle.membership_bits(Ab, *[np.ascontiguousarray(c) for c in p.T], threads=1)
         assert np.array_equal(full.numpy().view(np.uint32), want_bits)
         assert int(total.item()) == want_cnt
+        # gather to one rank only
+        only0 = gather_bitset(torch.from_numpy(bits.view(np.int32)), n, dst=0)
+        if rank == 0:
+            assert np.array_equal(only0.numpy().view(np.uint32), want_bits)
+        else:
+            assert only0 is None
         # async form
         handle, finish = gather_bitset(torch.from_numpy(bits.view(np.int32)), n, async_op=True)
         if handle is not None:
