@@ -17,6 +17,8 @@ namespace carmpc {
 namespace {
 
 constexpr int kPolishRounds = 10;
+constexpr int kPolishSmallActive = 32;
+constexpr int kAddPerRound = 3;      // violated rows added to the active set per repair round
 constexpr int kPolishThreads = 128;
 constexpr double kFeasTol = 1e-8;
 constexpr double kSignTol = 1e-9;
@@ -44,7 +46,7 @@ __host__ __device__ inline PolishSmemLayout polish_layout(int n, int mt, int na_
     if (L.na_max < 1) L.na_max = 1;
     size_t d = 0;
     d += 2 * (size_t)n;                                      // u_unc, u
-    d += 2 * (size_t)mt;                                     // A u_unc, per-row bound shift
+    d += (size_t)mt;                                         // t = A u_unc + bound shift
     d += (size_t)L.na_max * (L.na_max + 1) / 2;              // M, packed lower triangle
     d += 3 * (size_t)L.na_max;                               // rhs / lambda, b, diag0
     size_t bytes = d * sizeof(double);
@@ -57,6 +59,12 @@ __host__ __device__ inline PolishSmemLayout polish_layout(int n, int mt, int na_
 
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }     // j <= i
 
+// (A u_unc)_i = AUu_i . dx
+__device__ __forceinline__ double T_auu(const PolishTables& T, int i, const double (&dx)[4]) {
+    const double* w = T.AUu + (size_t)i * 4;
+    return w[0] * dx[0] + w[1] * dx[1] + w[2] * dx[2] + w[3] * dx[3];
+}
+
 __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTables T, const PolishBatch B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -66,9 +74,8 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
     unsigned char* base = smem_raw + (size_t)warp * L.per_warp;
     double* uunc = reinterpret_cast<double*>(base);
     double* u = uunc + n;
-    double* Auu = u + n;
-    double* shf = Auu + mt;
-    double* M = shf + mt;
+    double* tsh = u + n;                 // t_i = (A u_unc)_i + Gx_i x0 + Gc_i c: row i is within bounds iff lo_i <= t_i - corr_i <= hi_i
+    double* M = tsh + mt;
     double* rhs = M + (size_t)L.na_max * (L.na_max + 1) / 2;
     double* bact = rhs + L.na_max;
     double* diag0 = bact + L.na_max;
@@ -102,13 +109,12 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
         }
         for (int i = lane; i < mt; i += 32) {
             const double* w = T.AUu + (size_t)i * 4;
-            Auu[i] = w[0] * dx[0] + w[1] * dx[1] + w[2] * dx[2] + w[3] * dx[3];
-            double shift = 0.0;
+            double t = w[0] * dx[0] + w[1] * dx[1] + w[2] * dx[2] + w[3] * dx[3];
             if (i < m) {
                 const double* gx = T.Gx + (size_t)i * 4;
-                shift = gx[0] * x0[0] + gx[1] * x0[1] + gx[2] * x0[2] + gx[3] * x0[3] + T.Gc[i] * cd;
+                t += gx[0] * x0[0] + gx[1] * x0[1] + gx[2] * x0[2] + gx[3] * x0[3] + T.Gc[i] * cd;
             }
-            shf[i] = shift;
+            tsh[i] = t;
             sgn[i] = B.sign[(size_t)sample * mt + i];
         }
         int n_added = 0;
@@ -148,8 +154,9 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
             }
             for (int a = lane; a < na; a += 32) {
                 const int i = act[a];
-                bact[a] = (sgn[i] > 0 ? T.hi[i] : T.lo[i]) - shf[i];
-                rhs[a] = Auu[i] - bact[a];
+                const double bound = sgn[i] > 0 ? T.hi[i] : T.lo[i];
+                bact[a] = bound - (tsh[i] - T_auu(T, i, dx));          // bound on A u: hi - shift
+                rhs[a] = tsh[i] - bound;
             }
             __syncwarp();
             // ---- Cholesky with pivot skipping (a row that depends on earlier ones gets lambda = 0).  diag0[j] is
@@ -163,12 +170,15 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
                 if (lane == 0) diag0[j] = rinv;
                 for (int i = j + 1 + lane; i < na; i += 32) M[tri(i, 0) + j] *= rinv;      // L_ij (0 when skipped)
                 __syncwarp();
-                if (!skip)
-                    for (int i = j + 1 + lane; i < na; i += 32) {
+                if (!skip) {
+                    // trailing update M[i][k] -= L_ij L_kj over the triangle j < k <= i, lanes as an 8 x 4 grid of (i, k)
+                    const int li = lane >> 2, lk = lane & 3;
+                    for (int i = j + 1 + li; i < na; i += 8) {
                         const int ti = tri(i, 0);
                         const double lij = M[ti + j];
-                        for (int k = j + 1; k <= i; ++k) M[ti + k] -= lij * M[tri(k, 0) + j];
+                        for (int k = j + 1 + lk; k <= i; k += 4) M[ti + k] -= lij * M[tri(k, 0) + j];
                     }
+                }
                 __syncwarp();
             }
             // ---- L y = rhs, L' lambda = y ----
@@ -203,9 +213,9 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
             double worst = 0.0;
             int worst_i = -1, worst_sign = 0;
             for (int i = lane; i < mt; i += 32) {
-                const double h = T.hi[i] - shf[i], l = T.lo[i] - shf[i];
+                const double h = T.hi[i], l = T.lo[i];
                 if (isinf(h) && isinf(l)) continue;
-                double s0 = Auu[i], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                double s0 = tsh[i], s1 = 0.0, s2 = 0.0, s3 = 0.0;
                 int a = 0;
                 for (; a + 3 < na; a += 4) {
                     s0 -= T.AHA[(size_t)act[a] * mt + i] * rhs[a];
@@ -219,13 +229,21 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
                 const double v = fmax(vu, vl);
                 if (v > worst) { worst = v; worst_i = i; worst_sign = vu >= vl ? 1 : -1; }
             }
-            const double wmax = warp_max(worst);
-            const unsigned who = __ballot_sync(0xffffffffu, worst == wmax && worst_i >= 0);
-            int add_i = -1, add_sign = 0;
-            if (wmax > kFeasTol && who) {
-                const int src = __ffs(who) - 1;
-                add_i = __shfl_sync(0xffffffffu, worst_i, src);
-                add_sign = __shfl_sync(0xffffffffu, worst_sign, src);
+            // the (up to) kAddPerRound most violated rows, one per lane
+            int n_add = 0, add_is[kAddPerRound], add_sg[kAddPerRound];
+            {
+                double wv = worst_i >= 0 ? worst : -1.0;
+#pragma unroll
+                for (int t = 0; t < kAddPerRound; ++t) {
+                    const double wmax = warp_max(wv);
+                    if (!(wmax > kFeasTol)) break;                         // uniform
+                    const unsigned who = __ballot_sync(0xffffffffu, wv == wmax);
+                    const int src = __ffs(who) - 1;
+                    add_is[n_add] = __shfl_sync(0xffffffffu, worst_i, src);
+                    add_sg[n_add] = __shfl_sync(0xffffffffu, worst_sign, src);
+                    ++n_add;
+                    if (lane == src) wv = -1.0;
+                }
             }
             double lam_max = 0.0;
             for (int a = lane; a < na; a += 32) lam_max = fmax(lam_max, fabs(rhs[a]));
@@ -237,13 +255,14 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
             }
             n_bad = __reduce_add_sync(0xffffffffu, n_bad);
             __syncwarp();
-            if (add_i < 0 && n_bad == 0) { certified = true; break; }
-            if (add_i >= 0) {
+            if (n_add == 0 && n_bad == 0) { certified = true; break; }
+            for (int t = n_add - 1; t >= 0; --t) {                         // the most violated row ends up first
+                const int add_i = add_is[t];
                 int k = 0;
                 for (int a = 0; a < n_added; ++a) if (added[a] != add_i) ++k;
                 __syncwarp();
                 if (lane == 0) {
-                    sgn[add_i] = (signed char)add_sign;
+                    sgn[add_i] = (signed char)add_sg[t];
                     int w = 0;                                         // move / insert add_i at the front
                     for (int a = 0; a < n_added; ++a) if (added[a] != add_i) added[w++] = added[a];
                     const int keep = w < 15 ? w : 15;
@@ -251,6 +270,7 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
                     added[0] = add_i;
                 }
                 n_added = (k < 15 ? k : 15) + 1;
+                __syncwarp();
             }
             __syncwarp();
         }
@@ -321,19 +341,19 @@ static int polish_launch_cap(QPHandle* qh, const PolishBatch& b, cudaStream_t st
     return CARMPC_OK;
 }
 
-// Two launches: a small active-set budget (32 rows: 8 KB of shared memory per warp, 28 warps per SM) covers almost
+// Two launches: a small active-set budget (32 rows: 7 KB of shared memory per warp, 28 warps per SM) covers almost
 // every sample; the few with more active rows are listed and redone with the full-size layout.
 int polish_launch(QPHandle* qh, const PolishBatch& b_in, cudaStream_t st) {
     if (b_in.count <= 0) return CARMPC_OK;
     const int n = qh->polish.n, mt = qh->polish.mt;
     const int full = std::min(mt, std::min(kPolishMaxActive, n + 8));
     PolishBatch b = b_in;
-    if (full <= 32 || qh->ws_overflow == nullptr) {
+    if (full <= kPolishSmallActive || qh->ws_overflow == nullptr) {
         b.na_cap = full; b.overflow_list = nullptr; b.n_overflow = nullptr;
         return polish_launch_cap(qh, b, st);
     }
     CARMPC_CUDA(cudaMemsetAsync(qh->ws_counters + 4, 0, sizeof(int), st));
-    b.na_cap = 32; b.overflow_list = qh->ws_overflow; b.n_overflow = qh->ws_counters + 4;
+    b.na_cap = kPolishSmallActive; b.overflow_list = qh->ws_overflow; b.n_overflow = qh->ws_counters + 4;
     int rc = polish_launch_cap(qh, b, st);
     if (rc != CARMPC_OK) return rc;
     int n_over = 0;

@@ -19,15 +19,8 @@ if B < x0.shape[1]:
 c = _controller("RoadOneCarEnv", [29.9, 1.5, 0, 0], N)
 ref = None
 grid = []
-for eps in (2e-3, 3e-3, 5e-3):
+for eps in (1e-3, 1.5e-3, 2e-3, 2.5e-3, 4e-3):
     grid.append(dict(eps_abs=eps, eps_rel=eps))
-for ce in (5, 8):
-    grid.append(dict(check_every=ce))
-    grid.append(dict(check_every=ce, eps_abs=3e-3, eps_rel=3e-3))
-for rho in (0.15, 0.3):
-    grid.append(dict(rho=rho))
-for alpha in (1.7, 1.9):
-    grid.append(dict(alpha=alpha))
 for opts in [dict()] + grid:
     bq = BatchQP.from_controller(c, **opts)
     bq.solve(x0)
