@@ -21,12 +21,50 @@ int upload(QPHandle* q, const std::vector<T>& v, const T** dst) {
     return CARMPC_OK;
 }
 
+__global__ void aos_to_soa_kernel(const double* __restrict__ aos, double* __restrict__ soa, int64_t count, int width) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    for (int c = 0; c < width; ++c) soa[(size_t)c * count + i] = aos[i * width + c];
+}
+
+__global__ void soa_to_aos_kernel(const double* __restrict__ soa, double* __restrict__ aos, int64_t count, int width) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    for (int c = 0; c < width; ++c) aos[i * width + c] = soa[(size_t)c * count + i];
+}
+
 }  // namespace
+
+int QPHandle::ensure_io(int64_t batch, bool want_full) {
+    if (batch > io_cap) {
+        cudaFree(io_x0_aos); cudaFree(io_x0); cudaFree(io_c); cudaFree(io_u0); cudaFree(io_u0_aos); cudaFree(io_obj);
+        cudaFree(io_status); cudaFree(io_iters);
+        io_x0_aos = io_x0 = io_c = io_u0 = io_u0_aos = io_obj = nullptr; io_status = io_iters = nullptr;
+        io_cap = 0;
+        CARMPC_CUDA(cudaMalloc(&io_x0_aos, sizeof(double) * 4 * batch));
+        CARMPC_CUDA(cudaMalloc(&io_x0, sizeof(double) * 4 * batch));
+        CARMPC_CUDA(cudaMalloc(&io_c, sizeof(double) * batch));
+        CARMPC_CUDA(cudaMalloc(&io_u0, sizeof(double) * 2 * batch));
+        CARMPC_CUDA(cudaMalloc(&io_u0_aos, sizeof(double) * 2 * batch));
+        CARMPC_CUDA(cudaMalloc(&io_obj, sizeof(double) * batch));
+        CARMPC_CUDA(cudaMalloc(&io_status, sizeof(int32_t) * batch));
+        CARMPC_CUDA(cudaMalloc(&io_iters, sizeof(int32_t) * batch));
+        io_cap = batch;
+    }
+    if (want_full && batch > io_full_cap) {
+        cudaFree(io_full); io_full = nullptr; io_full_cap = 0;
+        CARMPC_CUDA(cudaMalloc(&io_full, sizeof(double) * (size_t)host.n * batch));
+        io_full_cap = batch;
+    }
+    return CARMPC_OK;
+}
 
 QPHandle::~QPHandle() {
     for (void* p : allocations) cudaFree(p);
     cudaFree(ws_sign); cudaFree(ws_u); cudaFree(ws_status); cudaFree(ws_iters); cudaFree(ws_failed);
     cudaFree(ws_counters); cudaFree(ws_total_iters); cudaFree(ws_polished); cudaFree(ws_warm); cudaFree(ws_overflow);
+    cudaFree(io_x0_aos); cudaFree(io_x0); cudaFree(io_c); cudaFree(io_u0); cudaFree(io_u0_aos); cudaFree(io_obj); cudaFree(io_full);
+    cudaFree(io_status); cudaFree(io_iters);
 }
 
 int QPHandle::ensure_workspace(int64_t batch) {
@@ -252,37 +290,29 @@ int carmpc_qp_solve_host(void* qp, const double* h_x0, const double* h_xref, con
     CARMPC_REQUIRE(batch >= 0 && batch < (int64_t)1 << 31, "batch");
     if (batch == 0) return CARMPC_OK;
     CARMPC_REQUIRE(h_x0 && h_xref && h_status, "null host pointer");
+    if (q->host_only) { set_error("carmpc_qp: this handle was created without a CUDA device; there is no CPU solver"); return CARMPC_ERR_CUDA; }
     const int n = q->host.n;
-    // AoS (batch x 4, as the reference passes states) -> SoA on the way in; results back in the reference's layouts
-    std::vector<double> soa((size_t)4 * batch);
-    for (int64_t i = 0; i < batch; ++i)
-        for (int c = 0; c < 4; ++c) soa[(size_t)c * batch + i] = h_x0[i * 4 + c];
-    double *d_x0 = nullptr, *d_c = nullptr, *d_u0 = nullptr, *d_obj = nullptr, *d_full = nullptr;
-    int32_t *d_status = nullptr, *d_iters = nullptr;
-    int rc = CARMPC_OK;
-    auto cleanup = [&]() { cudaFree(d_x0); cudaFree(d_c); cudaFree(d_u0); cudaFree(d_obj); cudaFree(d_full); cudaFree(d_status); cudaFree(d_iters); };
-#define TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(e__)); cleanup(); return CARMPC_ERR_CUDA; } } while (0)
-    TRY(cudaMalloc(&d_x0, sizeof(double) * 4 * batch));
-    TRY(cudaMalloc(&d_u0, sizeof(double) * 2 * batch));
-    TRY(cudaMalloc(&d_obj, sizeof(double) * batch));
-    TRY(cudaMalloc(&d_status, sizeof(int32_t) * batch));
-    TRY(cudaMalloc(&d_iters, sizeof(int32_t) * batch));
-    if (h_c) { TRY(cudaMalloc(&d_c, sizeof(double) * batch)); TRY(cudaMemcpy(d_c, h_c, sizeof(double) * batch, cudaMemcpyHostToDevice)); }
-    if (h_u_full) TRY(cudaMalloc(&d_full, sizeof(double) * (size_t)n * batch));
-    TRY(cudaMemcpy(d_x0, soa.data(), sizeof(double) * 4 * batch, cudaMemcpyHostToDevice));
-    rc = q->solve(d_x0, batch, h_xref, d_c, nullptr, batch, d_u0, d_obj, d_status, d_iters, d_full, nullptr, 0, 0, nullptr);
-    if (rc != CARMPC_OK) { cleanup(); return rc; }
+    int rc = q->ensure_io(batch, h_u_full != nullptr);
+    if (rc != CARMPC_OK) return rc;
+    cudaStream_t st = nullptr;
+    const int blocks = (int)((batch + 255) / 256);
+    // states arrive as the reference passes them (batch x 4, row-major): one copy, re-laid out to SoA on the device
+    CARMPC_CUDA(cudaMemcpyAsync(q->io_x0_aos, h_x0, sizeof(double) * 4 * batch, cudaMemcpyHostToDevice, st));
+    aos_to_soa_kernel<<<blocks, 256, 0, st>>>(q->io_x0_aos, q->io_x0, batch, 4);
+    if (h_c) CARMPC_CUDA(cudaMemcpyAsync(q->io_c, h_c, sizeof(double) * batch, cudaMemcpyHostToDevice, st));
+    rc = q->solve(q->io_x0, batch, h_xref, h_c ? q->io_c : nullptr, nullptr, batch, q->io_u0, q->io_obj, q->io_status,
+                  q->io_iters, h_u_full ? q->io_full : nullptr, nullptr, 0, 0, st);
+    if (rc != CARMPC_OK) return rc;
     if (h_u0) {
-        std::vector<double> u0((size_t)2 * batch);
-        TRY(cudaMemcpy(u0.data(), d_u0, sizeof(double) * 2 * batch, cudaMemcpyDeviceToHost));
-        for (int64_t i = 0; i < batch; ++i) { h_u0[2 * i] = u0[i]; h_u0[2 * i + 1] = u0[batch + i]; }
+        soa_to_aos_kernel<<<blocks, 256, 0, st>>>(q->io_u0, q->io_u0_aos, batch, 2);
+        CARMPC_CUDA(cudaMemcpyAsync(h_u0, q->io_u0_aos, sizeof(double) * 2 * batch, cudaMemcpyDeviceToHost, st));
     }
-    if (h_objective) TRY(cudaMemcpy(h_objective, d_obj, sizeof(double) * batch, cudaMemcpyDeviceToHost));
-    TRY(cudaMemcpy(h_status, d_status, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost));
-    if (h_iters) TRY(cudaMemcpy(h_iters, d_iters, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost));
-    if (h_u_full) TRY(cudaMemcpy(h_u_full, d_full, sizeof(double) * (size_t)n * batch, cudaMemcpyDeviceToHost));
-#undef TRY
-    cleanup();
+    if (h_objective) CARMPC_CUDA(cudaMemcpyAsync(h_objective, q->io_obj, sizeof(double) * batch, cudaMemcpyDeviceToHost, st));
+    CARMPC_CUDA(cudaMemcpyAsync(h_status, q->io_status, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
+    if (h_iters) CARMPC_CUDA(cudaMemcpyAsync(h_iters, q->io_iters, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
+    if (h_u_full) CARMPC_CUDA(cudaMemcpyAsync(h_u_full, q->io_full, sizeof(double) * (size_t)n * batch, cudaMemcpyDeviceToHost, st));
+    CARMPC_CUDA(cudaStreamSynchronize(st));
+    CARMPC_CUDA(cudaGetLastError());
     return CARMPC_OK;
 }
 

@@ -186,6 +186,12 @@ struct QPHandle : HandleBase {
     unsigned long long* ws_total_iters = nullptr;
     int8_t* ws_polished = nullptr;
     float* ws_warm = nullptr;                    // ADMM state of every sample (warm start of the second pass)
+    // device side of the host-buffer entry point (grown on demand, kept across calls)
+    int64_t io_cap = 0, io_full_cap = 0;
+    double *io_x0_aos = nullptr, *io_x0 = nullptr, *io_c = nullptr, *io_u0 = nullptr, *io_u0_aos = nullptr, *io_obj = nullptr,
+           *io_full = nullptr;
+    int32_t *io_status = nullptr, *io_iters = nullptr;
+    int ensure_io(int64_t batch, bool want_full);
     int64_t last_total_iters = 0, last_launches = 0, last_second_pass = 0;
     int sm = 148;
     bool host_only = false;
