@@ -442,7 +442,7 @@ int qp_host_setup(int n, int m_in, int kpre, const double* H_in, const double* F
             q.AUu[(size_t)i * 4 + c] = s;
         }
 
-    q.mats_in_smem = admm_smem_bytes(q, S, true) <= (size_t)226 * 1024;
+    q.mats_in_smem = GA < 4 && admm_smem_bytes(q, S, true) <= (size_t)226 * 1024;
     q.smem_bytes = admm_smem_bytes(q, S, q.mats_in_smem);
     if (q.smem_bytes > (size_t)227 * 1024) { set_error("carmpc_qp_create: shared-memory budget exceeded"); return CARMPC_ERR_UNSUPPORTED; }
     return CARMPC_OK;
