@@ -156,9 +156,9 @@ class CondensedQP:
             blocks_G.append(As @ self.S)
             blocks_Gx.append(As @ self.T)
             blocks_w.append(bs)
-        self.G = np.vstack(blocks_G)
-        self.Gx = np.vstack(blocks_Gx)
-        self.w = np.hstack(blocks_w)
+        self.G = np.vstack(blocks_G) if blocks_G else np.zeros((0, self.n))
+        self.Gx = np.vstack(blocks_Gx) if blocks_Gx else np.zeros((0, 4))
+        self.w = np.hstack(blocks_w) if blocks_w else np.zeros(0)
 
     def rhs(self, x0):
         """Upper bounds  w - Gx x0  for a batch x0 (B, 4)."""

@@ -180,3 +180,30 @@ def test_qp_oracle_known_answer():
     # the ADMM certificate gives the same flags as the LP
     _, _, st = orc.qp_solve_admm(qp, x0, goal, eps=1e-7, max_iter=6000)
     np.testing.assert_array_equal(np.where(st == 0, 0, 1), status)
+
+
+def test_qp_oracle_agrees_with_an_independent_solver():
+    """QP parity is unpinned against the reference's cvxpy -> OSQP (not installable here); as the next best thing the
+    oracle's exact solutions are cross-checked against an independent algorithm (scipy SLSQP, a sequential quadratic
+    programming method) on the reference's own QP data: same objective to 1e-8 relative, same inputs to SLSQP's
+    accuracy.  OSQP at its cvxpy defaults (eps 1e-5) would itself differ from both by ~1e-4."""
+    from scipy.optimize import minimize
+    Ab = np.load(os.path.join(GOLDEN, "terminal_sets", "RoadOneCarEnv_29.9_1.5_0_0.npy"))
+    qp = orc.CondensedQP("RoadOneCarEnv", 20, Ab)
+    goal = np.array([29.9, 1.5, 0, 0])
+    rng = np.random.default_rng(0)
+    x0 = rng.uniform([5, -3, -np.pi / 8, -1], [30, 3, np.pi / 8, 5], size=(10, 4))
+    u, obj, status, polished, slack = orc.qp_solve_exact(qp, x0, goal)
+    checked = 0
+    for i in np.flatnonzero((status == 0) & polished)[:5]:
+        q = qp.lin(x0[i:i + 1], goal)[0]
+        ub = qp.rhs(x0[i:i + 1])[0]
+        res = minimize(lambda z: 0.5 * z @ qp.H @ z + q @ z, np.zeros(qp.n), jac=lambda z: qp.H @ z + q,
+                       constraints=[{"type": "ineq", "fun": lambda z: ub - qp.G @ z, "jac": lambda z: -qp.G}],
+                       method="SLSQP", options={"ftol": 1e-14, "maxiter": 500})
+        assert (qp.G @ res.x - ub).max() <= 1e-7
+        assert abs(res.fun - obj[i]) <= 1e-8 * abs(obj[i])
+        assert np.abs(res.x - u[i]).max() <= 1e-3
+        assert obj[i] <= res.fun + 1e-9 * abs(obj[i])          # the oracle's point is at least as good
+        checked += 1
+    assert checked >= 3

@@ -322,3 +322,36 @@ def test_config4_monte_carlo_properties(torch_cuda):
     traj = small["traj"].cpu().numpy()
     for r in np.flatnonzero(f >= 0)[:50]:
         assert np.array_equal(traj[f[r]:, :, r], np.repeat(traj[f[r]:f[r] + 1, :, r], 60 - f[r], axis=0))
+
+
+@pytest.mark.parametrize("terminal,inputs,state", [(False, True, False), (False, False, False), (True, False, True),
+                                                   (False, True, True), (True, True, False)])
+def test_constraint_block_switches(torch_cuda, terminal, inputs, state):
+    """The reference's constructor flags (terminal_constraint / input_constraint / state_constraint, lib/mpc.py:22-31)
+    switch whole constraint blocks off; the condensed problem then has no general rows, no box, or neither."""
+    from oracle import carmpc_oracle as orc
+    from carmpc_b200.batch import BatchQP
+    env = make_env("RoadOneCarEnv", [29.9, 1.5, 0, 0])
+    c = make_controller(env, 10, terminal_constraint=terminal, input_constraint=inputs, state_constraint=state)
+    bq = BatchQP.from_controller(c)
+    Ab = np.load(os.path.join(GOLDEN, "terminal_sets", FIXTURE["RoadOneCarEnv"]))
+    oq = orc.CondensedQP("RoadOneCarEnv", 10, Ab, use_terminal=terminal, use_input=inputs, use_state=state)
+    g = np.array(c.goal, dtype=float)
+    x0 = _states(c, 120, seed=5, spread=(6.0, 1.0, 0.2, 1.5))
+    res = bq.solve_host(x0, want_u_full=True)
+    if not (terminal or state):
+        assert (res.status == 0).all()                     # nothing but (at most) the input box: always feasible
+    if not (terminal or inputs or state):
+        want = -np.linalg.solve(oq.H, oq.lin(x0, g).T).T    # unconstrained optimum
+        np.testing.assert_allclose(res.u_full, want, atol=1e-8)
+        return
+    ue, obje, ste, polished, slack = orc.qp_solve_exact(oq, x0, g)
+    ok = (ste == 0) & polished & (np.abs(slack) > 1e-6) & (res.status == 0)
+    assert ok.sum() >= 20
+    assert np.abs(res.u_full[ok] - ue[ok]).max() <= U_TOL
+    assert (np.abs(res.objective[ok] - obje[ok]) / np.maximum(1, np.abs(obje[ok]))).max() <= OBJ_RTOL
+    if inputs:                                             # with a finite input box the flags are exact
+        band = np.abs(slack) <= 1e-6
+        np.testing.assert_array_equal(np.where(res.status == 0, 0, 1)[~band], ste[~band])
+    else:                                                  # without it a feasible state is never called infeasible
+        assert not ((res.status == 1) & (ste == 0)).any()
