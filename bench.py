@@ -299,6 +299,62 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "d2h_bytes_per_step": int(words * 4 + 8),
                     "call": "carmpc_membership_grid (axes on the host, coordinates generated in-kernel) + D2H of the bitset"}
 
+    # ---- the rollout form of the same test (lib/terminal_set.py:53-59, 198-200 sampled): k* + 1 closed-loop steps, state rows
+    # at every step, input rows at t = 0; float32 screen over the expanded rows + float64 step-by-step rollout ----------
+    rollout = None
+    if not args.skip_rollout:
+        from carmpc_b200.batch import RolloutEvaluator
+        from carmpc_b200.lib.environments import RoadMultipleCarsEnv
+        k_star = 16
+        rv = RolloutEvaluator.from_env(RoadMultipleCarsEnv(), k_star)
+        rcount = torch.zeros(1, dtype=torch.int64, device=dev)
+        for _ in range(3):
+            rv.contains_bits(x, y, psi, v, bits=bits[0], count=rcount)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(args.rollout_steps):
+            rv.contains_bits(x, y, psi, v, bits=bits[0], count=rcount)
+        r1.record()
+        barrier()
+        r_ms = r0.elapsed_time(r1) / args.rollout_steps
+        tr = torch.tensor([r_ms], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        r_ms = float(tr.item())
+        r_members = int(rcount.item())
+        # the plain float64 kernel (one sample per thread; selected when the first violated step is requested)
+        rv.contains_bits(x, y, psi, v, want_first_violation=True, bits=bits[0], count=rcount)
+        torch.cuda.synchronize()
+        r0.record()
+        for _ in range(3):
+            rv.contains_bits(x, y, psi, v, want_first_violation=True, bits=bits[0], count=rcount)
+        r1.record()
+        torch.cuda.synchronize()
+        exact_ms = r0.elapsed_time(r1) / 3
+        peak, _ = _peaks()
+        s_rows, r_in = len(rv.b_con), len(rv.b_in)
+        rollout = {"metric": "rollout-form terminal-set samples/s", "value": world * n / (r_ms * 1e-3), "unit": "samples/s",
+                   "ms_per_step": r_ms, "steps": args.rollout_steps, "k_steps": k_star, "state_rows": s_rows, "input_rows": r_in,
+                   "screen_rows": s_rows * (k_star + 1) + r_in, "members": r_members, "members_hrep": members,
+                   "float64_kernel_ms": exact_ms, "float64_kernel_samples_per_s": n / (exact_ms * 1e-3),
+                   "float64_kernel_note": "rollout_kernel, also writes the first violated step (4 B/sample)",
+                   "roofline": {"bound": "hbm", "achieved": n * BYTES_PER_SAMPLE / (r_ms * 1e-3) / 1e9, "peak": peak,
+                                "unit": "GB/s", "frac": n * BYTES_PER_SAMPLE / (r_ms * 1e-3) / 1e9 / peak,
+                                "kernel": "membership_tma_kernel<1, rollout>"},
+                   "flop_per_sample_float64_form": (k_star + 1) * 8 * s_rows + 32 * k_star + 32}
+        if rank == 0 and world == 1 and not args.skip_cpu:
+            from oracle import c_oracle
+            cols = _cpu_sample(2_000_000)
+            t0 = time.perf_counter()
+            passes = 0
+            while time.perf_counter() - t0 < 4.0:
+                c_oracle.rollout_bits(rv.A_k, rv.A_con, rv.b_con, rv.A_in, rv.b_in, rv.goal, k_star, 0, *cols)
+                passes += 1
+            rollout["cpu_baseline"] = {"value": passes * 2_000_000 / (time.perf_counter() - t0), "unit": "samples/s",
+                                       "cores": c_oracle.max_threads(), "kind": "port",
+                                       "sample": f"{passes} passes over a 2000000-point strided slice of the 10^8 grid"}
+
     qp = None
     if not args.skip_qp:
         try:
@@ -342,6 +398,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                          "kernel": "membership_tma_kernel<1>" if args.mode == 1 else "membership_kernel<0,true>",
                          "bytes_per_sample": BYTES_PER_SAMPLE, "algorithmic_bytes_per_launch": n * BYTES_PER_SAMPLE},
             "cpu_baseline": cpu,
+            "rollout": rollout,
             "qp": qp,
         }
         print(json.dumps(line), flush=True)
@@ -361,6 +418,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-qp", action="store_true")
+    ap.add_argument("--skip-rollout", action="store_true")
+    ap.add_argument("--rollout-steps", type=int, default=20)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--qp-states", type=int, default=1_000_000)
     ap.add_argument("--qp-steps", type=int, default=5)

@@ -93,8 +93,11 @@ struct Polytope : HandleBase {
 struct Rollout : HandleBase {
     int s = 0, rin = 0, k_steps = 0, input_mode = 0;
     double* d_data = nullptr;        // [Ak 16 | goal 4 | Acon s*4 | bcon s | Ain rin*4 | bin rin]
+    RowF32* d_rows32 = nullptr;      // float32 screen: expanded rows a_r A_k^t in absolute coordinates (null: exact kernel only)
+    int rows_padded = 0;
+    float beta0 = 0.f, beta1 = 0.f;
     HostStage stage;
-    ~Rollout() override { cudaFree(d_data); }
+    ~Rollout() override { cudaFree(d_data); cudaFree(d_rows32); }
 };
 
 // spread the 8 bits of a byte to every fourth bit position (bit j -> bit 4 j)
@@ -130,6 +133,66 @@ __device__ __forceinline__ void decide64(const double* __restrict__ s_rows, int 
             for (int k = 0; k < kNS; ++k) in[k] &= (fma(a3, v[k], fma(a2, p[k], fma(a1, y[k], a0 * x[k]))) <= b);
         }
     }
+}
+
+// What the float64 decision works on: KIND 0 = the H-rep rows (rows x 5), KIND 1 = the rollout data
+// [Ak 16 | goal 4 | Acon s*4 | bcon s | Ain rin*4 | bin rin] (the float32 screen then runs on the expanded rows a_r A_k^t).
+struct ExactSpec {
+    int len;                 // doubles staged in shared memory
+    int rows;                // KIND 0
+    int s, rin, k_steps, input_mode;   // KIND 1
+};
+
+// float64 decision of the rollout form for the NS samples of this thread: the contract chain of rollout_kernel
+// (oracle/carmpc_oracle.c, lib/terminal_set.py:53-59 sampled), step by step
+__device__ __forceinline__ void rollout64(const double* __restrict__ s_data, const ExactSpec& es, const double (&x)[kNS],
+                                          const double (&y)[kNS], const double (&p)[kNS], const double (&v)[kNS],
+                                          bool (&in)[kNS]) {
+    const double* Ak = s_data;
+    const double* goal = s_data + 16;
+    const double* Acon = s_data + 20;
+    const double* bcon = Acon + 4 * es.s;
+    const double* Ain = bcon + es.s;
+    const double* bin = Ain + 4 * es.rin;
+    double e0[kNS], e1[kNS], e2[kNS], e3[kNS];
+#pragma unroll
+    for (int k = 0; k < kNS; ++k) { e0[k] = x[k] - goal[0]; e1[k] = y[k] - goal[1]; e2[k] = p[k] - goal[2]; e3[k] = v[k] - goal[3]; }
+    for (int t = 0; t <= es.k_steps; ++t) {
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < kNS; ++k) any |= in[k];
+        if (!__any_sync(0xffffffffu, any)) break;
+        for (int r = 0; r < es.s; ++r) {
+            const double* a = Acon + 4 * r;
+            const double a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3], b = bcon[r];
+#pragma unroll
+            for (int k = 0; k < kNS; ++k) in[k] &= (fma(a3, e3[k], fma(a2, e2[k], fma(a1, e1[k], a0 * e0[k]))) <= b);
+        }
+        if (t == 0 || es.input_mode == 1) {
+            for (int r = 0; r < es.rin; ++r) {
+                const double* a = Ain + 4 * r;
+                const double a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3], b = bin[r];
+#pragma unroll
+                for (int k = 0; k < kNS; ++k) in[k] &= (fma(a3, e3[k], fma(a2, e2[k], fma(a1, e1[k], a0 * e0[k]))) <= b);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kNS; ++k) {
+            const double n0 = fma(Ak[3], e3[k], fma(Ak[2], e2[k], fma(Ak[1], e1[k], Ak[0] * e0[k])));
+            const double n1 = fma(Ak[7], e3[k], fma(Ak[6], e2[k], fma(Ak[5], e1[k], Ak[4] * e0[k])));
+            const double n2 = fma(Ak[11], e3[k], fma(Ak[10], e2[k], fma(Ak[9], e1[k], Ak[8] * e0[k])));
+            const double n3 = fma(Ak[15], e3[k], fma(Ak[14], e2[k], fma(Ak[13], e1[k], Ak[12] * e0[k])));
+            e0[k] = n0; e1[k] = n1; e2[k] = n2; e3[k] = n3;
+        }
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ void decide_exact(const double* __restrict__ s_rows, const ExactSpec& es, const double (&x)[kNS],
+                                             const double (&y)[kNS], const double (&p)[kNS], const double (&v)[kNS],
+                                             bool (&in)[kNS]) {
+    if (KIND == 0) decide64(s_rows, es.rows, x, y, p, v, in);
+    else rollout64(s_rows, es, x, y, p, v, in);
 }
 
 // float32 screen: in[k] becomes "surely inside"; returns through amb[k] the samples only the float64 chain can decide
@@ -202,8 +265,8 @@ __device__ __forceinline__ void block_count(int warp_members, unsigned long long
 }
 
 __device__ __forceinline__ void stage_rows(const double* __restrict__ g_rows, const RowF32* __restrict__ g_rows32,
-                                           int rows, int rows_padded, double* s_rows, RowF32* s_rows32) {
-    for (int i = threadIdx.x; i < rows * 5; i += blockDim.x) s_rows[i] = g_rows[i];
+                                           int exact_len, int rows_padded, double* s_rows, RowF32* s_rows32) {
+    for (int i = threadIdx.x; i < exact_len; i += blockDim.x) s_rows[i] = g_rows[i];
     for (int i = threadIdx.x; i < rows_padded; i += blockDim.x) s_rows32[i] = g_rows32[i];
     __syncthreads();
 }
@@ -220,16 +283,16 @@ __device__ __forceinline__ void load4(const double* __restrict__ g, int64_t i0, 
     }
 }
 
-template <int MODE, bool VEC>
+template <int MODE, bool VEC, int KIND>
 __global__ void __launch_bounds__(kThreads)
-membership_kernel(const double* __restrict__ g_rows, const RowF32* __restrict__ g_rows32, int rows, int rows_padded,
+membership_kernel(const double* __restrict__ g_rows, const RowF32* __restrict__ g_rows32, const ExactSpec es, int rows_padded,
                   const ScreenConst sc, const double* __restrict__ gx, const double* __restrict__ gy,
                   const double* __restrict__ gp, const double* __restrict__ gv, int64_t n,
                   uint32_t* __restrict__ bits, unsigned long long* __restrict__ count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_rows = reinterpret_cast<double*>(smem_raw);
-    RowF32* s_rows32 = reinterpret_cast<RowF32*>(s_rows + ((rows * 5 + 1) & ~1));
-    stage_rows(g_rows, g_rows32, rows, rows_padded, s_rows, s_rows32);
+    RowF32* s_rows32 = reinterpret_cast<RowF32*>(s_rows + ((es.len + 1) & ~1));
+    stage_rows(g_rows, g_rows32, es.len, rows_padded, s_rows, s_rows32);
 
     int members = 0;
     const int64_t n_chunks = (n + kChunk - 1) / kChunk;
@@ -241,7 +304,7 @@ membership_kernel(const double* __restrict__ g_rows, const RowF32* __restrict__ 
         if (MODE == 0) {
             double x[kNS], y[kNS], p[kNS], v[kNS];
             load4<VEC>(gx, i0, n, x); load4<VEC>(gy, i0, n, y); load4<VEC>(gp, i0, n, p); load4<VEC>(gv, i0, n, v);
-            decide64(s_rows, rows, x, y, p, v, in);
+            decide_exact<KIND>(s_rows, es, x, y, p, v, in);
         } else {
             float xf[kNS], yf[kNS], pf[kNS], vf[kNS];
             {
@@ -260,7 +323,7 @@ membership_kernel(const double* __restrict__ g_rows, const RowF32* __restrict__ 
                 // read again (L2) and the float64 chain decides, exactly as in mode 0
                 double x[kNS], y[kNS], p[kNS], v[kNS];
                 load4<VEC>(gx, i0, n, x); load4<VEC>(gy, i0, n, y); load4<VEC>(gp, i0, n, p); load4<VEC>(gv, i0, n, v);
-                decide64(s_rows, rows, x, y, p, v, amb);
+                decide_exact<KIND>(s_rows, es, x, y, p, v, amb);
 #pragma unroll
                 for (int k = 0; k < kNS; ++k) in[k] |= amb[k];
             }
@@ -303,9 +366,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-template <int MODE>
+template <int MODE, int KIND>
 __global__ void __launch_bounds__(kThreads)
-membership_tma_kernel(const double* __restrict__ g_rows, const RowF32* __restrict__ g_rows32, int rows, int rows_padded,
+membership_tma_kernel(const double* __restrict__ g_rows, const RowF32* __restrict__ g_rows32, const ExactSpec es, int rows_padded,
                       const ScreenConst sc, const double* __restrict__ gx, const double* __restrict__ gy,
                       const double* __restrict__ gp, const double* __restrict__ gv, int64_t n_tiles,
                       uint32_t* __restrict__ bits, unsigned long long* __restrict__ count) {
@@ -314,7 +377,7 @@ membership_tma_kernel(const double* __restrict__ g_rows, const RowF32* __restric
     double* s_stage = reinterpret_cast<double*>(smem_raw);                       // [kWarps][kStages][4][kTile]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + (size_t)kWarps * kStages * 4 * kTile);   // [kWarps][kStages]
     double* s_rows = reinterpret_cast<double*>(s_bar + kWarps * kStages);
-    RowF32* s_rows32 = reinterpret_cast<RowF32*>(s_rows + ((rows * 5 + 1) & ~1));
+    RowF32* s_rows32 = reinterpret_cast<RowF32*>(s_rows + ((es.len + 1) & ~1));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double* src[4] = {gx, gy, gp, gv};
     constexpr uint32_t kArrayBytes = kTile * sizeof(double);
@@ -326,7 +389,7 @@ membership_tma_kernel(const double* __restrict__ g_rows, const RowF32* __restric
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    stage_rows(g_rows, g_rows32, rows, rows_padded, s_rows, s_rows32);          // ends with __syncthreads()
+    stage_rows(g_rows, g_rows32, es.len, rows_padded, s_rows, s_rows32);        // ends with __syncthreads()
 
     const int64_t first = (int64_t)blockIdx.x * kWarps + warp;                   // this warp's tiles: first, first + stride, ...
     const int64_t stride = (int64_t)gridDim.x * kWarps;
@@ -372,7 +435,7 @@ membership_tma_kernel(const double* __restrict__ g_rows, const RowF32* __restric
 #pragma unroll
         for (int k = 0; k < kNS; ++k) in[k] = true;
         if (MODE == 0) {
-            decide64(s_rows, rows, x, y, p, v, in);
+            decide_exact<KIND>(s_rows, es, x, y, p, v, in);
         } else {
             bool amb[kNS];
             screen32(s_rows32, rows_padded, sc, xf, yf, pf, vf, in, amb);
@@ -385,7 +448,7 @@ membership_tma_kernel(const double* __restrict__ g_rows, const RowF32* __restric
                 double x2[kNS], y2[kNS], p2[kNS], v2[kNS];
                 load4<true>(gx, i0, n_tiles * kTile, x2); load4<true>(gy, i0, n_tiles * kTile, y2);
                 load4<true>(gp, i0, n_tiles * kTile, p2); load4<true>(gv, i0, n_tiles * kTile, v2);
-                decide64(s_rows, rows, x2, y2, p2, v2, amb);
+                decide_exact<KIND>(s_rows, es, x2, y2, p2, v2, amb);
 #pragma unroll
                 for (int k = 0; k < kNS; ++k) in[k] |= amb[k];
             }
@@ -412,7 +475,7 @@ membership_grid_kernel(const double* __restrict__ g_rows, const RowF32* __restri
     double* s_axes = reinterpret_cast<double*>(s_rows32 + rows_padded);
     const int axes_len = gd.offset[3] + gd.dims[3];
     for (int i = threadIdx.x; i < axes_len; i += blockDim.x) s_axes[i] = g_axes[i];
-    stage_rows(g_rows, g_rows32, rows, rows_padded, s_rows, s_rows32);
+    stage_rows(g_rows, g_rows32, rows * 5, rows_padded, s_rows, s_rows32);
 
     int members = 0;
     const int64_t n_chunks = (n + kChunk - 1) / kChunk;
@@ -528,7 +591,7 @@ rollout_kernel(const double* __restrict__ g_data, int s, int rin, int k_steps, i
 
 // ---- host side -----------------------------------------------------------------------------------------------------------
 static int pad_rows(int rows) { return (rows + 7) & ~7; }
-static size_t membership_smem(int rows) { return sizeof(double) * ((rows * 5 + 1) & ~1) + sizeof(RowF32) * pad_rows(rows); }
+static size_t membership_smem(int rows) { return sizeof(double) * ((rows * 5 + 1) & ~1) + sizeof(RowF32) * pad_rows(rows); }   // grid kernel
 
 static int grid_blocks(int64_t n_chunks, int per_sm) {
     const int64_t cap = (int64_t)sm_count() * per_sm;
@@ -542,52 +605,52 @@ static ScreenConst screen_const(const Polytope* P) {
     return sc;
 }
 
-static size_t membership_tma_smem(int rows) {
+static size_t scan_smem(int exact_len, int rows_padded) {
+    return sizeof(double) * ((exact_len + 1) & ~1) + sizeof(RowF32) * rows_padded;
+}
+static size_t scan_tma_smem(int exact_len, int rows_padded) {
     return sizeof(double) * (kThreads / 32) * kStages * 4 * kTile + sizeof(uint64_t) * (kThreads / 32) * kStages +
-           membership_smem(rows) + 16;
+           scan_smem(exact_len, rows_padded) + 16;
 }
 
 static bool g_use_tma = getenv("CARMPC_NO_TMA") == nullptr;          // development knob
 
-static int launch_membership(Polytope* P, const double* x, const double* y, const double* p, const double* v,
-                             int64_t n, uint32_t* bits, unsigned long long* count, int mode, cudaStream_t st) {
+// Streaming scan shared by the H-rep membership (KIND 0) and the screened rollout form (KIND 1).
+template <int KIND>
+static int launch_scan(const double* d_exact, const RowF32* d_rows32, const ExactSpec es, int rows_padded,
+                       const ScreenConst sc, const double* x, const double* y, const double* p, const double* v,
+                       int64_t n, uint32_t* bits, unsigned long long* count, int mode, cudaStream_t st) {
     if (n == 0) return CARMPC_OK;
     const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
                        reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
     // Bulk-async staged kernel for the whole 128-sample tiles of 16-byte aligned arrays; whatever is left (a ragged
     // tail of fewer than 128 samples, or unaligned arrays) goes through the plain-load kernel below.
-    int64_t done = 0;
     // (mode 0 is FP64-pipe bound and prefers the higher occupancy of the plain kernel: measured 0.72 vs 0.82 ms)
     if (vec && g_use_tma && mode == 1 && n >= 64 * (int64_t)kChunk) {
         const int64_t n_tiles = n / kTile;
         const int64_t n_chunks = (n_tiles + kThreads / 32 - 1) / (kThreads / 32);
-        const size_t smem = membership_tma_smem(P->rows);
-#define LAUNCH_TMA(M)                                                                                             \
-    do {                                                                                                          \
-        CARMPC_CUDA(cudaFuncSetAttribute(membership_tma_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        int per_sm = 0;                                                                                           \
-        CARMPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, membership_tma_kernel<M>, kThreads, smem)); \
-        const int blocks = grid_blocks(n_chunks, per_sm > 0 ? per_sm : 1);                                        \
-        membership_tma_kernel<M><<<blocks, kThreads, smem, st>>>(P->d_rows, P->d_rows32, P->rows, pad_rows(P->rows), \
-                                                                 screen_const(P), x, y, p, v, n_tiles, bits, count); \
-    } while (0)
-        if (mode == 0) LAUNCH_TMA(0); else LAUNCH_TMA(1);
-#undef LAUNCH_TMA
+        const size_t smem = scan_tma_smem(es.len, rows_padded);
+        CARMPC_CUDA(cudaFuncSetAttribute(membership_tma_kernel<1, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CARMPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, membership_tma_kernel<1, KIND>, kThreads, smem));
+        const int blocks = grid_blocks(n_chunks, per_sm > 0 ? per_sm : 1);
+        membership_tma_kernel<1, KIND><<<blocks, kThreads, smem, st>>>(d_exact, d_rows32, es, rows_padded, sc, x, y, p, v,
+                                                                       n_tiles, bits, count);
         CARMPC_CUDA(cudaGetLastError());
-        done = n_tiles * kTile;
+        const int64_t done = n_tiles * kTile;
         if (done == n) return CARMPC_OK;
         x += done; y += done; p += done; v += done; bits += done >> 5; n -= done;
     }
-    const size_t smem = membership_smem(P->rows);
+    const size_t smem = scan_smem(es.len, rows_padded);
     const int64_t n_chunks = (n + kChunk - 1) / kChunk;
     // persistent grid: exactly the number of CTAs that are resident at once (a multiple of the SM count)
 #define LAUNCH(M, V)                                                                                              \
     do {                                                                                                          \
         int per_sm = 0;                                                                                           \
-        CARMPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, membership_kernel<M, V>, kThreads, smem)); \
+        CARMPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, membership_kernel<M, V, KIND>, kThreads, smem)); \
         const int blocks = grid_blocks(n_chunks, per_sm > 0 ? per_sm : 1);                                        \
-        membership_kernel<M, V><<<blocks, kThreads, smem, st>>>(P->d_rows, P->d_rows32, P->rows, pad_rows(P->rows),    \
-                                                                screen_const(P), x, y, p, v, n, bits, count);     \
+        membership_kernel<M, V, KIND><<<blocks, kThreads, smem, st>>>(d_exact, d_rows32, es, rows_padded, sc, x, y, p, v, \
+                                                                      n, bits, count);                            \
     } while (0)
     if (mode == 0) {
         if (vec) LAUNCH(0, true); else LAUNCH(0, false);
@@ -599,9 +662,28 @@ static int launch_membership(Polytope* P, const double* x, const double* y, cons
     return CARMPC_OK;
 }
 
+static int launch_membership(Polytope* P, const double* x, const double* y, const double* p, const double* v,
+                             int64_t n, uint32_t* bits, unsigned long long* count, int mode, cudaStream_t st) {
+    ExactSpec es{};
+    es.len = P->rows * 5;
+    es.rows = P->rows;
+    return launch_scan<0>(P->d_rows, P->d_rows32, es, pad_rows(P->rows), screen_const(P), x, y, p, v, n, bits, count, mode, st);
+}
+
+static const bool g_rollout_exact_only = getenv("CARMPC_ROLLOUT_EXACT") != nullptr;    // development knob
+
 static int launch_rollout(Rollout* R, const double* x, const double* y, const double* p, const double* v, int64_t n,
                           uint32_t* bits, int32_t* first, unsigned long long* count, cudaStream_t st) {
     if (n == 0) return CARMPC_OK;
+    if (first == nullptr && R->d_rows32 != nullptr && !g_rollout_exact_only) {
+        // float32 screen over the expanded rows a_r A_k^t, float64 step-by-step rollout for the samples it cannot decide
+        ExactSpec es{};
+        es.len = 20 + 5 * R->s + 5 * R->rin;
+        es.s = R->s; es.rin = R->rin; es.k_steps = R->k_steps; es.input_mode = R->input_mode;
+        ScreenConst sc;
+        sc.beta0 = R->beta0; sc.beta1 = R->beta1;
+        return launch_scan<1>(R->d_data, R->d_rows32, es, R->rows_padded, sc, x, y, p, v, n, bits, count, 1, st);
+    }
     const size_t smem = sizeof(double) * (20 + 5 * R->s + 5 * R->rin);
     const int64_t n_chunks = (n + kThreads - 1) / kThreads;
     rollout_kernel<<<grid_blocks(n_chunks, 8), kThreads, smem, st>>>(R->d_data, R->s, R->rin, R->k_steps, R->input_mode,
@@ -915,6 +997,72 @@ int carmpc_rollout_create(const double* h_Ak, const double* h_Acon, const double
         set_error("carmpc_rollout_create: %s", cudaGetErrorString(cudaGetLastError()));
         delete R;
         return CARMPC_ERR_CUDA;
+    }
+    // Float32 screen.  The row value at step t is linear in the sample: a_r A_k^t (p - goal) <= b_r, so the rollout is
+    // a membership test against the expanded rows g = a_r A_k^t, b' = b_r + g . goal (absolute coordinates).  They are
+    // built here in long double, stored as float32 and evaluated like the H-rep screen; a sample is decided by the
+    // screen only when its smallest margin clears the bound
+    //     8 u32 (|b'| + sum |g_k| |p_k|)   float32 evaluation (as for the H-rep rows)
+    //   + c64 G (sum |p_k| + |goal|_1)     float64 step-by-step rollout vs the exact linear functional, with
+    //                                      G = max entry of |a_r| |A_k|^t and c64 = 16 (k + 3) 2^-53,
+    // everything else is re-evaluated by the float64 contract chain (rollout64).
+    const long total_rows = (long)s * (k_steps + 1) + (long)rin * (input_check_mode == 1 ? k_steps + 1 : 1);
+    if (total_rows > 0 && total_rows <= kMaxRows) {
+        std::vector<RowF32> r32(pad_rows((int)total_rows));
+        for (RowF32& q : r32) { q.na0 = q.na1 = q.na2 = q.na3 = 0.f; q.b = INFINITY; q.pad0 = q.pad1 = q.pad2 = 0.f; }
+        long double M[16], Mabs[16];
+        for (int i = 0; i < 16; ++i) M[i] = Mabs[i] = (i % 5 == 0) ? 1.0L : 0.0L;
+        long double l1max = 0, bmax = 0, gabs_max = 0, goal1 = 0;
+        for (int k = 0; k < 4; ++k) goal1 += fabsl((long double)h_goal[k]);
+        bool finite = true;
+        int w = 0;
+        auto emit = [&](const double* a, double b) {
+            long double g[4], ga[4], bp = b, l1 = 0;
+            for (int j = 0; j < 4; ++j) {
+                g[j] = ga[j] = 0;
+                for (int i = 0; i < 4; ++i) { g[j] += (long double)a[i] * M[4 * i + j]; ga[j] += fabsl((long double)a[i]) * Mabs[4 * i + j]; }
+                bp += g[j] * (long double)h_goal[j];
+                l1 += fabsl(g[j]);
+                gabs_max = std::max(gabs_max, ga[j]);
+            }
+            RowF32 q;
+            q.na0 = (float)-g[0]; q.na1 = (float)-g[1]; q.na2 = (float)-g[2]; q.na3 = (float)-g[3];
+            q.b = (float)bp;
+            q.pad0 = q.pad1 = q.pad2 = 0.f;
+            finite = finite && std::isfinite(q.na0) && std::isfinite(q.na1) && std::isfinite(q.na2) && std::isfinite(q.na3) && !std::isnan(q.b);
+            if (b == INFINITY) q.b = INFINITY;
+            r32[w++] = q;
+            l1max = std::max(l1max, l1);
+            if (std::isfinite((double)bp)) bmax = std::max(bmax, fabsl(bp));
+        };
+        for (int t = 0; t <= k_steps; ++t) {
+            for (int r = 0; r < s; ++r) emit(h_Acon + 4 * r, h_bcon[r]);
+            if (t == 0 || input_check_mode == 1)
+                for (int r = 0; r < rin; ++r) emit(h_Ain + 4 * r, h_bin[r]);
+            long double N[16], Na[16];
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) {
+                    N[4 * i + j] = Na[4 * i + j] = 0;
+                    for (int l = 0; l < 4; ++l) {
+                        N[4 * i + j] += (long double)h_Ak[4 * i + l] * M[4 * l + j];
+                        Na[4 * i + j] += fabsl((long double)h_Ak[4 * i + l]) * Mabs[4 * l + j];
+                    }
+                }
+            for (int i = 0; i < 16; ++i) { M[i] = N[i]; Mabs[i] = Na[i]; }
+        }
+        const long double u8 = 8.0L * 5.9604644775390625e-08L, c64 = 16.0L * (k_steps + 3) * 1.1102230246251565e-16L;
+        const long double b0 = u8 * bmax * 1.000001L + c64 * gabs_max * goal1 + 1e-37L, b1 = u8 * l1max * 1.000001L + c64 * gabs_max + 1e-37L;
+        if (finite && std::isfinite((double)b0) && std::isfinite((double)b1) && (double)b0 < 1e30 && (double)b1 < 1e30) {
+            R->beta0 = nextafterf((float)b0, INFINITY);
+            R->beta1 = nextafterf((float)b1, INFINITY);
+            R->rows_padded = (int)r32.size();
+            if (cudaMalloc(&R->d_rows32, sizeof(RowF32) * r32.size()) != cudaSuccess ||
+                cudaMemcpy(R->d_rows32, r32.data(), sizeof(RowF32) * r32.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+                set_error("carmpc_rollout_create: %s", cudaGetErrorString(cudaGetLastError()));
+                delete R;
+                return CARMPC_ERR_CUDA;
+            }
+        }
     }
     *handle = R;
     return CARMPC_OK;

@@ -132,6 +132,11 @@ def test_rollout_bit_exact_vs_oracle_and_equals_hrep(torch_cuda, file):
         np.testing.assert_array_equal(_bits_np(bits), want_bits)
         np.testing.assert_array_equal(first.cpu().numpy(), want_first)
         assert int(count.item()) == want_cnt
+        # without the per-sample step output the float32-screened path runs (expanded rows a_r A_k^t, float64 rollout
+        # for the samples the screen cannot decide): same bits
+        bits, count = ev.contains_bits(*_dev(torch_cuda, *p.T))
+        np.testing.assert_array_equal(_bits_np(bits), want_bits)
+        assert int(count.item()) == want_cnt
     # the oracle's setup and the product's are the same numbers
     Ak, K, Ac, bc, Ai, bi = orc.rollout_setup(env_name, goal)
     ev = RolloutEvaluator.from_env(env, k)
@@ -148,6 +153,53 @@ def test_rollout_bit_exact_vs_oracle_and_equals_hrep(torch_cuda, file):
     _, _, margin_r = orc.rollout_membership(env_name, goal, k, *p.T)
     band = (np.abs(margin_h) <= 1e-6) | (np.abs(margin_r) <= 1e-6)
     assert not (diff & ~band).any(), f"{(diff & ~band).sum()} disagreements outside the boundary band"
+
+
+@pytest.mark.parametrize("env_name", ["RoadOneCarEnv", "RoadMultipleCarsEnv", "RoadEnv"])
+def test_screened_rollout_on_boundary_samples(torch_cuda, env_name):
+    """Samples placed on (and a few ulps around) facets of the rollout set, ties included, plus non-finite and huge
+    coordinates: the screened path must return the float64 step-by-step decision of the oracle for every one."""
+    from carmpc_b200.batch import RolloutEvaluator
+    from oracle import c_oracle, carmpc_oracle as orc
+    env = make_env(env_name)
+    goal = np.array(env.goal, dtype=float)
+    k = K_STAR[env_name]
+    ev = RolloutEvaluator.from_env(env, k)
+    Ak, K, Ac, bc, Ai, bi = orc.rollout_setup(env_name, list(goal))
+    rng = np.random.default_rng(23)
+    rows, M = [], np.eye(4)
+    for t in range(k + 1):
+        for a, b in zip(Ac, bc):
+            rows.append((a @ M, b))
+        if t == 0:
+            for a, b in zip(Ai, bi):
+                rows.append((a @ M, b))
+        M = Ak @ M
+    pts = []
+    for g, b in rows:
+        if not np.isfinite(b) or np.linalg.norm(g) < 1e-9:
+            continue
+        for _ in range(40):
+            e = rng.uniform(-1, 1, 4) * np.array([10.0, 2.0, 0.4, 3.0])
+            e = e + g * (b - g @ e) / (g @ g)                       # projected onto the facet g e = b
+            for scale in (0.0, 1e-15, -1e-15, 3e-9, -3e-9, 1e-6, -1e-6):
+                pts.append(goal + e + scale * g / np.linalg.norm(g))
+    pts = np.array(pts)
+    special = np.array([[np.nan, 1.5, 0, 0], [30, np.inf, 0, 0], [30, 1.5, -np.inf, 0], [1e300, 1.5, 0, 0], [-1e300, 1e300, 0, 0],
+                        [1e38, 0, 0, 0], list(goal), [30, 1.5, 0, 1e-310]])
+    pts = np.vstack((pts, special, pts[:37]))
+    cols = [np.ascontiguousarray(c) for c in pts.T]
+    want_bits, _, want_cnt = c_oracle.rollout_bits(ev.A_k, ev.A_con, ev.b_con, ev.A_in, ev.b_in, goal, k, 0, *cols)
+    bits, count = ev.contains_bits(*_dev(torch_cuda, *cols))
+    np.testing.assert_array_equal(_bits_np(bits), want_bits)
+    assert int(count.item()) == want_cnt and 0 < want_cnt < len(pts)
+    # large aligned batch through the bulk-async path: tile the boundary samples past 64 chunks
+    reps = (70 * 1024) // len(pts) + 1
+    big = [np.ascontiguousarray(np.tile(c, reps)) for c in cols]
+    want_bits, _, want_cnt = c_oracle.rollout_bits(ev.A_k, ev.A_con, ev.b_con, ev.A_in, ev.b_in, goal, k, 0, *big)
+    bits, count = ev.contains_bits(*_dev(torch_cuda, *big))
+    np.testing.assert_array_equal(_bits_np(bits), want_bits)
+    assert int(count.item()) == want_cnt
 
 
 def test_host_pipeline_multi_chunk(torch_cuda):
@@ -173,6 +225,9 @@ def test_host_pipeline_multi_chunk(torch_cuda):
     bits, cnt, first = rv.contains_bits_host(*[c[:m] for c in cols], want_first_violation=True)
     np.testing.assert_array_equal(bits, want_bits)
     np.testing.assert_array_equal(first, want_first)
+    assert cnt == want_cnt
+    bits, cnt = rv.contains_bits_host(*[c[:m] for c in cols])[:2]                  # screened path
+    np.testing.assert_array_equal(bits, want_bits)
     assert cnt == want_cnt
 
 
@@ -211,6 +266,27 @@ def test_config2_full_grid_properties(torch_cuda):
         assert torch.equal(b, bits[lo // 32: hi // 32])
         total += int(c.item())
     assert total == int(count.item())
+    # the whole grid against the C oracle (multi-threaded: 10^8 points in about a second), H-rep and rollout form.
+    # Known answers (reproduced by the oracle on the CPU): 3,028,578 members of the shipped H-rep, 3,026,913 of its
+    # rollout form with k* = 16; the 1,665 differences are exact ties of the H-rep (margin 0) that the rollout form
+    # misses by one rounding of p - goal (margin -7.8e-16): boundary-band samples, enumerated here.
+    from carmpc_b200.batch import RolloutEvaluator
+    host = [t.cpu().numpy() for t in (x, y, psi, v)]
+    want_bits, want_cnt = c_oracle.membership_bits(Ab, *host)
+    np.testing.assert_array_equal(_bits_np(bits), want_bits)
+    assert int(count.item()) == want_cnt == 3_028_578
+    rv = RolloutEvaluator.from_env(make_env("RoadMultipleCarsEnv"), 16)
+    rbits, rcount = rv.contains_bits(x, y, psi, v)
+    want_rbits, _, want_rcnt = c_oracle.rollout_bits(rv.A_k, rv.A_con, rv.b_con, rv.A_in, rv.b_in, rv.goal, 16, 0, *host)
+    np.testing.assert_array_equal(_bits_np(rbits), want_rbits)
+    assert int(rcount.item()) == want_rcnt == 3_026_913
+    differ = np.flatnonzero(unpack_bits(_bits_np(bits), n) != unpack_bits(_bits_np(rbits), n))
+    assert len(differ) == 1665
+    from oracle import carmpc_oracle as orc
+    pts = [h[differ] for h in host]
+    _, margin_h = orc.membership(Ab, *pts)
+    _, _, margin_r = orc.rollout_membership("RoadMultipleCarsEnv", [30, 1.5, 0, 0], 16, *pts)
+    assert np.abs(margin_h).max() <= 1e-6 and np.abs(margin_r).max() <= 1e-6
 
 
 def test_profile_guided_row_order_never_changes_results(torch_cuda):
