@@ -94,8 +94,10 @@ struct Rollout : HandleBase {
     int s = 0, rin = 0, k_steps = 0, input_mode = 0;
     double* d_data = nullptr;        // [Ak 16 | goal 4 | Acon s*4 | bcon s | Ain rin*4 | bin rin]
     RowF32* d_rows32 = nullptr;      // float32 screen: expanded rows a_r A_k^t in absolute coordinates (null: exact kernel only)
-    int rows_padded = 0;
+    int rows_padded = 0, rows32 = 0;
     float beta0 = 0.f, beta1 = 0.f;
+    std::vector<RowF32> h_rows32;    // host copy (re-ordered by the pilot)
+    bool tuned = false;
     HostStage stage;
     ~Rollout() override { cudaFree(d_data); cudaFree(d_rows32); }
 };
@@ -812,6 +814,76 @@ static int tune_row_order(Polytope* P, const double* x, const double* y, const d
 
 static const bool g_auto_tune = getenv("CARMPC_NO_TUNE") == nullptr;       // development knob
 
+// The same idea for the expanded rows of the screened rollout form (up to 512 rows, float32 images: the order is a
+// heuristic, the decisions do not depend on it): masks of `words` 64-bit words per subsample.
+__global__ void __launch_bounds__(256)
+pilot32_kernel(const RowF32* __restrict__ g_rows32, int rows, int words, const double* __restrict__ gx,
+               const double* __restrict__ gy, const double* __restrict__ gp, const double* __restrict__ gv, int64_t n,
+               int64_t stride, int n_sub, unsigned long long* __restrict__ masks) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_sub) return;
+    const int64_t i = (int64_t)k * stride;
+    unsigned long long* out = masks + (size_t)k * words;
+    for (int w = 0; w < words; ++w) out[w] = 0ull;
+    if (i >= n) return;
+    const float x = (float)gx[i], y = (float)gy[i], p = (float)gp[i], v = (float)gv[i];
+    for (int r = 0; r < rows; ++r) {
+        const RowF32 q = g_rows32[r];
+        const float m = fmaf(q.na3, v, fmaf(q.na2, p, fmaf(q.na1, y, fmaf(q.na0, x, q.b))));
+        if (!(m >= 0.f)) out[r >> 6] |= 1ull << (r & 63);
+    }
+}
+
+static int tune_rollout_order(Rollout* R, const double* x, const double* y, const double* p, const double* v, int64_t n,
+                              cudaStream_t st) {
+    R->tuned = true;
+    const int rows = R->rows32;
+    if (rows < 2 || n < 1024 || R->d_rows32 == nullptr) return CARMPC_OK;
+    const int words = (rows + 63) / 64;
+    const int n_sub = (int)std::min<int64_t>(1 << 16, n);
+    const int64_t stride = n / n_sub;
+    unsigned long long* d_masks = nullptr;
+    CARMPC_CUDA(cudaMalloc(&d_masks, sizeof(unsigned long long) * n_sub * words));
+    pilot32_kernel<<<(n_sub + 255) / 256, 256, 0, st>>>(R->d_rows32, rows, words, x, y, p, v, n, stride, n_sub, d_masks);
+    std::vector<unsigned long long> masks((size_t)n_sub * words);
+    cudaError_t err = cudaMemcpyAsync(masks.data(), d_masks, sizeof(unsigned long long) * masks.size(), cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    cudaFree(d_masks);
+    CARMPC_CUDA(err);
+    // greedy cover: the row that rejects most of the subsamples still alive comes next
+    std::vector<int> alive;
+    alive.reserve(n_sub);
+    for (int k = 0; k < n_sub; ++k) {
+        bool any = false;
+        for (int w = 0; w < words; ++w) any = any || masks[(size_t)k * words + w] != 0ull;
+        if (any) alive.push_back(k);
+    }
+    std::vector<int> order;
+    std::vector<char> used(rows, 0);
+    std::vector<int> cnt(rows);
+    while (!alive.empty() && (int)order.size() < rows) {
+        std::fill(cnt.begin(), cnt.end(), 0);
+        for (int k : alive)
+            for (int w = 0; w < words; ++w)
+                for (unsigned long long t = masks[(size_t)k * words + w]; t; t &= t - 1) ++cnt[64 * w + __builtin_ctzll(t)];
+        int best = -1;
+        for (int r = 0; r < rows; ++r) if (!used[r] && (best < 0 || cnt[r] > cnt[best])) best = r;
+        if (best < 0 || cnt[best] == 0) break;
+        used[best] = 1;
+        order.push_back(best);
+        size_t w = 0;
+        for (int k : alive) if (!((masks[(size_t)k * words + (best >> 6)] >> (best & 63)) & 1ull)) alive[w++] = k;
+        alive.resize(w);
+    }
+    for (int r = 0; r < rows; ++r) if (!used[r]) order.push_back(r);       // the rest keeps its relative order
+    std::vector<RowF32> sorted(R->h_rows32);
+    for (int i = 0; i < rows; ++i) sorted[i] = R->h_rows32[order[i]];
+    R->h_rows32.swap(sorted);
+    CARMPC_CUDA(cudaMemcpyAsync(R->d_rows32, R->h_rows32.data(), sizeof(RowF32) * R->h_rows32.size(), cudaMemcpyHostToDevice, st));
+    CARMPC_CUDA(cudaStreamSynchronize(st));
+    return CARMPC_OK;
+}
+
 }  // namespace carmpc
 
 using namespace carmpc;
@@ -1056,6 +1128,8 @@ int carmpc_rollout_create(const double* h_Ak, const double* h_Acon, const double
             R->beta0 = nextafterf((float)b0, INFINITY);
             R->beta1 = nextafterf((float)b1, INFINITY);
             R->rows_padded = (int)r32.size();
+            R->rows32 = (int)total_rows;
+            R->h_rows32 = r32;
             if (cudaMalloc(&R->d_rows32, sizeof(RowF32) * r32.size()) != cudaSuccess ||
                 cudaMemcpy(R->d_rows32, r32.data(), sizeof(RowF32) * r32.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
                 set_error("carmpc_rollout_create: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1078,6 +1152,10 @@ int carmpc_rollout_bitset(void* rollout, const double* d_x, const double* d_y, c
     if (d_count) CARMPC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
     if (n == 0) return CARMPC_OK;
     CARMPC_REQUIRE(d_x && d_y && d_psi && d_v && d_bits, "null device pointer");
+    if (!R->tuned && g_auto_tune && d_first_violation == nullptr && n >= ((int64_t)1 << 20)) {
+        const int rc = tune_rollout_order(R, d_x, d_y, d_psi, d_v, n, st);
+        if (rc != CARMPC_OK) return rc;
+    }
     return launch_rollout(R, d_x, d_y, d_psi, d_v, n, d_bits, d_first_violation,
                           reinterpret_cast<unsigned long long*>(d_count), st);
 }

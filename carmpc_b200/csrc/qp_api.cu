@@ -61,7 +61,7 @@ int QPHandle::ensure_io(int64_t batch, bool want_full) {
 
 QPHandle::~QPHandle() {
     for (void* p : allocations) cudaFree(p);
-    cudaFree(ws_sign); cudaFree(ws_u); cudaFree(ws_status); cudaFree(ws_iters); cudaFree(ws_failed);
+    cudaFree(ws_sign); cudaFree(ws_u); cudaFree(ws_status); cudaFree(ws_iters); cudaFree(ws_failed); cudaFree(ws_failed0);
     cudaFree(ws_counters); cudaFree(ws_total_iters); cudaFree(ws_polished); cudaFree(ws_warm); cudaFree(ws_overflow);
     cudaFree(io_x0_aos); cudaFree(io_x0); cudaFree(io_c); cudaFree(io_u0); cudaFree(io_u0_aos); cudaFree(io_obj); cudaFree(io_full);
     cudaFree(io_status); cudaFree(io_iters);
@@ -76,6 +76,7 @@ int QPHandle::ensure_workspace(int64_t batch) {
     cudaFree(ws_sign); cudaFree(ws_u); cudaFree(ws_status); cudaFree(ws_iters); cudaFree(ws_failed); cudaFree(ws_polished);
     cudaFree(ws_warm); ws_warm = nullptr;
     cudaFree(ws_overflow); ws_overflow = nullptr;
+    cudaFree(ws_failed0); ws_failed0 = nullptr;
     ws_sign = nullptr; ws_u = nullptr; ws_status = nullptr; ws_iters = nullptr; ws_failed = nullptr; ws_polished = nullptr;
     ws_batch = 0;
     CARMPC_CUDA(cudaMalloc(&ws_sign, (size_t)batch * admm.mt));
@@ -84,6 +85,7 @@ int QPHandle::ensure_workspace(int64_t batch) {
     CARMPC_CUDA(cudaMalloc(&ws_iters, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_failed, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_overflow, sizeof(int) * (size_t)batch));
+    CARMPC_CUDA(cudaMalloc(&ws_failed0, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_polished, (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_warm, sizeof(float) * (size_t)batch * admm.mt));
     ws_batch = batch;
@@ -92,7 +94,7 @@ int QPHandle::ensure_workspace(int64_t batch) {
 
 int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, const double* d_c, const int* d_idx,
                     int64_t count, double* d_u0, double* d_objective, int32_t* d_status, int32_t* d_iters,
-                    double* d_u_full, float* d_warm, int warm_in, int warm_out, cudaStream_t st) {
+                    double* d_u_full, float* d_warm, int warm_in, int warm_out, cudaStream_t st, int reuse_active_set) {
     // `stride` is the number of samples the per-sample arrays are sized for; `count` the number solved now
     // (all of them, or those listed in d_idx).
     if (host_only) { set_error("carmpc_qp: this handle was created without a CUDA device; there is no CPU solver"); return CARMPC_ERR_CUDA; }
@@ -100,10 +102,43 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
     if (rc != CARMPC_OK) return rc;
     last_launches = 0;
     last_second_pass = 0;
+    last_reused = 0;
     CARMPC_CUDA(cudaMemsetAsync(ws_counters, 0, sizeof(int) * 8, st));
     CARMPC_CUDA(cudaMemsetAsync(ws_total_iters, 0, sizeof(unsigned long long), st));
     int* status = d_status ? d_status : ws_status;
     int* iters = d_iters ? d_iters : ws_iters;
+
+    PolishBatch pb;
+    memset(&pb, 0, sizeof(pb));
+    pb.x0 = d_x0; pb.stride = stride; pb.cdist = d_c;
+    for (int c = 0; c < 4; ++c) pb.xref[c] = xref[c];
+    pb.idx_list = d_idx; pb.count = (int)count; pb.sign = ws_sign; pb.u_admm = ws_u; pb.status = status;
+    pb.u0 = d_u0; pb.objective = d_objective; pb.u_full = d_u_full; pb.polished = ws_polished;
+    pb.n_failed = ws_counters + 1; pb.failed_list = ws_failed;
+    pb.rounds = host.opts.polish ? -1 : 0;
+    pb.final_pass = host.opts.polish ? 0 : 1;
+    if (d_warm && warm_out) pb.sign_out = ws_sign;      // warm-started sequences keep the certified (repaired) active set
+
+    // Active-set reuse (closed loop): consecutive QPs of a run mostly share their active set, so the set certified at
+    // the previous step (kept in the workspace, same sample indexing) goes through the float64 polish first; only the
+    // samples it does not certify (set changed, or infeasible now) run ADMM iterations.
+    if (reuse_active_set && host.opts.polish) {
+        PolishBatch p0 = pb;
+        p0.rounds = 4; p0.final_pass = 0; p0.n_failed = ws_counters + 5; p0.failed_list = ws_failed0;
+        p0.precheck = 1; p0.Px = admm.Px; p0.Pc = admm.Pc; p0.pre_lo = admm.pre_lo; p0.pre_hi = admm.pre_hi; p0.kpre = admm.kpre;
+        p0.sign_out = ws_sign; p0.iters_out = iters;
+        rc = polish_launch(this, p0, st);
+        if (rc != CARMPC_OK) return rc;
+        ++last_launches;
+        int n_failed0 = 0;
+        CARMPC_CUDA(cudaMemcpyAsync(&n_failed0, ws_counters + 5, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CARMPC_CUDA(cudaStreamSynchronize(st));
+        last_reused = count - n_failed0;
+        if (n_failed0 == 0) { last_total_iters = 0; return CARMPC_OK; }
+        d_idx = ws_failed0;
+        count = n_failed0;
+        pb.idx_list = d_idx; pb.count = (int)count;
+    }
 
     AdmmBatch ab;
     memset(&ab, 0, sizeof(ab));
@@ -119,15 +154,6 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
     if (rc != CARMPC_OK) return rc;
     ++last_launches;
 
-    PolishBatch pb;
-    memset(&pb, 0, sizeof(pb));
-    pb.x0 = d_x0; pb.stride = stride; pb.cdist = d_c;
-    for (int c = 0; c < 4; ++c) pb.xref[c] = xref[c];
-    pb.idx_list = d_idx; pb.count = (int)count; pb.sign = ws_sign; pb.u_admm = ws_u; pb.status = status;
-    pb.u0 = d_u0; pb.objective = d_objective; pb.u_full = d_u_full; pb.polished = ws_polished;
-    pb.n_failed = ws_counters + 1; pb.failed_list = ws_failed;
-    pb.rounds = host.opts.polish ? -1 : 0;
-    pb.final_pass = host.opts.polish ? 0 : 1;
     rc = polish_launch(this, pb, st);
     if (rc != CARMPC_OK) return rc;
     ++last_launches;

@@ -134,6 +134,15 @@ struct PolishBatch {
     int na_cap;              // active rows this launch has shared memory for
     int* overflow_list;      // samples with more (nullable: they count as not certified)
     int* n_overflow;
+    // active-set reuse (closed loop: the previous step's certified set is tried before any ADMM iteration)
+    int precheck;            // 1: also evaluate the u-independent rows / finiteness the ADMM slot refill checks
+    const double* Px;        // [kpre][4]
+    const double* Pc;        // [kpre]
+    const double* pre_lo;
+    const double* pre_hi;
+    int kpre;
+    int8_t* sign_out;        // nullable: the certified active set is written back ([batch][mt])
+    int* iters_out;          // nullable: certified samples get 0 iterations
 };
 
 // Host-side setup product (qp_setup.cu)
@@ -181,6 +190,7 @@ struct QPHandle : HandleBase {
     int* ws_status = nullptr;
     int* ws_iters = nullptr;
     int* ws_failed = nullptr;
+    int* ws_failed0 = nullptr;                   // samples whose reused active set did not certify
     int* ws_overflow = nullptr;
     int* ws_counters = nullptr;                  // [0] work counter, [1] n_failed
     unsigned long long* ws_total_iters = nullptr;
@@ -200,7 +210,8 @@ struct QPHandle : HandleBase {
     // full solve on device buffers (all pointers device; any output may be null except status)
     int solve(const double* d_x0, int64_t stride, const double* xref, const double* d_c, const int* d_idx, int64_t count,
               double* d_u0, double* d_objective, int32_t* d_status, int32_t* d_iters, double* d_u_full, float* d_warm,
-              int warm_in, int warm_out, cudaStream_t st);
+              int warm_in, int warm_out, cudaStream_t st, int reuse_active_set = 0);
+    int64_t last_reused = 0;                     // samples certified from the reused active set in the last solve
 };
 
 }  // namespace carmpc

@@ -122,7 +122,17 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
 
         bool certified = false, overflow = false;
         int na = 0;
-        const int max_rounds = B.rounds < 0 ? kPolishRounds : B.rounds;
+        int max_rounds = B.rounds < 0 ? kPolishRounds : B.rounds;
+        if (B.precheck) {
+            // what the ADMM slot refill checks before it starts a sample: finite state, rows that do not depend on u
+            bool pre_ok = isfinite(x0[0]) && isfinite(x0[1]) && isfinite(x0[2]) && isfinite(x0[3]);
+            for (int k = 0; k < B.kpre; ++k) {
+                const double v = B.Px[k * 4 + 0] * x0[0] + B.Px[k * 4 + 1] * x0[1] + B.Px[k * 4 + 2] * x0[2] +
+                                 B.Px[k * 4 + 3] * x0[3] + B.Pc[k] * cd;
+                pre_ok = pre_ok && v <= B.pre_hi[k] && v >= B.pre_lo[k];
+            }
+            if (!pre_ok) max_rounds = 0;                                   // not certified: the ADMM pass decides
+        }
         for (int round = 0; round < max_rounds && !certified; ++round) {
             // ---- active list: rows added by the repair first (newest first: they keep their pivot when the set is
             //      linearly dependent, and an older guess gets the zero multiplier), then the ADMM guess by index ----
@@ -318,7 +328,9 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
             if (B.objective) B.objective[sample] = obj;
             if (B.polished) B.polished[sample] = certified ? 1 : 0;
             if (certified) B.status[sample] = CARMPC_QP_SOLVED;
+            if (certified && B.iters_out) B.iters_out[sample] = 0;
         }
+        if (certified && B.sign_out) for (int i = lane; i < mt; i += 32) B.sign_out[(size_t)sample * mt + i] = sgn[i];
         if (B.u_full) for (int j = lane; j < n; j += 32) B.u_full[(size_t)sample * n + j] = u[j];
     }
 }
