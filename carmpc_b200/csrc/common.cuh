@@ -62,4 +62,21 @@ __device__ __forceinline__ double ld_stream_f64(const double* p) {
     return r;
 }
 
+// Packed float32 pairs (sm_100a FFMA2): one instruction issues two IEEE fmas, lane-wise identical to fmaf.  A pair built
+// from the same scalar twice is folded by ptxas into a broadcast operand (R.F32), so "scalar x pair + pair" costs one slot.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 }  // namespace carmpc

@@ -210,6 +210,13 @@ __device__ __forceinline__ void screen32(const RowF32* __restrict__ s_rows32, in
         nbeta[k] = -fmaf(sc.beta1, psum, sc.beta0);
         mmin[k] = in[k] ? INFINITY : -INFINITY;              // padding lanes count as "already outside"
     }
+    // samples in pairs: the four fmas of a row run as FFMA2 (same IEEE result per sample as fmaf, half the issue slots)
+    f32x2 x2[kNS / 2], y2[kNS / 2], p2[kNS / 2], v2[kNS / 2];
+#pragma unroll
+    for (int k = 0; k < kNS / 2; ++k) {
+        x2[k] = pack2(xf[2 * k], xf[2 * k + 1]); y2[k] = pack2(yf[2 * k], yf[2 * k + 1]);
+        p2[k] = pack2(pf[2 * k], pf[2 * k + 1]); v2[k] = pack2(vf[2 * k], vf[2 * k + 1]);
+    }
     for (int r0 = 0; r0 < rows_padded; r0 += kRowBlock) {
         bool all_out = true;
 #pragma unroll
@@ -218,10 +225,15 @@ __device__ __forceinline__ void screen32(const RowF32* __restrict__ s_rows32, in
 #pragma unroll
         for (int r = 0; r < kRowBlock; ++r) {
             const RowF32 q = s_rows32[r0 + r];
+            const f32x2 a0 = pack2(q.na0, q.na0), a1 = pack2(q.na1, q.na1), a2 = pack2(q.na2, q.na2), a3 = pack2(q.na3, q.na3);
+            const f32x2 b = pack2(q.b, q.b);
 #pragma unroll
-            for (int k = 0; k < kNS; ++k) {
-                const float m = fmaf(q.na3, vf[k], fmaf(q.na2, pf[k], fmaf(q.na1, yf[k], fmaf(q.na0, xf[k], q.b))));
-                mmin[k] = fminf(mmin[k], m);                  // a NaN margin is ignored here; NaN inputs are caught by the bound
+            for (int k = 0; k < kNS / 2; ++k) {
+                const f32x2 m2 = ffma2(a3, v2[k], ffma2(a2, p2[k], ffma2(a1, y2[k], ffma2(a0, x2[k], b))));
+                float m_lo, m_hi;
+                unpack2(m2, m_lo, m_hi);
+                mmin[2 * k] = fminf(mmin[2 * k], m_lo);       // a NaN margin is ignored here; NaN inputs are caught by the bound
+                mmin[2 * k + 1] = fminf(mmin[2 * k + 1], m_hi);
             }
         }
     }

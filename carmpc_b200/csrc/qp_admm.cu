@@ -49,28 +49,64 @@ __device__ __forceinline__ float4 ld_mat(const float* p) {
 }
 
 // acc[r][s] += sum_{k in [kb, ke)} M[r][k] * B[k][s0 + s]      (kb, ke multiples of 4; M row stride ld; B row stride Bt)
+// S >= 2: the samples of a lane are processed in pairs with FFMA2 (matrix element broadcast, sample pair as loaded from
+// shared memory); every accumulator sees the same fma sequence as the scalar loop, so results are bit-identical.
 template <int R, int S, bool SMEM>
 __device__ __forceinline__ void tile_product(float (&acc)[R][S], const float* __restrict__ M, int ld,
                                              const float* __restrict__ B, int Bt, int s0, int kb, int ke) {
+    if constexpr (S == 1) {
 #pragma unroll 2
-    for (int k = kb; k < ke; k += 4) {
-        Vec<S> b0 = Vec<S>::ld(B + (k + 0) * Bt + s0);
-        Vec<S> b1 = Vec<S>::ld(B + (k + 1) * Bt + s0);
-        Vec<S> b2 = Vec<S>::ld(B + (k + 2) * Bt + s0);
-        Vec<S> b3 = Vec<S>::ld(B + (k + 3) * Bt + s0);
+        for (int k = kb; k < ke; k += 4) {
+            const float b0 = B[(k + 0) * Bt + s0], b1 = B[(k + 1) * Bt + s0], b2 = B[(k + 2) * Bt + s0], b3 = B[(k + 3) * Bt + s0];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float4 a = ld_mat<SMEM>(M + r * ld + k);
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-                float t = acc[r][s];
-                t = fmaf(a.x, b0.v[s], t);
-                t = fmaf(a.y, b1.v[s], t);
-                t = fmaf(a.z, b2.v[s], t);
-                t = fmaf(a.w, b3.v[s], t);
-                acc[r][s] = t;
+            for (int r = 0; r < R; ++r) {
+                const float4 a = ld_mat<SMEM>(M + r * ld + k);
+                float t = acc[r][0];
+                t = fmaf(a.x, b0, t);
+                t = fmaf(a.y, b1, t);
+                t = fmaf(a.z, b2, t);
+                t = fmaf(a.w, b3, t);
+                acc[r][0] = t;
             }
         }
+    } else {
+        constexpr int S2 = S / 2;
+        f32x2 acc2[R][S2];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int s = 0; s < S2; ++s) acc2[r][s] = pack2(acc[r][2 * s], acc[r][2 * s + 1]);
+#pragma unroll 2
+        for (int k = kb; k < ke; k += 4) {
+            const Vec<S> b0 = Vec<S>::ld(B + (k + 0) * Bt + s0);
+            const Vec<S> b1 = Vec<S>::ld(B + (k + 1) * Bt + s0);
+            const Vec<S> b2 = Vec<S>::ld(B + (k + 2) * Bt + s0);
+            const Vec<S> b3 = Vec<S>::ld(B + (k + 3) * Bt + s0);
+            f32x2 p0[S2], p1[S2], p2[S2], p3[S2];
+#pragma unroll
+            for (int s = 0; s < S2; ++s) {
+                p0[s] = pack2(b0.v[2 * s], b0.v[2 * s + 1]); p1[s] = pack2(b1.v[2 * s], b1.v[2 * s + 1]);
+                p2[s] = pack2(b2.v[2 * s], b2.v[2 * s + 1]); p3[s] = pack2(b3.v[2 * s], b3.v[2 * s + 1]);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 a = ld_mat<SMEM>(M + r * ld + k);
+                const f32x2 ax = pack2(a.x, a.x), ay = pack2(a.y, a.y), az = pack2(a.z, a.z), aw = pack2(a.w, a.w);
+#pragma unroll
+                for (int s = 0; s < S2; ++s) {
+                    f32x2 t = acc2[r][s];
+                    t = ffma2(ax, p0[s], t);
+                    t = ffma2(ay, p1[s], t);
+                    t = ffma2(az, p2[s], t);
+                    t = ffma2(aw, p3[s], t);
+                    acc2[r][s] = t;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int s = 0; s < S2; ++s) unpack2(acc2[r][s], acc[r][2 * s], acc[r][2 * s + 1]);
     }
 }
 
@@ -619,7 +655,8 @@ int admm_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
     if (debug_flags) const_cast<AdmmBatch&>(b).debug_flags = debug_flags;
     const int key = q->host.ga_per_warp * 100 + q->host.gb_per_warp * 10 + S;
     switch (key) {
-        // n <= 40: 16 warps as two sample-halves of 64 (measured equal to 8 warps x 4 samples per lane, fewer registers)
+        // n <= 40: 16 warps as two sample-halves of 64 (measured equal to 8 warps x 4 samples per lane, with and without
+        // FFMA2, fewer registers)
         case 124: return launch_variant<2, 2, 1, 2>(q, b, st);
         case 122: return launch_variant<2, 1, 1, 2>(q, b, st);
         case 121: return launch_variant<1, 1, 1, 2>(q, b, st);
