@@ -208,36 +208,47 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
                 __syncwarp();
             }
             // rhs now holds lambda (signed: positive pushes against an upper bound)
-            // ---- u = u_unc - (AH)'_act lambda ----
-            for (int j = lane; j < n; j += 32) {
-                double s0 = uunc[j], s1 = 0.0;
-                int a = 0;
-                for (; a + 1 < na; a += 2) {
-                    s0 -= T.AH[(size_t)act[a] * n + j] * rhs[a];
-                    s1 -= T.AH[(size_t)act[a + 1] * n + j] * rhs[a + 1];
+            // ---- u = u_unc - (AH)'_act lambda : kUChunk variables per lane at a time, so that every active row contributes
+            //      kUChunk independent loads (the tables live in L2: latency, not bandwidth, is what this loop waits for) ----
+            constexpr int kUChunk = 2, kRowChunk = 5;
+            for (int j0 = 0; j0 < n; j0 += 32 * kUChunk) {
+                double acc[kUChunk];
+                int jj[kUChunk];
+#pragma unroll
+                for (int c = 0; c < kUChunk; ++c) { jj[c] = j0 + 32 * c + lane; acc[c] = jj[c] < n ? uunc[jj[c]] : 0.0; if (jj[c] >= n) jj[c] = 0; }
+                for (int a = 0; a < na; ++a) {
+                    const double la = rhs[a];
+                    const double* row = T.AH + (size_t)act[a] * n;
+#pragma unroll
+                    for (int c = 0; c < kUChunk; ++c) acc[c] -= row[jj[c]] * la;
                 }
-                if (a < na) s0 -= T.AH[(size_t)act[a] * n + j] * rhs[a];
-                u[j] = s0 + s1;
+#pragma unroll
+                for (int c = 0; c < kUChunk; ++c) if (j0 + 32 * c + lane < n) u[j0 + 32 * c + lane] = acc[c];
             }
-            // ---- KKT check: every row within its bounds, multiplier signs right ----
+            // ---- KKT check: every row within its bounds, multiplier signs right (kRowChunk rows per lane at a time) ----
             double worst = 0.0;
             int worst_i = -1, worst_sign = 0;
-            for (int i = lane; i < mt; i += 32) {
-                const double h = T.hi[i], l = T.lo[i];
-                if (isinf(h) && isinf(l)) continue;
-                double s0 = tsh[i], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                int a = 0;
-                for (; a + 3 < na; a += 4) {
-                    s0 -= T.AHA[(size_t)act[a] * mt + i] * rhs[a];
-                    s1 -= T.AHA[(size_t)act[a + 1] * mt + i] * rhs[a + 1];
-                    s2 -= T.AHA[(size_t)act[a + 2] * mt + i] * rhs[a + 2];
-                    s3 -= T.AHA[(size_t)act[a + 3] * mt + i] * rhs[a + 3];
+            for (int i0 = 0; i0 < mt; i0 += 32 * kRowChunk) {
+                double acc[kRowChunk];
+                int ii[kRowChunk];
+#pragma unroll
+                for (int c = 0; c < kRowChunk; ++c) { ii[c] = i0 + 32 * c + lane; acc[c] = ii[c] < mt ? tsh[ii[c]] : 0.0; if (ii[c] >= mt) ii[c] = 0; }
+                for (int a = 0; a < na; ++a) {
+                    const double la = rhs[a];
+                    const double* row = T.AHA + (size_t)act[a] * mt;
+#pragma unroll
+                    for (int c = 0; c < kRowChunk; ++c) acc[c] -= row[ii[c]] * la;
                 }
-                for (; a < na; ++a) s0 -= T.AHA[(size_t)act[a] * mt + i] * rhs[a];
-                const double s = (s0 + s1) + (s2 + s3);
-                const double vu = s - h, vl = l - s;
-                const double v = fmax(vu, vl);
-                if (v > worst) { worst = v; worst_i = i; worst_sign = vu >= vl ? 1 : -1; }
+#pragma unroll
+                for (int c = 0; c < kRowChunk; ++c) {
+                    const int i = i0 + 32 * c + lane;
+                    if (i >= mt) continue;
+                    const double h = T.hi[i], l = T.lo[i];
+                    if (isinf(h) && isinf(l)) continue;
+                    const double vu = acc[c] - h, vl = l - acc[c];
+                    const double v = fmax(vu, vl);
+                    if (v > worst) { worst = v; worst_i = i; worst_sign = vu >= vl ? 1 : -1; }
+                }
             }
             // the (up to) kAddPerRound most violated rows, one per lane
             int n_add = 0, add_is[kAddPerRound], add_sg[kAddPerRound];
