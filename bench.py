@@ -424,6 +424,8 @@ def main():
     ap.add_argument("--qp-states", type=int, default=1_000_000)
     ap.add_argument("--qp-steps", type=int, default=5)
     ap.add_argument("--skip-sweep", action="store_true")
+    ap.add_argument("--skip-seeded", action="store_true")
+    ap.add_argument("--seed-blocks", default="2x8x1x1", help="comma-separated lattice blocks (points per axis) for the seeded map")
     ap.add_argument("--skip-closed-loop", action="store_true")
     ap.add_argument("--cl-runs", type=int, default=100_000)
     ap.add_argument("--cl-steps", type=int, default=200)

@@ -100,7 +100,7 @@ def run_qp_bench(args, rank, world, dev, barrier):
                    "tolerance": "ADMM float32 to 1e-3 (active set) + float64 polish with KKT check"},
         "feasible_frac": float((status == 0).float().mean().item()),
         "max_iter_count": int((status == 2).sum().item()),
-        "mean_admm_iters": iters / B, "gpu_launches": launches, "tiling": tiling,
+        "mean_admm_iters": iters / B, "gpu_launches": launches, "tiling": tiling, "polish": bq.polish_stats(),
     }
     if rank == 0:
         fp32_peak = measure_peak("fp32")
@@ -131,6 +131,44 @@ def run_qp_bench(args, rank, world, dev, barrier):
                   "d2h_bytes_per_step": B * (16 + 8 + 4 + 4), "call": "carmpc_qp_solve_host"}
     if rank == 0 and world == 1 and not args.skip_cpu:
         res["cpu_baseline"] = cpu_qp_rate()
+
+    # ---- config 3 as a region-of-attraction MAP: anchors of a sub-lattice solved cold, every other grid point first tries its
+    # anchor's certified active set in the float64 polish (carmpc_qp_solve_seeded); identical results, fewer ADMM iterations
+    if not args.skip_seeded and B == x0_full.shape[1]:
+        from carmpc_b200.grids import lattice_seeds
+        dims = [len(a) for a in axes]
+        blocks = [tuple(int(v) for v in b.split("x")) for b in args.seed_blocks.split(",")]
+        seeded = {}
+        for blk in blocks:
+            seed = torch.from_numpy(lattice_seeds(dims, block=blk)).to(dev)
+            for _ in range(2):
+                o = bq.solve(x0, seed=seed)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            it_sum = 0
+            e0.record()
+            for _ in range(steps):
+                o = bq.solve(x0, seed=seed)
+                it_sum += bq.last_stats()[0]
+            e1.record()
+            e1.synchronize()
+            ms_s = e0.elapsed_time(e1) / steps
+            ts = torch.tensor([ms_s], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            same = bool((o["status"] == out["status"]).all().item())
+            okm = out["status"] == 0
+            du = float((o["u0"][:, okm] - out["u0"][:, okm]).abs().max().item())
+            seeded["x".join(map(str, blk))] = {
+                "qps": world * B / (float(ts.item()) * 1e-3), "ms": float(ts.item()),
+                "anchors": int((seed == torch.arange(B, device=dev, dtype=torch.int32)).sum().item()),
+                "certified_from_seed": o["seeded"], "mean_admm_iters": it_sum / steps / B,
+                "flags_equal_cold": same, "max_du0_vs_cold": du, "polish": bq.polish_stats()}
+        best = max(seeded, key=lambda k: seeded[k]["qps"])
+        res["seeded_map"] = {"metric": "horizon-20 QPs/s (region-of-attraction map, active sets seeded from lattice anchors)",
+                             "value": seeded[best]["qps"], "unit": "QPs/s", "ms_per_step": seeded[best]["ms"],
+                             "block": best, "by_block": seeded,
+                             "call": "carmpc_qp_solve_seeded (same certified optima and flags as the cold solve)"}
 
     # ---- config 5: horizon sweep ----------------------------------------------------------------------------
     if not args.skip_sweep:

@@ -265,11 +265,23 @@ class BatchQP(_Handle):
         check(self._lib.carmpc_qp_last_stats(self._h, ctypes.byref(a), ctypes.byref(b)))
         return int(a.value), int(b.value)
 
+    def polish_stats(self) -> dict:
+        """Histogram of the float64 polish over the last solve (``carmpc_qp_polish_stats``)."""
+        h = (ctypes.c_int64 * 16)()
+        check(self._lib.carmpc_qp_polish_stats(self._h, h))
+        v = [int(x) for x in h]
+        return {"certified_after_rounds": v[:10], "handed_to_admm": v[10], "used_multiplier_map": v[11],
+                "certified_by_map_alone": v[12]}
+
     # ---- device tensors ---------------------------------------------------------------------------
     def solve(self, x0, x_ref=None, c=None, want_u_full: bool = False, warm=None, warm_in: bool = False,
-              warm_out: bool = False, stream=None) -> dict:
+              warm_out: bool = False, stream=None, seed=None) -> dict:
         """``x0``: (4, B) float64 CUDA tensor (SoA).  Returns a dict of CUDA tensors: ``u0`` (2, B), ``objective``
-        (B,), ``status`` (B,) int32, ``iters`` (B,) int32 and optionally ``u_full`` (B, 2N)."""
+        (B,), ``status`` (B,) int32, ``iters`` (B,) int32 and optionally ``u_full`` (B, 2N).
+
+        ``seed`` (int32 CUDA tensor of B entries, e.g. ``grids.lattice_seeds``): sample ``i`` first tries the certified
+        active set of sample ``seed[i]`` (an anchor: ``seed[a] == a``) and runs ADMM only if that does not certify;
+        ``out["seeded"]`` counts the samples that needed no ADMM iteration.  Same results as the cold solve."""
         torch = _torch()
         if not (x0.is_cuda and x0.dtype == torch.float64 and x0.dim() == 2 and x0.shape[0] == 4 and x0.is_contiguous()):
             raise ValueError("x0 must be a contiguous (4, B) float64 CUDA tensor")
@@ -284,6 +296,18 @@ class BatchQP(_Handle):
             out["u_full"] = torch.empty((B, self.n), dtype=torch.float64, device=dev)
         if warm is not None and not (warm.is_cuda and warm.dtype == torch.float32 and warm.numel() == B * (self.m + self.n)):
             raise ValueError("warm must be a float32 CUDA tensor of B * (m + n) elements")
+        if seed is not None:
+            if warm is not None:
+                raise ValueError("seed and warm are alternative starting points")
+            if not (seed.is_cuda and seed.dtype == torch.int32 and seed.numel() == B and seed.is_contiguous()):
+                raise ValueError("seed must be a contiguous int32 CUDA tensor of B entries")
+            seeded = ctypes.c_int64(0)
+            check(self._lib.carmpc_qp_solve_seeded(
+                self._h, x0.data_ptr(), _capi.ptr(xref), c.data_ptr() if c is not None else None, seed.data_ptr(), B,
+                out["u0"].data_ptr(), out["objective"].data_ptr(), out["status"].data_ptr(), out["iters"].data_ptr(),
+                out["u_full"].data_ptr() if want_u_full else None, ctypes.byref(seeded), _stream_ptr(stream)))
+            out["seeded"] = int(seeded.value)
+            return out
         check(self._lib.carmpc_qp_solve_batch(
             self._h, x0.data_ptr(), _capi.ptr(xref), c.data_ptr() if c is not None else None, B,
             out["u0"].data_ptr(), out["objective"].data_ptr(), out["status"].data_ptr(), out["iters"].data_ptr(),

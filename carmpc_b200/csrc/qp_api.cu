@@ -33,6 +33,35 @@ __global__ void soa_to_aos_kernel(const double* __restrict__ soa, double* __rest
     for (int c = 0; c < width; ++c) aos[i * width + c] = soa[(size_t)c * count + i];
 }
 
+// seeded solve: anchors are the samples that name themselves (or nothing valid) as their seed; a follower's seed must be
+// an anchor (single level), anything else is solved cold as well
+__global__ void split_seeds_kernel(const int* __restrict__ seed, int count, int* __restrict__ anchors, int* __restrict__ followers,
+                                   int* __restrict__ counters, int* __restrict__ rec_of) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool follow = false;
+    if (i < count) {
+        const int s = seed[i];
+        if (s >= 0 && s < count && s != i) { const int ss = seed[s]; follow = ss == s || ss < 0 || ss >= count; }
+    }
+    // order-preserving within a warp; warps append in arrival order (the lists only drive work queues)
+    const unsigned fm = __ballot_sync(0xffffffffu, i < count && follow), am = __ballot_sync(0xffffffffu, i < count && !follow);
+    const int lane = threadIdx.x & 31;
+    int fb = 0, abase = 0;
+    if (lane == 0) { if (fm) fb = atomicAdd(counters + 1, __popc(fm)); if (am) abase = atomicAdd(counters + 0, __popc(am)); }
+    fb = __shfl_sync(0xffffffffu, fb, 0); abase = __shfl_sync(0xffffffffu, abase, 0);
+    if (i < count) {
+        const unsigned below = (1u << lane) - 1u;
+        if (follow) {
+            followers[fb + __popc(fm & below)] = i;
+            rec_of[i] = -1;
+        } else {
+            const int pos = abase + __popc(am & below);
+            anchors[pos] = i;
+            rec_of[i] = pos;                 // an anchor's record (multiplier map of its critical region) sits at its list position
+        }
+    }
+}
+
 }  // namespace
 
 int QPHandle::ensure_io(int64_t batch, bool want_full) {
@@ -63,20 +92,26 @@ QPHandle::~QPHandle() {
     for (void* p : allocations) cudaFree(p);
     cudaFree(ws_sign); cudaFree(ws_u); cudaFree(ws_status); cudaFree(ws_iters); cudaFree(ws_failed); cudaFree(ws_failed0);
     cudaFree(ws_counters); cudaFree(ws_total_iters); cudaFree(ws_polished); cudaFree(ws_warm); cudaFree(ws_overflow);
+    cudaFree(ws_anchor); cudaFree(ws_follow); cudaFree(ws_rec_of); cudaFree(ws_rec_lam); cudaFree(ws_rec_act); cudaFree(ws_polish_stats);
     cudaFree(io_x0_aos); cudaFree(io_x0); cudaFree(io_c); cudaFree(io_u0); cudaFree(io_u0_aos); cudaFree(io_obj); cudaFree(io_full);
     cudaFree(io_status); cudaFree(io_iters);
 }
 
 int QPHandle::ensure_workspace(int64_t batch) {
     if (ws_counters == nullptr) {
-        CARMPC_CUDA(cudaMalloc(&ws_counters, sizeof(int) * 8));
+        CARMPC_CUDA(cudaMalloc(&ws_counters, sizeof(int) * 16));
         CARMPC_CUDA(cudaMalloc(&ws_total_iters, sizeof(unsigned long long)));
+        CARMPC_CUDA(cudaMalloc(&ws_polish_stats, sizeof(unsigned long long) * 16));
+        CARMPC_CUDA(cudaMemset(ws_polish_stats, 0, sizeof(unsigned long long) * 16));
     }
     if (batch <= ws_batch) return CARMPC_OK;
     cudaFree(ws_sign); cudaFree(ws_u); cudaFree(ws_status); cudaFree(ws_iters); cudaFree(ws_failed); cudaFree(ws_polished);
     cudaFree(ws_warm); ws_warm = nullptr;
     cudaFree(ws_overflow); ws_overflow = nullptr;
     cudaFree(ws_failed0); ws_failed0 = nullptr;
+    cudaFree(ws_anchor); ws_anchor = nullptr;
+    cudaFree(ws_follow); ws_follow = nullptr;
+    cudaFree(ws_rec_of); ws_rec_of = nullptr;
     ws_sign = nullptr; ws_u = nullptr; ws_status = nullptr; ws_iters = nullptr; ws_failed = nullptr; ws_polished = nullptr;
     ws_batch = 0;
     CARMPC_CUDA(cudaMalloc(&ws_sign, (size_t)batch * admm.mt));
@@ -86,6 +121,9 @@ int QPHandle::ensure_workspace(int64_t batch) {
     CARMPC_CUDA(cudaMalloc(&ws_failed, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_overflow, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_failed0, sizeof(int) * (size_t)batch));
+    CARMPC_CUDA(cudaMalloc(&ws_anchor, sizeof(int) * (size_t)batch));
+    CARMPC_CUDA(cudaMalloc(&ws_follow, sizeof(int) * (size_t)batch));
+    CARMPC_CUDA(cudaMalloc(&ws_rec_of, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_polished, (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_warm, sizeof(float) * (size_t)batch * admm.mt));
     ws_batch = batch;
@@ -94,7 +132,8 @@ int QPHandle::ensure_workspace(int64_t batch) {
 
 int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, const double* d_c, const int* d_idx,
                     int64_t count, double* d_u0, double* d_objective, int32_t* d_status, int32_t* d_iters,
-                    double* d_u_full, float* d_warm, int warm_in, int warm_out, cudaStream_t st, int reuse_active_set) {
+                    double* d_u_full, float* d_warm, int warm_in, int warm_out, cudaStream_t st, int reuse_active_set,
+                    const int* d_seed, int keep_sign) {
     // `stride` is the number of samples the per-sample arrays are sized for; `count` the number solved now
     // (all of them, or those listed in d_idx).
     if (host_only) { set_error("carmpc_qp: this handle was created without a CUDA device; there is no CPU solver"); return CARMPC_ERR_CUDA; }
@@ -117,7 +156,14 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
     pb.n_failed = ws_counters + 1; pb.failed_list = ws_failed;
     pb.rounds = host.opts.polish ? -1 : 0;
     pb.final_pass = host.opts.polish ? 0 : 1;
-    if (d_warm && warm_out) pb.sign_out = ws_sign;      // warm-started sequences keep the certified (repaired) active set
+    pb.stats = ws_polish_stats;
+    if (!stats_hold) CARMPC_CUDA(cudaMemsetAsync(ws_polish_stats, 0, sizeof(unsigned long long) * 16, st));
+    // warm-started sequences and seeded maps keep the certified (repaired) active set
+    if ((d_warm && warm_out) || keep_sign) pb.sign_out = ws_sign;
+    if (use_records) {
+        pb.rec_of = ws_rec_of; pb.rec_lam = ws_rec_lam; pb.rec_act = ws_rec_act;
+        pb.rec_write = d_seed == nullptr;                 // anchors export, followers read (p0 below)
+    }
 
     // Active-set reuse (closed loop): consecutive QPs of a run mostly share their active set, so the set certified at
     // the previous step (kept in the workspace, same sample indexing) goes through the float64 polish first; only the
@@ -126,7 +172,8 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
         PolishBatch p0 = pb;
         p0.rounds = 4; p0.final_pass = 0; p0.n_failed = ws_counters + 5; p0.failed_list = ws_failed0;
         p0.precheck = 1; p0.Px = admm.Px; p0.Pc = admm.Pc; p0.pre_lo = admm.pre_lo; p0.pre_hi = admm.pre_hi; p0.kpre = admm.kpre;
-        p0.sign_out = ws_sign; p0.iters_out = iters;
+        p0.sign_out = ws_sign; p0.iters_out = iters; p0.seed = d_seed;
+        p0.rec_write = 0; p0.rec_read = use_records && d_seed != nullptr;
         rc = polish_launch(this, p0, st);
         if (rc != CARMPC_OK) return rc;
         ++last_launches;
@@ -179,6 +226,56 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
     CARMPC_CUDA(cudaMemcpyAsync(&total, ws_total_iters, sizeof(total), cudaMemcpyDeviceToHost, st));
     CARMPC_CUDA(cudaStreamSynchronize(st));
     last_total_iters = (int64_t)total;
+    return CARMPC_OK;
+}
+
+int QPHandle::solve_seeded(const double* d_x0, int64_t batch, const double* xref, const double* d_c, const int* d_seed,
+                           double* d_u0, double* d_objective, int32_t* d_status, int32_t* d_iters, double* d_u_full,
+                           cudaStream_t st) {
+    if (host_only) { set_error("carmpc_qp: this handle was created without a CUDA device; there is no CPU solver"); return CARMPC_ERR_CUDA; }
+    if (!host.opts.polish) { set_error("carmpc_qp_solve_seeded needs the float64 polish (opts.polish = 1)"); return CARMPC_ERR_INVALID; }
+    int rc = ensure_workspace(batch);
+    if (rc != CARMPC_OK) return rc;
+    struct ResetOnExit { int& flag; ~ResetOnExit() { flag = 0; } } reset_records{use_records}, reset_hold{stats_hold};   // also on error returns
+    CARMPC_CUDA(cudaMemsetAsync(ws_polish_stats, 0, sizeof(unsigned long long) * 16, st));
+    stats_hold = 1;                                       // the histogram covers anchors and followers
+    CARMPC_CUDA(cudaMemsetAsync(ws_counters + 8, 0, sizeof(int) * 2, st));
+    CARMPC_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int32_t) * batch, st));     // followers enter the polish as "not infeasible"
+    split_seeds_kernel<<<(int)((batch + 255) / 256), 256, 0, st>>>(d_seed, (int)batch, ws_anchor, ws_follow, ws_counters + 8,
+                                                                   ws_rec_of);
+    int n_split[2] = {0, 0};
+    CARMPC_CUDA(cudaMemcpyAsync(n_split, ws_counters + 8, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+    CARMPC_CUDA(cudaStreamSynchronize(st));
+    // multiplier maps of the anchors (1.4 KB each); skipped when there is a per-sample disturbance or too many anchors
+    constexpr size_t kRecLam = sizeof(double) * 32 * 5, kRecAct = sizeof(int) * 33;
+    use_records = 0;
+    if (d_c == nullptr && n_split[0] > 0 && n_split[1] > 0 && (size_t)n_split[0] * (kRecLam + kRecAct) <= ((size_t)1 << 30)) {
+        if (n_split[0] > rec_cap) {
+            cudaFree(ws_rec_lam); cudaFree(ws_rec_act); ws_rec_lam = nullptr; ws_rec_act = nullptr; rec_cap = 0;
+            CARMPC_CUDA(cudaMalloc(&ws_rec_lam, kRecLam * n_split[0]));
+            CARMPC_CUDA(cudaMalloc(&ws_rec_act, kRecAct * n_split[0]));
+            rec_cap = n_split[0];
+        }
+        CARMPC_CUDA(cudaMemsetAsync(ws_rec_act, 0xFF, kRecAct * n_split[0], st));      // na = -1: no map yet
+        use_records = 1;
+    }
+    int64_t iters_sum = 0, launches = 1, second = 0;
+    if (n_split[0] > 0) {
+        rc = solve(d_x0, batch, xref, d_c, ws_anchor, n_split[0], d_u0, d_objective, d_status, d_iters, d_u_full, nullptr, 0, 0, st,
+                   0, nullptr, 1);
+        if (rc != CARMPC_OK) return rc;
+        iters_sum += last_total_iters; launches += last_launches; second += last_second_pass;
+    }
+    int64_t reused = 0;
+    if (n_split[1] > 0) {
+        rc = solve(d_x0, batch, xref, d_c, ws_follow, n_split[1], d_u0, d_objective, d_status, d_iters, d_u_full, nullptr, 0, 0, st,
+                   1, d_seed, 1);
+        if (rc != CARMPC_OK) return rc;
+        iters_sum += last_total_iters; launches += last_launches; second += last_second_pass; reused = last_reused;
+    }
+    use_records = 0;
+    last_total_iters = iters_sum; last_launches = launches; last_second_pass = second; last_reused = reused;
+    last_anchors = n_split[0];
     return CARMPC_OK;
 }
 
@@ -305,8 +402,25 @@ int carmpc_qp_solve_batch(void* qp, const double* d_x0, const double* h_xref, co
     CARMPC_REQUIRE(h_xref != nullptr, "h_xref");
     if (batch == 0) { q->last_total_iters = 0; q->last_launches = 0; return CARMPC_OK; }
     CARMPC_REQUIRE(d_x0 && d_status, "d_x0 and d_status are required");
+    q->use_records = 0;
     return q->solve(d_x0, batch, h_xref, d_c, nullptr, batch, d_u0, d_objective, d_status, d_iters, d_u_full, d_warm,
                     warm_in, warm_out, (cudaStream_t)stream);
+}
+
+int carmpc_qp_solve_seeded(void* qp, const double* d_x0, const double* h_xref, const double* d_c, const int32_t* d_seed,
+                           int64_t batch, double* d_u0, double* d_objective, int32_t* d_status, int32_t* d_iters,
+                           double* d_u_full, int64_t* h_seeded, void* stream) {
+    QPHandle* q = check_handle<QPHandle>(qp, kQP);
+    CARMPC_REQUIRE(q != nullptr, "not a QP handle");
+    CARMPC_REQUIRE(batch >= 0 && batch < (int64_t)1 << 31, "batch");
+    CARMPC_REQUIRE(h_xref != nullptr, "h_xref");
+    if (h_seeded) *h_seeded = 0;
+    if (batch == 0) { q->last_total_iters = 0; q->last_launches = 0; return CARMPC_OK; }
+    CARMPC_REQUIRE(d_x0 && d_status && d_seed, "d_x0, d_status and d_seed are required");
+    const int rc = q->solve_seeded(d_x0, batch, h_xref, d_c, d_seed, d_u0, d_objective, d_status, d_iters, d_u_full,
+                                   (cudaStream_t)stream);
+    if (rc == CARMPC_OK && h_seeded) *h_seeded = q->last_reused;
+    return rc;
 }
 
 int carmpc_qp_solve_host(void* qp, const double* h_x0, const double* h_xref, const double* h_c, int64_t batch,
@@ -339,6 +453,18 @@ int carmpc_qp_solve_host(void* qp, const double* h_x0, const double* h_xref, con
     if (h_u_full) CARMPC_CUDA(cudaMemcpyAsync(h_u_full, q->io_full, sizeof(double) * (size_t)n * batch, cudaMemcpyDeviceToHost, st));
     CARMPC_CUDA(cudaStreamSynchronize(st));
     CARMPC_CUDA(cudaGetLastError());
+    return CARMPC_OK;
+}
+
+int carmpc_qp_polish_stats(void* qp, int64_t* h_hist16) {
+    QPHandle* q = check_handle<QPHandle>(qp, kQP);
+    CARMPC_REQUIRE(q != nullptr, "not a QP handle");
+    CARMPC_REQUIRE(h_hist16 != nullptr, "h_hist16");
+    for (int i = 0; i < 16; ++i) h_hist16[i] = 0;
+    if (q->ws_polish_stats == nullptr) return CARMPC_OK;
+    unsigned long long tmp[16];
+    CARMPC_CUDA(cudaMemcpy(tmp, q->ws_polish_stats, sizeof(tmp), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 16; ++i) h_hist16[i] = (int64_t)tmp[i];
     return CARMPC_OK;
 }
 

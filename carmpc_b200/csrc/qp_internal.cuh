@@ -143,6 +143,15 @@ struct PolishBatch {
     int kpre;
     int8_t* sign_out;        // nullable: the certified active set is written back ([batch][mt])
     int* iters_out;          // nullable: certified samples get 0 iterations
+    // active-set seeding (region-of-attraction maps: neighbouring states mostly share their active set)
+    const int* seed;         // nullable: sample i starts from the certified set of sample seed[i] (an anchor solved before)
+    // multiplier maps of the anchors' critical regions: lambda(x0) = Lam [x0; 1] on the anchor's active rows
+    const int* rec_of;       // [batch] record of a sample (-1: none)
+    double* rec_lam;         // [records][32][5]
+    int* rec_act;            // [records][33]   na (-1: no map), then the active rows in the order of Lam's rows
+    int rec_write, rec_read;
+    unsigned long long* stats;   // nullable [16]: [r] samples certified after r repair rounds (r = 0..9), [10] not certified,
+                                 // [11] round 0 taken from a multiplier map, [12] certified by a multiplier map alone
 };
 
 // Host-side setup product (qp_setup.cu)
@@ -191,6 +200,15 @@ struct QPHandle : HandleBase {
     int* ws_iters = nullptr;
     int* ws_failed = nullptr;
     int* ws_failed0 = nullptr;                   // samples whose reused active set did not certify
+    int* ws_anchor = nullptr;                    // seeded solve: samples solved cold (anchors) / from a seed (followers)
+    int* ws_follow = nullptr;
+    int* ws_rec_of = nullptr;                    // [batch] record index of an anchor
+    double* ws_rec_lam = nullptr;                // multiplier maps of the anchors (grown on demand, capped)
+    int* ws_rec_act = nullptr;
+    int64_t rec_cap = 0;
+    int use_records = 0;                         // set by solve_seeded for the two solve() calls it makes
+    unsigned long long* ws_polish_stats = nullptr;   // [16] histogram of the polish launches of the last solve
+    int stats_hold = 0;
     int* ws_overflow = nullptr;
     int* ws_counters = nullptr;                  // [0] work counter, [1] n_failed
     unsigned long long* ws_total_iters = nullptr;
@@ -210,8 +228,14 @@ struct QPHandle : HandleBase {
     // full solve on device buffers (all pointers device; any output may be null except status)
     int solve(const double* d_x0, int64_t stride, const double* xref, const double* d_c, const int* d_idx, int64_t count,
               double* d_u0, double* d_objective, int32_t* d_status, int32_t* d_iters, double* d_u_full, float* d_warm,
-              int warm_in, int warm_out, cudaStream_t st, int reuse_active_set = 0);
+              int warm_in, int warm_out, cudaStream_t st, int reuse_active_set = 0, const int* d_seed = nullptr,
+              int keep_sign = 0);
+    // anchors (seed[i] == i or out of range) cold, then every other sample from its anchor's certified active set
+    int solve_seeded(const double* d_x0, int64_t batch, const double* xref, const double* d_c, const int* d_seed,
+                     double* d_u0, double* d_objective, int32_t* d_status, int32_t* d_iters, double* d_u_full,
+                     cudaStream_t st);
     int64_t last_reused = 0;                     // samples certified from the reused active set in the last solve
+    int64_t last_anchors = 0;                    // seeded solve: samples solved cold
 };
 
 }  // namespace carmpc

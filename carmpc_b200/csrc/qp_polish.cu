@@ -102,6 +102,9 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
 #pragma unroll
         for (int c = 0; c < 4; ++c) { x0[c] = B.x0[(size_t)c * B.stride + sample]; dx[c] = x0[c] - B.xref[c]; }
         const double cd = B.cdist ? B.cdist[sample] : 0.0;
+        // seeded: the guess is the certified set of the sample's anchor (nothing to try when the anchor was infeasible)
+        const int sign_src = B.seed ? B.seed[sample] : sample;
+        const bool seed_ok = !B.seed || B.status[sign_src] == CARMPC_QP_SOLVED;
         // everything unconstrained is linear in dx:  u_unc = -H^-1 F dx = Uu dx ,  A u_unc = (A Uu) dx
         for (int j = lane; j < n; j += 32) {
             const double* w = T.Uu + (size_t)j * 4;
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
                 t += gx[0] * x0[0] + gx[1] * x0[1] + gx[2] * x0[2] + gx[3] * x0[3] + T.Gc[i] * cd;
             }
             tsh[i] = t;
-            sgn[i] = B.sign[(size_t)sample * mt + i];
+            sgn[i] = B.sign[(size_t)sign_src * mt + i];
         }
         int n_added = 0;
         __syncwarp();
@@ -131,9 +134,52 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
                                  B.Px[k * 4 + 3] * x0[3] + B.Pc[k] * cd;
                 pre_ok = pre_ok && v <= B.pre_hi[k] && v >= B.pre_lo[k];
             }
-            if (!pre_ok) max_rounds = 0;                                   // not certified: the ADMM pass decides
+            if (!pre_ok || !seed_ok) max_rounds = 0;                       // not certified: the ADMM pass decides
         }
+        // L y = rhs, L' x = y in place (M holds the factor, diag0 the reciprocal pivots; skipped pivots give 0)
+        auto solve_in_place = [&]() {
+            for (int j = 0; j < na; ++j) {
+                const double y = rhs[j] * diag0[j];
+                __syncwarp();
+                if (lane == 0) rhs[j] = y;
+                for (int i = j + 1 + lane; i < na; i += 32) rhs[i] -= M[tri(i, 0) + j] * y;
+                __syncwarp();
+            }
+            for (int j = na - 1; j >= 0; --j) {
+                const double x = rhs[j] * diag0[j];
+                const int tj = tri(j, 0);
+                __syncwarp();
+                if (lane == 0) rhs[j] = x;
+                for (int i = lane; i < j; i += 32) rhs[i] -= M[tj + i] * x;
+                __syncwarp();
+            }
+        };
+        // Seeded from an anchor that exported its multiplier map: on the anchor's critical region lambda is affine in x0
+        // (explicit-MPC form), so round 0 needs no factorisation - only the KKT certificate below decides.
+        bool lam_ready = false;
+        if (B.rec_read && B.seed && seed_ok && max_rounds > 0 && B.cdist == nullptr) {
+            const int rec = B.rec_of[sign_src];
+            if (rec >= 0) {
+                const int* ra = B.rec_act + (size_t)rec * (kPolishSmallActive + 1);
+                const int rna = ra[0];
+                if (rna >= 0 && rna <= L.na_max) {
+                    na = rna;
+                    for (int a = lane; a < na; a += 32) {
+                        const int i = ra[1 + a];
+                        const double* lr = B.rec_lam + ((size_t)rec * kPolishSmallActive + a) * 5;
+                        act[a] = i;
+                        rhs[a] = lr[0] * x0[0] + lr[1] * x0[1] + lr[2] * x0[2] + lr[3] * x0[3] + lr[4];
+                        bact[a] = (sgn[i] > 0 ? T.hi[i] : T.lo[i]) - (tsh[i] - T_auu(T, i, dx));
+                    }
+                    lam_ready = true;
+                    __syncwarp();
+                }
+            }
+        }
+        int rounds_used = 0;
         for (int round = 0; round < max_rounds && !certified; ++round) {
+            rounds_used = round;
+            if (!(round == 0 && lam_ready)) {
             // ---- active list: rows added by the repair first (newest first: they keep their pivot when the set is
             //      linearly dependent, and an older guess gets the zero multiplier), then the ADMM guess by index ----
             na = 0;
@@ -191,21 +237,7 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
                 }
                 __syncwarp();
             }
-            // ---- L y = rhs, L' lambda = y ----
-            for (int j = 0; j < na; ++j) {
-                const double y = rhs[j] * diag0[j];
-                __syncwarp();
-                if (lane == 0) rhs[j] = y;
-                for (int i = j + 1 + lane; i < na; i += 32) rhs[i] -= M[tri(i, 0) + j] * y;
-                __syncwarp();
-            }
-            for (int j = na - 1; j >= 0; --j) {
-                const double x = rhs[j] * diag0[j];
-                const int tj = tri(j, 0);
-                __syncwarp();
-                if (lane == 0) rhs[j] = x;
-                for (int i = lane; i < j; i += 32) rhs[i] -= M[tj + i] * x;
-                __syncwarp();
+            solve_in_place();
             }
             // rhs now holds lambda (signed: positive pushes against an upper bound)
             // ---- u = u_unc - (AH)'_act lambda : kUChunk variables per lane at a time, so that every active row contributes
@@ -296,6 +328,11 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
             __syncwarp();
         }
 
+        if (B.stats && lane == 0 && !(overflow && !certified && B.overflow_list != nullptr)) {
+            atomicAdd(B.stats + (certified ? (rounds_used < 9 ? rounds_used : 9) : 10), 1ull);
+            if (lam_ready) atomicAdd(B.stats + 11, 1ull);
+            if (lam_ready && certified && rounds_used == 0) atomicAdd(B.stats + 12, 1ull);
+        }
         double obj;
         if (!certified && overflow && B.overflow_list != nullptr) {
             // more active rows than this launch's shared-memory budget: retried by a launch with the full-size layout
@@ -343,6 +380,29 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
         }
         if (certified && B.sign_out) for (int i = lane; i < mt; i += 32) B.sign_out[(size_t)sample * mt + i] = sgn[i];
         if (B.u_full) for (int j = lane; j < n; j += 32) B.u_full[(size_t)sample * n + j] = u[j];
+        // Anchor of a seeded map: export the active rows and the affine multiplier map lambda(x0) = Lam [x0; 1] of this
+        // critical region (five more right-hand sides through the factor already in shared memory).
+        if (certified && B.rec_write && B.cdist == nullptr) {
+            const int rec = B.rec_of[sample];
+            if (rec >= 0 && na <= kPolishSmallActive) {
+                for (int c = 0; c < 5; ++c) {
+                    __syncwarp();
+                    for (int a = lane; a < na; a += 32) {
+                        const int i = act[a];
+                        const double* w = T.AUu + (size_t)i * 4;
+                        double v;
+                        if (c < 4) v = w[c] + (i < m ? T.Gx[(size_t)i * 4 + c] : 0.0);
+                        else v = -(w[0] * B.xref[0] + w[1] * B.xref[1] + w[2] * B.xref[2] + w[3] * B.xref[3]) - (sgn[i] > 0 ? T.hi[i] : T.lo[i]);
+                        rhs[a] = v;
+                    }
+                    __syncwarp();
+                    solve_in_place();
+                    for (int a = lane; a < na; a += 32) B.rec_lam[((size_t)rec * kPolishSmallActive + a) * 5 + c] = rhs[a];
+                }
+                for (int a = lane; a < na; a += 32) B.rec_act[(size_t)rec * (kPolishSmallActive + 1) + 1 + a] = act[a];
+                if (lane == 0) B.rec_act[(size_t)rec * (kPolishSmallActive + 1)] = na;
+            }
+        }
     }
 }
 

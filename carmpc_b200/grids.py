@@ -64,3 +64,25 @@ def shard_range(n: int, rank: int, world: int, align: int = 32):
     per = -(-per // align) * align
     lo = min(rank * per, n)
     return lo, min(lo + per, n)
+
+
+def lattice_seeds(dims, block=(2, 8, 1, 1), start: int = 0, stop: int | None = None) -> np.ndarray:
+    """Seed map for ``BatchQP.solve(seed=...)`` on a C-order tensor grid: the grid is cut into blocks of ``block`` points
+    per axis and the centre point of each block is its anchor (solved cold); every other point of the block starts
+    from the anchor's certified active set.  Returns int32 indices local to the slice [start, stop); a point whose
+    anchor falls outside the slice is its own anchor."""
+    dims = [int(d) for d in dims]
+    n = int(np.prod(dims))
+    stop = n if stop is None else stop
+    idx = np.arange(start, stop, dtype=np.int64)
+    anchor = np.zeros_like(idx)
+    stride = n
+    for d, b in zip(dims, block):
+        stride //= d
+        k = (idx // stride) % d
+        b = max(1, int(b))
+        centre = np.minimum((k // b) * b + b // 2, d - 1)
+        anchor += centre * stride
+    inside = (anchor >= start) & (anchor < stop)
+    local = np.where(inside, anchor - start, idx - start)
+    return local.astype(np.int32)

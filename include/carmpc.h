@@ -168,6 +168,19 @@ int carmpc_qp_solve_batch(void* qp, const double* d_x0, const double* h_xref, co
                           int32_t* d_iters, double* d_u_full, float* d_warm, int warm_in, int warm_out,
                           void* stream);
 
+/* Region-of-attraction maps (the grid search of the reference's paper section III-E: lib/mpc.py:318-338 evaluated
+ * on a grid of initial states): neighbouring states mostly share their active set, so only a sub-lattice of
+ * "anchor" samples is solved cold (ADMM + polish); every other sample i first tries the certified active set of its
+ * anchor d_seed[i] in the float64 polish (one Schur-complement solve + KKT certificate, repaired a few rounds) and
+ * runs ADMM iterations only if that does not certify (set too different, or outside the region of attraction).
+ * d_seed: batch int32; d_seed[i] == i (or out of range) marks an anchor; a follower's seed must be an anchor.
+ * Results are the same certified optima / infeasibility flags as carmpc_qp_solve_batch, whatever the seeds are.
+ * h_seeded (nullable): number of samples certified from their seed without any ADMM iteration. */
+int carmpc_qp_solve_seeded(void* qp, const double* d_x0, const double* h_xref, const double* d_c,
+                           const int32_t* d_seed, int64_t batch, double* d_u0, double* d_objective,
+                           int32_t* d_status, int32_t* d_iters, double* d_u_full, int64_t* h_seeded,
+                           void* stream);
+
 /* Host-buffer convenience: h_x0 is batch x 4 row-major (AoS, as the reference passes states). */
 int carmpc_qp_solve_host(void* qp, const double* h_x0, const double* h_xref, const double* h_c, int64_t batch,
                          double* h_u0 /* batch x 2 */, double* h_objective, int32_t* h_status,
@@ -176,6 +189,11 @@ int carmpc_qp_solve_host(void* qp, const double* h_x0, const double* h_xref, con
 /* Sum over the last solve of the per-sample iteration counts and launches issued (for roofline
  * accounting); both int64. */
 int carmpc_qp_last_stats(void* qp, int64_t* h_total_iters, int64_t* h_launches);
+
+/* Histogram of the float64 polish over the last solve (16 int64): [r] samples certified after r repair rounds
+ * (r = 0..9), [10] handed back to the ADMM, [11] samples whose first round used an anchor's multiplier map,
+ * [12] samples certified by that map alone (seeded solve). */
+int carmpc_qp_polish_stats(void* qp, int64_t* h_hist16);
 
 /* ------------------------------------------------------------------------------------------------
  * Monte-Carlo closed loop against the nonlinear bicycle (lib/simulator.py:51-69), in the order of

@@ -355,3 +355,72 @@ def test_constraint_block_switches(torch_cuda, terminal, inputs, state):
         np.testing.assert_array_equal(np.where(res.status == 0, 0, 1)[~band], ste[~band])
     else:                                                  # without it a feasible state is never called infeasible
         assert not ((res.status == 1) & (ste == 0)).any()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# seeded solve (region-of-attraction maps): same certified optima and flags as the cold solve, whatever the seeds
+# ----------------------------------------------------------------------------------------------------------------
+def _grid_states(torch, axes):
+    from carmpc_b200.grids import materialise_grid
+    return torch.stack(materialise_grid(axes, device="cuda")).contiguous()
+
+
+def _assert_same_solution(a, b):
+    sa, sb = a["status"].cpu().numpy(), b["status"].cpu().numpy()
+    np.testing.assert_array_equal(sa, sb)
+    ok = sa == 0
+    ua, ub = a["u0"].cpu().numpy()[:, ok], b["u0"].cpu().numpy()[:, ok]
+    assert np.abs(ua - ub).max() <= 1e-7                      # two certified KKT points of a strictly convex QP
+    oa, ob = a["objective"].cpu().numpy(), b["objective"].cpu().numpy()
+    assert np.abs(oa[ok] - ob[ok]).max() <= 1e-8 * max(1.0, np.abs(oa[ok]).max())
+    assert np.all(np.isinf(ob[sa == 1])) and np.all(np.isnan(b["u0"].cpu().numpy()[:, sa == 1]))
+    if "u_full" in a:
+        assert np.abs(a["u_full"].cpu().numpy()[ok] - b["u_full"].cpu().numpy()[ok]).max() <= 1e-7
+
+
+@pytest.mark.parametrize("env_name,N", [("RoadOneCarEnv", 20), ("RoadMultipleCarsEnv", 10), ("RoadEnv", 40)])
+def test_seeded_grid_solve_matches_cold_solve_and_oracle(torch_cuda, env_name, N):
+    torch = torch_cuda
+    from carmpc_b200.grids import lattice_seeds
+    c, bq, oq = _setup(env_name, N)
+    g = np.array(c.goal, dtype=float)
+    axes = [np.linspace(g[0] - 20.0, g[0] + 0.5, 24), np.linspace(-3.0, 3.0, 40), np.linspace(-0.3, 0.3, 3),
+            np.linspace(-1.0, 4.0, 4)]
+    x0 = _grid_states(torch, axes)
+    B = x0.shape[1]
+    cold = bq.solve(x0, want_u_full=True)
+    seed = torch.from_numpy(lattice_seeds([len(a) for a in axes], block=(2, 8, 1, 1))).cuda()
+    warm = bq.solve(x0, want_u_full=True, seed=seed)
+    _assert_same_solution(cold, warm)
+    st = cold["status"].cpu().numpy()
+    assert (st == 0).sum() > B // 10 and (st == 1).sum() > 0, "the grid should cross the region-of-attraction boundary"
+    n_anchor = int((seed.cpu().numpy() == np.arange(B)).sum())
+    assert warm["seeded"] >= ((st == 0).sum() - n_anchor) // 2, "most feasible followers should certify from their seed"
+    assert int(warm["iters"].sum().item()) < int(cold["iters"].sum().item())
+    # oracle spot check of the seeded result (BASELINE tolerances)
+    from carmpc_b200.batch import QPResult
+    pick = np.random.default_rng(1).choice(B, size=60, replace=False)
+    res = QPResult(u0=warm["u0"].cpu().numpy().T[pick], objective=warm["objective"].cpu().numpy()[pick],
+                   status=st[pick], iters=warm["iters"].cpu().numpy()[pick], u_full=warm["u_full"].cpu().numpy()[pick])
+    _compare(res, x0.cpu().numpy().T[pick], oq, g, min_feasible=3)
+
+
+def test_seeded_solve_is_independent_of_the_seeds(torch_cuda):
+    """Arbitrary seed maps (random anchors far away, chains, out-of-range entries, all-anchor, single anchor)."""
+    torch = torch_cuda
+    c, bq, oq = _setup("RoadOneCarEnv", 20)
+    x0 = torch.from_numpy(np.ascontiguousarray(_states(c, 3000, seed=7).T)).cuda()
+    B = x0.shape[1]
+    cold = bq.solve(x0)
+    rng = np.random.default_rng(3)
+    ident = np.arange(B, dtype=np.int32)
+    maps = {"identity": ident, "single anchor": np.zeros(B, dtype=np.int32),
+            "random": rng.integers(0, B, size=B).astype(np.int32),
+            "out of range": np.where(rng.random(B) < 0.5, -1, B + 5).astype(np.int32),
+            "chain": np.maximum(ident - 1, 0).astype(np.int32)}
+    for name, m in maps.items():
+        out = bq.solve(x0, seed=torch.from_numpy(m).cuda())
+        _assert_same_solution(cold, out)
+    # the empty batch
+    out = bq.solve(torch.empty((4, 0), dtype=torch.float64, device="cuda"), seed=torch.empty(0, dtype=torch.int32, device="cuda"))
+    assert out["status"].numel() == 0 and out["seeded"] == 0
