@@ -178,7 +178,23 @@ def run_qp_bench(args, rank, world, dev, barrier):
             bN = bq if N == 20 else BatchQP.from_controller(cN)
             ms_n, it_n, _, o = _time_solves(bN, x0, 2, 1, torch)      # one full-size warm-up (workspace allocation)
             tl = bN.tiling()
-            sweep[str(N)] = {"qps": B / (ms_n * 1e-3), "ms": ms_n, "mean_iters": it_n / B,
+            seeded_n = None
+            if not args.skip_seeded and B == x0_full.shape[1]:
+                from carmpc_b200.grids import lattice_seeds
+                blk = tuple(int(v) for v in args.seed_blocks.split(",")[0].split("x"))
+                seed = torch.from_numpy(lattice_seeds([len(a) for a in axes], block=blk)).to(dev)
+                bN.solve(x0, seed=seed)
+                torch.cuda.synchronize()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                for _ in range(2):
+                    os_ = bN.solve(x0, seed=seed)
+                s1.record()
+                s1.synchronize()
+                ms_s = s0.elapsed_time(s1) / 2
+                seeded_n = {"qps": B / (ms_s * 1e-3), "ms": ms_s, "mean_iters": bN.last_stats()[0] / B,
+                            "flags_equal_cold": bool((os_["status"] == o["status"]).all().item())}
+            sweep[str(N)] = {"seeded_map": seeded_n,"qps": B / (ms_n * 1e-3), "ms": ms_n, "mean_iters": it_n / B,
                              "feasible_frac": float((o["status"] == 0).float().mean().item()),
                              "max_iter_count": int((o["status"] == 2).sum().item()),
                              "executed_tflops": it_n * tl["flop_per_iter"] / (ms_n * 1e-3) / 1e12,

@@ -1,5 +1,6 @@
 // C ABI of the batched QP solver (include/carmpc.h, part B): handle creation (host setup + upload), the two-pass
 // ADMM -> polish orchestration, host-buffer convenience entry point and statistics.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -196,6 +197,12 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
     // the ADMM state of every sample is kept (caller's buffer or the workspace): the second pass resumes from it
     ab.warm = d_warm ? d_warm : ws_warm; ab.warm_in = d_warm ? warm_in : 0; ab.warm_out = 1;
     ab.total_iters = ws_total_iters; ab.eps_scale = 1.f; ab.max_iter = host.opts.max_iter; ab.iters_accumulate = 0;
+    // First pass capped at kFirstPassIters: on the region-of-attraction grid every solvable state converges within 90
+    // iterations and only barely infeasible states run longer (up to ~400).  On 128-sample tiles such stragglers hold a
+    // whole tile at ~10 us per iteration; handed to the second pass they continue on narrow tiles (~3 us per iteration).
+    // Batches that run on narrow tiles anyway (closed-loop steps) keep the full budget: a second pass would only add launches.
+    if (host.opts.polish && count >= (int64_t)64 * sm)
+        ab.max_iter = std::min(ab.max_iter, std::max(kFirstPassIters, admm.check_every));
     ab.write_u = host.opts.polish ? 0 : 1;        // with the polish on, only the final pass may fall back to the iterate
     rc = admm_launch(this, ab, st);
     if (rc != CARMPC_OK) return rc;
@@ -214,6 +221,7 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
         // second pass on the samples whose active set the polish could not certify: tighter ADMM, then accept
         last_second_pass = n_failed;
         ab.idx_list = ws_failed; ab.count = n_failed; ab.next = ws_counters + 2; ab.eps_scale = 0.01f;
+        ab.max_iter = host.opts.max_iter;
         ab.warm_in = 1; ab.iters_accumulate = 1; ab.write_u = 1;
         rc = admm_launch(this, ab, st);
         if (rc != CARMPC_OK) return rc;
@@ -265,6 +273,11 @@ int QPHandle::solve_seeded(const double* d_x0, int64_t batch, const double* xref
                    0, nullptr, 1);
         if (rc != CARMPC_OK) return rc;
         iters_sum += last_total_iters; launches += last_launches; second += last_second_pass;
+        if (use_records && n_split[1] > 0) {
+            rc = farkas_export_launch(this, ws_anchor, n_split[0], d_status, ws_warm, d_x0, batch, st);
+            if (rc != CARMPC_OK) return rc;
+            ++launches;
+        }
     }
     int64_t reused = 0;
     if (n_split[1] > 0) {
@@ -342,6 +355,7 @@ int carmpc_qp_create(int n, int m, int k, const double* h_H, const double* h_F, 
     p.n = n; p.m = m; p.mt = m + n;
 #define UP(vec, field) do { rc = upload(q, h.vec, &p.field); if (rc != CARMPC_OK) { delete q; return rc; } } while (0)
     UP(H, H); UP(Hinv, Hinv); UP(F, F); UP(Uu, Uu); UP(AUu, AUu); UP(AH, AH); UP(AHA, AHA); UP(Gx, Gx); UP(Gc, Gc); UP(hi, hi); UP(lo, lo);
+    UP(G, G); UP(Eg, Eg);
 #undef UP
     *handle = q;
     return CARMPC_OK;

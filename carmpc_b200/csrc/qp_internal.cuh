@@ -29,6 +29,7 @@ constexpr int kAdmmThreads = kAdmmWarps * 32;
 constexpr int kMaxN = 160;        // variables (2 x horizon 80)
 constexpr int kMaxM = 392;        // general rows (8 warps x 7 groups x 7 rows)
 constexpr int kPolishMaxActive = 64;
+constexpr int kFirstPassIters = 100;  // iteration cap of the first ADMM pass (stragglers continue in the second pass)
 
 enum SlotState : int { kSlotIdle = -1, kSlotRunning = 0, kSlotSolved = 1, kSlotInfeasible = 2, kSlotMaxIter = 3,
                        kSlotPreInfeasible = 4 };
@@ -110,6 +111,8 @@ struct PolishTables {
     const double* Gc;        // [m]
     const double* hi;        // [mt]  (general rows then box)
     const double* lo;        // [mt]
+    const double* G;         // [m][n]      general rows (rows bounded only from below negated, as hi / lo)
+    const double* Eg;        // [m]         row scaling of the ADMM (its dual iterate is in scaled units)
     int n, m, mt;
 };
 
@@ -151,7 +154,8 @@ struct PolishBatch {
     int* rec_act;            // [records][33]   na (-1: no map), then the active rows in the order of Lam's rows
     int rec_write, rec_read;
     unsigned long long* stats;   // nullable [16]: [r] samples certified after r repair rounds (r = 0..9), [10] not certified,
-                                 // [11] round 0 taken from a multiplier map, [12] certified by a multiplier map alone
+                                 // [11] round 0 taken from a multiplier map, [12] certified by a multiplier map alone,
+                                 // [13] proven infeasible by the anchor's Farkas certificate (or the u-independent rows)
 };
 
 // Host-side setup product (qp_setup.cu)
@@ -185,6 +189,9 @@ int qp_host_setup(int n, int m, int k, const double* H, const double* F, const d
 struct QPHandle;
 int admm_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st);
 int polish_launch(QPHandle* q, const PolishBatch& b, cudaStream_t st);
+// infeasible anchors of a seeded map: turn the ADMM dual iterate into an exact Farkas certificate, affine in x0
+int farkas_export_launch(QPHandle* q, const int* d_anchors, int count, const int* d_status, const float* d_warm,
+                         const double* d_x0, int64_t stride, cudaStream_t st);
 size_t admm_smem_bytes(const QPHost& h, int samples_per_lane, bool mats_in_smem);
 
 struct QPHandle : HandleBase {

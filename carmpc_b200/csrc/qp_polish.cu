@@ -59,13 +59,24 @@ __host__ __device__ inline PolishSmemLayout polish_layout(int n, int mt, int na_
 
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }     // j <= i
 
+// Table gathers of the u update / KKT check: the tables (A H^-1, A H^-1 A') live in L2, so what these loops wait for is load
+// latency.  Volatile asm keeps the loads of a batch together in front of the multiply-adds that consume them (left to
+// itself ptxas interleaves load -> DFMA -> load through one register pair, one L2 round trip after the other).
+__device__ __forceinline__ double ldg_table(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 // (A u_unc)_i = AUu_i . dx
 __device__ __forceinline__ double T_auu(const PolishTables& T, int i, const double (&dx)[4]) {
     const double* w = T.AUu + (size_t)i * 4;
     return w[0] * dx[0] + w[1] * dx[1] + w[2] * dx[2] + w[3] * dx[3];
 }
 
-__global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTables T, const PolishBatch B) {
+// 7 CTAs of 4 warps per SM (72 registers, 28.6 KB of shared memory each): measured against 3..10 CTAs per SM with the
+// matching register budgets, fewer warps with more registers (deeper load batching) is slower, more warps no faster.
+__global__ void __launch_bounds__(kPolishThreads, 7) polish_kernel(const PolishTables T, const PolishBatch B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int warps_per_cta = kPolishThreads / 32;
@@ -135,6 +146,31 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
                 pre_ok = pre_ok && v <= B.pre_hi[k] && v >= B.pre_lo[k];
             }
             if (!pre_ok || !seed_ok) max_rounds = 0;                       // not certified: the ADMM pass decides
+            // Seeded map: a violated u-independent row is infeasibility by itself; an infeasible anchor may have exported a
+            // Farkas certificate y (A'y = 0 exactly, box rows absorb the residual), whose support value is affine in x0:
+            // S(x0) = c0 - cx.x0 < 0 proves that THIS state is infeasible as well.
+            bool proven_infeasible = B.seed != nullptr && !pre_ok;
+            if (B.seed && B.rec_read && pre_ok && B.status[sign_src] == CARMPC_QP_INFEASIBLE) {
+                const int rec = B.rec_of[sign_src];
+                if (rec >= 0 && B.rec_act[(size_t)rec * (kPolishSmallActive + 1)] == -2) {
+                    const double* r = B.rec_lam + (size_t)rec * kPolishSmallActive * 5;
+                    const double S = r[4] - (r[0] * x0[0] + r[1] * x0[1] + r[2] * x0[2] + r[3] * x0[3]);
+                    const double margin = 1e-9 * (r[9] + r[5] * fabs(x0[0]) + r[6] * fabs(x0[1]) + r[7] * fabs(x0[2]) + r[8] * fabs(x0[3]));
+                    proven_infeasible = S < -margin;
+                }
+            }
+            if (proven_infeasible) {
+                if (lane == 0) {
+                    B.status[sample] = CARMPC_QP_INFEASIBLE;
+                    if (B.iters_out) B.iters_out[sample] = 0;
+                    if (B.u0) { B.u0[sample] = NaN; B.u0[B.stride + sample] = NaN; }
+                    if (B.objective) B.objective[sample] = INFINITY;
+                    if (B.polished) B.polished[sample] = 0;
+                    if (B.stats) atomicAdd(B.stats + 13, 1ull);
+                }
+                if (B.u_full) for (int j = lane; j < n; j += 32) B.u_full[(size_t)sample * n + j] = NaN;
+                continue;
+            }
         }
         // L y = rhs, L' x = y in place (M holds the factor, diag0 the reciprocal pivots; skipped pivots give 0)
         auto solve_in_place = [&]() {
@@ -248,11 +284,29 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
                 int jj[kUChunk];
 #pragma unroll
                 for (int c = 0; c < kUChunk; ++c) { jj[c] = j0 + 32 * c + lane; acc[c] = jj[c] < n ? uunc[jj[c]] : 0.0; if (jj[c] >= n) jj[c] = 0; }
-                for (int a = 0; a < na; ++a) {
+                int a = 0;
+                for (; a + 4 <= na; a += 4) {                         // 4 active rows x kUChunk loads in flight
+                    double v[4][kUChunk], la[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        la[r] = rhs[a + r];
+                        const double* row = T.AH + (size_t)act[a + r] * n;
+#pragma unroll
+                        for (int c = 0; c < kUChunk; ++c) v[r][c] = ldg_table(row + jj[c]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c < kUChunk; ++c) acc[c] -= v[r][c] * la[r];
+                }
+                for (; a < na; ++a) {
                     const double la = rhs[a];
                     const double* row = T.AH + (size_t)act[a] * n;
+                    double v[kUChunk];
 #pragma unroll
-                    for (int c = 0; c < kUChunk; ++c) acc[c] -= row[jj[c]] * la;
+                    for (int c = 0; c < kUChunk; ++c) v[c] = ldg_table(row + jj[c]);
+#pragma unroll
+                    for (int c = 0; c < kUChunk; ++c) acc[c] -= v[c] * la;
                 }
 #pragma unroll
                 for (int c = 0; c < kUChunk; ++c) if (j0 + 32 * c + lane < n) u[j0 + 32 * c + lane] = acc[c];
@@ -265,11 +319,29 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
                 int ii[kRowChunk];
 #pragma unroll
                 for (int c = 0; c < kRowChunk; ++c) { ii[c] = i0 + 32 * c + lane; acc[c] = ii[c] < mt ? tsh[ii[c]] : 0.0; if (ii[c] >= mt) ii[c] = 0; }
-                for (int a = 0; a < na; ++a) {
+                int a = 0;
+                for (; a + 2 <= na; a += 2) {                         // 2 active rows x kRowChunk loads in flight
+                    double v[2][kRowChunk], la[2];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        la[r] = rhs[a + r];
+                        const double* row = T.AHA + (size_t)act[a + r] * mt;
+#pragma unroll
+                        for (int c = 0; c < kRowChunk; ++c) v[r][c] = ldg_table(row + ii[c]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+#pragma unroll
+                        for (int c = 0; c < kRowChunk; ++c) acc[c] -= v[r][c] * la[r];
+                }
+                for (; a < na; ++a) {
                     const double la = rhs[a];
                     const double* row = T.AHA + (size_t)act[a] * mt;
+                    double v[kRowChunk];
 #pragma unroll
-                    for (int c = 0; c < kRowChunk; ++c) acc[c] -= row[ii[c]] * la;
+                    for (int c = 0; c < kRowChunk; ++c) v[c] = ldg_table(row + ii[c]);
+#pragma unroll
+                    for (int c = 0; c < kRowChunk; ++c) acc[c] -= v[c] * la;
                 }
 #pragma unroll
                 for (int c = 0; c < kRowChunk; ++c) {
@@ -406,7 +478,82 @@ __global__ void __launch_bounds__(kPolishThreads) polish_kernel(const PolishTabl
     }
 }
 
+// One warp per infeasible anchor.  The ADMM dual iterate of an infeasible problem grows along a Farkas direction; taken
+// as it is (y = E (w - clip(w)) from the stored ADMM state, box multipliers y_b = -G'y so that A'y = 0 holds exactly) it is
+// a certificate whenever its support value is negative, and that value is affine in the state.  Record (10 doubles in
+// the anchor's multiplier-map slot, type tag -2): cx[4], c0, |cx|-bound[4], |c0|-bound, so that a follower evaluates
+// S(x0) = c0 - cx.x0 < -1e-9 (A0 + Ax.|x0|).
+__global__ void __launch_bounds__(128) farkas_export_kernel(const PolishTables T, const int* __restrict__ anchors, int count,
+                                                            const int* __restrict__ status, const float* __restrict__ warm,
+                                                            const double* __restrict__ x0s, int64_t stride,
+                                                            const int* __restrict__ rec_of, double* __restrict__ rec_lam,
+                                                            int* __restrict__ rec_act) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = T.n, m = T.m, mt = T.mt;
+    double* y = reinterpret_cast<double*>(smem_raw) + (size_t)warp * m;
+    const int gw = blockIdx.x * 4 + warp, nw = gridDim.x * 4;
+    for (int q = gw; q < count; q += nw) {
+        const int sample = anchors[q];
+        const int rec = rec_of[sample];
+        if (status[sample] != CARMPC_QP_INFEASIBLE || rec < 0) continue;
+        double x0[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) x0[c] = x0s[(size_t)c * stride + sample];
+        double c0 = 0.0, A0 = 0.0, cx[4] = {0, 0, 0, 0}, Ax[4] = {0, 0, 0, 0};
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) {
+            const double* gx = T.Gx + (size_t)i * 4;
+            const double shift = gx[0] * x0[0] + gx[1] * x0[1] + gx[2] * x0[2] + gx[3] * x0[3];
+            const double e = T.Eg[i], hi = T.hi[i], lo = T.lo[i];
+            const double w = (double)warm[(size_t)sample * mt + i];
+            const double hs = e * (hi - shift), ls = e * (lo - shift);
+            double yu = 0.0;
+            if (isfinite(w)) yu = e * (w > hs ? w - hs : (w < ls ? w - ls : 0.0));
+            y[i] = yu;
+            if (yu != 0.0) {
+                const double t = (yu > 0.0 ? hi : lo) * yu;
+                c0 += t; A0 += fabs(t);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { cx[c] += yu * gx[c]; Ax[c] += fabs(yu * gx[c]); }
+            }
+        }
+        __syncwarp();
+        for (int j = lane; j < n; j += 32) {
+            double s = 0.0;
+            for (int i = 0; i < m; ++i) s += T.G[(size_t)i * n + j] * y[i];
+            const double yb = -s;
+            if (yb != 0.0) {
+                const double t = (yb > 0.0 ? T.hi[m + j] : T.lo[m + j]) * yb;
+                c0 += t; A0 += fabs(t);
+            }
+        }
+        c0 = warp_sum(c0); A0 = warp_sum(A0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { cx[c] = warp_sum(cx[c]); Ax[c] = warp_sum(Ax[c]); }
+        const double S = c0 - (cx[0] * x0[0] + cx[1] * x0[1] + cx[2] * x0[2] + cx[3] * x0[3]);
+        const double margin = 1e-9 * (A0 + Ax[0] * fabs(x0[0]) + Ax[1] * fabs(x0[1]) + Ax[2] * fabs(x0[2]) + Ax[3] * fabs(x0[3]));
+        if (lane == 0 && isfinite(S) && isfinite(margin) && S < -margin) {
+            double* r = rec_lam + (size_t)rec * kPolishSmallActive * 5;
+            r[0] = cx[0]; r[1] = cx[1]; r[2] = cx[2]; r[3] = cx[3]; r[4] = c0;
+            r[5] = Ax[0]; r[6] = Ax[1]; r[7] = Ax[2]; r[8] = Ax[3]; r[9] = A0;
+            rec_act[(size_t)rec * (kPolishSmallActive + 1)] = -2;
+        }
+    }
+}
+
 }  // namespace
+
+int farkas_export_launch(QPHandle* qh, const int* d_anchors, int count, const int* d_status, const float* d_warm,
+                         const double* d_x0, int64_t stride, cudaStream_t st) {
+    if (count <= 0) return CARMPC_OK;
+    const size_t smem = sizeof(double) * 4 * (size_t)qh->polish.m;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((count + 3) / 4, (int64_t)qh->sm * 8));
+    farkas_export_kernel<<<blocks, 128, smem, st>>>(qh->polish, d_anchors, count, d_status, d_warm, d_x0, stride,
+                                                     qh->ws_rec_of, qh->ws_rec_lam, qh->ws_rec_act);
+    CARMPC_CUDA(cudaGetLastError());
+    return CARMPC_OK;
+}
 
 static int polish_launch_cap(QPHandle* qh, const PolishBatch& b, cudaStream_t st) {
     const PolishSmemLayout L = polish_layout(qh->polish.n, qh->polish.mt, b.na_cap);

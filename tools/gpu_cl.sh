@@ -1,12 +1,11 @@
 #!/bin/bash
+# closed loop (config 4) only, three repeats
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_qp_gpu.py -x -q 2>&1 | tail -8
-for v in 1 0; do
-if [ $v = 1 ]; then export CARMPC_NO_ACTIVE_SET_REUSE=1; else unset CARMPC_NO_ACTIVE_SET_REUSE; fi
-timeout 600 python bench.py --steps 20 --skip-e2e --skip-rollout --skip-cpu --skip-sweep --qp-steps 2 > gpurun_out/bench_cl_$v.json 2> gpurun_out/bench_cl_$v.err; echo "bench exit $?"
-python - <<PY
+for r in 1 2 3; do
+timeout 600 python bench.py --steps 5 --skip-e2e --skip-cpu --skip-rollout --skip-sweep --skip-seeded --qp-steps 2 > gpurun_out/bench_cl.json 2> gpurun_out/bench_cl.err
+python - <<'PY'
 import json
-d=json.load(open('gpurun_out/bench_cl_$v.json'))
-print('no_reuse=$v', json.dumps(d['qp']['closed_loop']))
+q=json.load(open('gpurun_out/bench_cl.json'))['qp']
+print('qp ms %.3f'%q['ms_per_step'], {k:(round(v,4) if isinstance(v,float) else v) for k,v in q['closed_loop'].items() if k!='workload'})
 PY
 done
