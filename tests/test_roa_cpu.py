@@ -80,3 +80,34 @@ def test_exact_projection_matches_lp_feasibility():
     band = (np.abs(slack).min(axis=1) <= 1e-6) | (np.abs(margin) <= 1e-6)
     assert 20 < inside.sum() < 380
     np.testing.assert_array_equal(inside[~band], np.asarray(feas, dtype=bool)[~band])
+
+
+def test_lattice_seeds_form_a_single_level_forest():
+    """Seed maps of carmpc_qp_solve_seeded: anchors name themselves, every follower names an anchor of its own block, and
+    shard-local maps never point outside the shard (contiguous index ranges per rank)."""
+    from carmpc_b200.grids import lattice_seeds, shard_range
+    dims = (12, 10, 3, 4)
+    n = int(np.prod(dims))
+    for block in ((3, 8, 1, 1), (1, 1, 1, 1), (5, 4, 2, 3), (20, 20, 20, 20)):
+        s = lattice_seeds(dims, block=block)
+        assert s.dtype == np.int32 and s.shape == (n,)
+        anchors = np.flatnonzero(s == np.arange(n))
+        assert np.array_equal(s[s], s), "a follower's seed must be an anchor"
+        idx = np.stack(np.unravel_index(np.arange(n), dims), axis=1)
+        same_block = np.all(idx // np.array(block) == idx[s] // np.array(block), axis=1)
+        assert same_block.all()
+        expected = int(np.prod([-(-d // min(b, d)) if b <= d else 1 for d, b in zip(dims, block)]))
+        assert len(anchors) == expected
+    for world in (2, 3):
+        for rank in range(world):
+            lo, hi = shard_range(n, rank, world)
+            s = lattice_seeds(dims, block=(3, 8, 1, 1), start=lo, stop=hi)
+            assert s.shape == (hi - lo,) and s.min() >= 0 and s.max() < hi - lo
+            assert np.array_equal(s[s], s)
+
+
+def test_default_seed_block_follows_the_grid_spacing():
+    from carmpc_b200.grids import config3_axes, config2_axes
+    assert roa.default_seed_block(config3_axes()) == (3, 8, 1, 1)
+    assert roa.default_seed_block(config2_axes()) == (1, 7, 1, 1)
+    assert roa.default_seed_block([np.array([1.0]), np.linspace(0, 1, 2), np.linspace(0, 1, 9), np.linspace(0, 1, 9)]) == (1, 1, 1, 1)

@@ -53,3 +53,19 @@ def test_feasibility_map_matches_exact_projection_at_tiny_horizon():
     band = np.abs(slack).min(axis=1) <= 1e-6
     assert 50 < inside.sum() < len(pts) - 50
     np.testing.assert_array_equal(flags[~band], inside[~band])
+
+
+def test_seeded_and_cold_feasibility_maps_are_identical():
+    """The default map goes through carmpc_qp_solve_seeded (lattice anchors + active-set / Farkas reuse); its flags must
+    equal the cold solve's point for point, for the default block and for odd ones."""
+    c = make_controller(make_env("RoadOneCarEnv", [29.9, 1.5, 0, 0]), 20)
+    axes = _grid(40, 48, 4, 5)
+    from carmpc_b200.batch import BatchQP
+    bq = BatchQP.from_controller(c)
+    cold = roa.feasibility_map(c, axes, batch_solver=bq, seeded=False)
+    assert 0.3 < cold.mean() < 0.99
+    for block in (None, (1, 5, 1, 1), (4, 3, 2, 1), (7, 7, 4, 5)):
+        flags = roa.feasibility_map(c, axes, batch_solver=bq, block=block)
+        np.testing.assert_array_equal(flags, cold)
+    st = bq.polish_stats()
+    assert st["used_multiplier_map"] > 0 and sum(st["certified_after_rounds"]) > 0
