@@ -200,8 +200,10 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
     // First pass capped at kFirstPassIters: on the region-of-attraction grid every solvable state converges within 90
     // iterations and only barely infeasible states run longer (up to ~400).  On 128-sample tiles such stragglers hold a
     // whole tile at ~10 us per iteration; handed to the second pass they continue on narrow tiles (~3 us per iteration).
-    // Batches that run on narrow tiles anyway (closed-loop steps) keep the full budget: a second pass would only add launches.
-    if (host.opts.polish && count >= (int64_t)64 * sm)
+    // The cap does not depend on the batch, so a state sees the same iteration schedule however it is batched (cold grid,
+    // seeded map, alone): the statuses of cold solves are path-independent.  Warm-started solves (closed-loop steps: small
+    // batches on narrow tiles, where a second pass only adds launches) keep the full budget.
+    if (host.opts.polish && !(d_warm && warm_in))
         ab.max_iter = std::min(ab.max_iter, std::max(kFirstPassIters, admm.check_every));
     ab.write_u = host.opts.polish ? 0 : 1;        // with the polish on, only the final pass may fall back to the iterate
     rc = admm_launch(this, ab, st);
@@ -228,6 +230,14 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
         pb.idx_list = ws_failed; pb.count = n_failed; pb.n_failed = ws_counters + 3; pb.final_pass = 1;
         rc = polish_launch(this, pb, st);
         if (rc != CARMPC_OK) return rc;
+        // whoever is still at "max_iter" is almost always barely infeasible: the dual iterate of its final ADMM state,
+        // evaluated exactly, settles it (the disturbance-shifted form has no certificate kernel: those keep max_iter)
+        if (d_c == nullptr) {
+            rc = farkas_decide_launch(this, ws_failed, n_failed, status, ab.warm, d_x0, stride, d_u0, d_objective, d_u_full,
+                                      ws_polished, st);
+            if (rc != CARMPC_OK) return rc;
+            ++last_launches;
+        }
         last_launches += 2;
     }
     unsigned long long total = 0;

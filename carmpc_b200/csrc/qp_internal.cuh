@@ -155,7 +155,8 @@ struct PolishBatch {
     int rec_write, rec_read;
     unsigned long long* stats;   // nullable [16]: [r] samples certified after r repair rounds (r = 0..9), [10] not certified,
                                  // [11] round 0 taken from a multiplier map, [12] certified by a multiplier map alone,
-                                 // [13] proven infeasible by the anchor's Farkas certificate (or the u-independent rows)
+                                 // [13] proven infeasible by the anchor's Farkas certificate (or the u-independent rows),
+                                 // [14] max_iter samples proven infeasible by the certificate of their own ADMM state
 };
 
 // Host-side setup product (qp_setup.cu)
@@ -192,6 +193,10 @@ int polish_launch(QPHandle* q, const PolishBatch& b, cudaStream_t st);
 // infeasible anchors of a seeded map: turn the ADMM dual iterate into an exact Farkas certificate, affine in x0
 int farkas_export_launch(QPHandle* q, const int* d_anchors, int count, const int* d_status, const float* d_warm,
                          const double* d_x0, int64_t stride, cudaStream_t st);
+// samples that ran out of ADMM iterations: a valid certificate from their final ADMM state makes them proven infeasible
+int farkas_decide_launch(QPHandle* q, const int* d_list, int count, int* d_status, const float* d_warm, const double* d_x0,
+                         int64_t stride, double* d_u0, double* d_objective, double* d_u_full, int8_t* d_polished,
+                         cudaStream_t st);
 size_t admm_smem_bytes(const QPHost& h, int samples_per_lane, bool mats_in_smem);
 
 struct QPHandle : HandleBase {

@@ -478,35 +478,41 @@ __global__ void __launch_bounds__(kPolishThreads, 7) polish_kernel(const PolishT
     }
 }
 
-// One warp per infeasible anchor.  The ADMM dual iterate of an infeasible problem grows along a Farkas direction; taken
-// as it is (y = E (w - clip(w)) from the stored ADMM state, box multipliers y_b = -G'y so that A'y = 0 holds exactly) it is
-// a certificate whenever its support value is negative, and that value is affine in the state.  Record (10 doubles in
-// the anchor's multiplier-map slot, type tag -2): cx[4], c0, |cx|-bound[4], |c0|-bound, so that a follower evaluates
-// S(x0) = c0 - cx.x0 < -1e-9 (A0 + Ax.|x0|).
-__global__ void __launch_bounds__(128) farkas_export_kernel(const PolishTables T, const int* __restrict__ anchors, int count,
-                                                            const int* __restrict__ status, const float* __restrict__ warm,
-                                                            const double* __restrict__ x0s, int64_t stride,
-                                                            const int* __restrict__ rec_of, double* __restrict__ rec_lam,
-                                                            int* __restrict__ rec_act) {
+// Exact Farkas certificates from the ADMM state.  The ADMM dual iterate of an infeasible problem grows along a Farkas
+// direction; taken as it is (y = E (w - clip(w)) from the stored ADMM state, box multipliers y_b = -G'y so that A'y = 0 holds
+// exactly) it is a certificate whenever its support value is negative - and that value is affine in the state.
+//   mode 0 (anchors of a seeded map, status infeasible): store cx[4], c0, |cx|-bound[4], |c0|-bound in the anchor's
+//          multiplier-map slot (type tag -2); a follower evaluates S(x0) = c0 - cx.x0 < -1e-9 (A0 + Ax.|x0|).
+//   mode 1 (samples that ran out of ADMM iterations): a valid certificate turns "max_iter" into a proven "infeasible".
+// One warp per sample.
+struct FarkasArgs {
+    const int* list; int count; int mode;
+    int* status; const float* warm; const double* x0; int64_t stride;
+    const int* rec_of; double* rec_lam; int* rec_act;                  // mode 0
+    double* u0; double* objective; double* u_full; int8_t* polished;   // mode 1 (nullable)
+    unsigned long long* stats;
+};
+
+__global__ void __launch_bounds__(128) farkas_kernel(const PolishTables T, const FarkasArgs F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = T.n, m = T.m, mt = T.mt;
     double* y = reinterpret_cast<double*>(smem_raw) + (size_t)warp * m;
     const int gw = blockIdx.x * 4 + warp, nw = gridDim.x * 4;
-    for (int q = gw; q < count; q += nw) {
-        const int sample = anchors[q];
-        const int rec = rec_of[sample];
-        if (status[sample] != CARMPC_QP_INFEASIBLE || rec < 0) continue;
+    for (int q = gw; q < F.count; q += nw) {
+        const int sample = F.list[q];
+        const int rec = F.mode == 0 ? F.rec_of[sample] : 0;
+        if (F.status[sample] != (F.mode == 0 ? CARMPC_QP_INFEASIBLE : CARMPC_QP_MAX_ITER) || rec < 0) continue;
         double x0[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) x0[c] = x0s[(size_t)c * stride + sample];
+        for (int c = 0; c < 4; ++c) x0[c] = F.x0[(size_t)c * F.stride + sample];
         double c0 = 0.0, A0 = 0.0, cx[4] = {0, 0, 0, 0}, Ax[4] = {0, 0, 0, 0};
         __syncwarp();
         for (int i = lane; i < m; i += 32) {
             const double* gx = T.Gx + (size_t)i * 4;
             const double shift = gx[0] * x0[0] + gx[1] * x0[1] + gx[2] * x0[2] + gx[3] * x0[3];
             const double e = T.Eg[i], hi = T.hi[i], lo = T.lo[i];
-            const double w = (double)warm[(size_t)sample * mt + i];
+            const double w = (double)F.warm[(size_t)sample * mt + i];
             const double hs = e * (hi - shift), ls = e * (lo - shift);
             double yu = 0.0;
             if (isfinite(w)) yu = e * (w > hs ? w - hs : (w < ls ? w - ls : 0.0));
@@ -533,26 +539,55 @@ __global__ void __launch_bounds__(128) farkas_export_kernel(const PolishTables T
         for (int c = 0; c < 4; ++c) { cx[c] = warp_sum(cx[c]); Ax[c] = warp_sum(Ax[c]); }
         const double S = c0 - (cx[0] * x0[0] + cx[1] * x0[1] + cx[2] * x0[2] + cx[3] * x0[3]);
         const double margin = 1e-9 * (A0 + Ax[0] * fabs(x0[0]) + Ax[1] * fabs(x0[1]) + Ax[2] * fabs(x0[2]) + Ax[3] * fabs(x0[3]));
-        if (lane == 0 && isfinite(S) && isfinite(margin) && S < -margin) {
-            double* r = rec_lam + (size_t)rec * kPolishSmallActive * 5;
-            r[0] = cx[0]; r[1] = cx[1]; r[2] = cx[2]; r[3] = cx[3]; r[4] = c0;
-            r[5] = Ax[0]; r[6] = Ax[1]; r[7] = Ax[2]; r[8] = Ax[3]; r[9] = A0;
-            rec_act[(size_t)rec * (kPolishSmallActive + 1)] = -2;
+        const bool valid = isfinite(S) && isfinite(margin) && S < -margin;
+        if (!valid) continue;
+        if (F.mode == 0) {
+            if (lane == 0) {
+                double* r = F.rec_lam + (size_t)rec * kPolishSmallActive * 5;
+                r[0] = cx[0]; r[1] = cx[1]; r[2] = cx[2]; r[3] = cx[3]; r[4] = c0;
+                r[5] = Ax[0]; r[6] = Ax[1]; r[7] = Ax[2]; r[8] = Ax[3]; r[9] = A0;
+                F.rec_act[(size_t)rec * (kPolishSmallActive + 1)] = -2;
+            }
+        } else {
+            const double NaN = __longlong_as_double(0x7ff8000000000000ll);
+            if (lane == 0) {
+                F.status[sample] = CARMPC_QP_INFEASIBLE;
+                if (F.u0) { F.u0[sample] = NaN; F.u0[F.stride + sample] = NaN; }
+                if (F.objective) F.objective[sample] = INFINITY;
+                if (F.polished) F.polished[sample] = 0;
+                if (F.stats) atomicAdd(F.stats + 14, 1ull);
+            }
+            if (F.u_full) for (int j = lane; j < n; j += 32) F.u_full[(size_t)sample * n + j] = NaN;
         }
     }
 }
 
 }  // namespace
 
-int farkas_export_launch(QPHandle* qh, const int* d_anchors, int count, const int* d_status, const float* d_warm,
-                         const double* d_x0, int64_t stride, cudaStream_t st) {
-    if (count <= 0) return CARMPC_OK;
+static int farkas_launch(QPHandle* qh, const FarkasArgs& f, cudaStream_t st) {
+    if (f.count <= 0) return CARMPC_OK;
     const size_t smem = sizeof(double) * 4 * (size_t)qh->polish.m;
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((count + 3) / 4, (int64_t)qh->sm * 8));
-    farkas_export_kernel<<<blocks, 128, smem, st>>>(qh->polish, d_anchors, count, d_status, d_warm, d_x0, stride,
-                                                     qh->ws_rec_of, qh->ws_rec_lam, qh->ws_rec_act);
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((f.count + 3) / 4, (int64_t)qh->sm * 8));
+    farkas_kernel<<<blocks, 128, smem, st>>>(qh->polish, f);
     CARMPC_CUDA(cudaGetLastError());
     return CARMPC_OK;
+}
+
+int farkas_export_launch(QPHandle* qh, const int* d_anchors, int count, const int* d_status, const float* d_warm,
+                         const double* d_x0, int64_t stride, cudaStream_t st) {
+    FarkasArgs f = {};
+    f.list = d_anchors; f.count = count; f.mode = 0; f.status = const_cast<int*>(d_status); f.warm = d_warm; f.x0 = d_x0;
+    f.stride = stride; f.rec_of = qh->ws_rec_of; f.rec_lam = qh->ws_rec_lam; f.rec_act = qh->ws_rec_act;
+    return farkas_launch(qh, f, st);
+}
+
+int farkas_decide_launch(QPHandle* qh, const int* d_list, int count, int* d_status, const float* d_warm, const double* d_x0,
+                         int64_t stride, double* d_u0, double* d_objective, double* d_u_full, int8_t* d_polished,
+                         cudaStream_t st) {
+    FarkasArgs f = {};
+    f.list = d_list; f.count = count; f.mode = 1; f.status = d_status; f.warm = d_warm; f.x0 = d_x0; f.stride = stride;
+    f.u0 = d_u0; f.objective = d_objective; f.u_full = d_u_full; f.polished = d_polished; f.stats = qh->ws_polish_stats;
+    return farkas_launch(qh, f, st);
 }
 
 static int polish_launch_cap(QPHandle* qh, const PolishBatch& b, cudaStream_t st) {

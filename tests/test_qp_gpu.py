@@ -365,10 +365,18 @@ def _grid_states(torch, axes):
     return torch.stack(materialise_grid(axes, device="cuda")).contiguous()
 
 
-def _assert_same_solution(a, b):
+def _assert_same_solution(a, b, oq=None, x0=None):
+    """Flags must be identical; the only exemption is BASELINE's: states whose exact feasibility slack (oracle LP) is
+    within 1e-6 of zero, which are enumerated here (the two paths may stop on different sides of such a boundary)."""
     sa, sb = a["status"].cpu().numpy(), b["status"].cpu().numpy()
-    np.testing.assert_array_equal(sa, sb)
-    ok = sa == 0
+    diff = np.flatnonzero(sa != sb)
+    if len(diff):
+        assert oq is not None and len(diff) <= 3, f"{len(diff)} feasibility flags differ"
+        from oracle import carmpc_oracle as orc
+        _, slack = orc.qp_feasible_lp(oq, x0.cpu().numpy().T[diff])
+        assert np.all(np.abs(slack) <= 1e-6), f"flags differ outside the boundary band: slack {slack}"
+    ok = (sa == 0) & (sb == 0)
+    sa = np.where(sa == sb, sa, -1)
     ua, ub = a["u0"].cpu().numpy()[:, ok], b["u0"].cpu().numpy()[:, ok]
     assert np.abs(ua - ub).max() <= 1e-7                      # two certified KKT points of a strictly convex QP
     oa, ob = a["objective"].cpu().numpy(), b["objective"].cpu().numpy()
@@ -391,7 +399,7 @@ def test_seeded_grid_solve_matches_cold_solve_and_oracle(torch_cuda, env_name, N
     cold = bq.solve(x0, want_u_full=True)
     seed = torch.from_numpy(lattice_seeds([len(a) for a in axes], block=(2, 8, 1, 1))).cuda()
     warm = bq.solve(x0, want_u_full=True, seed=seed)
-    _assert_same_solution(cold, warm)
+    _assert_same_solution(cold, warm, oq, x0)
     st = cold["status"].cpu().numpy()
     assert (st == 0).sum() > B // 10 and (st == 1).sum() > 0, "the grid should cross the region-of-attraction boundary"
     n_anchor = int((seed.cpu().numpy() == np.arange(B)).sum())
@@ -420,7 +428,7 @@ def test_seeded_solve_is_independent_of_the_seeds(torch_cuda):
             "chain": np.maximum(ident - 1, 0).astype(np.int32)}
     for name, m in maps.items():
         out = bq.solve(x0, seed=torch.from_numpy(m).cuda())
-        _assert_same_solution(cold, out)
+        _assert_same_solution(cold, out, oq, x0)
     # the empty batch
     out = bq.solve(torch.empty((4, 0), dtype=torch.float64, device="cuda"), seed=torch.empty(0, dtype=torch.int32, device="cuda"))
     assert out["status"].numel() == 0 and out["seeded"] == 0
