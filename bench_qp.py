@@ -164,10 +164,25 @@ def run_qp_bench(args, rank, world, dev, barrier):
                 "anchors": int((seed == torch.arange(B, device=dev, dtype=torch.int32)).sum().item()),
                 "certified_from_seed": o["seeded"], "mean_admm_iters": it_sum / steps / B,
                 "flags_equal_cold": same, "max_du0_vs_cold": du, "polish": bq.polish_stats()}
+        # end to end for the map: grid axes on the host in, status / u0 / objective on the host out
+        blk0 = blocks[0]
+        bq.solve_map_host(axes, block=blk0)
+        dts = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rm = bq.solve_map_host(axes, block=blk0)
+            dts.append(time.perf_counter() - t0)
+        tm = torch.tensor([float(np.median(dts))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        map_e2e = {"value": world * B / float(tm.item()), "unit": "QPs/s", "h2d_bytes_per_step": int(sum(len(a) for a in axes) * 8),
+                   "d2h_bytes_per_step": B * (16 + 8 + 4 + 4), "call": "carmpc_qp_map_host (grid axes in, status / u0 / objective / iters out)",
+                   "flags_equal_cold": bool(np.array_equal(rm.status, out["status"].cpu().numpy()))}
         best = max(seeded, key=lambda k: seeded[k]["qps"])
         res["seeded_map"] = {"metric": "horizon-20 QPs/s (region-of-attraction map, active sets seeded from lattice anchors)",
                              "value": seeded[best]["qps"], "unit": "QPs/s", "ms_per_step": seeded[best]["ms"],
-                             "block": best, "by_block": seeded,
+                             "block": best, "by_block": seeded, "e2e": map_e2e,
                              "call": "carmpc_qp_solve_seeded (same certified optima and flags as the cold solve)"}
 
     # ---- config 4: output-feedback Monte-Carlo closed loop --------------------------------------------------------

@@ -45,6 +45,8 @@ SIGNATURES = {
     "carmpc_qp_get_setup": (_i32, [_vp, _i32, _dp, _i32]),
     "carmpc_qp_solve_batch": (_i32, [_vp, _dp, _dp, _dp, _i64, _dp, _dp, _vp, _vp, _dp, _vp, _i32, _i32, _vp]),
     "carmpc_qp_solve_seeded": (_i32, [_vp, _dp, _dp, _dp, _vp, _i64, _dp, _dp, _vp, _vp, _dp, ctypes.POINTER(_i64), _vp]),
+    "carmpc_qp_map_host": (_i32, [_vp, _dp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                  ctypes.POINTER(ctypes.c_int32), _dp, _dp, _dp, _vp, _vp, ctypes.POINTER(_i64)]),
     "carmpc_qp_solve_host": (_i32, [_vp, _dp, _dp, _dp, _i64, _dp, _dp, _vp, _vp, _dp]),
     "carmpc_qp_polish_stats": (_i32, [_vp, ctypes.POINTER(_i64)]),
     "carmpc_qp_last_stats": (_i32, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),

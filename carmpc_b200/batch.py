@@ -213,6 +213,7 @@ class QPResult:
     status: np.ndarray          # (B,)     0 solved, 1 infeasible (outside the region of attraction), 2 max_iter
     iters: np.ndarray           # (B,)     ADMM iterations spent
     u_full: Optional[np.ndarray] = None     # (B, 2N)
+    seeded: int = 0                         # map solves: samples certified from their anchor without ADMM iterations
 
 
 class BatchQP(_Handle):
@@ -329,6 +330,29 @@ class BatchQP(_Handle):
         check(self._lib.carmpc_qp_solve_host(self._h, _capi.ptr(x0), _capi.ptr(xref), _capi.ptr(cc), B,
                                              _capi.ptr(res.u0), _capi.ptr(res.objective), _capi.ptr(res.status),
                                              _capi.ptr(res.iters), _capi.ptr(res.u_full)))
+        return res
+
+    def solve_map_host(self, axes, block=None, x_ref=None, axis_to_state=(0, 1, 2, 3), want_u0: bool = True,
+                       want_objective: bool = True) -> QPResult:
+        """Region-of-attraction map of the C-order tensor grid ``axes`` (four 1-D arrays; axis k is state component
+        ``axis_to_state[k]``), numpy in / numpy out (``carmpc_qp_map_host``).  ``block``: points per axis of the lattice
+        blocks for the seeded solve (None: every point cold).  ``result.seeded`` = points certified from their anchor."""
+        ax = [_f64(np.atleast_1d(a)) for a in axes]
+        if len(ax) != 4:
+            raise ValueError("axes must be four 1-D arrays")
+        dims = (ctypes.c_int32 * 4)(*[len(a) for a in ax])
+        a2s = (ctypes.c_int32 * 4)(*axis_to_state)
+        blk = (ctypes.c_int32 * 4)(*[int(b) for b in block]) if block is not None else None
+        flat = _f64(np.concatenate(ax))
+        B = int(np.prod([len(a) for a in ax]))
+        xref = _f64(self.pq.goal if x_ref is None else x_ref)
+        res = QPResult(u0=np.zeros((B, 2)) if want_u0 else None, objective=np.zeros(B) if want_objective else None,
+                       status=np.zeros(B, dtype=np.int32), iters=np.zeros(B, dtype=np.int32))
+        seeded = ctypes.c_int64(0)
+        check(self._lib.carmpc_qp_map_host(self._h, _capi.ptr(flat), dims, a2s, blk, _capi.ptr(xref), _capi.ptr(res.u0),
+                                           _capi.ptr(res.objective), _capi.ptr(res.status), _capi.ptr(res.iters),
+                                           ctypes.byref(seeded)))
+        res.seeded = int(seeded.value)
         return res
 
     # ---- Monte-Carlo closed loop ------------------------------------------------------------------------

@@ -63,12 +63,35 @@ __global__ void split_seeds_kernel(const int* __restrict__ seed, int count, int*
     }
 }
 
+// region-of-attraction map: expand the C-order tensor grid into SoA states and name every point's lattice anchor (the
+// centre of its block of `block` points per axis)
+struct MapGrid {
+    int dims[4], state_of_axis[4], offset[4], block[4];
+};
+
+__global__ void map_expand_kernel(const double* __restrict__ axes, MapGrid g, int64_t n, double* __restrict__ x0, int* __restrict__ seed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t rem = i, anchor = 0, stride = n;
+    for (int k = 0; k < 4; ++k) {
+        stride /= g.dims[k];
+        const int idx = (int)(rem / stride);
+        rem -= (int64_t)idx * stride;
+        x0[(size_t)g.state_of_axis[k] * n + i] = axes[g.offset[k] + idx];
+        const int b = g.block[k];
+        const int centre = min((idx / b) * b + b / 2, g.dims[k] - 1);
+        anchor += (int64_t)centre * stride;
+    }
+    seed[i] = (int)anchor;
+}
+
 }  // namespace
 
 int QPHandle::ensure_io(int64_t batch, bool want_full) {
     if (batch > io_cap) {
         cudaFree(io_x0_aos); cudaFree(io_x0); cudaFree(io_c); cudaFree(io_u0); cudaFree(io_u0_aos); cudaFree(io_obj);
-        cudaFree(io_status); cudaFree(io_iters);
+        cudaFree(io_status); cudaFree(io_iters); cudaFree(io_seed);
+        io_seed = nullptr;
         io_x0_aos = io_x0 = io_c = io_u0 = io_u0_aos = io_obj = nullptr; io_status = io_iters = nullptr;
         io_cap = 0;
         CARMPC_CUDA(cudaMalloc(&io_x0_aos, sizeof(double) * 4 * batch));
@@ -79,6 +102,7 @@ int QPHandle::ensure_io(int64_t batch, bool want_full) {
         CARMPC_CUDA(cudaMalloc(&io_obj, sizeof(double) * batch));
         CARMPC_CUDA(cudaMalloc(&io_status, sizeof(int32_t) * batch));
         CARMPC_CUDA(cudaMalloc(&io_iters, sizeof(int32_t) * batch));
+        CARMPC_CUDA(cudaMalloc(&io_seed, sizeof(int32_t) * batch));
         io_cap = batch;
     }
     if (want_full && batch > io_full_cap) {
@@ -95,7 +119,7 @@ QPHandle::~QPHandle() {
     cudaFree(ws_counters); cudaFree(ws_total_iters); cudaFree(ws_polished); cudaFree(ws_warm); cudaFree(ws_overflow);
     cudaFree(ws_anchor); cudaFree(ws_follow); cudaFree(ws_rec_of); cudaFree(ws_rec_lam); cudaFree(ws_rec_act); cudaFree(ws_polish_stats);
     cudaFree(io_x0_aos); cudaFree(io_x0); cudaFree(io_c); cudaFree(io_u0); cudaFree(io_u0_aos); cudaFree(io_obj); cudaFree(io_full);
-    cudaFree(io_status); cudaFree(io_iters);
+    cudaFree(io_status); cudaFree(io_iters); cudaFree(io_seed); cudaFree(io_axes);
 }
 
 int QPHandle::ensure_workspace(int64_t batch) {
@@ -475,6 +499,60 @@ int carmpc_qp_solve_host(void* qp, const double* h_x0, const double* h_xref, con
     CARMPC_CUDA(cudaMemcpyAsync(h_status, q->io_status, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
     if (h_iters) CARMPC_CUDA(cudaMemcpyAsync(h_iters, q->io_iters, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
     if (h_u_full) CARMPC_CUDA(cudaMemcpyAsync(h_u_full, q->io_full, sizeof(double) * (size_t)n * batch, cudaMemcpyDeviceToHost, st));
+    CARMPC_CUDA(cudaStreamSynchronize(st));
+    CARMPC_CUDA(cudaGetLastError());
+    return CARMPC_OK;
+}
+
+int carmpc_qp_map_host(void* qp, const double* h_axes, const int32_t dims[4], const int32_t axis_to_state[4],
+                       const int32_t block[4], const double* h_xref, double* h_u0, double* h_objective, int32_t* h_status,
+                       int32_t* h_iters, int64_t* h_seeded) {
+    QPHandle* q = check_handle<QPHandle>(qp, kQP);
+    CARMPC_REQUIRE(q != nullptr, "not a QP handle");
+    CARMPC_REQUIRE(h_axes && dims && axis_to_state && h_xref && h_status, "null pointer");
+    if (q->host_only) { set_error("carmpc_qp: this handle was created without a CUDA device; there is no CPU solver"); return CARMPC_ERR_CUDA; }
+    MapGrid g;
+    int64_t n = 1;
+    int off = 0, seen = 0;
+    bool blocked = false;
+    for (int k = 0; k < 4; ++k) {
+        CARMPC_REQUIRE(dims[k] >= 1 && dims[k] <= 4096, "each axis must have 1..4096 points");
+        CARMPC_REQUIRE(axis_to_state[k] >= 0 && axis_to_state[k] < 4, "axis_to_state entries must be 0..3");
+        CARMPC_REQUIRE(block == nullptr || block[k] >= 1, "block entries must be >= 1");
+        seen |= 1 << axis_to_state[k];
+        g.dims[k] = dims[k]; g.state_of_axis[k] = axis_to_state[k]; g.offset[k] = off;
+        g.block[k] = block ? block[k] : 1;
+        blocked = blocked || g.block[k] > 1;
+        off += dims[k];
+        n *= dims[k];
+    }
+    CARMPC_REQUIRE(seen == 15, "axis_to_state must be a permutation of 0..3");
+    CARMPC_REQUIRE(n < (int64_t)1 << 31, "grid too large for one call");
+    if (h_seeded) *h_seeded = 0;
+    int rc = q->ensure_io(n, false);
+    if (rc != CARMPC_OK) return rc;
+    if (q->io_axes == nullptr) CARMPC_CUDA(cudaMalloc(&q->io_axes, sizeof(double) * 4 * 4096));
+    cudaStream_t st = nullptr;
+    CARMPC_CUDA(cudaMemcpyAsync(q->io_axes, h_axes, sizeof(double) * off, cudaMemcpyHostToDevice, st));
+    map_expand_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(q->io_axes, g, n, q->io_x0, q->io_seed);
+    CARMPC_CUDA(cudaGetLastError());
+    q->use_records = 0;
+    if (blocked && q->host.opts.polish) {
+        rc = q->solve_seeded(q->io_x0, n, h_xref, nullptr, q->io_seed, h_u0 ? q->io_u0 : nullptr, h_objective ? q->io_obj : nullptr,
+                             q->io_status, q->io_iters, nullptr, st);
+        if (rc == CARMPC_OK && h_seeded) *h_seeded = q->last_reused;
+    } else {
+        rc = q->solve(q->io_x0, n, h_xref, nullptr, nullptr, n, h_u0 ? q->io_u0 : nullptr, h_objective ? q->io_obj : nullptr,
+                      q->io_status, q->io_iters, nullptr, nullptr, 0, 0, st);
+    }
+    if (rc != CARMPC_OK) return rc;
+    if (h_u0) {
+        soa_to_aos_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(q->io_u0, q->io_u0_aos, n, 2);
+        CARMPC_CUDA(cudaMemcpyAsync(h_u0, q->io_u0_aos, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, st));
+    }
+    if (h_objective) CARMPC_CUDA(cudaMemcpyAsync(h_objective, q->io_obj, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CARMPC_CUDA(cudaMemcpyAsync(h_status, q->io_status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    if (h_iters) CARMPC_CUDA(cudaMemcpyAsync(h_iters, q->io_iters, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
     CARMPC_CUDA(cudaStreamSynchronize(st));
     CARMPC_CUDA(cudaGetLastError());
     return CARMPC_OK;

@@ -230,7 +230,8 @@ struct QPHandle : HandleBase {
     int64_t io_cap = 0, io_full_cap = 0;
     double *io_x0_aos = nullptr, *io_x0 = nullptr, *io_c = nullptr, *io_u0 = nullptr, *io_u0_aos = nullptr, *io_obj = nullptr,
            *io_full = nullptr;
-    int32_t *io_status = nullptr, *io_iters = nullptr;
+    int32_t *io_status = nullptr, *io_iters = nullptr, *io_seed = nullptr;
+    double* io_axes = nullptr;                   // grid axes of carmpc_qp_map_host
     int ensure_io(int64_t batch, bool want_full);
     int64_t last_total_iters = 0, last_launches = 0, last_second_pass = 0;
     int sm = 148;

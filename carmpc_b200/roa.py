@@ -47,19 +47,13 @@ def feasibility_map(controller, axes: Sequence[np.ndarray], x_ref=None, batch_so
     controller's QP is feasible.  Solved on the GPU (no CPU fallback).  ``seeded`` (default) solves only a sub-lattice
     of anchors cold and certifies every other point from its anchor's active set / Farkas certificate
     (``carmpc_qp_solve_seeded``: same flags, 1.7 - 4.6 x faster on 10^6-point maps)."""
-    import torch
     from .batch import BatchQP
-    from .grids import materialise_grid, lattice_seeds
     bq = batch_solver if batch_solver is not None else BatchQP.from_controller(controller)
-    cols = materialise_grid(axes, device="cuda")
-    x0 = torch.stack(cols).contiguous()
-    seed = None
+    blk = None
     if seeded and bq.opts.polish:
-        blk = tuple(block) if block is not None else default_seed_block(axes)
-        if int(np.prod(blk)) > 1:
-            seed = torch.from_numpy(lattice_seeds([len(a) for a in axes], block=blk)).cuda()
-    out = bq.solve(x0, x_ref=x_ref, seed=seed)
-    return (out["status"] == 0).cpu().numpy()
+        blk = tuple(int(v) for v in block) if block is not None else default_seed_block(axes)
+    res = bq.solve_map_host(axes, block=blk, x_ref=x_ref, want_u0=False, want_objective=False)
+    return res.status == 0
 
 
 def boundary_layer(flags: np.ndarray, shape: Sequence[int]) -> np.ndarray:

@@ -181,6 +181,16 @@ int carmpc_qp_solve_seeded(void* qp, const double* d_x0, const double* h_xref, c
                            int32_t* d_status, int32_t* d_iters, double* d_u_full, int64_t* h_seeded,
                            void* stream);
 
+/* Region-of-attraction map from the host: the states are the C-order tensor grid of four axes (h_axes: the axes
+ * concatenated, dims[k] points each, 1..4096; axis k is state component axis_to_state[k]), expanded on the device.
+ * block (nullable = every point cold): points per axis of the lattice blocks whose centre points are the anchors
+ * of carmpc_qp_solve_seeded.  Outputs as carmpc_qp_solve_host (h_u0 batch x 2 row-major, any may be NULL except
+ * h_status); batch = dims[0] dims[1] dims[2] dims[3].  This is the sampled counterpart of the reference's exact
+ * but impractical projection lib/in_adm_set.py:4-77 ("grid search" of the paper, section III-E). */
+int carmpc_qp_map_host(void* qp, const double* h_axes, const int32_t dims[4], const int32_t axis_to_state[4],
+                       const int32_t block[4], const double* h_xref, double* h_u0, double* h_objective,
+                       int32_t* h_status, int32_t* h_iters, int64_t* h_seeded);
+
 /* Host-buffer convenience: h_x0 is batch x 4 row-major (AoS, as the reference passes states). */
 int carmpc_qp_solve_host(void* qp, const double* h_x0, const double* h_xref, const double* h_c, int64_t batch,
                          double* h_u0 /* batch x 2 */, double* h_objective, int32_t* h_status,

@@ -432,3 +432,31 @@ def test_seeded_solve_is_independent_of_the_seeds(torch_cuda):
     # the empty batch
     out = bq.solve(torch.empty((4, 0), dtype=torch.float64, device="cuda"), seed=torch.empty(0, dtype=torch.int32, device="cuda"))
     assert out["status"].numel() == 0 and out["seeded"] == 0
+
+
+def test_map_host_entry_point_matches_the_batched_solve(torch_cuda):
+    """carmpc_qp_map_host (grid axes in, numpy out): cold and seeded maps against the batched solve of the materialised grid,
+    including a permuted axis order (the state of axis k is axis_to_state[k])."""
+    torch = torch_cuda
+    c, bq, oq = _setup("RoadOneCarEnv", 20)
+    axes = [np.linspace(8.0, 30.4, 18), np.linspace(-2.8, 2.9, 33), np.linspace(-0.3, 0.3, 3), np.linspace(-1.0, 4.0, 4)]
+    x0 = _grid_states(torch, axes)
+    ref = bq.solve(x0)
+    st, u0, obj = ref["status"].cpu().numpy(), ref["u0"].cpu().numpy().T, ref["objective"].cpu().numpy()
+    ok = st == 0
+    for block in (None, (3, 8, 1, 1), (2, 5, 3, 2)):
+        res = bq.solve_map_host(axes, block=block)
+        np.testing.assert_array_equal(res.status, st)
+        assert np.abs(res.u0[ok] - u0[ok]).max() <= 1e-7 and np.abs(res.objective[ok] - obj[ok]).max() <= 1e-7
+        assert np.all(np.isnan(res.u0[~ok])) and np.all(np.isinf(res.objective[~ok]))
+        assert (res.seeded > 0) == (block is not None)
+    # axes given as (v, y, x, psi): same states in another order
+    perm = (3, 1, 0, 2)
+    res = bq.solve_map_host([axes[k] for k in perm], block=(1, 8, 3, 1), axis_to_state=perm, want_objective=False)
+    dims = [len(axes[k]) for k in perm]
+    idx = np.stack(np.unravel_index(np.arange(int(np.prod(dims))), dims), axis=0)      # index along each given axis
+    flat = np.ravel_multi_index([idx[perm.index(s)] for s in range(4)], [len(a) for a in axes])
+    np.testing.assert_array_equal(res.status, st[flat])
+    assert res.objective is None and np.abs(res.u0[ok[flat]] - u0[flat][ok[flat]]).max() <= 1e-7
+    with pytest.raises(Exception):
+        bq.solve_map_host(axes, axis_to_state=(0, 1, 1, 3))
