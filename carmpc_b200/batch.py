@@ -272,7 +272,8 @@ class BatchQP(_Handle):
         check(self._lib.carmpc_qp_polish_stats(self._h, h))
         v = [int(x) for x in h]
         return {"certified_after_rounds": v[:10], "handed_to_admm": v[10], "used_multiplier_map": v[11],
-                "certified_by_map_alone": v[12]}
+                "certified_by_map_alone": v[12], "infeasible_by_anchor_certificate": v[13],
+                "max_iter_settled_by_own_certificate": v[14], "infeasible_before_second_pass": v[15]}
 
     # ---- device tensors ---------------------------------------------------------------------------
     def solve(self, x0, x_ref=None, c=None, want_u_full: bool = False, warm=None, warm_in: bool = False,

@@ -243,21 +243,35 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
         CARMPC_CUDA(cudaMemcpyAsync(&n_failed, ws_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         CARMPC_CUDA(cudaStreamSynchronize(st));
     }
+    const int* second_list = ws_failed;
+    if (n_failed > 0 && d_c == nullptr) {
+        // most of what the first pass could not settle is barely infeasible: the exact certificate test on the first-pass
+        // state removes those before the (long) tighter pass
+        CARMPC_CUDA(cudaMemsetAsync(ws_counters + 7, 0, sizeof(int), st));
+        rc = farkas_filter_launch(this, ws_failed, n_failed, status, ab.warm, d_x0, stride, d_u0, d_objective, d_u_full,
+                                  ws_polished, ws_overflow, ws_counters + 7, st);
+        if (rc != CARMPC_OK) return rc;
+        ++last_launches;
+        CARMPC_CUDA(cudaMemcpyAsync(&n_failed, ws_counters + 7, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CARMPC_CUDA(cudaStreamSynchronize(st));
+        // the survivors move to ws_failed (the polish launches below reuse ws_overflow)
+        if (n_failed > 0) CARMPC_CUDA(cudaMemcpyAsync(ws_failed, ws_overflow, sizeof(int) * n_failed, cudaMemcpyDeviceToDevice, st));
+    }
     if (n_failed > 0) {
         // second pass on the samples whose active set the polish could not certify: tighter ADMM, then accept
         last_second_pass = n_failed;
-        ab.idx_list = ws_failed; ab.count = n_failed; ab.next = ws_counters + 2; ab.eps_scale = 0.01f;
+        ab.idx_list = second_list; ab.count = n_failed; ab.next = ws_counters + 2; ab.eps_scale = 0.01f;
         ab.max_iter = host.opts.max_iter;
         ab.warm_in = 1; ab.iters_accumulate = 1; ab.write_u = 1;
         rc = admm_launch(this, ab, st);
         if (rc != CARMPC_OK) return rc;
-        pb.idx_list = ws_failed; pb.count = n_failed; pb.n_failed = ws_counters + 3; pb.final_pass = 1;
+        pb.idx_list = second_list; pb.count = n_failed; pb.n_failed = ws_counters + 3; pb.final_pass = 1;
         rc = polish_launch(this, pb, st);
         if (rc != CARMPC_OK) return rc;
         // whoever is still at "max_iter" is almost always barely infeasible: the dual iterate of its final ADMM state,
         // evaluated exactly, settles it (the disturbance-shifted form has no certificate kernel: those keep max_iter)
         if (d_c == nullptr) {
-            rc = farkas_decide_launch(this, ws_failed, n_failed, status, ab.warm, d_x0, stride, d_u0, d_objective, d_u_full,
+            rc = farkas_decide_launch(this, second_list, n_failed, status, ab.warm, d_x0, stride, d_u0, d_objective, d_u_full,
                                       ws_polished, st);
             if (rc != CARMPC_OK) return rc;
             ++last_launches;

@@ -156,7 +156,8 @@ struct PolishBatch {
     unsigned long long* stats;   // nullable [16]: [r] samples certified after r repair rounds (r = 0..9), [10] not certified,
                                  // [11] round 0 taken from a multiplier map, [12] certified by a multiplier map alone,
                                  // [13] proven infeasible by the anchor's Farkas certificate (or the u-independent rows),
-                                 // [14] max_iter samples proven infeasible by the certificate of their own ADMM state
+                                 // [14] max_iter samples proven infeasible by the certificate of their own ADMM state,
+                                 // [15] samples proven infeasible the same way before the second pass
 };
 
 // Host-side setup product (qp_setup.cu)
@@ -193,6 +194,10 @@ int polish_launch(QPHandle* q, const PolishBatch& b, cudaStream_t st);
 // infeasible anchors of a seeded map: turn the ADMM dual iterate into an exact Farkas certificate, affine in x0
 int farkas_export_launch(QPHandle* q, const int* d_anchors, int count, const int* d_status, const float* d_warm,
                          const double* d_x0, int64_t stride, cudaStream_t st);
+// before the second pass: samples the certificate of their first-pass state proves infeasible are done, the rest is listed
+int farkas_filter_launch(QPHandle* q, const int* d_list, int count, int* d_status, const float* d_warm, const double* d_x0,
+                         int64_t stride, double* d_u0, double* d_objective, double* d_u_full, int8_t* d_polished,
+                         int* d_survivors, int* d_n_survivors, cudaStream_t st);
 // samples that ran out of ADMM iterations: a valid certificate from their final ADMM state makes them proven infeasible
 int farkas_decide_launch(QPHandle* q, const int* d_list, int count, int* d_status, const float* d_warm, const double* d_x0,
                          int64_t stride, double* d_u0, double* d_objective, double* d_u_full, int8_t* d_polished,

@@ -484,12 +484,16 @@ __global__ void __launch_bounds__(kPolishThreads, 7) polish_kernel(const PolishT
 //   mode 0 (anchors of a seeded map, status infeasible): store cx[4], c0, |cx|-bound[4], |c0|-bound in the anchor's
 //          multiplier-map slot (type tag -2); a follower evaluates S(x0) = c0 - cx.x0 < -1e-9 (A0 + Ax.|x0|).
 //   mode 1 (samples that ran out of ADMM iterations): a valid certificate turns "max_iter" into a proven "infeasible".
+//   mode 2 (samples the first pass could not settle: iteration cap hit, or active set not certified): the same test
+//          before the second pass; proven-infeasible samples are done, the others are listed for the tighter ADMM pass
+//          (barely infeasible states are most of that list, and they are the ones that iterate longest).
 // One warp per sample.
 struct FarkasArgs {
     const int* list; int count; int mode;
     int* status; const float* warm; const double* x0; int64_t stride;
     const int* rec_of; double* rec_lam; int* rec_act;                  // mode 0
-    double* u0; double* objective; double* u_full; int8_t* polished;   // mode 1 (nullable)
+    double* u0; double* objective; double* u_full; int8_t* polished;   // mode 1, 2 (nullable)
+    int* survivors; int* n_survivors;                                  // mode 2
     unsigned long long* stats;
 };
 
@@ -502,7 +506,8 @@ __global__ void __launch_bounds__(128) farkas_kernel(const PolishTables T, const
     for (int q = gw; q < F.count; q += nw) {
         const int sample = F.list[q];
         const int rec = F.mode == 0 ? F.rec_of[sample] : 0;
-        if (F.status[sample] != (F.mode == 0 ? CARMPC_QP_INFEASIBLE : CARMPC_QP_MAX_ITER) || rec < 0) continue;
+        const int want = F.mode == 0 ? CARMPC_QP_INFEASIBLE : (F.mode == 1 ? CARMPC_QP_MAX_ITER : kStatusNeedsMoreAdmm);
+        if (F.status[sample] != want || rec < 0) continue;
         double x0[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) x0[c] = F.x0[(size_t)c * F.stride + sample];
@@ -540,7 +545,10 @@ __global__ void __launch_bounds__(128) farkas_kernel(const PolishTables T, const
         const double S = c0 - (cx[0] * x0[0] + cx[1] * x0[1] + cx[2] * x0[2] + cx[3] * x0[3]);
         const double margin = 1e-9 * (A0 + Ax[0] * fabs(x0[0]) + Ax[1] * fabs(x0[1]) + Ax[2] * fabs(x0[2]) + Ax[3] * fabs(x0[3]));
         const bool valid = isfinite(S) && isfinite(margin) && S < -margin;
-        if (!valid) continue;
+        if (!valid) {
+            if (F.mode == 2 && lane == 0) F.survivors[atomicAdd(F.n_survivors, 1)] = sample;
+            continue;
+        }
         if (F.mode == 0) {
             if (lane == 0) {
                 double* r = F.rec_lam + (size_t)rec * kPolishSmallActive * 5;
@@ -555,7 +563,7 @@ __global__ void __launch_bounds__(128) farkas_kernel(const PolishTables T, const
                 if (F.u0) { F.u0[sample] = NaN; F.u0[F.stride + sample] = NaN; }
                 if (F.objective) F.objective[sample] = INFINITY;
                 if (F.polished) F.polished[sample] = 0;
-                if (F.stats) atomicAdd(F.stats + 14, 1ull);
+                if (F.stats) atomicAdd(F.stats + (F.mode == 1 ? 14 : 15), 1ull);
             }
             if (F.u_full) for (int j = lane; j < n; j += 32) F.u_full[(size_t)sample * n + j] = NaN;
         }
@@ -587,6 +595,16 @@ int farkas_decide_launch(QPHandle* qh, const int* d_list, int count, int* d_stat
     FarkasArgs f = {};
     f.list = d_list; f.count = count; f.mode = 1; f.status = d_status; f.warm = d_warm; f.x0 = d_x0; f.stride = stride;
     f.u0 = d_u0; f.objective = d_objective; f.u_full = d_u_full; f.polished = d_polished; f.stats = qh->ws_polish_stats;
+    return farkas_launch(qh, f, st);
+}
+
+int farkas_filter_launch(QPHandle* qh, const int* d_list, int count, int* d_status, const float* d_warm, const double* d_x0,
+                         int64_t stride, double* d_u0, double* d_objective, double* d_u_full, int8_t* d_polished,
+                         int* d_survivors, int* d_n_survivors, cudaStream_t st) {
+    FarkasArgs f = {};
+    f.list = d_list; f.count = count; f.mode = 2; f.status = d_status; f.warm = d_warm; f.x0 = d_x0; f.stride = stride;
+    f.u0 = d_u0; f.objective = d_objective; f.u_full = d_u_full; f.polished = d_polished; f.stats = qh->ws_polish_stats;
+    f.survivors = d_survivors; f.n_survivors = d_n_survivors;
     return farkas_launch(qh, f, st);
 }
 
