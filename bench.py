@@ -393,7 +393,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": 3.2125e9, "traffic_source": "ncu --set full: dram__bytes_read.sum 3.200 GB + "
-                         "dram__bytes_write.sum 12.5 MB per launch (profiles/r01_final_membership_tma_ncu_full.txt)",
+                         "dram__bytes_write.sum 12.5 MB per launch (profiles/r01_s5_membership_tma_ncu_full.txt)",
                          "peak_source": peak_src, "launch_ms": launch_ms, "isolated_launch_ms": kernel_ms,
                          "kernel": "membership_tma_kernel<1>" if args.mode == 1 else "membership_kernel<0,true>",
                          "bytes_per_sample": BYTES_PER_SAMPLE, "algorithmic_bytes_per_launch": n * BYTES_PER_SAMPLE},

@@ -1,9 +1,18 @@
-"""Text summary of an .ncu-rep (selected raw metrics of the first profiled launch): python tools/ncu_summary.py rep"""
+"""Text summary of an .ncu-rep (selected raw metrics of one profiled launch): python tools/ncu_summary.py rep [index|max]
+(default: the first launch; "max": the launch with the longest duration)."""
 import csv, io, subprocess, sys
 rep = sys.argv[1]
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hdr, units, r = rows[0], rows[1], rows[2]
+hdr, units = rows[0], rows[1]
+which = sys.argv[2] if len(sys.argv) > 2 else "0"
+data = rows[2:]
+if which == "max":
+    it = hdr.index("gpu__time_duration.sum")
+    r = max(data, key=lambda row: float(row[it].replace(",", "")))
+    print(f"(launch {data.index(r)} of {len(data)} in the report)")
+else:
+    r = data[int(which)]
 keys = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "gpu__time_duration.sum", "sm__cycles_elapsed.max", "smsp__cycles_active.avg",
