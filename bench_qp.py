@@ -114,21 +114,23 @@ def run_qp_bench(args, rank, world, dev, barrier):
                            "dense_equivalent_tflops": flops_dense / (ms * 1e-3) / 1e12,
                            "note": "whole solve (ADMM + polish) time; executed flops exclude structural zeros"}
     # end to end through the host entry point (numpy AoS states in, numpy results out)
-    xh = np.ascontiguousarray(x0.cpu().numpy().T)
-    bq.solve_host(xh)
+    xh_t = torch.empty((B, 4), dtype=torch.float64, pin_memory=True)            # states in pinned host memory, AoS
+    xh_t.copy_(x0.t())
+    xh = xh_t.numpy()
+    bq.solve_host(xh, pinned=True)
     torch.cuda.synchronize()
     e2e_steps = 3
     dts = []
     for _ in range(e2e_steps):
         t0 = time.perf_counter()
-        r = bq.solve_host(xh)
+        r = bq.solve_host(xh, pinned=True)
         dts.append(time.perf_counter() - t0)
     dt = float(np.median(dts))
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     res["e2e"] = {"value": world * B / float(tt.item()), "unit": "QPs/s", "h2d_bytes_per_step": B * 32,
-                  "d2h_bytes_per_step": B * (16 + 8 + 4 + 4), "call": "carmpc_qp_solve_host"}
+                  "d2h_bytes_per_step": B * (16 + 8 + 4 + 4), "call": "carmpc_qp_solve_host (pinned host buffers)"}
     if rank == 0 and world == 1 and not args.skip_cpu:
         res["cpu_baseline"] = cpu_qp_rate()
 
@@ -166,12 +168,12 @@ def run_qp_bench(args, rank, world, dev, barrier):
                 "flags_equal_cold": same, "max_du0_vs_cold": du, "polish": bq.polish_stats()}
         # end to end for the map: grid axes on the host in, status / u0 / objective on the host out
         blk0 = blocks[0]
-        bq.solve_map_host(axes, block=blk0)
+        bq.solve_map_host(axes, block=blk0, pinned=True)
         dts = []
         for _ in range(3):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            rm = bq.solve_map_host(axes, block=blk0)
+            rm = bq.solve_map_host(axes, block=blk0, pinned=True)
             dts.append(time.perf_counter() - t0)
         tm = torch.tensor([float(np.median(dts))], dtype=torch.float64, device=dev)
         if world > 1:

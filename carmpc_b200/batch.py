@@ -318,15 +318,37 @@ class BatchQP(_Handle):
         return out
 
     # ---- host arrays ---------------------------------------------------------------------------------
-    def solve_host(self, x0, x_ref=None, want_u_full: bool = False, c=None) -> QPResult:
-        """``x0``: (B, 4) numpy states, as the reference passes them to ``.step`` one at a time."""
+    def _host_result(self, B: int, want_u0=True, want_objective=True, want_u_full=False, pinned=False) -> QPResult:
+        """Host result arrays; ``pinned``: page-locked buffers owned by this object and reused by the next call of the same
+        size (device -> host copies then run at the full PCIe rate instead of through the driver's staging buffer)."""
+        if not pinned:
+            return QPResult(u0=np.zeros((B, 2)) if want_u0 else None, objective=np.zeros(B) if want_objective else None,
+                            status=np.zeros(B, dtype=np.int32), iters=np.zeros(B, dtype=np.int32),
+                            u_full=np.zeros((B, self.n)) if want_u_full else None)
+        torch = _torch()
+        cache = getattr(self, "_pinned", None)
+        if cache is None or cache[0] != B:
+            bufs = {"u0": torch.empty((B, 2), dtype=torch.float64, pin_memory=True),
+                    "objective": torch.empty(B, dtype=torch.float64, pin_memory=True),
+                    "status": torch.empty(B, dtype=torch.int32, pin_memory=True),
+                    "iters": torch.empty(B, dtype=torch.int32, pin_memory=True)}
+            cache = self._pinned = (B, bufs)
+        bufs = cache[1]
+        if want_u_full and "u_full" not in bufs:
+            bufs["u_full"] = torch.empty((B, self.n), dtype=torch.float64, pin_memory=True)
+        return QPResult(u0=bufs["u0"].numpy() if want_u0 else None, objective=bufs["objective"].numpy() if want_objective else None,
+                        status=bufs["status"].numpy(), iters=bufs["iters"].numpy(),
+                        u_full=bufs["u_full"].numpy() if want_u_full else None)
+
+    def solve_host(self, x0, x_ref=None, want_u_full: bool = False, c=None, pinned: bool = False) -> QPResult:
+        """``x0``: (B, 4) numpy states, as the reference passes them to ``.step`` one at a time.  ``pinned``: return the
+        results in page-locked buffers that the next call of the same size overwrites."""
         x0 = _f64(np.atleast_2d(x0))
         if x0.shape[1] != 4:
             raise ValueError("x0 must be (B, 4)")
         B = len(x0)
         xref = _f64(self.pq.goal if x_ref is None else x_ref)
-        res = QPResult(u0=np.zeros((B, 2)), objective=np.zeros(B), status=np.zeros(B, dtype=np.int32),
-                       iters=np.zeros(B, dtype=np.int32), u_full=np.zeros((B, self.n)) if want_u_full else None)
+        res = self._host_result(B, want_u_full=want_u_full, pinned=pinned)
         cc = _f64(c) if c is not None else None
         check(self._lib.carmpc_qp_solve_host(self._h, _capi.ptr(x0), _capi.ptr(xref), _capi.ptr(cc), B,
                                              _capi.ptr(res.u0), _capi.ptr(res.objective), _capi.ptr(res.status),
@@ -334,10 +356,11 @@ class BatchQP(_Handle):
         return res
 
     def solve_map_host(self, axes, block=None, x_ref=None, axis_to_state=(0, 1, 2, 3), want_u0: bool = True,
-                       want_objective: bool = True) -> QPResult:
+                       want_objective: bool = True, pinned: bool = False) -> QPResult:
         """Region-of-attraction map of the C-order tensor grid ``axes`` (four 1-D arrays; axis k is state component
         ``axis_to_state[k]``), numpy in / numpy out (``carmpc_qp_map_host``).  ``block``: points per axis of the lattice
-        blocks for the seeded solve (None: every point cold).  ``result.seeded`` = points certified from their anchor."""
+        blocks for the seeded solve (None: every point cold).  ``result.seeded`` = points certified from their anchor.
+        ``pinned``: results in page-locked buffers that the next call of the same size overwrites."""
         ax = [_f64(np.atleast_1d(a)) for a in axes]
         if len(ax) != 4:
             raise ValueError("axes must be four 1-D arrays")
@@ -347,8 +370,7 @@ class BatchQP(_Handle):
         flat = _f64(np.concatenate(ax))
         B = int(np.prod([len(a) for a in ax]))
         xref = _f64(self.pq.goal if x_ref is None else x_ref)
-        res = QPResult(u0=np.zeros((B, 2)) if want_u0 else None, objective=np.zeros(B) if want_objective else None,
-                       status=np.zeros(B, dtype=np.int32), iters=np.zeros(B, dtype=np.int32))
+        res = self._host_result(B, want_u0=want_u0, want_objective=want_objective, pinned=pinned)
         seeded = ctypes.c_int64(0)
         check(self._lib.carmpc_qp_map_host(self._h, _capi.ptr(flat), dims, a2s, blk, _capi.ptr(xref), _capi.ptr(res.u0),
                                            _capi.ptr(res.objective), _capi.ptr(res.status), _capi.ptr(res.iters),

@@ -460,3 +460,16 @@ def test_map_host_entry_point_matches_the_batched_solve(torch_cuda):
     assert res.objective is None and np.abs(res.u0[ok[flat]] - u0[flat][ok[flat]]).max() <= 1e-7
     with pytest.raises(Exception):
         bq.solve_map_host(axes, axis_to_state=(0, 1, 1, 3))
+
+
+def test_pinned_host_results_equal_pageable_ones(torch_cuda):
+    c, bq, oq = _setup("RoadOneCarEnv", 20)
+    x0 = _states(c, 500, seed=11)
+    a = bq.solve_host(x0, want_u_full=True)
+    b = bq.solve_host(x0, want_u_full=True, pinned=True)
+    for name in ("u0", "objective", "status", "iters", "u_full"):
+        np.testing.assert_array_equal(getattr(a, name), getattr(b, name))
+    keep = b.u0.copy()
+    b2 = bq.solve_host(x0[::-1].copy(), pinned=True)                  # same size: the pinned buffers are reused
+    assert b2.u0.ctypes.data == b.u0.ctypes.data and b2.u_full is None
+    np.testing.assert_array_equal(b2.u0[::-1], keep)
