@@ -144,7 +144,7 @@ extern "C" int carmpc_closed_loop(void* qp, int mode, const double* h_A, const d
     int *live_list = nullptr, *live_count = nullptr;
     float* warm = nullptr;
     int rc = CARMPC_OK;
-    auto cleanup = [&]() { cudaFree(xhat); cudaFree(est); cudaFree(u_prev); cudaFree(u0); cudaFree(status); cudaFree(live_list); cudaFree(live_count); cudaFree(warm); };
+    auto cleanup = [&]() { q->defer_total = 0; cudaFree(xhat); cudaFree(est); cudaFree(u_prev); cudaFree(u0); cudaFree(status); cudaFree(live_list); cudaFree(live_count); cudaFree(warm); };
 #define TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(e__)); cleanup(); return CARMPC_ERR_CUDA; } } while (0)
     TRY(cudaMalloc(&xhat, sizeof(double) * 4 * runs));
     TRY(cudaMalloc(&est, sizeof(double) * 4 * runs));
@@ -161,6 +161,11 @@ extern "C" int carmpc_closed_loop(void* qp, int mode, const double* h_A, const d
     fill_i32<<<blocks, 256, 0, st>>>(d_fail_step, runs, -1);
     int64_t total_iters = 0;
     bool warm_valid = false;
+    // the iteration total accumulates on the device over the steps (one read at the end instead of one per step)
+    rc = q->ensure_workspace(runs);
+    if (rc != CARMPC_OK) { cleanup(); return rc; }
+    TRY(cudaMemsetAsync(q->ws_total_iters, 0, sizeof(unsigned long long), st));
+    q->defer_total = 1;
     for (int k = 0; k < steps; ++k) {
         TRY(cudaMemsetAsync(live_count, 0, sizeof(int), st));
         loop_advance_kernel<<<blocks, 256, 0, st>>>(K, runs, x, xhat, u_prev, d_fail_step, est, live_list, live_count,
@@ -172,15 +177,18 @@ extern "C" int carmpc_closed_loop(void* qp, int mode, const double* h_A, const d
             // from the second step on, the active set certified at the previous step is tried first
             rc = q->solve(est, runs, h_xref, nullptr, live_list, live, u0, nullptr, status, nullptr, nullptr, warm,
                           warm_valid ? 1 : 0, warm ? 1 : 0, st, warm_valid && g_reuse_active_set ? 1 : 0);
-            if (rc != CARMPC_OK) { cleanup(); return rc; }
+            if (rc != CARMPC_OK) { q->defer_total = 0; cleanup(); return rc; }
             warm_valid = warm != nullptr;
-            total_iters += q->last_total_iters;
             loop_apply_kernel<<<(live + 255) / 256, 256, 0, st>>>(runs, k, live_list, live, u0, status, u_prev, d_fail_step);
         }
         if (d_u_log)      // the input each run will apply at the next plant step (unchanged for stopped runs)
             TRY(cudaMemcpyAsync(d_u_log + (size_t)k * 2 * runs, u_prev, sizeof(double) * 2 * runs, cudaMemcpyDeviceToDevice, st));
     }
+    q->defer_total = 0;
+    unsigned long long total_dev = 0;
+    TRY(cudaMemcpyAsync(&total_dev, q->ws_total_iters, sizeof(total_dev), cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(st));
+    total_iters = (int64_t)total_dev;
     TRY(cudaGetLastError());
 #undef TRY
     cleanup();

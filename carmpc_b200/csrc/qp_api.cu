@@ -168,7 +168,7 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
     last_second_pass = 0;
     last_reused = 0;
     CARMPC_CUDA(cudaMemsetAsync(ws_counters, 0, sizeof(int) * 8, st));
-    CARMPC_CUDA(cudaMemsetAsync(ws_total_iters, 0, sizeof(unsigned long long), st));
+    if (!defer_total) CARMPC_CUDA(cudaMemsetAsync(ws_total_iters, 0, sizeof(unsigned long long), st));
     int* status = d_status ? d_status : ws_status;
     int* iters = d_iters ? d_iters : ws_iters;
 
@@ -206,7 +206,7 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
         CARMPC_CUDA(cudaMemcpyAsync(&n_failed0, ws_counters + 5, sizeof(int), cudaMemcpyDeviceToHost, st));
         CARMPC_CUDA(cudaStreamSynchronize(st));
         last_reused = count - n_failed0;
-        if (n_failed0 == 0) { last_total_iters = 0; return CARMPC_OK; }
+        if (n_failed0 == 0) { last_total_iters = 0; return CARMPC_OK; }        // (deferred totals: nothing was added)
         d_idx = ws_failed0;
         count = n_failed0;
         pb.idx_list = d_idx; pb.count = (int)count;
@@ -278,6 +278,7 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
         }
         last_launches += 2;
     }
+    if (defer_total) { last_total_iters = 0; return CARMPC_OK; }
     unsigned long long total = 0;
     CARMPC_CUDA(cudaMemcpyAsync(&total, ws_total_iters, sizeof(total), cudaMemcpyDeviceToHost, st));
     CARMPC_CUDA(cudaStreamSynchronize(st));

@@ -123,6 +123,7 @@ struct PolishBatch {
     double xref[4];
     const int* idx_list;
     int count;
+    const int* count_dev;    // nullable: the number of list entries lives on the device (count is then an upper bound)
     const int8_t* sign;
     const float* u_admm;
     int* status;             // in: 0 / 2 from ADMM -> out: 0 solved (polished or accepted), 3 needs more ADMM
@@ -226,6 +227,7 @@ struct QPHandle : HandleBase {
     int use_records = 0;                         // set by solve_seeded for the two solve() calls it makes
     unsigned long long* ws_polish_stats = nullptr;   // [16] histogram of the polish launches of the last solve
     int stats_hold = 0;
+    int defer_total = 0;                         // closed loop: ws_total_iters accumulates over the steps, read once at the end
     int* ws_overflow = nullptr;
     int* ws_counters = nullptr;                  // [0] work counter, [1] n_failed
     unsigned long long* ws_total_iters = nullptr;

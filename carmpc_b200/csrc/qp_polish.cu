@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(kPolishThreads, 7) polish_kernel(const PolishT
     const double NaN = __longlong_as_double(0x7ff8000000000000ll);
 
     const int gw = blockIdx.x * warps_per_cta + warp, nw = gridDim.x * warps_per_cta;
-    for (int qi = gw; qi < B.count; qi += nw) {
+    const int count = B.count_dev ? min(*B.count_dev, B.count) : B.count;
+    for (int qi = gw; qi < count; qi += nw) {
         const int sample = B.idx_list ? B.idx_list[qi] : qi;
         const int st_in = B.status[sample];
         __syncwarp();
@@ -268,7 +269,16 @@ __global__ void __launch_bounds__(kPolishThreads, 7) polish_kernel(const PolishT
                     for (int i = j + 1 + li; i < na; i += 8) {
                         const int ti = tri(i, 0);
                         const double lij = M[ti + j];
-                        for (int k = j + 1 + lk; k <= i; k += 4) M[ti + k] -= lij * M[tri(k, 0) + j];
+                        int k = j + 1 + lk;
+                        // four independent (load, load, fma, store) chains per pass: with many active rows this loop is
+                        // a chain of shared-memory round trips otherwise (no lane writes what another one reads here)
+                        for (; k + 12 <= i; k += 16) {
+                            const double c0 = M[tri(k, 0) + j], c1 = M[tri(k + 4, 0) + j], c2 = M[tri(k + 8, 0) + j], c3 = M[tri(k + 12, 0) + j];
+                            const double m0 = M[ti + k], m1 = M[ti + k + 4], m2 = M[ti + k + 8], m3 = M[ti + k + 12];
+                            M[ti + k] = m0 - lij * c0; M[ti + k + 4] = m1 - lij * c1;
+                            M[ti + k + 8] = m2 - lij * c2; M[ti + k + 12] = m3 - lij * c3;
+                        }
+                        for (; k <= i; k += 4) M[ti + k] -= lij * M[tri(k, 0) + j];
                     }
                 }
                 __syncwarp();
@@ -639,14 +649,9 @@ int polish_launch(QPHandle* qh, const PolishBatch& b_in, cudaStream_t st) {
     b.na_cap = kPolishSmallActive; b.overflow_list = qh->ws_overflow; b.n_overflow = qh->ws_counters + 4;
     int rc = polish_launch_cap(qh, b, st);
     if (rc != CARMPC_OK) return rc;
-    int n_over = 0;
-    CARMPC_CUDA(cudaMemcpyAsync(&n_over, qh->ws_counters + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CARMPC_CUDA(cudaStreamSynchronize(st));
-    if (n_over > 0) {
-        b.na_cap = full; b.idx_list = qh->ws_overflow; b.count = n_over; b.overflow_list = nullptr; b.n_overflow = nullptr;
-        rc = polish_launch_cap(qh, b, st);
-    }
-    return rc;
+    // the overflow launch reads its sample count on the device (no host round trip; with nothing listed its CTAs exit at once)
+    b.na_cap = full; b.idx_list = qh->ws_overflow; b.count_dev = qh->ws_counters + 4; b.overflow_list = nullptr; b.n_overflow = nullptr;
+    return polish_launch_cap(qh, b, st);
 }
 
 }  // namespace carmpc
