@@ -473,3 +473,25 @@ def test_pinned_host_results_equal_pageable_ones(torch_cuda):
     b2 = bq.solve_host(x0[::-1].copy(), pinned=True)                  # same size: the pinned buffers are reused
     assert b2.u0.ctypes.data == b.u0.ctypes.data and b2.u_full is None
     np.testing.assert_array_equal(b2.u0[::-1], keep)
+
+
+def test_seeded_solve_with_per_sample_disturbance(torch_cuda):
+    """With a per-sample disturbance the anchors export no multiplier maps / certificates (they assume a common shift),
+    but the seeded solve must still reproduce the cold one: anchor's active set -> polish -> ADMM for the rest."""
+    torch = torch_cuda
+    from carmpc_b200.batch import BatchQP
+    from carmpc_b200.grids import lattice_seeds
+    ctl = make_controller(make_env("RoadEnv"), 20, cls="MPCOutputFBWithDisturbance", init_state=[20, 0.5, 0, 2])
+    bq = BatchQP.from_controller(ctl)
+    x_ref = np.array([30, 1.5, 0, 0.0])
+    axes = [np.linspace(12.0, 30.5, 20), np.linspace(-2.6, 2.6, 24), np.linspace(-0.2, 0.2, 3), np.linspace(0.0, 4.0, 3)]
+    x0 = _grid_states(torch, axes)
+    B = x0.shape[1]
+    d = torch.from_numpy(np.random.default_rng(5).uniform(-0.02, 0.02, size=B)).cuda()
+    cold = bq.solve(x0, x_ref=x_ref, c=d)
+    seed = torch.from_numpy(lattice_seeds([len(a) for a in axes], block=(2, 6, 1, 1))).cuda()
+    warm = bq.solve(x0, x_ref=x_ref, c=d, seed=seed)
+    _assert_same_solution(cold, warm)
+    st = cold["status"].cpu().numpy()
+    assert (st == 0).sum() > B // 10 and warm["seeded"] > 0
+    assert bq.polish_stats()["used_multiplier_map"] == 0
