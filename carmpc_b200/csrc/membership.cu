@@ -488,41 +488,87 @@ membership_grid_kernel(const double* __restrict__ g_rows, const RowF32* __restri
     RowF32* s_rows32 = reinterpret_cast<RowF32*>(s_rows + ((rows * 5 + 1) & ~1));
     double* s_axes = reinterpret_cast<double*>(s_rows32 + rows_padded);
     const int axes_len = gd.offset[3] + gd.dims[3];
-    for (int i = threadIdx.x; i < axes_len; i += blockDim.x) s_axes[i] = g_axes[i];
+    float* s_axes32 = reinterpret_cast<float*>(s_axes + axes_len);          // float32 images for the screen (converted once)
+    for (int i = threadIdx.x; i < axes_len; i += blockDim.x) { const double a = g_axes[i]; s_axes[i] = a; s_axes32[i] = (float)a; }
     stage_rows(g_rows, g_rows32, rows * 5, rows_padded, s_rows, s_rows32);
 
     int members = 0;
     const int64_t n_chunks = (n + kChunk - 1) / kChunk;
     for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const int64_t i0 = chunk * kChunk + kNS * (int64_t)threadIdx.x;
-        double c[4][kNS];
         bool in[kNS];
+        // multi-index of the thread's first sample: one decomposition per chunk (32-bit divisions when the grid allows),
+        // the following kNS - 1 samples by incrementing with carry
+        uint32_t idx0[4];
+        {
+            const uint64_t first = i0 < n ? (uint64_t)i0 : 0;
+            if (n <= 0xffffffffll) {
+                uint32_t rem = (uint32_t)first;
 #pragma unroll
-        for (int k = 0; k < kNS; ++k) {
-            in[k] = i0 + k < n;
-            uint64_t rem = in[k] ? (uint64_t)(i0 + k) : 0;
+                for (int ax = 3; ax >= 1; --ax) {
+                    const uint32_t d = (uint32_t)gd.dims[ax], qd = rem / d;
+                    idx0[ax] = rem - qd * d;
+                    rem = qd;
+                }
+                idx0[0] = rem;
+            } else {
+                uint64_t rem = first;
 #pragma unroll
-            for (int ax = 3; ax >= 0; --ax) {
-                const uint32_t d = (uint32_t)gd.dims[ax];
-                const uint64_t qd = rem / d;
-                const uint32_t idx = (uint32_t)(rem - qd * d);
-                rem = qd;
-                const double val = s_axes[gd.offset[ax] + idx];
-                // state_of_axis is a permutation of 0..3
-#pragma unroll
-                for (int st = 0; st < 4; ++st)
-                    if (gd.state_of_axis[ax] == st) c[st][k] = val;
+                for (int ax = 3; ax >= 1; --ax) {
+                    const uint32_t d = (uint32_t)gd.dims[ax];
+                    const uint64_t qd = rem / d;
+                    idx0[ax] = (uint32_t)(rem - qd * d);
+                    rem = qd;
+                }
+                idx0[0] = (uint32_t)rem;
             }
         }
-        float xf[kNS], yf[kNS], pf[kNS], vf[kNS];
+        auto advance = [&](uint32_t (&idx)[4]) {
+            if (++idx[3] == (uint32_t)gd.dims[3]) {
+                idx[3] = 0;
+                if (++idx[2] == (uint32_t)gd.dims[2]) {
+                    idx[2] = 0;
+                    if (++idx[1] == (uint32_t)gd.dims[1]) { idx[1] = 0; ++idx[0]; }       // past the end: clamped below, masked by in[]
+                }
+            }
+        };
+        float cf[4][kNS];
+        {
+            uint32_t idx[4] = {idx0[0], idx0[1], idx0[2], idx0[3]};
 #pragma unroll
-        for (int k = 0; k < kNS; ++k) { xf[k] = (float)c[0][k]; yf[k] = (float)c[1][k]; pf[k] = (float)c[2][k]; vf[k] = (float)c[3][k]; }
+            for (int k = 0; k < kNS; ++k) {
+                in[k] = i0 + k < n;
+#pragma unroll
+                for (int ax = 0; ax < 4; ++ax) {
+                    const float val = s_axes32[gd.offset[ax] + min(idx[ax], (uint32_t)gd.dims[ax] - 1u)];
+                    // state_of_axis is a permutation of 0..3
+#pragma unroll
+                    for (int st = 0; st < 4; ++st)
+                        if (gd.state_of_axis[ax] == st) cf[st][k] = val;
+                }
+                advance(idx);
+            }
+        }
         bool amb[kNS];
-        screen32(s_rows32, rows_padded, sc, xf, yf, pf, vf, in, amb);
+        screen32(s_rows32, rows_padded, sc, cf[0], cf[1], cf[2], cf[3], in, amb);
         bool any_amb = false;
 #pragma unroll
         for (int k = 0; k < kNS; ++k) any_amb |= amb[k];
         if (__any_sync(0xffffffffu, any_amb)) {
+            // the float64 coordinates are only needed for the samples the screen could not decide
+            double c[4][kNS];
+            uint32_t idx[4] = {idx0[0], idx0[1], idx0[2], idx0[3]};
+#pragma unroll
+            for (int k = 0; k < kNS; ++k) {
+#pragma unroll
+                for (int ax = 0; ax < 4; ++ax) {
+                    const double val = s_axes[gd.offset[ax] + min(idx[ax], (uint32_t)gd.dims[ax] - 1u)];
+#pragma unroll
+                    for (int st = 0; st < 4; ++st)
+                        if (gd.state_of_axis[ax] == st) c[st][k] = val;
+                }
+                advance(idx);
+            }
             decide64(s_rows, rows, c[0], c[1], c[2], c[3], amb);
 #pragma unroll
             for (int k = 0; k < kNS; ++k) in[k] |= amb[k];
@@ -1029,8 +1075,31 @@ int carmpc_membership_grid(void* polytope, const double* h_axes, const int32_t d
     for (int i = 0; i < off; ++i) P->h_axes[i] = h_axes[i];
     double* d_axes = P->d_axes;
     CARMPC_CUDA(cudaMemcpyAsync(d_axes, P->h_axes, sizeof(double) * off, cudaMemcpyHostToDevice, st));
+    if (!P->tuned && g_auto_tune && n >= ((int64_t)1 << 20)) {
+        // profile-guided row order from a strided subsample of the grid, expanded on the host (65,536 points, once per polytope)
+        const int n_sub = 1 << 16;
+        const int64_t stride = n / n_sub;
+        std::vector<double> sub((size_t)4 * n_sub);
+        for (int k = 0; k < n_sub; ++k) {
+            int64_t rem = (int64_t)k * stride;
+            for (int ax = 3; ax >= 0; --ax) {
+                const int64_t q = rem / dims[ax];
+                sub[(size_t)axis_to_state[ax] * n_sub + k] = h_axes[gd.offset[ax] + (int)(rem - q * dims[ax])];
+                rem = q;
+            }
+        }
+        double* d_sub = nullptr;
+        CARMPC_CUDA(cudaMalloc(&d_sub, sizeof(double) * 4 * n_sub));
+        cudaError_t err = cudaMemcpyAsync(d_sub, sub.data(), sizeof(double) * 4 * n_sub, cudaMemcpyHostToDevice, st);
+        int rc = CARMPC_OK;
+        if (err == cudaSuccess) rc = tune_row_order(P, d_sub, d_sub + n_sub, d_sub + 2 * n_sub, d_sub + 3 * n_sub, n_sub, st);
+        cudaStreamSynchronize(st);
+        cudaFree(d_sub);
+        CARMPC_CUDA(err);
+        if (rc != CARMPC_OK) return rc;
+    }
     if (d_count) CARMPC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
-    const size_t smem = membership_smem(P->rows) + sizeof(double) * off;
+    const size_t smem = membership_smem(P->rows) + (sizeof(double) + sizeof(float)) * off;
     CARMPC_CUDA(cudaFuncSetAttribute(membership_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_chunks = (n + kChunk - 1) / kChunk;
     membership_grid_kernel<<<grid_blocks(n_chunks, 4), kThreads, smem, st>>>(

@@ -320,3 +320,29 @@ def test_profile_guided_row_order_never_changes_results(torch_cuda):
     bits, count = evb.contains_bits(*_dev(torch_cuda, *p1.T))
     np.testing.assert_array_equal(_bits_np(bits), want_bits)
     assert int(count.item()) == want_cnt
+
+
+@pytest.mark.parametrize("dims", [(3, 5, 7, 11), (1, 1, 1, 1), (2, 1, 129, 1), (1, 37, 1, 5), (13, 2, 3, 257)])
+def test_implicit_grid_equals_explicit_points_on_ragged_grids(torch_cuda, dims):
+    """carmpc_membership_grid generates the coordinates in-kernel (one index decomposition per thread, then increments
+    with carry): odd axis lengths, single-point axes and sizes that are no multiple of a tile must give the bits of the
+    explicit SoA call."""
+    torch = torch_cuda
+    from carmpc_b200.batch import TerminalSetEvaluator, unpack_bits
+    from carmpc_b200.grids import materialise_grid
+    Ab = np.load(os.path.join(GOLDEN, "terminal_sets", "RoadMultipleCarsEnv_30_1.5_0_0.npy"))
+    ev = TerminalSetEvaluator(Ab)
+    lo, hi = np.array([20.0, -1.0, -0.2, -0.5]), np.array([40.0, 3.5, 0.2, 1.5])
+    axes = [np.linspace(lo[k], hi[k], d) if d > 1 else np.array([0.5 * (lo[k] + hi[k])]) for k, d in enumerate(dims)]
+    n = int(np.prod(dims))
+    x, y, psi, v = materialise_grid(axes, device="cuda")
+    want_bits, want_count = ev.contains_bits(x, y, psi, v, mode=0)
+    want = unpack_bits(_bits_np(want_bits), n)
+    bits, count = ev.contains_grid_bits(axes)
+    np.testing.assert_array_equal(unpack_bits(_bits_np(bits), n), want)
+    assert int(count.item()) == int(want_count.item()) == int(want.sum())
+    # the same grid with the axes given in another order
+    perm = (2, 0, 3, 1)
+    bits2, count2 = ev.contains_grid_bits([axes[k] for k in perm], axis_to_state=perm)
+    got2 = unpack_bits(_bits_np(bits2), n).reshape([dims[k] for k in perm])
+    np.testing.assert_array_equal(np.transpose(got2, np.argsort(perm)).ravel(), want)
