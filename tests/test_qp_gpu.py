@@ -495,3 +495,25 @@ def test_seeded_solve_with_per_sample_disturbance(torch_cuda):
     st = cold["status"].cpu().numpy()
     assert (st == 0).sum() > B // 10 and warm["seeded"] > 0
     assert bq.polish_stats()["used_multiplier_map"] == 0
+
+
+def test_seeded_entry_points_reject_what_they_cannot_do(torch_cuda):
+    """Error behaviour of the seeded / map entry points: no float64 polish -> no seeded solve; malformed arguments."""
+    torch = torch_cuda
+    from carmpc_b200._capi import CarmpcError
+    c, bq, oq = _setup("RoadOneCarEnv", 20, polish=0)
+    x0 = torch.from_numpy(np.ascontiguousarray(_states(c, 64, seed=1).T)).cuda()
+    seed = torch.arange(64, dtype=torch.int32, device="cuda")
+    with pytest.raises(CarmpcError, match="polish"):
+        bq.solve(x0, seed=seed)
+    c, bq, oq = _setup("RoadOneCarEnv", 20)
+    with pytest.raises(ValueError):
+        bq.solve(x0, seed=seed[:10])
+    with pytest.raises(ValueError):
+        bq.solve(x0, seed=seed.to(torch.int64))
+    with pytest.raises(CarmpcError, match="axis"):
+        bq.solve_map_host([np.zeros(5000), [0.0], [0.0], [1.0]])
+    with pytest.raises(CarmpcError, match="block"):
+        bq.solve_map_host([np.linspace(20, 30, 4), [1.0], [0.0], [1.0]], block=(0, 1, 1, 1))
+    res = bq.solve_map_host([np.linspace(20, 30, 4), [1.0], [0.0], [1.0]], block=(2, 1, 1, 1))
+    assert res.status.shape == (4,) and res.u0.shape == (4, 2)
