@@ -36,3 +36,21 @@ bl = BatchQP.from_controller(ofb)
 x_init = torch.from_numpy(np.ascontiguousarray((np.array([20, 0.5, 0, 2.0]) + rng.uniform(-1, 1, size=(400, 4)) * np.array([8, 1.5, 0.1, 1.0])).T)).cuda()
 out = bl.closed_loop(x_init, 12, ofb.A, ofb.B, C=_C_XYV, L=_L_OBSERVER, want_traj=True, want_inputs=True)
 print("closed loop", int((out["fail_step"] < 0).sum().item()), out["total_iters"])
+# seeded maps: anchors' multiplier maps / Farkas certificates, followers, certificate filter, map entry point
+from carmpc_b200.grids import lattice_seeds, materialise_grid
+for env, goal, N in (("RoadOneCarEnv", [29.9, 1.5, 0, 0], 20), ("RoadMultipleCarsEnv", None, 10), ("RoadEnv", None, 40)):
+    c = _controller(env, goal, N)
+    bq = BatchQP.from_controller(c)
+    g = np.array(c.goal, dtype=float)
+    axes = [np.linspace(g[0] - 20.0, g[0] + 0.5, 14), np.linspace(-3.0, 3.0, 26), np.linspace(-0.3, 0.3, 3), np.linspace(-1.0, 4.0, 3)]
+    x0 = torch.stack(materialise_grid(axes, device="cuda")).contiguous()
+    seed = torch.from_numpy(lattice_seeds([len(a) for a in axes], block=(3, 8, 1, 1))).cuda()
+    out = bq.solve(x0, seed=seed, want_u_full=True)
+    res = bq.solve_map_host(axes, block=(2, 5, 2, 1), pinned=True)
+    print("seeded", env, N, out["seeded"], res.seeded, np.bincount(res.status, minlength=3), bq.polish_stats()["infeasible_by_anchor_certificate"])
+# ragged implicit grids
+for dims in ((3, 5, 7, 11), (1, 1, 1, 1), (2, 1, 129, 1), (13, 2, 3, 257)):
+    ax = [np.linspace(20.0, 40.0, d) if d > 1 else np.array([30.0]) for d in dims]
+    ax[1] = ax[1] * 0.05; ax[2] = ax[2] * 0.0; ax[3] = ax[3] * 0.02
+    bits, count = ev.contains_grid_bits(ax)
+    print("grid", dims, int(count.item()))
