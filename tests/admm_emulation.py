@@ -31,8 +31,9 @@ class KernelTables:
         self.alpha = np.float32(bq.opts.alpha)
 
 
-def emulate(T: KernelTables, x0, xref, iters, return_trace=False):
-    """Runs `iters` iterations for a batch x0 (B, 4).  Returns (u (B, n) unscaled, sign (B, m + n), w state)."""
+def emulate(T: KernelTables, x0, xref, iters, return_trace=False, return_state=False):
+    """Runs `iters` iterations for a batch x0 (B, 4).  Returns (u (B, n) unscaled, sign (B, m + n)) and optionally the
+    residual trace or the final ADMM state of the general rows in LOGICAL row order (w, lo, hi: (B, m), scaled)."""
     f32 = np.float32
     x0 = np.atleast_2d(np.asarray(x0, dtype=float))
     B = len(x0)
@@ -90,6 +91,10 @@ def emulate(T: KernelTables, x0, xref, iters, return_trace=False):
     sign[:, T.row_id[live]] = ((wB > hi).astype(np.int8) - (wB < lo).astype(np.int8))[:, live]
     if return_trace:
         return u, sign, np.array(res_trace)
+    if return_state:
+        w = np.zeros((B, T.m), dtype=f32)
+        w[:, T.row_id[live]] = wB[:, live]
+        return u, sign, w
     return u, sign
 
 
