@@ -14,7 +14,7 @@ ncu --set full --clock-control none --import-source on -k regex:membership_tma -
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:admm_kernel -s 2 -c 1 -o gpurun_out/prof_admm $CMD > gpurun_out/ncu_b.log 2>&1
 $CMD > gpurun_out/plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:polish_kernel -s 3 -c 1 -o gpurun_out/prof_polish $CMD > gpurun_out/ncu_c.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:polish_kernel -s 4 -c 1 -o gpurun_out/prof_polish $CMD > gpurun_out/ncu_c.log 2>&1
 bash tools/gpu_prof_seeded.sh
 python - <<'PY'
 import json
