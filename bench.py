@@ -5,9 +5,10 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Headline line (one JSON object on stdout, rank 0): terminal-set samples/s on BASELINE config 2
-(RoadMultipleCarsEnv H-rep, 100^4 = 10^8-point float64 SoA grid per GPU, resident in HBM).  One "step" = one
-membership pass over the whole grid -> bitset + count.  The same line carries the QP half of the metric under
-``"qp"`` (config 3: 10^6 horizon-20 condensed QPs, RoadOneCarEnv).
+(RoadMultipleCarsEnv H-rep, 100^4 = 10^8-point float64 SoA grid, resident in HBM).  One "step" = one
+membership pass over the whole grid -> bitset + count.  With N > 1 GPUs the ONE grid is sharded over the ranks (strong
+scaling) and the all-gather of the bitsets is part of the step (fused into the scan kernel over NVLink peer windows).
+The same line carries the QP half of the metric under ``"qp"`` / ``"qp_summary"`` (config 3: 10^6 horizon-20 QPs).
 
 ``--impl reference`` times the reference's CPU path (its per-point membership test, restated in oracle/ because the
 reference is pure Python with third-party solvers that are not installed) on the host cores.
@@ -92,75 +93,103 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------
+# workload description shared by both arms (the driver compares them)
+# ------------------------------------------------------------------------------------------------------------
+def workload_config():
+    return {"workload": "config 2: RoadMultipleCarsEnv terminal set (42 rows, terminal_sets/RoadMultipleCarsEnv_30_1.5_0_0.npy) "
+                        "on the 100^4 = 10^8-point float64 SoA grid (x, y, psi, v); one step = one membership pass over the "
+                        "WHOLE grid -> bitset + member count; with N GPUs the grid is sharded over them",
+            "samples_per_step": 100_000_000,
+            "l2": "inputs (3.2 GB in total, 400 MB per GPU at 8 GPUs) exceed the 126 MB L2; no flush between iterations"}
+
+
+# ------------------------------------------------------------------------------------------------------------
 # CPU legs (the only places that execute oracle/)
 # ------------------------------------------------------------------------------------------------------------
-def _cpu_sample(points: int):
-    """Bounded sample of the config-2 grid: every (10^8 / points)-th grid point, in grid order."""
-    from carmpc_b200.grids import config2_axes, grid_size
-    axes = config2_axes()
-    n = grid_size(axes)
-    idx = np.arange(0, n, n // points, dtype=np.int64)[:points]
-    dims = [len(a) for a in axes]
-    cols, stride = [], n
-    for a, d in zip(axes, dims):
-        stride //= d
-        cols.append(np.ascontiguousarray(a[(idx // stride) % d]))
-    return cols
+_HOST_GRID = None
 
 
-def cpu_membership_rate(min_seconds: float, points: int = 10_000_000, threads: int = 0):
-    """samples/s of the C restatement of lib/terminal_set.py:107-113 on all host threads."""
+def _host_grid():
+    """The whole config-2 grid as four host SoA arrays (3.2 GB), built once per process."""
+    global _HOST_GRID
+    if _HOST_GRID is None:
+        from carmpc_b200.grids import config2_axes
+        axes = config2_axes()
+        dims = [len(a) for a in axes]
+        cols = []
+        for k, a in enumerate(axes):
+            shape = [1] * 4
+            shape[k] = dims[k]
+            cols.append(np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64).reshape(shape), dims)).ravel())
+        _HOST_GRID = cols
+    return _HOST_GRID
+
+
+def cpu_membership_pass(threads: int = 0):
+    """One pass of the C restatement of lib/terminal_set.py:107-113 over the WHOLE 10^8 grid on all host threads;
+    returns (seconds, threads, members)."""
     from oracle import c_oracle
     Ab = np.load(TERMINAL_SET)
-    cols = _cpu_sample(points)
+    cols = _host_grid()
     threads = threads or c_oracle.max_threads()
-    c_oracle.membership_bits(Ab, *[c[:100000] for c in cols], threads=threads)       # warm-up / build
     t0 = time.perf_counter()
-    passes = 0
+    _, count = c_oracle.membership_bits(Ab, *cols, threads=threads)
+    return time.perf_counter() - t0, threads, int(count)
+
+
+def cpu_membership_rate(min_seconds: float):
+    n = len(_host_grid()[0])
+    cpu_membership_pass()                                  # warm-up (library build, page faults)
+    t0, passes = time.perf_counter(), 0
     while True:
-        c_oracle.membership_bits(Ab, *cols, threads=threads)
+        _, threads, members = cpu_membership_pass()
         passes += 1
         dt = time.perf_counter() - t0
         if dt >= min_seconds:
             break
-    return passes * points / dt, threads, f"{passes} passes over a {points}-point strided slice of the 10^8 grid", dt / passes
+    return passes * n / dt, threads, f"{passes} passes over the full 10^8-point grid ({dt:.1f} s)", members
 
 
 def cpu_pointwise_rate(points: int = 60000):
     """The reference's literal per-point Python loop (np.all(A @ point <= b)), one core."""
     from oracle import carmpc_oracle as orc
     Ab = np.load(TERMINAL_SET)
-    cols = _cpu_sample(points)
-    pts = np.stack(cols, axis=1)
+    cols = _host_grid()
+    n = len(cols[0])
+    idx = np.arange(0, n, n // points, dtype=np.int64)[:points]
+    pts = np.stack([c[idx] for c in cols], axis=1)
     t0 = time.perf_counter()
     orc.membership_pointwise(Ab, pts)
     return points / (time.perf_counter() - t0)
 
 
 def run_reference(args, rank: int, world: int):
+    """The reference's own CPU implementation of the path (lib/terminal_set.py:107-113) on the box's host cores.  The
+    reference is pure Python with nothing to compile, so this is the C restatement in oracle/ on all
+    host threads, on the SAME workload as the GPU arm: every step is one pass over the whole 10^8-point grid."""
     if rank != 0:
         return
     steps, warmup = args.steps, args.warmup
-    per_step_s = min(1.0, 120.0 / max(1, steps))          # bounded sample per step: the whole run ends within minutes
+    n = len(_host_grid()[0])
     for _ in range(warmup):
-        cpu_membership_rate(0.0, points=2_000_000)
-    rates, step_ms = [], []
+        cpu_membership_pass()
+    secs, members, threads = [], None, 0
     for _ in range(steps):
-        rate, threads, sample, dt = cpu_membership_rate(per_step_s)
-        rates.append(rate)
-        step_ms.append(dt * 1e3)
-    value = float(np.mean(rates))
+        dt, threads, members = cpu_membership_pass()
+        secs.append(dt)
+    value = n * steps / float(np.sum(secs))
     line = {
         "impl": "reference", "metric": "terminal-set samples/s", "value": value, "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": float(np.mean(step_ms)),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config 2: RoadMultipleCarsEnv terminal set (42 rows) on the 100^4 float64 grid",
-                   "note": "the reference is pure Python (cvxpy/polytope not installed, no build); this arm is the "
-                           "C restatement of lib/terminal_set.py:107-113 in oracle/, all host threads"},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": float(np.mean(secs)) * 1e3,
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} passes over the full 10^8-point grid, one per step",
                          "pointwise_python_samples_per_s": cpu_pointwise_rate()},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "members": members,
+        "note": "the reference is pure Python (cvxpy / polytope not installed, nothing to build); this arm is the C "
+                "restatement of lib/terminal_set.py:107-113 in oracle/ on all host threads",
     }
     print(json.dumps(line), flush=True)
 
@@ -168,11 +197,27 @@ def run_reference(args, rank: int, world: int):
 # ------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------
+def _pinned_copy_gbs(torch, dev, nbytes=1 << 30):
+    """Measured host->device bandwidth of one pinned cudaMemcpyAsync (the link peak the end-to-end path is held against)."""
+    src = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    e1.synchronize()
+    return 3 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
     from carmpc_b200.batch import TerminalSetEvaluator
-    from carmpc_b200.grids import config2_axes, materialise_grid, grid_size
+    from carmpc_b200.grids import config2_axes, materialise_grid, grid_size, shard_range
+    from carmpc_b200.sharding import PeerWindow, contains_bits_sharded, gather_bitset, reduce_count
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
@@ -199,22 +244,61 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     Ab = np.load(TERMINAL_SET)
     ev = TerminalSetEvaluator(Ab)
+    if args.staging:
+        ev.set_staging(*[int(t) for t in args.staging.split(",")])
     axes = config2_axes()
     n = grid_size(axes)
-    x, y, psi, v = materialise_grid(axes, device=dev)                 # 3.2 GB of float64 SoA per GPU
+    # strong scaling: ONE 10^8-point grid; rank r holds and scans samples [lo, hi) (whole 1024-sample groups)
+    lo, hi = shard_range(n, rank, world, align=1024)
+    n_local = hi - lo
+    x, y, psi, v = materialise_grid(axes, device=dev, start=lo, stop=hi)         # 3.2 GB / world of float64 SoA
     words = (n + 31) // 32
-    bits = [torch.empty(words, dtype=torch.int32, device=dev) for _ in range(2)]
+    words_local = (n_local + 31) // 32
+    bits = [torch.empty(max(words_local, 1), dtype=torch.int32, device=dev) for _ in range(2)]
     count = torch.zeros(1, dtype=torch.int64, device=dev)
-    from carmpc_b200.sharding import gather_bitset, reduce_count
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    gather_mode, window, window_error = "none (single GPU)", None, None
+    if distributed:
+        try:
+            window = PeerWindow(n)
+            gather_mode = "fused: the scan kernel stores its bitset words into every rank's window over NVLink (CUDA IPC " \
+                          "peer mappings), counts + completion flags by a one-warp exchange kernel; no NCCL call in the step"
+        except Exception as exc:                              # no peer access on this box: NCCL carries the gather
+            window_error = f"{type(exc).__name__}: {exc}"
+        ok = torch.tensor([1 if window is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            window = None
+            gather_mode = "nccl: all_gather_into_tensor of the bitset words + all_reduce of the count inside the step"
+    full_bits = torch.empty(world * ((shard_range(n, 0, world, align=1024)[1] + 31) // 32), dtype=torch.int32, device=dev) \
+        if distributed else None
     launches = 0
 
-    def step(i):
-        # samples shard with no data-path collective: a step is this rank's membership pass over its own grid
-        nonlocal launches
+    def step_nccl(i):
         ev.contains_bits(x, y, psi, v, mode=args.mode, bits=bits[i & 1], count=count)
-        launches += 1
+        gather_bitset(bits[i & 1], n, out=full_bits, shard_align=1024)
+        total.copy_(count)
+        reduce_count(total)
+
+    def step(i):
+        nonlocal launches
+        if not distributed:
+            ev.contains_bits(x, y, psi, v, mode=args.mode, bits=bits[i & 1], count=total)
+            launches += 1
+        elif window is not None:
+            contains_bits_sharded(ev, window, x, y, psi, v, mode=args.mode, total=total)
+            launches += 2                                   # scan (+ stores to every peer) and the exchange kernel
+        else:
+            step_nccl(i)
+            launches += 1
 
     for i in range(args.warmup):
         step(i)
@@ -228,26 +312,23 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         stop.record()
         barrier()
     ms = start.elapsed_time(stop)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    members = int(count.item())
-    # result collection (outside the timed steps): bitset words of every rank over NCCL / NVLink, and the member count
-    gather_ms = None
-    if distributed:
-        gather_bitset(bits[0], world * n)                    # communicator warm-up
-        torch.cuda.synchronize()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        full = gather_bitset(bits[(args.steps - 1) & 1], world * n)
-        total_members = reduce_count(count.clone())
-        g1.record()
-        g1.synchronize()
-        gather_ms = g0.elapsed_time(g1)
-        assert full.numel() == world * words and int(total_members.item()) == world * members
+    ms_total = max_over_ranks(ms)
+    members = int(total.item())
+    if window is not None:
+        window.check()
 
-    # kernel-only timing for the roofline (no gather), same inputs (3.2 GB >> 126 MB L2, so no flush is needed)
+    # ---- outside the timed steps: the gathered result of the last step equals an independent NCCL gather -----------
+    verify = None
+    if distributed:
+        ev.contains_bits(x, y, psi, v, mode=0, bits=bits[0], count=count)          # float64 kernel, local shard
+        ref_full = gather_bitset(bits[0], n, shard_align=1024).clone()
+        ref_total = int(reduce_count(count.clone()).item())
+        got = window.result_bits() if window is not None else full_bits[:words]
+        verify = {"bitset_equal_nccl_gather_of_float64_scan": bool(torch.equal(got[:words], ref_full[:words])),
+                  "count_equal": members == ref_total, "members": ref_total}
+        assert verify["bitset_equal_nccl_gather_of_float64_scan"] and verify["count_equal"], verify
+
+    # ---- this rank's scan alone (no peers, no exchange): the kernel the roofline is about --------------------------------
     k_ms = []
     for i in range(min(args.steps, 50)):
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -256,12 +337,35 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         s1.record()
         s1.synchronize()
         k_ms.append(s0.elapsed_time(s1))
-    kernel_ms = float(np.mean(k_ms))
+    kernel_ms = max_over_ranks(float(np.mean(k_ms)))
+    # back-to-back launches of the same kernel (what a step is at N = 1)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for i in range(args.steps):
+        ev.contains_bits(x, y, psi, v, mode=args.mode, bits=bits[0], count=count)
+    s1.record()
+    s1.synchronize()
+    stream_ms = max_over_ranks(s0.elapsed_time(s1) / args.steps)
+
+    nccl_variant = None
+    if distributed and window is not None:
+        for i in range(3):
+            step_nccl(i)
+        barrier()
+        s0.record()
+        for i in range(args.steps):
+            step_nccl(i)
+        s1.record()
+        barrier()
+        nccl_ms = max_over_ranks(s0.elapsed_time(s1) / args.steps)
+        nccl_variant = {"ms_per_step": nccl_ms, "value": n / (nccl_ms * 1e-3), "unit": "samples/s",
+                        "what": "same sharded scan, bitset all_gather_into_tensor + count all_reduce over NCCL inside the step"}
 
     # ---- end to end through the host-buffer C-ABI call (pinned host SoA in, host bitset out) -----------------
     e2e = None
     if not args.skip_e2e:
-        hn = args.e2e_samples
+        hn = min(args.e2e_samples, n_local)
         host = [torch.empty(hn, dtype=torch.float64, pin_memory=True).copy_(t[:hn]) for t in (x, y, psi, v)]
         hx, hy, hp, hv = [h.numpy() for h in host]
         ev.contains_bits_host(hx[:1 << 20], hy[:1 << 20], hp[:1 << 20], hv[:1 << 20], mode=args.mode)   # warm-up
@@ -272,18 +376,21 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         for _ in range(e2e_steps):
             hbits, hcount = ev.contains_bits_host(hx, hy, hp, hv, mode=args.mode)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if distributed:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * hn * e2e_steps / float(tt.item()), "unit": "samples/s",
+        dt = max_over_ranks(time.perf_counter() - t0)
+        hn_all = hn * world if hn == n_local else hn * world
+        link_peak = _pinned_copy_gbs(torch, dev)
+        link_gbs = hn * 32 * e2e_steps / dt / 1e9
+        e2e = {"value": hn_all * e2e_steps / dt, "unit": "samples/s",
                "h2d_bytes_per_step": int(hn * 32), "d2h_bytes_per_step": int((hn + 31) // 32 * 4 + 8),
-               "samples_per_step": hn, "steps": e2e_steps,
-               "call": "carmpc_membership_bitset_host (pinned host SoA -> chunked H2D | kernel | D2H pipeline)"}
+               "samples_per_step_per_gpu": hn, "steps": e2e_steps,
+               "call": "carmpc_membership_bitset_host (pinned host SoA -> chunked H2D | kernel | D2H pipeline), each rank its shard",
+               "roofline": {"bound": "host link (PCIe H2D)", "achieved": link_gbs, "peak": link_peak, "unit": "GB/s",
+                            "frac": link_gbs / link_peak, "peak_source": "measured live: 1 GiB pinned cudaMemcpyAsync H2D, per GPU"}}
+        del host
 
     # the same grid through the implicit-grid entry point: host axes in (3.2 KB), host bitset out (12.5 MB)
     e2e_grid = None
-    if not args.skip_e2e:
+    if not args.skip_e2e and not distributed:
         gbits = torch.empty(words, dtype=torch.int32, device=dev)
         hbits = torch.empty(words, dtype=torch.int32, pin_memory=True)
         ev.contains_grid_bits(axes, bits=gbits, count=count)
@@ -295,7 +402,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             hbits.copy_(gbits, non_blocking=True)
             torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / 20
-        e2e_grid = {"value": world * n / dt, "unit": "samples/s", "h2d_bytes_per_step": int(sum(len(a) for a in axes) * 8),
+        e2e_grid = {"value": n / dt, "unit": "samples/s", "h2d_bytes_per_step": int(sum(len(a) for a in axes) * 8),
                     "d2h_bytes_per_step": int(words * 4 + 8),
                     "call": "carmpc_membership_grid (axes on the host, coordinates generated in-kernel) + D2H of the bitset"}
 
@@ -307,53 +414,72 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         from carmpc_b200.lib.environments import RoadMultipleCarsEnv
         k_star = 16
         rv = RolloutEvaluator.from_env(RoadMultipleCarsEnv(), k_star)
-        rcount = torch.zeros(1, dtype=torch.int64, device=dev)
+        rwin = None
+        if window is not None:
+            rwin = PeerWindow(n)
+        rtotal = torch.zeros(1, dtype=torch.int64, device=dev)
+
+        def rstep():
+            if rwin is not None:
+                contains_bits_sharded(rv, rwin, x, y, psi, v, total=rtotal)
+            else:
+                rv.contains_bits(x, y, psi, v, bits=bits[0], count=rtotal)
+                if distributed:
+                    gather_bitset(bits[0], n, out=full_bits, shard_align=1024)
+                    reduce_count(rtotal)
+
         for _ in range(3):
-            rv.contains_bits(x, y, psi, v, bits=bits[0], count=rcount)
+            rstep()
         barrier()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record()
         for _ in range(args.rollout_steps):
-            rv.contains_bits(x, y, psi, v, bits=bits[0], count=rcount)
+            rstep()
         r1.record()
         barrier()
-        r_ms = r0.elapsed_time(r1) / args.rollout_steps
-        tr = torch.tensor([r_ms], dtype=torch.float64, device=dev)
-        if distributed:
-            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
-        r_ms = float(tr.item())
-        r_members = int(rcount.item())
-        # the plain float64 kernel (one sample per thread; selected when the first violated step is requested)
-        rv.contains_bits(x, y, psi, v, want_first_violation=True, bits=bits[0], count=rcount)
-        torch.cuda.synchronize()
+        r_ms = max_over_ranks(r0.elapsed_time(r1) / args.rollout_steps)
+        r_members = int(rtotal.item())
+        rcount = torch.zeros(1, dtype=torch.int64, device=dev)
         r0.record()
-        for _ in range(3):
-            rv.contains_bits(x, y, psi, v, want_first_violation=True, bits=bits[0], count=rcount)
+        for _ in range(args.rollout_steps):
+            rv.contains_bits(x, y, psi, v, bits=bits[0], count=rcount)
         r1.record()
-        torch.cuda.synchronize()
-        exact_ms = r0.elapsed_time(r1) / 3
+        r1.synchronize()
+        rk_ms = max_over_ranks(r0.elapsed_time(r1) / args.rollout_steps)
+        # the plain float64 kernel (one sample per thread; selected when the first violated step is requested)
+        exact_ms = None
+        if not distributed:
+            rv.contains_bits(x, y, psi, v, want_first_violation=True, bits=bits[0], count=rcount)
+            torch.cuda.synchronize()
+            r0.record()
+            for _ in range(3):
+                rv.contains_bits(x, y, psi, v, want_first_violation=True, bits=bits[0], count=rcount)
+            r1.record()
+            torch.cuda.synchronize()
+            exact_ms = r0.elapsed_time(r1) / 3
         peak, _ = _peaks()
         s_rows, r_in = len(rv.b_con), len(rv.b_in)
-        rollout = {"metric": "rollout-form terminal-set samples/s", "value": world * n / (r_ms * 1e-3), "unit": "samples/s",
+        ach = n_local * BYTES_PER_SAMPLE / (rk_ms * 1e-3) / 1e9
+        rollout = {"metric": "rollout-form terminal-set samples/s", "value": n / (r_ms * 1e-3), "unit": "samples/s",
                    "ms_per_step": r_ms, "steps": args.rollout_steps, "k_steps": k_star, "state_rows": s_rows, "input_rows": r_in,
                    "screen_rows": s_rows * (k_star + 1) + r_in, "members": r_members, "members_hrep": members,
-                   "float64_kernel_ms": exact_ms, "float64_kernel_samples_per_s": n / (exact_ms * 1e-3),
+                   "float64_kernel_ms": exact_ms,
                    "float64_kernel_note": "rollout_kernel, also writes the first violated step (4 B/sample)",
-                   "roofline": {"bound": "hbm", "achieved": n * BYTES_PER_SAMPLE / (r_ms * 1e-3) / 1e9, "peak": peak,
-                                "unit": "GB/s", "frac": n * BYTES_PER_SAMPLE / (r_ms * 1e-3) / 1e9 / peak,
-                                "kernel": "membership_tma_kernel<1, rollout>"},
+                   "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                "launch_ms": rk_ms, "kernel": "membership_tma_kernel<1, rollout>",
+                                "note": "this rank's scan alone, per GPU"},
                    "flop_per_sample_float64_form": (k_star + 1) * 8 * s_rows + 32 * k_star + 32}
         if rank == 0 and world == 1 and not args.skip_cpu:
             from oracle import c_oracle
-            cols = _cpu_sample(2_000_000)
+            cols = [c[::50].copy() for c in _host_grid()]
             t0 = time.perf_counter()
             passes = 0
             while time.perf_counter() - t0 < 4.0:
                 c_oracle.rollout_bits(rv.A_k, rv.A_con, rv.b_con, rv.A_in, rv.b_in, rv.goal, k_star, 0, *cols)
                 passes += 1
-            rollout["cpu_baseline"] = {"value": passes * 2_000_000 / (time.perf_counter() - t0), "unit": "samples/s",
+            rollout["cpu_baseline"] = {"value": passes * len(cols[0]) / (time.perf_counter() - t0), "unit": "samples/s",
                                        "cores": c_oracle.max_threads(), "kind": "port",
-                                       "sample": f"{passes} passes over a 2000000-point strided slice of the 10^8 grid"}
+                                       "sample": f"{passes} passes over every 50th point of the 10^8 grid"}
 
     qp = None
     if not args.skip_qp:
@@ -365,39 +491,51 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     if rank == 0:
         peak, peak_src = _peaks()
-        # at N = 1 a step is exactly one launch of the kernel: its average duration over the timed region (back-to-back
-        # launches, CUDA events on the launching stream); with the gather in the step (N > 1) the isolated timing is used
-        launch_ms = ms / args.steps if not distributed else kernel_ms
-        achieved = n * BYTES_PER_SAMPLE / (launch_ms * 1e-3) / 1e9
+        # The dominant kernel is this rank's membership scan.  At N = 1 a step IS one launch of it, so its average
+        # duration over the timed region (back-to-back launches, CUDA events on the launching stream) is ms / steps;
+        # at N > 1 the step also holds the exchange kernel, so the scan is timed alone, back to back, right after.
+        launch_ms = ms_total / args.steps if not distributed else stream_ms
+        achieved = n_local * BYTES_PER_SAMPLE / (launch_ms * 1e-3) / 1e9
         cpu = None
         if world == 1 and not args.skip_cpu:
-            rate, threads, sample, _ = cpu_membership_rate(10.0)
+            rate, threads, sample, cpu_members = cpu_membership_rate(10.0)
             cpu = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
+                   "members_equal_gpu": cpu_members == members,
                    "pointwise_python_samples_per_s": cpu_pointwise_rate()}
+        qp_summary = None
+        if isinstance(qp, dict) and "value" in qp:
+            qp_summary = {"metric": qp["metric"], "value": qp["value"], "unit": "QPs/s", "ms_per_step": qp["ms_per_step"],
+                          "scaling": qp.get("scaling"), "roofline_frac": (qp.get("roofline") or {}).get("frac"),
+                          "roofline_bound": (qp.get("roofline") or {}).get("bound"),
+                          "e2e": (qp.get("e2e") or {}).get("value"),
+                          "cpu_baseline": (qp.get("cpu_baseline") or {}).get("value"),
+                          "seeded_map": (qp.get("seeded_map") or {}).get("value"),
+                          "closed_loop_s": (qp.get("closed_loop") or {}).get("seconds"),
+                          "sweep_qps": {k: v["qps"] for k, v in (qp.get("horizon_sweep") or {}).items()}}
         line = {
-            "metric": "terminal-set samples/s", "value": world * n * args.steps / (ms_total * 1e-3),
+            "metric": "terminal-set samples/s", "value": n * args.steps / (ms_total * 1e-3),
             "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config 2: RoadMultipleCarsEnv terminal set (42 rows) on the 100^4 = 10^8-point "
-                                   "float64 SoA grid per GPU; one step = one membership pass -> bitset + count",
-                       "samples_per_gpu_per_step": n, "kernel_mode": "fp32 screen + fp64 re-check" if args.mode else "fp64",
-                       "l2": "inputs (3.2 GB) exceed the 126 MB L2; no flush between iterations",
-                       "members": members,
-                       "multi_gpu": "each rank scans its own 10^8 grid, no data-path collective; the bitsets are all-gathered "
-                                    "over NCCL after the timed steps (result_gather_ms)" if distributed else "single GPU",
-                       "result_gather_ms": gather_ms},
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if distributed else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(),
             "clocks": clocks.summary(),
             "e2e": e2e,
-            "e2e_grid": e2e_grid,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": 3.2125e9, "traffic_source": "ncu --set full: dram__bytes_read.sum 3.200 GB + "
-                         "dram__bytes_write.sum 12.5 MB per launch (profiles/r01_s5_membership_tma_ncu_full.txt)",
+                         "traffic": n_local * 32.125 if not distributed else None,
+                         "traffic_source": "ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch = "
+                                           "algorithmic bytes (profiles/)",
                          "peak_source": peak_src, "launch_ms": launch_ms, "isolated_launch_ms": kernel_ms,
-                         "kernel": "membership_tma_kernel<1>" if args.mode == 1 else "membership_kernel<0,true>",
-                         "bytes_per_sample": BYTES_PER_SAMPLE, "algorithmic_bytes_per_launch": n * BYTES_PER_SAMPLE},
+                         "kernel": "membership_tma_kernel<1, hrep>" if args.mode == 1 else "membership_kernel<0,true>",
+                         "bytes_per_sample": BYTES_PER_SAMPLE, "samples_per_launch": n_local,
+                         "algorithmic_bytes_per_launch": n_local * BYTES_PER_SAMPLE,
+                         "note": "per GPU: this rank's scan of its shard"},
             "cpu_baseline": cpu,
+            "qp_summary": qp_summary,
+            "sharding": {"samples_per_gpu": n_local, "gather": gather_mode, "window_error": window_error,
+                         "scan_alone_ms": stream_ms, "step_overhead_ms": ms_total / args.steps - stream_ms,
+                         "verify": verify, "nccl_variant": nccl_variant,
+                         "kernel_mode": "fp32 screen + fp64 re-check" if args.mode else "fp64", "members": members},
+            "e2e_grid": e2e_grid,
             "rollout": rollout,
             "qp": qp,
         }
@@ -414,6 +552,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", type=int, default=1, help="membership kernel: 0 = float64, 1 = float32 screen + float64 re-check")
+    ap.add_argument("--staging", default="", help="threads,ring_slots,tiles_per_slot of the scan kernel (tuning)")
     ap.add_argument("--e2e-samples", type=int, default=100_000_000)
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--skip-e2e", action="store_true")

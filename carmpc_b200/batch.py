@@ -60,6 +60,12 @@ class _Handle:
             pass
 
 
+class _ScanTuning:
+    def set_staging(self, threads_per_cta: int = 256, ring_slots: int = 3, tiles_per_slot: int = 1) -> None:
+        """Staging geometry of the bulk-async scan kernel (``carmpc_scan_staging``); results never depend on it."""
+        check(self._lib.carmpc_scan_staging(self._h, int(threads_per_cta), int(ring_slots), int(tiles_per_slot)))
+
+
 def _check_soa(x, y, psi, v):
     torch = _torch()
     n = x.numel()
@@ -69,7 +75,7 @@ def _check_soa(x, y, psi, v):
     return n
 
 
-class TerminalSetEvaluator(_Handle):
+class TerminalSetEvaluator(_Handle, _ScanTuning):
     """``A x <= b`` for every sample; results as a bitset (1 bit per sample, warp-ballot packed)."""
 
     def __init__(self, A: np.ndarray, b: Optional[np.ndarray] = None):
@@ -143,7 +149,7 @@ class TerminalSetEvaluator(_Handle):
         return unpack_bits(bits, len(np.atleast_1d(x)))
 
 
-class RolloutEvaluator(_Handle):
+class RolloutEvaluator(_Handle, _ScanTuning):
     """Sampled form of the terminal set: e(0) = p - goal, e(t+1) = A_k e(t); state rows for t = 0..k_steps, input
     rows at t = 0 only (``input_every_step=False``, what the reference's construction does) or at every step."""
 

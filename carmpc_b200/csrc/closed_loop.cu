@@ -112,8 +112,6 @@ __global__ void fill_i32(int32_t* p, int64_t n, int32_t v) {
 
 using namespace carmpc;
 
-static const bool g_reuse_active_set = getenv("CARMPC_NO_ACTIVE_SET_REUSE") == nullptr;    // development knob
-
 extern "C" int carmpc_closed_loop(void* qp, int mode, const double* h_A, const double* h_B, const double* h_C,
                                   const double* h_L, const double* h_xref, double dt, double l1, int steps,
                                   int warm_start, const double* d_x_init, const double* d_xhat_init, int64_t runs,
@@ -176,7 +174,7 @@ extern "C" int carmpc_closed_loop(void* qp, int mode, const double* h_A, const d
         if (live > 0) {
             // from the second step on, the active set certified at the previous step is tried first
             rc = q->solve(est, runs, h_xref, nullptr, live_list, live, u0, nullptr, status, nullptr, nullptr, warm,
-                          warm_valid ? 1 : 0, warm ? 1 : 0, st, warm_valid && g_reuse_active_set ? 1 : 0);
+                          warm_valid ? 1 : 0, warm ? 1 : 0, st, warm_valid ? 1 : 0);
             if (rc != CARMPC_OK) { q->defer_total = 0; cleanup(); return rc; }
             warm_valid = warm != nullptr;
             loop_apply_kernel<<<(live + 255) / 256, 256, 0, st>>>(runs, k, live_list, live, u0, status, u_prev, d_fail_step);

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "shard.cuh"
 
 namespace carmpc {
 
@@ -35,6 +36,11 @@ constexpr int kChunk = kThreads * kNS;                     // samples per block 
 struct __align__(16) RowF32 {
     float na0, na1, na2, na3;
     float b, pad0, pad1, pad2;
+};
+
+// staging geometry of the bulk-async scan: threads per CTA, ring slots per warp, 128-sample tiles per slot
+struct Staging {
+    int threads = 256, stages = 3, tps = 1;
 };
 
 // Device staging of the host-buffer entry points: two slots so that the H2D copy of chunk c+1 overlaps the kernel
@@ -80,6 +86,7 @@ struct Polytope : HandleBase {
     HostStage stage;
     std::vector<double> h_rows;      // rows x 5 in device order (host copy, for re-ordering)
     bool tuned = false;              // row order already adapted to a sample set
+    Staging staging;                 // geometry of the bulk-async scan (carmpc_scan_staging)
     double* d_axes = nullptr;        // grid axes of carmpc_membership_grid (4 x 4096 doubles at most)
     double* h_axes = nullptr;        // pinned staging copy
     ~Polytope() override {
@@ -98,6 +105,7 @@ struct Rollout : HandleBase {
     float beta0 = 0.f, beta1 = 0.f;
     std::vector<RowF32> h_rows32;    // host copy (re-ordered by the pilot)
     bool tuned = false;
+    Staging staging;
     HostStage stage;
     ~Rollout() override { cudaFree(d_data); cudaFree(d_rows32); }
 };
@@ -245,35 +253,71 @@ __device__ __forceinline__ void screen32(const RowF32* __restrict__ s_rows32, in
     }
 }
 
-// write the 128 decisions of a warp (lane t holds samples 4t .. 4t+3 of the warp's chunk) as four words
-__device__ __forceinline__ int store_bits(uint32_t* __restrict__ bits, int64_t warp_base, int64_t n, const bool (&in)[kNS]) {
+// Where the bitset words of a scan go.  One destination for a plain call; for a scan that is one shard of a sample set
+// partitioned over the GPUs of a box, one destination per rank (the rank's own full bitset and, through NVLink peer
+// mappings, every other rank's), each already pointing at the first word of this shard - the scan kernel itself
+// performs the all-gather, no separate collective.
+constexpr int kMaxPeers = 8;
+struct BitSink {
+    uint32_t* dst[kMaxPeers];
+    int n;
+};
+
+static BitSink single_sink(uint32_t* bits) {
+    BitSink s{};
+    s.dst[0] = bits;
+    s.n = 1;
+    return s;
+}
+
+static BitSink offset_sink(const BitSink& in, int64_t words) {
+    BitSink s = in;
+    for (int d = 0; d < s.n; ++d) s.dst[d] += words;
+    return s;
+}
+
+// The 128 decisions of a warp tile (lane t holds samples 4t .. 4t+3) as four words: returns to EVERY lane the word
+// (lane & 3) of the tile, and the number of members through `members`.
+__device__ __forceinline__ uint32_t tile_word(const bool (&in)[kNS], int& members) {
     uint32_t bal[kNS];
-    int members = 0;
 #pragma unroll
     for (int k = 0; k < kNS; ++k) {
         bal[k] = __ballot_sync(0xffffffffu, in[k]);
         members += __popc(bal[k]);
     }
+    const int q = threadIdx.x & 3;
+    uint32_t word = 0;
+#pragma unroll
+    for (int k = 0; k < kNS; ++k) word |= spread8x4(bal[k] >> (8 * q)) << k;
+    return word;
+}
+
+// write the 128 decisions of a warp (lane t holds samples 4t .. 4t+3 of the warp's chunk) as four words
+__device__ __forceinline__ int store_bits(const BitSink& sink, int64_t warp_base, int64_t n, const bool (&in)[kNS]) {
+    int members = 0;
+    const uint32_t word = tile_word(in, members);
     const int lane = threadIdx.x & 31;
     if (lane < 4) {
-        uint32_t word = 0;
-#pragma unroll
-        for (int k = 0; k < kNS; ++k) word |= spread8x4(bal[k] >> (8 * lane)) << k;
         const int64_t first = warp_base + 32 * lane;
-        if (first < n) bits[first >> 5] = word;
+        if (first < n) {
+#pragma unroll
+            for (int d = 0; d < kMaxPeers; ++d)
+                if (d < sink.n) sink.dst[d][first >> 5] = word;
+        }
     }
     return members;
 }
 
+template <int THREADS = kThreads>
 __device__ __forceinline__ void block_count(int warp_members, unsigned long long* __restrict__ count) {
-    __shared__ int s_partial[kThreads / 32];
+    __shared__ int s_partial[THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) s_partial[warp] = warp_members;
     __syncthreads();
     if (threadIdx.x == 0 && count != nullptr) {
         int total = 0;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) total += s_partial[w];
+        for (int w = 0; w < THREADS / 32; ++w) total += s_partial[w];
         if (total) atomicAdd(count, (unsigned long long)total);
     }
 }
@@ -302,7 +346,7 @@ __global__ void __launch_bounds__(kThreads)
 membership_kernel(const double* __restrict__ g_rows, const RowF32* __restrict__ g_rows32, const ExactSpec es, int rows_padded,
                   const ScreenConst sc, const double* __restrict__ gx, const double* __restrict__ gy,
                   const double* __restrict__ gp, const double* __restrict__ gv, int64_t n,
-                  uint32_t* __restrict__ bits, unsigned long long* __restrict__ count) {
+                  const BitSink sink, unsigned long long* __restrict__ count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_rows = reinterpret_cast<double*>(smem_raw);
     RowF32* s_rows32 = reinterpret_cast<RowF32*>(s_rows + ((es.len + 1) & ~1));
@@ -343,20 +387,25 @@ membership_kernel(const double* __restrict__ g_rows, const RowF32* __restrict__ 
             }
         }
         const int64_t warp_base = chunk * kChunk + 32 * kNS * (int64_t)(threadIdx.x >> 5);
-        members += store_bits(bits, warp_base, n, in);
+        members += store_bits(sink, warp_base, n, in);
     }
     block_count(members, count);
 }
 
 // ---- bulk-async (TMA) staged variant ---------------------------------------------------------------------------------
 // The scan is HBM-bound, and with plain loads the bytes in flight are limited by the registers that receive them
-// (8 x 128-bit loads per thread) times the occupancy.  Here every warp runs its own 3-stage shared-memory ring: lane 0
-// streams the warp's next tiles (4 arrays x 128 samples x 8 B = 4 KB) with cp.async.bulk, completion is tracked by one
-// mbarrier per stage (expect_tx / complete_tx), the warp waits on the stage, pulls its samples into registers,
+// (8 x 128-bit loads per thread) times the occupancy.  Here every warp runs its own STAGES-deep shared-memory ring: lane 0
+// streams the warp's next stage (4 arrays x TPS tiles x 128 samples x 8 B) with cp.async.bulk, completion is tracked by
+// one mbarrier per stage (expect_tx / complete_tx), the warp waits on the stage, pulls its samples into registers,
 // __syncwarp()s, and lane 0 immediately refills the stage.  Warps never wait for each other (the early exits make
-// their tiles very unequal), and ~12 KB of reads per warp are in flight regardless of register allocation.
-constexpr int kStages = 3;
+// their tiles very unequal), and the bytes in flight do not depend on register allocation.
+//
+// Work unit of a warp: a GROUP of 8 consecutive tiles = 1024 samples = 32 bitset words, handed out round-robin over
+// all warps of the grid.  The 32 words of a group are collected one per lane and leave as ONE 128-byte store per
+// destination (the local bitset and, for a sharded scan, every peer's copy over NVLink).
 constexpr int kTile = 32 * kNS;                 // samples per warp tile
+constexpr int kGroupTiles = 8;                  // tiles per group
+constexpr int kGroup = kTile * kGroupTiles;     // samples per group (1024)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -380,96 +429,113 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-template <int MODE, int KIND>
-__global__ void __launch_bounds__(kThreads)
+// THREADS per CTA, STAGES ring slots per warp, TPS tiles (of 128 samples) per slot
+template <int MODE, int KIND, int THREADS, int STAGES, int TPS>
+__global__ void __launch_bounds__(THREADS)
 membership_tma_kernel(const double* __restrict__ g_rows, const RowF32* __restrict__ g_rows32, const ExactSpec es, int rows_padded,
                       const ScreenConst sc, const double* __restrict__ gx, const double* __restrict__ gy,
-                      const double* __restrict__ gp, const double* __restrict__ gv, int64_t n_tiles,
-                      uint32_t* __restrict__ bits, unsigned long long* __restrict__ count) {
+                      const double* __restrict__ gp, const double* __restrict__ gv, int64_t n_groups,
+                      const BitSink sink, unsigned long long* __restrict__ count) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int kWarps = kThreads / 32;
-    double* s_stage = reinterpret_cast<double*>(smem_raw);                       // [kWarps][kStages][4][kTile]
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + (size_t)kWarps * kStages * 4 * kTile);   // [kWarps][kStages]
-    double* s_rows = reinterpret_cast<double*>(s_bar + kWarps * kStages);
+    constexpr int kWarps = THREADS / 32;
+    constexpr int kSlot = TPS * kTile;                    // samples per ring slot and array
+    constexpr int kSlotsPerGroup = kGroupTiles / TPS;
+    static_assert(kGroupTiles % TPS == 0, "a group is a whole number of ring slots");
+    double* s_stage = reinterpret_cast<double*>(smem_raw);                       // [kWarps][STAGES][4][kSlot]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + (size_t)kWarps * STAGES * 4 * kSlot);   // [kWarps][STAGES]
+    double* s_rows = reinterpret_cast<double*>(s_bar + kWarps * STAGES);
     RowF32* s_rows32 = reinterpret_cast<RowF32*>(s_rows + ((es.len + 1) & ~1));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double* src[4] = {gx, gy, gp, gv};
-    constexpr uint32_t kArrayBytes = kTile * sizeof(double);
-    double* w_stage = s_stage + (size_t)warp * kStages * 4 * kTile;
-    uint64_t* w_bar = s_bar + warp * kStages;
+    constexpr uint32_t kArrayBytes = kSlot * sizeof(double);
+    double* w_stage = s_stage + (size_t)warp * STAGES * 4 * kSlot;
+    uint64_t* w_bar = s_bar + warp * STAGES;
 
     if (lane == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(w_bar + s, 1);
+        for (int s = 0; s < STAGES; ++s) mbar_init(w_bar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     stage_rows(g_rows, g_rows32, es.len, rows_padded, s_rows, s_rows32);        // ends with __syncthreads()
 
-    const int64_t first = (int64_t)blockIdx.x * kWarps + warp;                   // this warp's tiles: first, first + stride, ...
+    const int64_t first = (int64_t)blockIdx.x * kWarps + warp;                   // this warp's groups: first, first + stride, ...
     const int64_t stride = (int64_t)gridDim.x * kWarps;
-    auto issue = [&](int64_t tile, int stage) {                                  // producer: lane 0 of the warp
+    // slot sequence of this warp: slot j carries tiles [TPS (j % kSlotsPerGroup), ...) of group first + (j / kSlotsPerGroup) stride
+    auto issue = [&](int j) {                                                    // producer: lane 0 of the warp
+        const int64_t group = first + (int64_t)(j / kSlotsPerGroup) * stride;
+        if (group >= n_groups) return;
+        const int64_t sample = group * kGroup + (int64_t)(j % kSlotsPerGroup) * kSlot;
+        const int stage = j % STAGES;
         mbar_expect_tx(w_bar + stage, 4 * kArrayBytes);
 #pragma unroll
         for (int a = 0; a < 4; ++a)
-            bulk_load(w_stage + ((size_t)stage * 4 + a) * kTile, src[a] + tile * kTile, kArrayBytes, w_bar + stage);
+            bulk_load(w_stage + ((size_t)stage * 4 + a) * kSlot, src[a] + sample, kArrayBytes, w_bar + stage);
     };
     if (lane == 0)
-        for (int s = 0; s < kStages; ++s) {
-            const int64_t tile = first + (int64_t)s * stride;
-            if (tile < n_tiles) issue(tile, s);
-        }
+        for (int s = 0; s < STAGES; ++s) issue(s);
 
     int members = 0;
-    int it = 0;
-    for (int64_t tile = first; tile < n_tiles; tile += stride, ++it) {
-        const int stage = it % kStages;
-        mbar_wait(w_bar + stage, (uint32_t)(it / kStages) & 1u);
-        const double* st = w_stage + (size_t)stage * 4 * kTile + kNS * lane;
-        double x[kNS], y[kNS], p[kNS], v[kNS];
+    int j = 0;
+    for (int64_t group = first; group < n_groups; group += stride) {
+        uint32_t acc = 0;                                  // lane l collects word l of the group's 32
+#pragma unroll 1
+        for (int sg = 0; sg < kSlotsPerGroup; ++sg, ++j) {
+            const int stage = j % STAGES;
+            mbar_wait(w_bar + stage, (uint32_t)(j / STAGES) & 1u);
 #pragma unroll
-        for (int k = 0; k < kNS; k += 2) {
-            const double2 X = *reinterpret_cast<const double2*>(st + k);
-            const double2 Y = *reinterpret_cast<const double2*>(st + kTile + k);
-            const double2 P = *reinterpret_cast<const double2*>(st + 2 * kTile + k);
-            const double2 V = *reinterpret_cast<const double2*>(st + 3 * kTile + k);
-            x[k] = X.x; x[k + 1] = X.y; y[k] = Y.x; y[k + 1] = Y.y;
-            p[k] = P.x; p[k + 1] = P.y; v[k] = V.x; v[k + 1] = V.y;
-        }
-        float xf[kNS], yf[kNS], pf[kNS], vf[kNS];
-        if (MODE == 1) {
+            for (int t = 0; t < TPS; ++t) {
+                const double* st = w_stage + (size_t)stage * 4 * kSlot + t * kTile + kNS * lane;
+                double x[kNS], y[kNS], p[kNS], v[kNS];
 #pragma unroll
-            for (int k = 0; k < kNS; ++k) { xf[k] = (float)x[k]; yf[k] = (float)y[k]; pf[k] = (float)p[k]; vf[k] = (float)v[k]; }
-        }
-        __syncwarp();                                      // every lane has its samples in registers: stage is free
-        if (lane == 0) {
-            const int64_t next = tile + (int64_t)kStages * stride;
-            if (next < n_tiles) issue(next, stage);
-        }
-        bool in[kNS];
+                for (int k = 0; k < kNS; k += 2) {
+                    const double2 X = *reinterpret_cast<const double2*>(st + k);
+                    const double2 Y = *reinterpret_cast<const double2*>(st + kSlot + k);
+                    const double2 P = *reinterpret_cast<const double2*>(st + 2 * kSlot + k);
+                    const double2 V = *reinterpret_cast<const double2*>(st + 3 * kSlot + k);
+                    x[k] = X.x; x[k + 1] = X.y; y[k] = Y.x; y[k + 1] = Y.y;
+                    p[k] = P.x; p[k + 1] = P.y; v[k] = V.x; v[k + 1] = V.y;
+                }
+                float xf[kNS], yf[kNS], pf[kNS], vf[kNS];
+                if (MODE == 1) {
 #pragma unroll
-        for (int k = 0; k < kNS; ++k) in[k] = true;
-        if (MODE == 0) {
-            decide_exact<KIND>(s_rows, es, x, y, p, v, in);
-        } else {
-            bool amb[kNS];
-            screen32(s_rows32, rows_padded, sc, xf, yf, pf, vf, in, amb);
-            bool any_amb = false;
+                    for (int k = 0; k < kNS; ++k) { xf[k] = (float)x[k]; yf[k] = (float)y[k]; pf[k] = (float)p[k]; vf[k] = (float)v[k]; }
+                }
+                if (t == TPS - 1) {
+                    __syncwarp();                          // every lane has the slot's last samples in registers: slot is free
+                    if (lane == 0) issue(j + STAGES);
+                }
+                bool in[kNS];
 #pragma unroll
-            for (int k = 0; k < kNS; ++k) any_amb |= amb[k];
-            if (__any_sync(0xffffffffu, any_amb)) {
-                // rare: re-read the float64 coordinates (L2) and let the float64 chain decide, as in mode 0
-                const int64_t i0 = tile * kTile + kNS * (int64_t)lane;
-                double x2[kNS], y2[kNS], p2[kNS], v2[kNS];
-                load4<true>(gx, i0, n_tiles * kTile, x2); load4<true>(gy, i0, n_tiles * kTile, y2);
-                load4<true>(gp, i0, n_tiles * kTile, p2); load4<true>(gv, i0, n_tiles * kTile, v2);
-                decide_exact<KIND>(s_rows, es, x2, y2, p2, v2, amb);
+                for (int k = 0; k < kNS; ++k) in[k] = true;
+                if (MODE == 0) {
+                    decide_exact<KIND>(s_rows, es, x, y, p, v, in);
+                } else {
+                    bool amb[kNS];
+                    screen32(s_rows32, rows_padded, sc, xf, yf, pf, vf, in, amb);
+                    bool any_amb = false;
 #pragma unroll
-                for (int k = 0; k < kNS; ++k) in[k] |= amb[k];
+                    for (int k = 0; k < kNS; ++k) any_amb |= amb[k];
+                    if (__any_sync(0xffffffffu, any_amb)) {
+                        // rare: re-read the float64 coordinates (L2) and let the float64 chain decide, as in mode 0
+                        const int64_t i0 = group * kGroup + (int64_t)(sg * TPS + t) * kTile + kNS * (int64_t)lane;
+                        double x2[kNS], y2[kNS], p2[kNS], v2[kNS];
+                        load4<true>(gx, i0, n_groups * kGroup, x2); load4<true>(gy, i0, n_groups * kGroup, y2);
+                        load4<true>(gp, i0, n_groups * kGroup, p2); load4<true>(gv, i0, n_groups * kGroup, v2);
+                        decide_exact<KIND>(s_rows, es, x2, y2, p2, v2, amb);
+#pragma unroll
+                        for (int k = 0; k < kNS; ++k) in[k] |= amb[k];
+                    }
+                }
+                const uint32_t word = tile_word(in, members);
+                if ((lane >> 2) == sg * TPS + t) acc = word;
             }
         }
-        members += store_bits(bits, tile * kTile, n_tiles * kTile, in);
+        const int64_t w0 = group * (kGroup / 32) + lane;
+#pragma unroll
+        for (int d = 0; d < kMaxPeers; ++d)
+            if (d < sink.n) sink.dst[d][w0] = acc;
     }
-    block_count(members, count);
+    block_count<THREADS>(members, count);
 }
 
 struct GridDesc {
@@ -574,7 +640,10 @@ membership_grid_kernel(const double* __restrict__ g_rows, const RowF32* __restri
             for (int k = 0; k < kNS; ++k) in[k] |= amb[k];
         }
         const int64_t warp_base = chunk * kChunk + 32 * kNS * (int64_t)(threadIdx.x >> 5);
-        members += store_bits(bits, warp_base, n, in);
+        BitSink sink;
+        sink.dst[0] = bits;
+        sink.n = 1;
+        members += store_bits(sink, warp_base, n, in);
     }
     block_count(members, count);
 }
@@ -584,7 +653,7 @@ membership_grid_kernel(const double* __restrict__ g_rows, const RowF32* __restri
 __global__ void __launch_bounds__(kThreads)
 rollout_kernel(const double* __restrict__ g_data, int s, int rin, int k_steps, int input_mode,
                const double* __restrict__ gx, const double* __restrict__ gy, const double* __restrict__ gp,
-               const double* __restrict__ gv, int64_t n, uint32_t* __restrict__ bits,
+               const double* __restrict__ gv, int64_t n, const BitSink sink,
                int32_t* __restrict__ first_violation, unsigned long long* __restrict__ count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_data = reinterpret_cast<double*>(smem_raw);
@@ -634,7 +703,11 @@ rollout_kernel(const double* __restrict__ g_data, int s, int rin, int k_steps, i
             e0 = n0; e1 = n1; e2 = n2; e3 = n3;
         }
         const uint32_t word = __ballot_sync(0xffffffffu, in);
-        if ((threadIdx.x & 31) == 0 && i < n) bits[i >> 5] = word;
+        if ((threadIdx.x & 31) == 0 && i < n) {
+#pragma unroll
+            for (int d = 0; d < kMaxPeers; ++d)
+                if (d < sink.n) sink.dst[d][i >> 5] = word;
+        }
         if (first_violation != nullptr && valid) first_violation[i] = first;
         if ((threadIdx.x & 31) == 0) members += __popc(word);
     }
@@ -668,38 +741,70 @@ static ScreenConst screen_const(const Polytope* P) {
 static size_t scan_smem(int exact_len, int rows_padded) {
     return sizeof(double) * ((exact_len + 1) & ~1) + sizeof(RowF32) * rows_padded;
 }
-static size_t scan_tma_smem(int exact_len, int rows_padded) {
-    return sizeof(double) * (kThreads / 32) * kStages * 4 * kTile + sizeof(uint64_t) * (kThreads / 32) * kStages +
+static size_t scan_tma_smem(int exact_len, int rows_padded, const Staging& g) {
+    return sizeof(double) * (g.threads / 32) * g.stages * 4 * g.tps * kTile + sizeof(uint64_t) * (g.threads / 32) * g.stages +
            scan_smem(exact_len, rows_padded) + 16;
 }
+static bool staging_supported(const Staging& g) {
+    static const int ok[][3] = {{256, 3, 1}, {128, 3, 1}, {128, 4, 1}, {128, 2, 2}, {128, 3, 2}, {256, 2, 1}, {128, 2, 1}, {256, 2, 2}};
+    for (const auto& v : ok)
+        if (v[0] == g.threads && v[1] == g.stages && v[2] == g.tps) return true;
+    return false;
+}
 
-static bool g_use_tma = getenv("CARMPC_NO_TMA") == nullptr;          // development knob
+template <int KIND, int THREADS, int STAGES, int TPS>
+static int launch_tma(const double* d_exact, const RowF32* d_rows32, const ExactSpec& es, int rows_padded, const ScreenConst& sc,
+                      const double* x, const double* y, const double* p, const double* v, int64_t n_groups,
+                      const BitSink& sink, unsigned long long* count, size_t smem, cudaStream_t st) {
+    auto kernel = membership_tma_kernel<1, KIND, THREADS, STAGES, TPS>;
+    // the function attribute is per device and the occupancy depends on smem only through the row count, which rarely
+    // changes between calls: both are cached per device
+    static int per_sm_cached[64];
+    static size_t smem_cached[64];
+    int dev = 0;
+    CARMPC_CUDA(cudaGetDevice(&dev));
+    dev &= 63;
+    if (per_sm_cached[dev] <= 0 || smem_cached[dev] != smem) {
+        CARMPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CARMPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem));
+        per_sm_cached[dev] = per_sm > 0 ? per_sm : 1;
+        smem_cached[dev] = smem;
+    }
+    const int64_t n_units = (n_groups + THREADS / 32 - 1) / (THREADS / 32);
+    kernel<<<grid_blocks(n_units, per_sm_cached[dev]), THREADS, smem, st>>>(d_exact, d_rows32, es, rows_padded, sc, x, y, p, v,
+                                                                      n_groups, sink, count);
+    CARMPC_CUDA(cudaGetLastError());
+    return CARMPC_OK;
+}
 
 // Streaming scan shared by the H-rep membership (KIND 0) and the screened rollout form (KIND 1).
 template <int KIND>
 static int launch_scan(const double* d_exact, const RowF32* d_rows32, const ExactSpec es, int rows_padded,
                        const ScreenConst sc, const double* x, const double* y, const double* p, const double* v,
-                       int64_t n, uint32_t* bits, unsigned long long* count, int mode, cudaStream_t st) {
+                       int64_t n, BitSink sink, unsigned long long* count, int mode, const Staging& geo, cudaStream_t st) {
     if (n == 0) return CARMPC_OK;
     const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
                        reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
-    // Bulk-async staged kernel for the whole 128-sample tiles of 16-byte aligned arrays; whatever is left (a ragged
-    // tail of fewer than 128 samples, or unaligned arrays) goes through the plain-load kernel below.
+    // Bulk-async staged kernel for the whole 1024-sample groups of 16-byte aligned arrays; whatever is left (a ragged
+    // tail of fewer than 1024 samples, or unaligned arrays) goes through the plain-load kernel below.
     // (mode 0 is FP64-pipe bound and prefers the higher occupancy of the plain kernel: measured 0.72 vs 0.82 ms)
-    if (vec && g_use_tma && mode == 1 && n >= 64 * (int64_t)kChunk) {
-        const int64_t n_tiles = n / kTile;
-        const int64_t n_chunks = (n_tiles + kThreads / 32 - 1) / (kThreads / 32);
-        const size_t smem = scan_tma_smem(es.len, rows_padded);
-        CARMPC_CUDA(cudaFuncSetAttribute(membership_tma_kernel<1, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        CARMPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, membership_tma_kernel<1, KIND>, kThreads, smem));
-        const int blocks = grid_blocks(n_chunks, per_sm > 0 ? per_sm : 1);
-        membership_tma_kernel<1, KIND><<<blocks, kThreads, smem, st>>>(d_exact, d_rows32, es, rows_padded, sc, x, y, p, v,
-                                                                       n_tiles, bits, count);
-        CARMPC_CUDA(cudaGetLastError());
-        const int64_t done = n_tiles * kTile;
+    if (vec && mode == 1 && n >= 64 * (int64_t)kChunk) {
+        const int64_t n_groups = n / kGroup;
+        const size_t smem = scan_tma_smem(es.len, rows_padded, geo);
+        int rc = CARMPC_ERR_UNSUPPORTED;
+#define TMA_CASE(T, S, P)                                                                                              \
+        if (geo.threads == T && geo.stages == S && geo.tps == P)                                                           \
+            rc = launch_tma<KIND, T, S, P>(d_exact, d_rows32, es, rows_padded, sc, x, y, p, v, n_groups, sink, count, smem, st)
+        TMA_CASE(256, 3, 1); TMA_CASE(128, 3, 1); TMA_CASE(128, 4, 1); TMA_CASE(128, 2, 2);
+        TMA_CASE(128, 3, 2); TMA_CASE(256, 2, 1); TMA_CASE(128, 2, 1); TMA_CASE(256, 2, 2);
+#undef TMA_CASE
+        if (rc == CARMPC_ERR_UNSUPPORTED) set_error("membership scan: staging geometry %d/%d/%d is not built", geo.threads, geo.stages, geo.tps);
+        if (rc != CARMPC_OK) return rc;
+        const int64_t done = n_groups * kGroup;
         if (done == n) return CARMPC_OK;
-        x += done; y += done; p += done; v += done; bits += done >> 5; n -= done;
+        x += done; y += done; p += done; v += done; n -= done;
+        sink = offset_sink(sink, done >> 5);
     }
     const size_t smem = scan_smem(es.len, rows_padded);
     const int64_t n_chunks = (n + kChunk - 1) / kChunk;
@@ -710,7 +815,7 @@ static int launch_scan(const double* d_exact, const RowF32* d_rows32, const Exac
         CARMPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, membership_kernel<M, V, KIND>, kThreads, smem)); \
         const int blocks = grid_blocks(n_chunks, per_sm > 0 ? per_sm : 1);                                        \
         membership_kernel<M, V, KIND><<<blocks, kThreads, smem, st>>>(d_exact, d_rows32, es, rows_padded, sc, x, y, p, v, \
-                                                                      n, bits, count);                            \
+                                                                      n, sink, count);                            \
     } while (0)
     if (mode == 0) {
         if (vec) LAUNCH(0, true); else LAUNCH(0, false);
@@ -723,31 +828,30 @@ static int launch_scan(const double* d_exact, const RowF32* d_rows32, const Exac
 }
 
 static int launch_membership(Polytope* P, const double* x, const double* y, const double* p, const double* v,
-                             int64_t n, uint32_t* bits, unsigned long long* count, int mode, cudaStream_t st) {
+                             int64_t n, const BitSink& sink, unsigned long long* count, int mode, cudaStream_t st) {
     ExactSpec es{};
     es.len = P->rows * 5;
     es.rows = P->rows;
-    return launch_scan<0>(P->d_rows, P->d_rows32, es, pad_rows(P->rows), screen_const(P), x, y, p, v, n, bits, count, mode, st);
+    return launch_scan<0>(P->d_rows, P->d_rows32, es, pad_rows(P->rows), screen_const(P), x, y, p, v, n, sink, count, mode,
+                          P->staging, st);
 }
 
-static const bool g_rollout_exact_only = getenv("CARMPC_ROLLOUT_EXACT") != nullptr;    // development knob
-
 static int launch_rollout(Rollout* R, const double* x, const double* y, const double* p, const double* v, int64_t n,
-                          uint32_t* bits, int32_t* first, unsigned long long* count, cudaStream_t st) {
+                          const BitSink& sink, int32_t* first, unsigned long long* count, cudaStream_t st) {
     if (n == 0) return CARMPC_OK;
-    if (first == nullptr && R->d_rows32 != nullptr && !g_rollout_exact_only) {
+    if (first == nullptr && R->d_rows32 != nullptr) {
         // float32 screen over the expanded rows a_r A_k^t, float64 step-by-step rollout for the samples it cannot decide
         ExactSpec es{};
         es.len = 20 + 5 * R->s + 5 * R->rin;
         es.s = R->s; es.rin = R->rin; es.k_steps = R->k_steps; es.input_mode = R->input_mode;
         ScreenConst sc;
         sc.beta0 = R->beta0; sc.beta1 = R->beta1;
-        return launch_scan<1>(R->d_data, R->d_rows32, es, R->rows_padded, sc, x, y, p, v, n, bits, count, 1, st);
+        return launch_scan<1>(R->d_data, R->d_rows32, es, R->rows_padded, sc, x, y, p, v, n, sink, count, 1, R->staging, st);
     }
     const size_t smem = sizeof(double) * (20 + 5 * R->s + 5 * R->rin);
     const int64_t n_chunks = (n + kThreads - 1) / kThreads;
     rollout_kernel<<<grid_blocks(n_chunks, 8), kThreads, smem, st>>>(R->d_data, R->s, R->rin, R->k_steps, R->input_mode,
-                                                                     x, y, p, v, n, bits, first, count);
+                                                                     x, y, p, v, n, sink, first, count);
     CARMPC_CUDA(cudaGetLastError());
     return CARMPC_OK;
 }
@@ -769,7 +873,7 @@ static int host_pipeline(HostStage& S, const double* h_x, const double* h_y, con
         const double* src[4] = {h_x, h_y, h_psi, h_v};
         for (int a = 0; a < 4; ++a)
             CARMPC_CUDA(cudaMemcpyAsync(d + a * chunk, src[a] + s, sizeof(double) * len, cudaMemcpyHostToDevice, st));
-        rc = launch(d, d + chunk, d + 2 * chunk, d + 3 * chunk, len, S.d_bits[slot], S.d_first[slot], S.d_count, st);
+        rc = launch(d, d + chunk, d + 2 * chunk, d + 3 * chunk, len, single_sink(S.d_bits[slot]), S.d_first[slot], S.d_count, st);
         if (rc != CARMPC_OK) return rc;
         CARMPC_CUDA(cudaMemcpyAsync(h_bits + (s >> 5), S.d_bits[slot], sizeof(uint32_t) * ((len + 31) / 32),
                                     cudaMemcpyDeviceToHost, st));
@@ -869,8 +973,6 @@ static int tune_row_order(Polytope* P, const double* x, const double* y, const d
     P->h_rows.swap(sorted);
     return upload_rows(P, st);
 }
-
-static const bool g_auto_tune = getenv("CARMPC_NO_TUNE") == nullptr;       // development knob
 
 // The same idea for the expanded rows of the screened rollout form (up to 512 rows, float32 images: the order is a
 // heuristic, the decisions do not depend on it): masks of `words` 64-bit words per subsample.
@@ -1028,12 +1130,12 @@ int carmpc_membership_bitset(void* polytope, const double* d_x, const double* d_
     }
     CARMPC_REQUIRE(d_x && d_y && d_psi && d_v && d_bits, "null device pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    if (!P->tuned && g_auto_tune && n >= ((int64_t)1 << 20)) {
+    if (!P->tuned && n >= ((int64_t)1 << 20)) {
         const int rc = tune_row_order(P, d_x, d_y, d_psi, d_v, n, st);
         if (rc != CARMPC_OK) return rc;
     }
     if (d_count) CARMPC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
-    return launch_membership(P, d_x, d_y, d_psi, d_v, n, d_bits, reinterpret_cast<unsigned long long*>(d_count),
+    return launch_membership(P, d_x, d_y, d_psi, d_v, n, single_sink(d_bits), reinterpret_cast<unsigned long long*>(d_count),
                              mode, st);
 }
 
@@ -1075,7 +1177,7 @@ int carmpc_membership_grid(void* polytope, const double* h_axes, const int32_t d
     for (int i = 0; i < off; ++i) P->h_axes[i] = h_axes[i];
     double* d_axes = P->d_axes;
     CARMPC_CUDA(cudaMemcpyAsync(d_axes, P->h_axes, sizeof(double) * off, cudaMemcpyHostToDevice, st));
-    if (!P->tuned && g_auto_tune && n >= ((int64_t)1 << 20)) {
+    if (!P->tuned && n >= ((int64_t)1 << 20)) {
         // profile-guided row order from a strided subsample of the grid, expanded on the host (65,536 points, once per polytope)
         const int n_sub = 1 << 16;
         const int64_t stride = n / n_sub;
@@ -1120,7 +1222,7 @@ int carmpc_membership_bitset_host(void* polytope, const double* h_x, const doubl
     CARMPC_REQUIRE(h_x && h_y && h_psi && h_v && h_bits, "null host pointer");
     return host_pipeline(P->stage, h_x, h_y, h_psi, h_v, n, h_bits, nullptr, h_count,
                          [&](const double* x, const double* y, const double* p, const double* v, int64_t len,
-                             uint32_t* bits, int32_t*, unsigned long long* count, cudaStream_t st) {
+                             const BitSink& bits, int32_t*, unsigned long long* count, cudaStream_t st) {
                              return launch_membership(P, x, y, p, v, len, bits, count, mode, st);
                          });
 }
@@ -1233,11 +1335,11 @@ int carmpc_rollout_bitset(void* rollout, const double* d_x, const double* d_y, c
     if (d_count) CARMPC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
     if (n == 0) return CARMPC_OK;
     CARMPC_REQUIRE(d_x && d_y && d_psi && d_v && d_bits, "null device pointer");
-    if (!R->tuned && g_auto_tune && d_first_violation == nullptr && n >= ((int64_t)1 << 20)) {
+    if (!R->tuned && d_first_violation == nullptr && n >= ((int64_t)1 << 20)) {
         const int rc = tune_rollout_order(R, d_x, d_y, d_psi, d_v, n, st);
         if (rc != CARMPC_OK) return rc;
     }
-    return launch_rollout(R, d_x, d_y, d_psi, d_v, n, d_bits, d_first_violation,
+    return launch_rollout(R, d_x, d_y, d_psi, d_v, n, single_sink(d_bits), d_first_violation,
                           reinterpret_cast<unsigned long long*>(d_count), st);
 }
 
@@ -1252,10 +1354,88 @@ int carmpc_rollout_bitset_host(void* rollout, const double* h_x, const double* h
     CARMPC_REQUIRE(h_x && h_y && h_psi && h_v && h_bits, "null host pointer");
     return host_pipeline(R->stage, h_x, h_y, h_psi, h_v, n, h_bits, h_first_violation, h_count,
                          [&](const double* x, const double* y, const double* p, const double* v, int64_t len,
-                             uint32_t* bits, int32_t* first, unsigned long long* count, cudaStream_t st) {
+                             const BitSink& bits, int32_t* first, unsigned long long* count, cudaStream_t st) {
                              return launch_rollout(R, x, y, p, v, len, bits, h_first_violation ? first : nullptr, count,
                                                    st);
                          });
+}
+
+// ---- sharded scans: the all-gather of the bitsets is fused into the scan kernel (shard.cuh) ------------------------------
+static int shard_sink(ShardWindow* W, int64_t n_local, int64_t first_sample, BitSink* sink, unsigned long long* step_out) {
+    CARMPC_REQUIRE(W->connected, "the shard window is not connected to its peers (carmpc_shard_connect)");
+    CARMPC_REQUIRE(n_local >= 0 && first_sample >= 0 && (first_sample & 31) == 0, "a shard starts on a whole bitset word");
+    CARMPC_REQUIRE(first_sample + n_local <= W->n_total, "the shard exceeds the sample set of the window");
+    const unsigned long long step = W->step + 1;
+    sink->n = W->world;
+    for (int r = 0; r < W->world; ++r) sink->dst[r] = W->bits(r, (int)(step & 1ull)) + (first_sample >> 5);
+    *step_out = step;
+    return CARMPC_OK;
+}
+
+int carmpc_membership_bitset_sharded(void* polytope, void* shard, const double* d_x, const double* d_y, const double* d_psi,
+                                     const double* d_v, int64_t n_local, int64_t first_sample, int mode,
+                                     int64_t* d_total_count, void* stream) {
+    Polytope* P = check_handle<Polytope>(polytope, kPolytope);
+    CARMPC_REQUIRE(P != nullptr, "not a polytope handle");
+    ShardWindow* W = check_handle<ShardWindow>(shard, kShard);
+    CARMPC_REQUIRE(W != nullptr, "not a shard window");
+    CARMPC_REQUIRE(mode == 0 || mode == 1, "mode must be 0 or 1");
+    CARMPC_REQUIRE(n_local == 0 || (d_x && d_y && d_psi && d_v), "null device pointer");
+    BitSink sink{};
+    unsigned long long step = 0;
+    int rc = shard_sink(W, n_local, first_sample, &sink, &step);
+    if (rc != CARMPC_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!P->tuned && n_local >= ((int64_t)1 << 20)) {
+        rc = tune_row_order(P, d_x, d_y, d_psi, d_v, n_local, st);
+        if (rc != CARMPC_OK) return rc;
+    }
+    CARMPC_CUDA(cudaMemsetAsync(W->d_local_count, 0, sizeof(unsigned long long), st));
+    rc = launch_membership(P, d_x, d_y, d_psi, d_v, n_local, sink, W->d_local_count, mode, st);
+    if (rc != CARMPC_OK) return rc;
+    rc = shard_exchange_launch(W, step, d_total_count, st);
+    if (rc != CARMPC_OK) return rc;
+    W->step = step;
+    return CARMPC_OK;
+}
+
+int carmpc_rollout_bitset_sharded(void* rollout, void* shard, const double* d_x, const double* d_y, const double* d_psi,
+                                  const double* d_v, int64_t n_local, int64_t first_sample, int64_t* d_total_count,
+                                  void* stream) {
+    Rollout* R = check_handle<Rollout>(rollout, kRollout);
+    CARMPC_REQUIRE(R != nullptr, "not a rollout handle");
+    ShardWindow* W = check_handle<ShardWindow>(shard, kShard);
+    CARMPC_REQUIRE(W != nullptr, "not a shard window");
+    CARMPC_REQUIRE(n_local == 0 || (d_x && d_y && d_psi && d_v), "null device pointer");
+    BitSink sink{};
+    unsigned long long step = 0;
+    int rc = shard_sink(W, n_local, first_sample, &sink, &step);
+    if (rc != CARMPC_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!R->tuned && n_local >= ((int64_t)1 << 20)) {
+        rc = tune_rollout_order(R, d_x, d_y, d_psi, d_v, n_local, st);
+        if (rc != CARMPC_OK) return rc;
+    }
+    CARMPC_CUDA(cudaMemsetAsync(W->d_local_count, 0, sizeof(unsigned long long), st));
+    rc = launch_rollout(R, d_x, d_y, d_psi, d_v, n_local, sink, nullptr, W->d_local_count, st);
+    if (rc != CARMPC_OK) return rc;
+    rc = shard_exchange_launch(W, step, d_total_count, st);
+    if (rc != CARMPC_OK) return rc;
+    W->step = step;
+    return CARMPC_OK;
+}
+
+int carmpc_scan_staging(void* handle, int threads_per_cta, int ring_slots, int tiles_per_slot) {
+    Staging g;
+    g.threads = threads_per_cta; g.stages = ring_slots; g.tps = tiles_per_slot;
+    if (!staging_supported(g)) {
+        set_error("carmpc_scan_staging: geometry %d/%d/%d is not built into the library", threads_per_cta, ring_slots, tiles_per_slot);
+        return CARMPC_ERR_UNSUPPORTED;
+    }
+    if (Polytope* P = check_handle<Polytope>(handle, kPolytope)) { P->staging = g; return CARMPC_OK; }
+    if (Rollout* R = check_handle<Rollout>(handle, kRollout)) { R->staging = g; return CARMPC_OK; }
+    set_error("carmpc_scan_staging: not a polytope or rollout handle");
+    return CARMPC_ERR_INVALID;
 }
 
 }  // extern "C"

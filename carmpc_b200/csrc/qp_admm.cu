@@ -263,10 +263,8 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
 #pragma unroll
                     for (int s = 0; s < S; ++s) acc[r][s] = x0t[g][r][s];
                 const float* Mrow = Pm + (size_t)(pg * kRA) * T.ktot;
-                if (!(Bq.debug_flags & 1)) {
-                    tile_product<kRA, S, MATS>(acc, Mrow, T.ktot, sm.V, Bt, s0, sg.x, sg.y);
-                    tile_product<kRA, S, MATS>(acc, Mrow, T.ktot, sm.V, Bt, s0, sg.z, sg.w);
-                }
+                tile_product<kRA, S, MATS>(acc, Mrow, T.ktot, sm.V, Bt, s0, sg.x, sg.y);
+                tile_product<kRA, S, MATS>(acc, Mrow, T.ktot, sm.V, Bt, s0, sg.z, sg.w);
 #pragma unroll
                 for (int r = 0; r < kRA; ++r) {
                     Vec<S> o;
@@ -286,7 +284,7 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
 #pragma unroll
         for (int g = 0; g < GA; ++g) {
             const int pg = g * kAdmmWarps + warp;
-            if (pg < T.nGA && !(Bq.debug_flags & 2)) {
+            if (pg < T.nGA) {
 #pragma unroll
                 for (int r = 0; r < kRA; ++r) {
                     const int j = pg * kRA + r;
@@ -321,9 +319,7 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
             for (int r = 0; r < kRB; ++r)
 #pragma unroll
                 for (int s = 0; s < S; ++s) acc[r][s] = 0.f;
-            if (!(Bq.debug_flags & 1))
-                tile_product<kRB, S, MATS>(acc, Gm + (size_t)(pg * kRB) * T.npad4, T.npad4, sm.Xt, Bt, s0, sg.x, sg.y);
-            if (Bq.debug_flags & 2) continue;
+            tile_product<kRB, S, MATS>(acc, Gm + (size_t)(pg * kRB) * T.npad4, T.npad4, sm.Xt, Bt, s0, sg.x, sg.y);
 #pragma unroll
             for (int r = 0; r < kRB; ++r) {
                 const int i = pg * kRB + r;
@@ -651,8 +647,6 @@ int admm_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
     const int smax = q->host.samples_per_lane;
     int S = 1;
     while (S * 2 <= smax && (int64_t)b.count >= (int64_t)32 * (S * 2) * q->sm) S *= 2;
-    static const int debug_flags = getenv("CARMPC_ADMM_DEBUG") ? atoi(getenv("CARMPC_ADMM_DEBUG")) : 0;   // development knob
-    if (debug_flags) const_cast<AdmmBatch&>(b).debug_flags = debug_flags;
     const int key = q->host.ga_per_warp * 100 + q->host.gb_per_warp * 10 + S;
     switch (key) {
         // n <= 40: 16 warps as two sample-halves of 64 (measured equal to 8 warps x 4 samples per lane, with and without

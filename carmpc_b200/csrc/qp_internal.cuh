@@ -96,7 +96,6 @@ struct AdmmBatch {
     int max_iter;
     int iters_accumulate;    // second pass: add to the iteration count of the first
     int write_u;             // also write the ADMM iterate (needed when the polish may pass it through)
-    int debug_flags;         // development: 1 skip the tile products, 2 skip the elementwise updates (timing only)
 };
 
 struct PolishTables {

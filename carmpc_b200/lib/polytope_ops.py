@@ -5,7 +5,7 @@ The reference leans on the third-party ``polytope`` package for four operations
 intersection and redundancy removal.  ``polytope`` is not part of the reference tree (and not
 installed); its behaviour for these four operations is restated here on top of
 ``scipy.optimize.linprog`` so that ``calc_terminal_set`` reproduces the shipped ``terminal_sets/*.npy``
-row for row (tests/test_terminal_set_construction.py pins five fixtures to < 1e-9).
+row for row (tests/test_lib_golden.py::test_calc_terminal_set_regenerates_shipped_fixture pins five fixtures to < 1e-9).
 
 Conventions: a polytope is {x : A x <= b}; every constructed polytope has unit-norm rows; rows
 whose norm is <= 1e-10 are dropped at construction.

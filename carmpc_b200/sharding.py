@@ -4,6 +4,12 @@ Every sample / initial state / Monte-Carlo run is independent and every matrix i
 GPU, so the hot path needs no data-path collective: rank r evaluates the contiguous index range ``shard_range(n, r,
 world)`` (whole bitset words per rank).  ``torch.distributed`` (NCCL over NVLink on the box, gloo in the CPU tests) is
 used only to collect results: the membership bitset words, member counts, and the per-sample QP outputs.
+
+Two ways to collect the membership bitsets:
+  * ``gather_bitset`` / ``reduce_count`` - NCCL all-gather / all-reduce after the scan (any backend; gloo in the CPU tests);
+  * ``PeerWindow`` + ``contains_bits_sharded`` - the scan kernel itself writes every rank's copy of the bitset through
+    NVLink peer mappings (CUDA IPC), and a one-warp kernel exchanges counts and completion flags: the all-gather is
+    fused into the kernel, one collective step is two launches and no NCCL call (what ``bench.py --gpus N`` times).
 """
 from __future__ import annotations
 
@@ -30,13 +36,14 @@ def padded_shard_len(n: int, world: int, align: int = 32) -> int:
     return -(-per // align) * align
 
 
-def gather_bitset(local_bits, n: int, async_op: bool = False, out=None, dst: Optional[int] = None):
+def gather_bitset(local_bits, n: int, async_op: bool = False, out=None, dst: Optional[int] = None, shard_align: int = 32):
     """Gather the per-rank bitset words of an n-sample set sharded with ``shard_range(n, rank, world)``.
 
     ``local_bits``: int32 tensor with the words of this rank's range (ceil(len / 32) words).  With ``dst=None`` every
     rank receives the full bitset (all-gather); with ``dst=r`` only rank r does (gather: 1/world of the traffic per
     sender).  Returns the full bitset (ceil(n / 32) int32 words; ``None`` on the ranks that do not receive) - or
-    ``(handle, finish)`` when ``async_op`` - where ``finish()`` trims the padding."""
+    ``(handle, finish)`` when ``async_op`` - where ``finish()`` trims the padding.  ``shard_align``: the alignment the
+    set was sharded with (``shard_range(..., align=shard_align)``; 1024 for the group-aligned shards of ``PeerWindow``)."""
     import torch
     dist = _dist()
     rank, world = world_info()
@@ -44,7 +51,7 @@ def gather_bitset(local_bits, n: int, async_op: bool = False, out=None, dst: Opt
     if world == 1:
         res = local_bits[:words_total]
         return (None, lambda: res) if async_op else res
-    per_words = padded_shard_len(n, world) // 32
+    per_words = padded_shard_len(n, world, shard_align) // 32
     send = local_bits
     if send.numel() != per_words:                       # last ranks own fewer (or zero) words: pad with zeros
         send = torch.zeros(per_words, dtype=local_bits.dtype, device=local_bits.device)
@@ -99,6 +106,121 @@ def gather_samples(local: Dict[str, "object"], n: int, sample_dim: Dict[str, int
     return out
 
 
+class PeerWindow:
+    """This rank's window of a sample set sharded over the GPUs of one box (``carmpc_shard_*``): the full bitset
+    (double-buffered), per-rank member counts and per-rank step flags in peer-mapped device memory.  The scan kernels
+    write their words into every rank's window over NVLink; no collective call gathers them afterwards.
+
+    ``PeerWindow(n)`` under ``torch.distributed`` (one process per GPU) exchanges the CUDA IPC handles with
+    ``all_gather_object``; ``PeerWindow.local_group(n, world)`` builds all windows of a group inside one process
+    (several ranks on one or more devices: tests, single-process multi-GPU drivers)."""
+
+    def __init__(self, n_total: int, rank: Optional[int] = None, world: Optional[int] = None, _connect: bool = True):
+        import ctypes
+        from . import _capi
+        self._lib = _capi.load()
+        r, w = world_info()
+        self.rank = r if rank is None else rank
+        self.world = w if world is None else world
+        self.n_total = int(n_total)
+        self._h = ctypes.c_void_p()
+        _capi.check(self._lib.carmpc_shard_create(self.rank, self.world, self.n_total, ctypes.byref(self._h)))
+        if _connect:
+            self._connect_ipc()
+
+    def _connect_ipc(self):
+        import ctypes
+        from . import _capi
+        if self.world == 1:
+            return
+        mine = (ctypes.c_ubyte * 64)()
+        _capi.check(self._lib.carmpc_shard_export(self._h, mine))
+        handles = [None] * self.world
+        _dist().all_gather_object(handles, bytes(mine))
+        blob = (ctypes.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(handles))
+        _capi.check(self._lib.carmpc_shard_connect(self._h, blob))
+        _dist().barrier()                      # nobody writes into a window before every rank has mapped it
+
+    @classmethod
+    def local_group(cls, n_total: int, world: int, devices=None):
+        """All ``world`` windows in this process; ``devices[r]`` is the CUDA device index of rank r (default: current)."""
+        import ctypes
+        import torch
+        from . import _capi
+        wins = []
+        for r in range(world):
+            if devices is not None:
+                with torch.cuda.device(devices[r]):
+                    wins.append(cls(n_total, rank=r, world=world, _connect=False))
+            else:
+                wins.append(cls(n_total, rank=r, world=world, _connect=False))
+        arr = (ctypes.c_void_p * world)(*[w._h for w in wins])
+        for w in wins:
+            _capi.check(w._lib.carmpc_shard_connect_local(w._h, arr))
+        return wins
+
+    def shard(self) -> Tuple[int, int]:
+        """[lo, hi) of this rank: whole 1024-sample groups (one 128-byte bitset line per group and destination)."""
+        return shard_range(self.n_total, self.rank, self.world, align=1024)
+
+    def result_bits(self):
+        """The full bitset of the last completed step as an int32 CUDA tensor view of the window (valid until the
+        second-next collective step)."""
+        import ctypes
+        import torch
+        ptr, steps = ctypes.c_void_p(), ctypes.c_int64(0)
+        from . import _capi
+        _capi.check(self._lib.carmpc_shard_result(self._h, ctypes.byref(ptr), ctypes.byref(steps)))
+        words = (self.n_total + 31) // 32
+        if words == 0:
+            return torch.empty(0, dtype=torch.int32, device="cuda")
+        iface = {"shape": (words,), "typestr": "<i4", "data": (ptr.value, False), "version": 2}
+        holder = type("_WindowView", (), {"__cuda_array_interface__": iface, "_keep": self})()
+        return torch.as_tensor(holder, device="cuda")
+
+    def check(self) -> None:
+        from . import _capi
+        _capi.check(self._lib.carmpc_shard_check(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.carmpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def contains_bits_sharded(evaluator, window: "PeerWindow", x, y, psi, v, mode: int = 1, total=None, stream=None):
+    """One collective step: membership (``TerminalSetEvaluator``) or rollout form (``RolloutEvaluator``) of this rank's
+    shard ``window.shard()``, bitset words written into every rank's window by the scan kernel itself, member counts
+    and completion flags exchanged by a one-warp kernel.  ``total``: int64 CUDA tensor (1,) receiving the global
+    member count.  Nothing is synchronised; ``window.result_bits()`` is valid in stream order."""
+    import ctypes
+    import torch
+    from . import _capi
+    from .batch import RolloutEvaluator, _check_soa
+    n = _check_soa(x, y, psi, v) if x.numel() else 0
+    lo, hi = window.shard()
+    if n != hi - lo:
+        raise ValueError(f"rank {window.rank} owns samples [{lo}, {hi}) of the set, got {n}")
+    if total is None:
+        total = torch.empty(1, dtype=torch.int64, device=x.device)
+    s = torch.cuda.current_stream() if stream is None else stream
+    st = ctypes.c_void_p(s.cuda_stream)
+    if isinstance(evaluator, RolloutEvaluator):
+        _capi.check(evaluator._lib.carmpc_rollout_bitset_sharded(evaluator._h, window._h, x.data_ptr(), y.data_ptr(),
+                                                                 psi.data_ptr(), v.data_ptr(), n, lo, total.data_ptr(), st))
+    else:
+        _capi.check(evaluator._lib.carmpc_membership_bitset_sharded(evaluator._h, window._h, x.data_ptr(), y.data_ptr(),
+                                                                    psi.data_ptr(), v.data_ptr(), n, lo, mode,
+                                                                    total.data_ptr(), st))
+    return total
+
+
 class ShardedTerminalSet:
     """Membership of a sample set that is partitioned over the ranks: each rank scans its own range with the CUDA
     kernel; ``contains_bits`` returns the local words, ``gather`` the full bitset and the global count."""
@@ -115,3 +237,7 @@ class ShardedTerminalSet:
 
     def gather(self, local_bits, local_count, n: int):
         return gather_bitset(local_bits, n), reduce_count(local_count.clone())
+
+    def contains_bits_fused(self, window: PeerWindow, x, y, psi, v, mode: int = 1, total=None):
+        """Scan + all-gather in one step (no NCCL call): see ``contains_bits_sharded``."""
+        return contains_bits_sharded(self.evaluator, window, x, y, psi, v, mode=mode, total=total)

@@ -104,6 +104,45 @@ int carmpc_rollout_bitset_host(void* rollout, const double* h_x, const double* h
                                const double* h_v, int64_t n, uint32_t* h_bits, int32_t* h_first_violation,
                                int64_t* h_count);
 
+/* Tuning hook for the streaming scans (polytope or rollout handle): staging geometry of the bulk-async kernel -
+ * threads per CTA, ring slots per warp, 128-sample tiles per ring slot.  Results never depend on it; combinations the
+ * library was not built with return CARMPC_ERR_UNSUPPORTED.  Default 256 / 3 / 1. */
+int carmpc_scan_staging(void* handle, int threads_per_cta, int ring_slots, int tiles_per_slot);
+
+/* ------------------------------------------------------------------------------------------------
+ * (A') one sample set sharded over the GPUs of a box (BASELINE config 2: "a 10^8-point grid sharded
+ *      across 1/2/4/8 B200"; north_star: the membership bitsets are gathered over NVLink)
+ *
+ * Every rank owns a WINDOW: the full bitset of the n_total samples (double-buffered), one member count per rank and
+ * one step flag per rank, in peer-mappable device memory.  A sharded scan stores the words of its shard straight into
+ * the windows of ALL ranks from inside the scan kernel (one 128-byte store per 1024 samples and destination, over
+ * NVLink), then a one-warp kernel publishes the rank's count and flag and waits for every other rank's: there is no
+ * separate all-gather.  One process per GPU: exchange the 64-byte handles of carmpc_shard_export with any host
+ * mechanism (torch.distributed all_gather in carmpc_b200/sharding.py) and pass all `world` of them, in rank order, to
+ * carmpc_shard_connect.  Several ranks inside one process: carmpc_shard_connect_local.
+ * All ranks must call the *_sharded functions the same number of times (they are collective steps).
+ * ---------------------------------------------------------------------------------------------- */
+int carmpc_shard_create(int rank, int world /* <= 8 */, int64_t n_total, void** handle);
+int carmpc_shard_export(void* shard, unsigned char* h_ipc_handle64);
+int carmpc_shard_connect(void* shard, const unsigned char* h_ipc_handles /* world x 64 bytes, rank order */);
+int carmpc_shard_connect_local(void* shard, void* const* peer_shards /* world handles, entry [rank] ignored */);
+
+/* Membership of this rank's shard: samples [first_sample, first_sample + n_local) of the set, first_sample a
+ * multiple of 32.  When the step has completed (stream order) the rank's window holds the bitset of ALL n_total
+ * samples and *d_total_count (nullable, device int64) the member count over all ranks. */
+int carmpc_membership_bitset_sharded(void* polytope, void* shard, const double* d_x, const double* d_y,
+                                     const double* d_psi, const double* d_v, int64_t n_local, int64_t first_sample,
+                                     int mode, int64_t* d_total_count, void* stream);
+int carmpc_rollout_bitset_sharded(void* rollout, void* shard, const double* d_x, const double* d_y,
+                                  const double* d_psi, const double* d_v, int64_t n_local, int64_t first_sample,
+                                  int64_t* d_total_count, void* stream);
+
+/* d_bits: the full bitset (ceil(n_total / 32) words, device memory of this rank) of the last completed step; it stays
+ * valid until the second-next sharded call on this window.  h_steps: collective steps done so far. */
+int carmpc_shard_result(void* shard, const uint32_t** d_bits, int64_t* h_steps);
+/* Synchronous health check: fails if a peer never published its flag (the exchange kernel gives up after 5 s). */
+int carmpc_shard_check(void* shard);
+
 /* ------------------------------------------------------------------------------------------------
  * (B) batched condensed MPC QP
  *

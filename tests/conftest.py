@@ -9,6 +9,10 @@ import sys
 import numpy as np
 import pytest
 
+# tests/test_sharded_gpu.py runs the ranks of a group as streams of ONE process; their exchange kernels wait for each
+# other, so no two of those streams may share a hardware queue (the default is 8 queues).  Read at context creation.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

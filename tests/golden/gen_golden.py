@@ -22,6 +22,13 @@ What is recorded (all float64, straight from reference objects):
   * terminal_sets/*.npy   byte copies of the reference's shipped H-rep fixtures (data, not source)
   * grid_config1.npz membership of the lib/terminal_set.py:96-113 grid, evaluated with the
                      reference's own expression ``np.all(A @ point <= b)``
+  * qp_<env>_N*.npz  everything lib/mpc.py:318-332 (MPCStateFB.step) / :461-478 (MPCOutputFB.step) puts into
+                     the QP, straight from the reference controller object: H, h, T, S, the three constraint
+                     stacks, goal.  The BASELINE configs: RoadOneCarEnv N = 10/20/40/80 (configs 3 and 5),
+                     RoadEnv N = 20 (config 4), RoadMultipleCarsEnv N = 20.  tests/kkt_check.py verifies
+                     solver outputs against these with no oracle solver in the loop
+  * disturbance.npz  ABd of MPCOutputFBWithDisturbance.step, computed by the reference's own expression
+                     (lib/mpc.py:631-635) for N in {1, 5, 20}, with Bd, Cd, L1, L2 (lib/mpc.py:536-549)
 """
 import os
 import shutil
@@ -189,6 +196,38 @@ def main():
                 margin[idx, i, j] = np.min(b - r)
     np.savez_compressed(os.path.join(OUT, "grid_config1.npz"), member=member, margin=margin, xx=xx, yy=yy)
     print("members:", member.sum(), member.reshape(6, -1).sum(1), "ties:", (margin[member] == 0).sum())
+
+    # ---- the QP of lib/mpc.py:318-332 / :461-478, as the reference controller object holds it --------------
+    qp_cases = [("RoadOneCarEnv", RoadOneCarEnv, [29.9, 1.5, 0, 0], (10, 20, 40, 80)),
+                ("RoadEnv", RoadEnv, None, (20,)),
+                ("RoadMultipleCarsEnv", RoadMultipleCarsEnv, None, (20,))]
+    for tag, cls, goal, horizons in qp_cases:
+        for N in horizons:
+            e = cls()
+            if goal is not None:
+                e.set_goal(goal)
+            cN = ctrl(e, N)
+            cN.set_goal(e.goal)
+            At, bt = cN.terminal_constraint()
+            Ai, bi = cN.input_constraint()
+            As, bs = cN.state_constraint()
+            # float32-exact structural zeros stay zeros; everything float64
+            np.savez_compressed(os.path.join(OUT, f"qp_{tag}_N{N}.npz"), H=cN.H, h=cN.h, T=cN.T, S=cN.S, P=cN.P, Q=cN.Q,
+                                R=cN.R, At=At, bt=bt, Ai=Ai, bi=bi, As=As, bs=bs, goal=np.array(cN.goal, dtype=float))
+
+    # ---- ABd of the disturbance controller (lib/mpc.py:631-635), the reference's own expression ----------------
+    from lib.mpc import MPCOutputFBWithDisturbance
+    dist = {}
+    for N in (1, 5, 20):
+        dc = MPCOutputFBWithDisturbance(dt=cfg.DT_CONTROL, N=N, lin_state=cfg.LINEARIZE_STATE,
+                                        lin_input=cfg.LINEARIZE_INPUT, init_state=[20, 0.5, 0, 2], env=RoadEnv())
+        to_stack = [np.vstack(
+            [np.linalg.matrix_power(dc.A, i - j) @ dc.Bd if (i - j) >= 0 else np.zeros(4) for i in range(dc.N)]).T
+                    for j in range(dc.N + 1)]
+        to_stack.reverse()
+        dist[f"ABd_N{N}"] = np.vstack(to_stack).sum(axis=1)
+    dist.update(Bd=dc.Bd.astype(float), Cd=dc.Cd.astype(float), L1=dc.L1, L2=dc.L2.astype(float), C=dc.C.astype(float))
+    np.savez(os.path.join(OUT, "disturbance.npz"), **dist)
 
 
 if __name__ == "__main__":

@@ -154,3 +154,17 @@ def test_condensed_qp_is_equivalent_to_reference_rows():
         pre = pq.Px @ xi
         ok_new = np.all(gu <= pq.hi) and np.all(gu >= pq.lo) and np.all(pre <= pq.pre_hi) and np.all(pre >= pq.pre_lo)
         assert ok_ref == ok_new
+
+
+@pytest.mark.parametrize("N", [1, 5, 20])
+def test_disturbance_response_matches_reference_expression(N):
+    """``MPCOutputFBWithDisturbance.disturbance_response()`` against ABd as the reference's own expression computes it
+    (lib/mpc.py:631-635, recorded by gen_golden.py), and the disturbance model constants (:536-549)."""
+    g = golden("disturbance.npz")
+    ctl = make_controller(make_env("RoadEnv"), N, cls="MPCOutputFBWithDisturbance", init_state=[20, 0.5, 0, 2])
+    np.testing.assert_allclose(ctl.disturbance_response(), g[f"ABd_N{N}"], rtol=0, atol=1e-12 * max(1.0, np.abs(g[f"ABd_N{N}"]).max()))
+    np.testing.assert_array_equal(ctl.Bd, g["Bd"])
+    np.testing.assert_array_equal(ctl.Cd, g["Cd"])
+    np.testing.assert_array_equal(ctl.L1, g["L1"])
+    np.testing.assert_array_equal(ctl.L2, g["L2"])
+    np.testing.assert_array_equal(ctl.C, g["C"])

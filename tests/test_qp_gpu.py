@@ -517,3 +517,86 @@ def test_seeded_entry_points_reject_what_they_cannot_do(torch_cuda):
         bq.solve_map_host([np.linspace(20, 30, 4), [1.0], [0.0], [1.0]], block=(0, 1, 1, 1))
     res = bq.solve_map_host([np.linspace(20, 30, 4), [1.0], [0.0], [1.0]], block=(2, 1, 1, 1))
     assert res.status.shape == (4,) and res.u0.shape == (4, 2)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# parity on the BASELINE configurations themselves ("close the parity holes")
+# ----------------------------------------------------------------------------------------------------------------
+def _config_states(ref, n_states, seed):
+    """Half of the states from the config-3/5 region-of-attraction grid (strided), half uniform around the goal."""
+    from carmpc_b200.grids import config3_axes, materialise_grid_host, grid_size
+    axes = config3_axes()
+    n = grid_size(axes)
+    k = n_states // 2
+    idx = (np.arange(k, dtype=np.int64) * (n // k) + seed * 7919) % n
+    dims = [len(a) for a in axes]
+    sub = np.stack([a[i] for a, i in zip(axes, np.unravel_index(idx, dims))], axis=1)
+    sub[:, 0] += ref.goal[0] - 29.9                       # the grid is laid out for the RoadOneCarEnv goal
+    rng = np.random.default_rng(seed)
+    rnd = ref.goal + rng.uniform(-1, 1, size=(n_states - k, 4)) * np.array([12.0, 1.4, 0.25, 2.5])
+    return np.vstack((sub, rnd))
+
+
+@pytest.mark.parametrize("env_name,N,n_states,n_lp", [("RoadOneCarEnv", 20, 10000, 300), ("RoadEnv", 20, 10000, 300),
+                                                      ("RoadMultipleCarsEnv", 20, 10000, 300), ("RoadOneCarEnv", 10, 10000, 300),
+                                                      ("RoadOneCarEnv", 40, 4000, 100), ("RoadOneCarEnv", 80, 2000, 40)])
+def test_gpu_results_are_kkt_points_of_the_reference_qp(torch_cuda, env_name, N, n_states, n_lp):
+    """No oracle solver in the loop: the QP is assembled from the matrices the unmodified reference controller produced
+    (tests/golden/qp_*.npz, lib/mpc.py:318-332) and every GPU result must satisfy its optimality conditions in float64
+    (primal residual <= 1e-8, stationarity <= 1e-6 with non-negative multipliers on the active rows); a sample of the
+    'infeasible' flags is confirmed by a phase-1 LP on the same rows."""
+    from kkt_check import ReferenceQP, assert_results_satisfy_reference_qp
+    ref = ReferenceQP(env_name, N)
+    c, bq, _ = _setup(env_name, N)
+    np.testing.assert_array_equal(np.array(c.goal, dtype=float), ref.goal)
+    x0 = _config_states(ref, n_states, seed=N)
+    res = bq.solve_host(x0, want_u_full=True)
+    info = assert_results_satisfy_reference_qp(ref, x0, res.u_full, res.status, objective=res.objective, n_lp=n_lp, seed=N)
+    assert info["solved"] >= n_states // 10 and info["infeasible"] >= n_states // 50, info
+    np.testing.assert_array_equal(res.u0[res.status == 0], res.u_full[res.status == 0][:, :2])
+    print(f"{env_name} N={N}: {info}")
+
+
+@pytest.mark.parametrize("N,n_states", [(10, 400), (40, 320), (80, 300)])
+def test_config5_grid_states_match_exact_oracle(torch_cuda, N, n_states):
+    """BASELINE config 5: strided states OF THE CONFIG GRID at the other horizons of the sweep, against the exact
+    oracle at BASELINE's tolerances (N = 20 is covered by test_config3_full_grid_properties)."""
+    torch = torch_cuda
+    from carmpc_b200.grids import config3_axes, materialise_grid, grid_size
+    c, bq, oq = _setup("RoadOneCarEnv", N)
+    axes = config3_axes()
+    n = grid_size(axes)
+    x0 = torch.stack(materialise_grid(axes, device="cuda")).contiguous()
+    out = bq.solve(x0)
+    status = out["status"].cpu().numpy()
+    assert (status == 2).sum() <= 2, "undecided (max_iter) states on the config grid"
+    idx = np.arange(0, n, n // n_states)[:n_states] + (N % 7) * 13
+    xs = x0[:, torch.from_numpy(idx).cuda()].cpu().numpy().T
+    from carmpc_b200.batch import QPResult
+    res = QPResult(u0=out["u0"].cpu().numpy().T[idx], objective=out["objective"].cpu().numpy()[idx], status=status[idx],
+                   iters=out["iters"].cpu().numpy()[idx])
+    n_band, du, rel = _compare(res, xs, oq, np.array(c.goal, dtype=float), min_feasible=n_states // 10)
+    assert n_band <= 3
+
+
+def test_config4_closed_loops_match_the_oracle_fixture(torch_cuda):
+    """BASELINE config 4 in its own shape: 200 runs x 200 steps, output feedback and state feedback, against the
+    oracle's closed loop with exact QP solutions (tests/golden/closed_loop_config4.npz, written by
+    gen_oracle_fixtures.py; tests/test_oracle_golden.py re-derives part of it live): fail_step equal, trajectories
+    and final states within 1e-6."""
+    torch = torch_cuda
+    from carmpc_b200.lib.mpc import _C_XYV, _L_OBSERVER
+    fx = np.load(os.path.join(GOLDEN, "closed_loop_config4.npz"))
+    c, bq, _ = _setup("RoadEnv", 20)
+    x_init = fx["x_init"]
+    steps, stride = int(fx["steps"]), int(fx["stride"])
+    for tag, fb in (("ofb", True), ("sfb", False)):
+        out = bq.closed_loop(torch.from_numpy(np.ascontiguousarray(x_init.T)).cuda(), steps, c.A, c.B,
+                             C=_C_XYV if fb else None, L=_L_OBSERVER if fb else None, want_traj=True)
+        fail, want_fail = out["fail_step"].cpu().numpy(), fx[f"fail_{tag}"]
+        np.testing.assert_array_equal(fail, want_fail)
+        alive = want_fail < 0
+        assert alive.sum() >= len(alive) // 4
+        traj = out["traj"].cpu().numpy().transpose(0, 2, 1)[stride - 1::stride]
+        assert np.abs(traj[:, alive] - fx[f"traj_{tag}"][:, alive]).max() <= 1e-6
+        np.testing.assert_allclose(out["final"].cpu().numpy().T, fx[f"final_{tag}"], atol=1e-6)

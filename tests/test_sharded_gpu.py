@@ -1,0 +1,112 @@
+"""Sharded scans with the all-gather fused into the kernel (carmpc_shard_*), on ONE device: the ranks of a
+group live in one process, each with its own window and stream; the peer stores and the flag protocol are exactly the
+ones that run between GPUs (the bench exercises the CUDA-IPC form at 2/4/8 GPUs and asserts the same equalities)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _samples(torch, n, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    lo = torch.tensor([5.0, -3.2, -0.42, -1.2], dtype=torch.float64, device="cuda")
+    hi = torch.tensor([55.0, 3.2, 0.42, 5.2], dtype=torch.float64, device="cuda")
+    u = torch.rand((4, n), generator=g, dtype=torch.float64, device="cuda")
+    return [(lo[k] + (hi[k] - lo[k]) * u[k]).contiguous() for k in range(4)]
+
+
+@pytest.mark.parametrize("world,n", [(2, 3_000_077), (3, 1_500_000), (8, 9_000_001), (4, 5000), (2, 0)])
+def test_fused_sharded_membership_equals_single_scan(world, n):
+    import torch
+    from carmpc_b200.batch import TerminalSetEvaluator
+    from carmpc_b200.sharding import PeerWindow, contains_bits_sharded
+    ev = TerminalSetEvaluator(np.load(os.path.join(GOLDEN, "terminal_sets", "RoadMultipleCarsEnv_30_1.5_0_0.npy")))
+    x, y, psi, v = _samples(torch, n, seed=world)
+    words = (n + 31) // 32
+    if n:
+        want_bits, want_count = ev.contains_bits(x, y, psi, v)
+        want_bits, want_count = want_bits.clone(), int(want_count.item())
+    else:
+        want_bits, want_count = torch.empty(0, dtype=torch.int32, device="cuda"), 0
+    wins = PeerWindow.local_group(n, world)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    totals = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    covered = 0
+    for r, w in enumerate(wins):
+        lo, hi = w.shard()
+        assert lo % 1024 == 0 and lo == covered
+        covered = hi
+    assert covered == n
+    torch.cuda.synchronize()
+    for step in range(3):                                   # three steps: both buffer slots, flags keep counting
+        for r, w in enumerate(wins):
+            lo, hi = w.shard()
+            with torch.cuda.stream(streams[r]):
+                contains_bits_sharded(ev, w, x[lo:hi], y[lo:hi], psi[lo:hi], v[lo:hi], total=totals[r])
+        torch.cuda.synchronize()
+        for r, w in enumerate(wins):
+            w.check()
+            assert int(totals[r].item()) == want_count
+            got = w.result_bits()
+            assert got.numel() == words and torch.equal(got, want_bits), f"rank {r} step {step}: gathered bitset differs"
+
+
+def test_fused_sharded_rollout_equals_single_scan():
+    import torch
+    from carmpc_b200.batch import RolloutEvaluator
+    from carmpc_b200.lib.environments import RoadMultipleCarsEnv
+    from carmpc_b200.sharding import PeerWindow, contains_bits_sharded
+    rv = RolloutEvaluator.from_env(RoadMultipleCarsEnv(), 16)
+    n, world = 2_100_000, 3
+    x, y, psi, v = _samples(torch, n, seed=5)
+    want_bits, want_count = rv.contains_bits(x, y, psi, v)
+    want_bits, want_count = want_bits.clone(), int(want_count.item())
+    wins = PeerWindow.local_group(n, world)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    totals = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    torch.cuda.synchronize()
+    for r, w in enumerate(wins):
+        lo, hi = w.shard()
+        with torch.cuda.stream(streams[r]):
+            contains_bits_sharded(rv, w, x[lo:hi], y[lo:hi], psi[lo:hi], v[lo:hi], total=totals[r])
+    torch.cuda.synchronize()
+    for r, w in enumerate(wins):
+        w.check()
+        assert int(totals[r].item()) == want_count and torch.equal(w.result_bits(), want_bits)
+
+
+def test_shard_argument_errors():
+    import torch
+    from carmpc_b200._capi import CarmpcError
+    from carmpc_b200.batch import TerminalSetEvaluator
+    from carmpc_b200.sharding import PeerWindow, contains_bits_sharded
+    ev = TerminalSetEvaluator(np.load(os.path.join(GOLDEN, "terminal_sets", "RoadMultipleCarsEnv_30_1.5_0_0.npy")))
+    x, y, psi, v = _samples(torch, 4096, seed=1)
+    w = PeerWindow(4096, rank=0, world=2, _connect=False)          # never connected to rank 1
+    with pytest.raises(CarmpcError, match="not connected"):
+        contains_bits_sharded(ev, w, x[:2048], y[:2048], psi[:2048], v[:2048])
+    with pytest.raises(ValueError):
+        contains_bits_sharded(ev, w, x, y, psi, v)                 # not this rank's shard
+    with pytest.raises(CarmpcError):
+        PeerWindow(100, rank=0, world=9, _connect=False)
+
+
+@pytest.mark.parametrize("geometry", [(256, 3, 1), (128, 3, 1), (128, 4, 1), (128, 2, 2), (128, 3, 2), (256, 2, 1), (128, 2, 1), (256, 2, 2)])
+def test_every_staging_geometry_gives_the_same_bits(geometry):
+    import torch
+    from carmpc_b200._capi import CarmpcError
+    from carmpc_b200.batch import TerminalSetEvaluator
+    Ab = np.load(os.path.join(GOLDEN, "terminal_sets", "RoadMultipleCarsEnv_30_1.5_0_0.npy"))
+    x, y, psi, v = _samples(torch, 2_000_333, seed=9)
+    ref = TerminalSetEvaluator(Ab)
+    want_bits, want_count = ref.contains_bits(x, y, psi, v, mode=0)
+    ev = TerminalSetEvaluator(Ab)
+    ev.set_staging(*geometry)
+    bits, count = ev.contains_bits(x, y, psi, v, mode=1)
+    assert torch.equal(bits, want_bits) and int(count.item()) == int(want_count.item())
+    with pytest.raises(CarmpcError, match="not built"):
+        ev.set_staging(96, 3, 1)

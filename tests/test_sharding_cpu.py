@@ -81,3 +81,19 @@ def _worker(rank, world, port, n, tmp):
 def test_gathers_over_gloo(world, n, tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), f"ok{r}")) for r in range(world))
+
+
+def test_group_aligned_shards_tile_the_sample_set():
+    """The fused (peer-window) scans shard on whole 1024-sample groups: one 128-byte bitset line per group."""
+    from carmpc_b200.grids import shard_range
+    for n in (0, 1, 1023, 1024, 1025, 10 ** 8, 3_000_077):
+        for world in (1, 2, 3, 4, 8):
+            covered = 0
+            for r in range(world):
+                lo, hi = shard_range(n, r, world, align=1024)
+                assert lo == covered and lo % 1024 == 0 or lo == n
+                assert hi >= lo
+                covered = hi
+            assert covered == n
+    lens = [shard_range(10 ** 8, r, 8, align=1024) for r in range(8)]
+    assert max(h - l for l, h in lens) - min(h - l for l, h in lens) <= 8 * 1024
