@@ -207,3 +207,21 @@ def test_qp_oracle_agrees_with_an_independent_solver():
         assert obj[i] <= res.fun + 1e-9 * abs(obj[i])          # the oracle's point is at least as good
         checked += 1
     assert checked >= 3
+
+
+def test_closed_loop_fixture_is_what_the_oracle_computes():
+    """tests/golden/closed_loop_config4.npz (the oracle's 200 x 200 closed loops, generated offline because they take
+    six minutes) cannot drift from the oracle: eight of its runs are re-derived live for 40 steps, both feedback modes."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_oracle_fixtures", os.path.join(GOLDEN, "gen_oracle_fixtures.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    fx = np.load(os.path.join(GOLDEN, "closed_loop_config4.npz"))
+    np.testing.assert_array_equal(fx["x_init"], gen.config4_initial_states())
+    pick = np.array([0, 3, 17, 42, 77, 101, 150, 199])
+    stride = int(fx["stride"])
+    for tag, fb in (("ofb", True), ("sfb", False)):
+        x, fail, traj = gen.run_oracle_loop(fx["x_init"][pick], 40, fb)
+        want_fail = fx[f"fail_{tag}"][pick]
+        np.testing.assert_array_equal(fail, np.where((want_fail >= 0) & (want_fail < 40), want_fail, -1))
+        np.testing.assert_allclose(traj[stride - 1::stride], fx[f"traj_{tag}"][:40 // stride, pick], rtol=0, atol=1e-9)
