@@ -274,12 +274,14 @@ class BatchQP(_Handle):
 
     def polish_stats(self) -> dict:
         """Histogram of the float64 polish over the last solve (``carmpc_qp_polish_stats``)."""
-        h = (ctypes.c_int64 * 16)()
+        h = (ctypes.c_int64 * 20)()
         check(self._lib.carmpc_qp_polish_stats(self._h, h))
         v = [int(x) for x in h]
         return {"certified_after_rounds": v[:10], "handed_to_admm": v[10], "used_multiplier_map": v[11],
                 "certified_by_map_alone": v[12], "infeasible_by_anchor_certificate": v[13],
-                "max_iter_settled_by_own_certificate": v[14], "infeasible_before_second_pass": v[15]}
+                "max_iter_settled_by_own_certificate": v[14], "infeasible_before_second_pass": v[15],
+                "final_polish_uncertified": v[16], "fallback_solved": v[17], "fallback_infeasible": v[18],
+                "fallback_undecided": v[19]}
 
     # ---- device tensors ---------------------------------------------------------------------------
     def solve(self, x0, x_ref=None, c=None, want_u_full: bool = False, warm=None, warm_in: bool = False,

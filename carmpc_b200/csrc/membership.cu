@@ -1363,7 +1363,8 @@ int carmpc_rollout_bitset_host(void* rollout, const double* h_x, const double* h
 // ---- sharded scans: the all-gather of the bitsets is fused into the scan kernel (shard.cuh) ------------------------------
 static int shard_sink(ShardWindow* W, int64_t n_local, int64_t first_sample, BitSink* sink, unsigned long long* step_out) {
     CARMPC_REQUIRE(W->connected, "the shard window is not connected to its peers (carmpc_shard_connect)");
-    CARMPC_REQUIRE(n_local >= 0 && first_sample >= 0 && (first_sample & 31) == 0, "a shard starts on a whole bitset word");
+    CARMPC_REQUIRE(n_local >= 0 && first_sample >= 0, "n_local, first_sample");
+    CARMPC_REQUIRE(n_local == 0 || (first_sample & 31) == 0, "a shard starts on a whole bitset word");
     CARMPC_REQUIRE(first_sample + n_local <= W->n_total, "the shard exceeds the sample set of the window");
     const unsigned long long step = W->step + 1;
     sink->n = W->world;

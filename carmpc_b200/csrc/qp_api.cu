@@ -1,5 +1,6 @@
 // C ABI of the batched QP solver (include/carmpc.h, part B): handle creation (host setup + upload), the two-pass
 // ADMM -> polish orchestration, host-buffer convenience entry point and statistics.
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -116,7 +117,7 @@ int QPHandle::ensure_io(int64_t batch, bool want_full) {
 QPHandle::~QPHandle() {
     for (void* p : allocations) cudaFree(p);
     cudaFree(ws_sign); cudaFree(ws_u); cudaFree(ws_status); cudaFree(ws_iters); cudaFree(ws_failed); cudaFree(ws_failed0);
-    cudaFree(ws_counters); cudaFree(ws_total_iters); cudaFree(ws_polished); cudaFree(ws_warm); cudaFree(ws_overflow);
+    cudaFree(ws_counters); cudaFree(ws_total_iters); cudaFree(ws_polished); cudaFree(ws_warm); cudaFree(ws_overflow); cudaFree(ws_unproven);
     cudaFree(ws_anchor); cudaFree(ws_follow); cudaFree(ws_rec_of); cudaFree(ws_rec_lam); cudaFree(ws_rec_act); cudaFree(ws_polish_stats);
     cudaFree(io_x0_aos); cudaFree(io_x0); cudaFree(io_c); cudaFree(io_u0); cudaFree(io_u0_aos); cudaFree(io_obj); cudaFree(io_full);
     cudaFree(io_status); cudaFree(io_iters); cudaFree(io_seed); cudaFree(io_axes);
@@ -126,13 +127,14 @@ int QPHandle::ensure_workspace(int64_t batch) {
     if (ws_counters == nullptr) {
         CARMPC_CUDA(cudaMalloc(&ws_counters, sizeof(int) * 16));
         CARMPC_CUDA(cudaMalloc(&ws_total_iters, sizeof(unsigned long long)));
-        CARMPC_CUDA(cudaMalloc(&ws_polish_stats, sizeof(unsigned long long) * 16));
-        CARMPC_CUDA(cudaMemset(ws_polish_stats, 0, sizeof(unsigned long long) * 16));
+        CARMPC_CUDA(cudaMalloc(&ws_polish_stats, sizeof(unsigned long long) * kPolishStats));
+        CARMPC_CUDA(cudaMemset(ws_polish_stats, 0, sizeof(unsigned long long) * kPolishStats));
     }
     if (batch <= ws_batch) return CARMPC_OK;
     cudaFree(ws_sign); cudaFree(ws_u); cudaFree(ws_status); cudaFree(ws_iters); cudaFree(ws_failed); cudaFree(ws_polished);
     cudaFree(ws_warm); ws_warm = nullptr;
     cudaFree(ws_overflow); ws_overflow = nullptr;
+    cudaFree(ws_unproven); ws_unproven = nullptr;
     cudaFree(ws_failed0); ws_failed0 = nullptr;
     cudaFree(ws_anchor); ws_anchor = nullptr;
     cudaFree(ws_follow); ws_follow = nullptr;
@@ -145,6 +147,7 @@ int QPHandle::ensure_workspace(int64_t batch) {
     CARMPC_CUDA(cudaMalloc(&ws_iters, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_failed, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_overflow, sizeof(int) * (size_t)batch));
+    CARMPC_CUDA(cudaMalloc(&ws_unproven, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_failed0, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_anchor, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_follow, sizeof(int) * (size_t)batch));
@@ -167,6 +170,7 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
     last_launches = 0;
     last_second_pass = 0;
     last_reused = 0;
+    last_fallback = 0;
     CARMPC_CUDA(cudaMemsetAsync(ws_counters, 0, sizeof(int) * 8, st));
     if (!defer_total) CARMPC_CUDA(cudaMemsetAsync(ws_total_iters, 0, sizeof(unsigned long long), st));
     int* status = d_status ? d_status : ws_status;
@@ -182,7 +186,7 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
     pb.rounds = host.opts.polish ? -1 : 0;
     pb.final_pass = host.opts.polish ? 0 : 1;
     pb.stats = ws_polish_stats;
-    if (!stats_hold) CARMPC_CUDA(cudaMemsetAsync(ws_polish_stats, 0, sizeof(unsigned long long) * 16, st));
+    if (!stats_hold) CARMPC_CUDA(cudaMemsetAsync(ws_polish_stats, 0, sizeof(unsigned long long) * kPolishStats, st));
     // warm-started sequences and seeded maps keep the certified (repaired) active set
     if ((d_warm && warm_out) || keep_sign) pb.sign_out = ws_sign;
     if (use_records) {
@@ -240,6 +244,11 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
 
     int n_failed = 0;
     if (host.opts.polish) {
+        // "infeasible" verdicts of the float32 ADMM are accepted only with a float64 Farkas certificate of their final
+        // dual iterate (or a violated u-independent row); the others join the list of the second pass
+        rc = farkas_verify_launch(this, d_idx, (int)count, status, ab.warm, d_x0, stride, d_c, xref, ws_failed, ws_counters + 1, st);
+        if (rc != CARMPC_OK) return rc;
+        ++last_launches;
         CARMPC_CUDA(cudaMemcpyAsync(&n_failed, ws_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         CARMPC_CUDA(cudaStreamSynchronize(st));
     }
@@ -277,6 +286,18 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
             ++last_launches;
         }
         last_launches += 2;
+        if (host.opts.polish) {
+            // second-pass "infeasible" verdicts need their float64 certificate as well (unverified ones join the fallback)
+            CARMPC_CUDA(cudaMemsetAsync(ws_counters + 13, 0, sizeof(int), st));
+            rc = farkas_verify_launch(this, second_list, n_failed, status, ab.warm, d_x0, stride, d_c, xref, ws_overflow, ws_counters + 13, st);
+            if (rc != CARMPC_OK) return rc;
+            // whatever is still without a proof (no KKT certificate, or out of iterations): float64 fallback
+            int handled = 0;
+            rc = exact_fallback(this, pb, second_list, n_failed, ab.warm, iters, st, &handled);
+            if (rc != CARMPC_OK) return rc;
+            last_launches += handled > 0 ? 4 : 1;
+            last_fallback = handled;
+        }
     }
     if (defer_total) { last_total_iters = 0; return CARMPC_OK; }
     unsigned long long total = 0;
@@ -294,7 +315,7 @@ int QPHandle::solve_seeded(const double* d_x0, int64_t batch, const double* xref
     int rc = ensure_workspace(batch);
     if (rc != CARMPC_OK) return rc;
     struct ResetOnExit { int& flag; ~ResetOnExit() { flag = 0; } } reset_records{use_records}, reset_hold{stats_hold};   // also on error returns
-    CARMPC_CUDA(cudaMemsetAsync(ws_polish_stats, 0, sizeof(unsigned long long) * 16, st));
+    CARMPC_CUDA(cudaMemsetAsync(ws_polish_stats, 0, sizeof(unsigned long long) * kPolishStats, st));
     stats_hold = 1;                                       // the histogram covers anchors and followers
     CARMPC_CUDA(cudaMemsetAsync(ws_counters + 8, 0, sizeof(int) * 2, st));
     CARMPC_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int32_t) * batch, st));     // followers enter the polish as "not infeasible"
@@ -406,6 +427,30 @@ int carmpc_qp_create(int n, int m, int k, const double* h_H, const double* h_F, 
     UP(H, H); UP(Hinv, Hinv); UP(F, F); UP(Uu, Uu); UP(AUu, AUu); UP(AH, AH); UP(AHA, AHA); UP(Gx, Gx); UP(Gc, Gc); UP(hi, hi); UP(lo, lo);
     UP(G, G); UP(Eg, Eg);
 #undef UP
+    {
+        ExactTables& e = q->exact;
+        std::vector<double> GsT((size_t)n * m), lam64(n);
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < n; ++j) GsT[(size_t)j * m + i] = h.Gs64[(size_t)i * n + j];
+        for (int j = 0; j < n; ++j) lam64[j] = h.Eb[j] * h.D[j];
+#define UPV(vec, field) do { rc = upload(q, vec, &e.field); if (rc != CARMPC_OK) { delete q; return rc; } } while (0)
+        // reach of every general row over the input box (single-row Farkas certificates: a row whose bound lies outside
+        // [rowmin, rowmax] proves infeasibility by itself)
+        std::vector<double> rowmin(m, 0.0), rowmax(m, 0.0), rowabs(m, 0.0);
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < n; ++j) {
+                const double g = h.G[(size_t)i * n + j];
+                if (g == 0.0) continue;
+                const double a = g * h.lo[m + j], b = g * h.hi[m + j];       // box bounds sit behind the general rows
+                rowmin[i] += std::min(a, b);
+                rowmax[i] += std::max(a, b);
+                rowabs[i] += fabs(g) * std::max(fabs(h.lo[m + j]), fabs(h.hi[m + j]));
+            }
+        UPV(h.Gs64, Gs); UPV(GsT, GsT); UPV(h.Kinv, Kinv); UPV(lam64, lam); UPV(h.Eb, Eb); UPV(h.D, D);
+        UPV(rowmin, rowmin); UPV(rowmax, rowmax); UPV(rowabs, rowabs);
+#undef UPV
+        e.cs = h.cscale; e.rho = o.rho; e.alpha = o.alpha;
+    }
     *handle = q;
     return CARMPC_OK;
 }
@@ -573,15 +618,15 @@ int carmpc_qp_map_host(void* qp, const double* h_axes, const int32_t dims[4], co
     return CARMPC_OK;
 }
 
-int carmpc_qp_polish_stats(void* qp, int64_t* h_hist16) {
+int carmpc_qp_polish_stats(void* qp, int64_t* h_hist20) {
     QPHandle* q = check_handle<QPHandle>(qp, kQP);
     CARMPC_REQUIRE(q != nullptr, "not a QP handle");
-    CARMPC_REQUIRE(h_hist16 != nullptr, "h_hist16");
-    for (int i = 0; i < 16; ++i) h_hist16[i] = 0;
+    CARMPC_REQUIRE(h_hist20 != nullptr, "h_hist20");
+    for (int i = 0; i < kPolishStats; ++i) h_hist20[i] = 0;
     if (q->ws_polish_stats == nullptr) return CARMPC_OK;
-    unsigned long long tmp[16];
+    unsigned long long tmp[kPolishStats];
     CARMPC_CUDA(cudaMemcpy(tmp, q->ws_polish_stats, sizeof(tmp), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 16; ++i) h_hist16[i] = (int64_t)tmp[i];
+    for (int i = 0; i < kPolishStats; ++i) h_hist20[i] = (int64_t)tmp[i];
     return CARMPC_OK;
 }
 

@@ -29,6 +29,7 @@ constexpr int kAdmmThreads = kAdmmWarps * 32;
 constexpr int kMaxN = 160;        // variables (2 x horizon 80)
 constexpr int kMaxM = 392;        // general rows (8 warps x 7 groups x 7 rows)
 constexpr int kPolishMaxActive = 64;
+constexpr int kPolishStats = 20;       // counters of carmpc_qp_polish_stats
 constexpr int kFirstPassIters = 100;  // iteration cap of the first ADMM pass (stragglers continue in the second pass)
 
 enum SlotState : int { kSlotIdle = -1, kSlotRunning = 0, kSlotSolved = 1, kSlotInfeasible = 2, kSlotMaxIter = 3,
@@ -153,11 +154,27 @@ struct PolishBatch {
     double* rec_lam;         // [records][32][5]
     int* rec_act;            // [records][33]   na (-1: no map), then the active rows in the order of Lam's rows
     int rec_write, rec_read;
-    unsigned long long* stats;   // nullable [16]: [r] samples certified after r repair rounds (r = 0..9), [10] not certified,
+    unsigned long long* stats;   // nullable [20]: [r] samples certified after r repair rounds (r = 0..9), [10] not certified,
                                  // [11] round 0 taken from a multiplier map, [12] certified by a multiplier map alone,
                                  // [13] proven infeasible by the anchor's Farkas certificate (or the u-independent rows),
                                  // [14] max_iter samples proven infeasible by the certificate of their own ADMM state,
                                  // [15] samples proven infeasible the same way before the second pass
+                                 // [16] samples the final polish could not certify (handed to the float64 fallback),
+                                 // [17] of those solved + certified, [18] proven infeasible, [19] left undecided (status 2)
+};
+
+// float64 images of the equilibrated problem for the fallback solver (qp_exact.cu), logical order
+struct ExactTables {
+    const double* Gs;        // [m][n]   Eg G D (rows without a finite bound: zero)
+    const double* GsT;       // [n][m]
+    const double* Kinv;      // [n][n]   (Hs + rho (Gs'Gs + lam^2))^-1
+    const double* lam;       // [n]      Eb D
+    const double* Eb;        // [n]
+    const double* D;         // [n]
+    const double* rowmin;    // [m]      min over the input box of G_i u  (-inf when a needed box side is infinite)
+    const double* rowmax;    // [m]      max over the input box of G_i u
+    const double* rowabs;    // [m]      sum_j |G_ij| max(|lb_j|, |ub_j|): rounding scale of the two
+    double cs, rho, alpha;
 };
 
 // Host-side setup product (qp_setup.cu)
@@ -202,12 +219,19 @@ int farkas_filter_launch(QPHandle* q, const int* d_list, int count, int* d_statu
 int farkas_decide_launch(QPHandle* q, const int* d_list, int count, int* d_status, const float* d_warm, const double* d_x0,
                          int64_t stride, double* d_u0, double* d_objective, double* d_u_full, int8_t* d_polished,
                          cudaStream_t st);
+// ADMM verdicts "infeasible" are only accepted with a float64 certificate: the others re-enter the second pass
+int farkas_verify_launch(QPHandle* q, const int* d_list, int count, int* d_status, const float* d_warm, const double* d_x0,
+                         int64_t stride, const double* d_c, const double* xref, int* d_failed, int* d_n_failed, cudaStream_t st);
+// float64 fallback for what the second pass could not prove (qp_exact.cu)
+int exact_fallback(QPHandle* q, const PolishBatch& pb_final, const int* d_list, int count, float* d_warm, int* d_iters,
+                   cudaStream_t st, int* h_handled);
 size_t admm_smem_bytes(const QPHost& h, int samples_per_lane, bool mats_in_smem);
 
 struct QPHandle : HandleBase {
     QPHost host;
     AdmmTables admm;
     PolishTables polish;
+    ExactTables exact;
     std::vector<void*> allocations;
     // per-batch workspace (grown on demand)
     int64_t ws_batch = 0;
@@ -224,10 +248,11 @@ struct QPHandle : HandleBase {
     int* ws_rec_act = nullptr;
     int64_t rec_cap = 0;
     int use_records = 0;                         // set by solve_seeded for the two solve() calls it makes
-    unsigned long long* ws_polish_stats = nullptr;   // [16] histogram of the polish launches of the last solve
+    unsigned long long* ws_polish_stats = nullptr;   // [kPolishStats] histogram of the polish launches of the last solve
     int stats_hold = 0;
     int defer_total = 0;                         // closed loop: ws_total_iters accumulates over the steps, read once at the end
     int* ws_overflow = nullptr;
+    int* ws_unproven = nullptr;                  // samples the second pass left without a proof (float64 fallback)
     int* ws_counters = nullptr;                  // [0] work counter, [1] n_failed
     unsigned long long* ws_total_iters = nullptr;
     int8_t* ws_polished = nullptr;
@@ -239,7 +264,7 @@ struct QPHandle : HandleBase {
     int32_t *io_status = nullptr, *io_iters = nullptr, *io_seed = nullptr;
     double* io_axes = nullptr;                   // grid axes of carmpc_qp_map_host
     int ensure_io(int64_t batch, bool want_full);
-    int64_t last_total_iters = 0, last_launches = 0, last_second_pass = 0;
+    int64_t last_total_iters = 0, last_launches = 0, last_second_pass = 0, last_fallback = 0;
     int sm = 148;
     bool host_only = false;
     ~QPHandle() override;

@@ -430,7 +430,21 @@ __global__ void __launch_bounds__(kPolishThreads, 7) polish_kernel(const PolishT
                 }
                 continue;
             }
-            // accept the float32 ADMM iterate: objective 1/2 u'Hu + q'u evaluated directly
+            if (B.final_pass == 2) {
+                // after the float64 fallback: no certificate, no answer (undecided, never an unproven "solved")
+                if (lane == 0) {
+                    B.status[sample] = CARMPC_QP_MAX_ITER;
+                    if (B.u0) { B.u0[sample] = NaN; B.u0[B.stride + sample] = NaN; }
+                    if (B.objective) B.objective[sample] = NaN;
+                    if (B.polished) B.polished[sample] = 0;
+                    if (B.stats) atomicAdd(B.stats + 19, 1ull);
+                }
+                if (B.u_full) for (int j = lane; j < n; j += 32) B.u_full[(size_t)sample * n + j] = NaN;
+                continue;
+            }
+            if (B.stats && lane == 0 && B.rounds != 0) atomicAdd(B.stats + 16, 1ull);
+            // the float32 ADMM iterate, objective 1/2 u'Hu + q'u evaluated directly: what opts.polish = 0 returns, and a
+            // placeholder (polished = 0) for samples that the float64 fallback (qp_exact.cu) settles next
             for (int j = lane; j < n; j += 32) u[j] = (double)B.u_admm[(size_t)sample * n + j];
             __syncwarp();
             double part = 0.0;
@@ -459,6 +473,7 @@ __global__ void __launch_bounds__(kPolishThreads, 7) polish_kernel(const PolishT
             if (B.polished) B.polished[sample] = certified ? 1 : 0;
             if (certified) B.status[sample] = CARMPC_QP_SOLVED;
             if (certified && B.iters_out) B.iters_out[sample] = 0;
+            if (certified && B.final_pass == 2 && B.stats) atomicAdd(B.stats + 17, 1ull);
         }
         if (certified && B.sign_out) for (int i = lane; i < mt; i += 32) B.sign_out[(size_t)sample * mt + i] = sgn[i];
         if (B.u_full) for (int j = lane; j < n; j += 32) B.u_full[(size_t)sample * n + j] = u[j];
@@ -501,6 +516,7 @@ __global__ void __launch_bounds__(kPolishThreads, 7) polish_kernel(const PolishT
 struct FarkasArgs {
     const int* list; int count; int mode;
     int* status; const float* warm; const double* x0; int64_t stride;
+    const double* cdist;                                               // nullable per-sample disturbance
     const int* rec_of; double* rec_lam; int* rec_act;                  // mode 0
     double* u0; double* objective; double* u_full; int8_t* polished;   // mode 1, 2 (nullable)
     int* survivors; int* n_survivors;                                  // mode 2
@@ -514,18 +530,21 @@ __global__ void __launch_bounds__(128) farkas_kernel(const PolishTables T, const
     double* y = reinterpret_cast<double*>(smem_raw) + (size_t)warp * m;
     const int gw = blockIdx.x * 4 + warp, nw = gridDim.x * 4;
     for (int q = gw; q < F.count; q += nw) {
-        const int sample = F.list[q];
+        const int sample = F.list ? F.list[q] : q;
         const int rec = F.mode == 0 ? F.rec_of[sample] : 0;
         const int want = F.mode == 0 ? CARMPC_QP_INFEASIBLE : (F.mode == 1 ? CARMPC_QP_MAX_ITER : kStatusNeedsMoreAdmm);
         if (F.status[sample] != want || rec < 0) continue;
         double x0[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) x0[c] = F.x0[(size_t)c * F.stride + sample];
+        const double cd = F.cdist ? F.cdist[sample] : 0.0;
+
         double c0 = 0.0, A0 = 0.0, cx[4] = {0, 0, 0, 0}, Ax[4] = {0, 0, 0, 0};
         __syncwarp();
         for (int i = lane; i < m; i += 32) {
             const double* gx = T.Gx + (size_t)i * 4;
-            const double shift = gx[0] * x0[0] + gx[1] * x0[1] + gx[2] * x0[2] + gx[3] * x0[3];
+            const double dshift = T.Gc[i] * cd;                        // the per-sample disturbance moves the bounds
+            const double shift = gx[0] * x0[0] + gx[1] * x0[1] + gx[2] * x0[2] + gx[3] * x0[3] + dshift;
             const double e = T.Eg[i], hi = T.hi[i], lo = T.lo[i];
             const double w = (double)F.warm[(size_t)sample * mt + i];
             const double hs = e * (hi - shift), ls = e * (lo - shift);
@@ -533,8 +552,8 @@ __global__ void __launch_bounds__(128) farkas_kernel(const PolishTables T, const
             if (isfinite(w)) yu = e * (w > hs ? w - hs : (w < ls ? w - ls : 0.0));
             y[i] = yu;
             if (yu != 0.0) {
-                const double t = (yu > 0.0 ? hi : lo) * yu;
-                c0 += t; A0 += fabs(t);
+                const double t = ((yu > 0.0 ? hi : lo) - dshift) * yu;
+                c0 += t; A0 += fabs(t) + fabs(dshift * yu);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) { cx[c] += yu * gx[c]; Ax[c] += fabs(yu * gx[c]); }
             }

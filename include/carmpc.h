@@ -239,7 +239,7 @@ int carmpc_qp_solve_host(void* qp, const double* h_x0, const double* h_xref, con
  * accounting); both int64. */
 int carmpc_qp_last_stats(void* qp, int64_t* h_total_iters, int64_t* h_launches);
 
-/* Histogram of the float64 polish over the last solve (16 int64): [r] samples certified after r repair rounds
+/* Histogram of the float64 polish over the last solve (20 int64): [r] samples certified after r repair rounds
  * (r = 0..9), [10] handed back to the ADMM, [11] samples whose first round used an anchor's multiplier map,
  * [12] samples certified by that map alone (seeded solve), [13] samples proven infeasible by their anchor's Farkas
  * certificate, [14] max_iter samples proven infeasible by the certificate of their own final ADMM state,
