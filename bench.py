@@ -216,7 +216,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
     from carmpc_b200.batch import TerminalSetEvaluator
-    from carmpc_b200.grids import config2_axes, materialise_grid, grid_size, shard_range
+    from carmpc_b200.grids import config2_axes, materialise_grid, materialise_grid_at, grid_size, shard_range
     from carmpc_b200.sharding import PeerWindow, contains_bits_sharded, gather_bitset, reduce_count
 
     if not torch.cuda.is_available():
@@ -256,19 +256,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         ev.set_staging(*[int(t) for t in args.staging.split(",")])
     axes = config2_axes()
     n = grid_size(axes)
-    # strong scaling: ONE 10^8-point grid; rank r holds and scans samples [lo, hi) (whole 1024-sample groups)
-    lo, hi = shard_range(n, rank, world, align=1024)
-    n_local = hi - lo
-    x, y, psi, v = materialise_grid(axes, device=dev, start=lo, stop=hi)         # 3.2 GB / world of float64 SoA
     words = (n + 31) // 32
-    words_local = (n_local + 31) // 32
-    bits = [torch.empty(max(words_local, 1), dtype=torch.int32, device=dev) for _ in range(2)]
     count = torch.zeros(1, dtype=torch.int64, device=dev)
     total = torch.zeros(1, dtype=torch.int64, device=dev)
     gather_mode, window, window_error = "none (single GPU)", None, None
     if distributed:
         try:
-            window = PeerWindow(n)
+            window = PeerWindow(n, layout=args.layout)
             gather_mode = "fused: the scan kernel stores its bitset words into every rank's window over NVLink (CUDA IPC " \
                           "peer mappings), counts + completion flags by a one-warp exchange kernel; no NCCL call in the step"
         except Exception as exc:                              # no peer access on this box: NCCL carries the gather
@@ -278,11 +272,28 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         if int(ok.item()) == 0:
             window = None
             gather_mode = "nccl: all_gather_into_tensor of the bitset words + all_reduce of the count inside the step"
+    # strong scaling: ONE 10^8-point grid.  Cyclic layout (default): its 1024-sample groups are dealt round-robin to the
+    # ranks - the cost of a sample depends on where it lies (a warp leaves a tile as soon as all of it is rejected), so
+    # contiguous slabs of the grid would leave the ranks with up to 1.8x different work.  Contiguous: rank r scans [lo, hi).
+    if window is not None and args.layout == "cyclic":
+        local_index = window.local_index(dev)
+        x, y, psi, v = materialise_grid_at(axes, local_index)                    # 3.2 GB / world of float64 SoA
+        n_local = int(local_index.numel())
+        layout = f"cyclic: 1024-sample group g of the grid belongs to rank g % {world}"
+    else:
+        lo, hi = shard_range(n, rank, world, align=1024)
+        n_local = hi - lo
+        local_index = None
+        x, y, psi, v = materialise_grid(axes, device=dev, start=lo, stop=hi)
+        layout = "contiguous ranges of whole 1024-sample groups" if distributed else "whole grid"
+    words_local = (n_local + 31) // 32
+    bits = [torch.empty(max(words_local, 1), dtype=torch.int32, device=dev) for _ in range(2)]
     full_bits = torch.empty(world * ((shard_range(n, 0, world, align=1024)[1] + 31) // 32), dtype=torch.int32, device=dev) \
         if distributed else None
     launches = 0
 
     def step_nccl(i):
+        # (with the cyclic layout the gathered words arrive in rank-major order: same traffic, not the same layout)
         ev.contains_bits(x, y, psi, v, mode=args.mode, bits=bits[i & 1], count=count)
         gather_bitset(bits[i & 1], n, out=full_bits, shard_align=1024)
         total.copy_(count)
@@ -317,16 +328,30 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if window is not None:
         window.check()
 
-    # ---- outside the timed steps: the gathered result of the last step equals an independent NCCL gather -----------
+    # ---- outside the timed steps: the gathered result of the last step against an independent evaluation -----------
     verify = None
     if distributed:
-        ev.contains_bits(x, y, psi, v, mode=0, bits=bits[0], count=count)          # float64 kernel, local shard
-        ref_full = gather_bitset(bits[0], n, shard_align=1024).clone()
+        ev.contains_bits(x, y, psi, v, mode=0, bits=bits[0], count=count)          # float64 kernel, this rank's samples
         ref_total = int(reduce_count(count.clone()).item())
         got = window.result_bits() if window is not None else full_bits[:words]
-        verify = {"bitset_equal_nccl_gather_of_float64_scan": bool(torch.equal(got[:words], ref_full[:words])),
-                  "count_equal": members == ref_total, "members": ref_total}
-        assert verify["bitset_equal_nccl_gather_of_float64_scan"] and verify["count_equal"], verify
+        gidx = local_index if local_index is not None else torch.arange(lo, hi, device=dev, dtype=torch.int64)
+        lidx = torch.arange(n_local, device=dev, dtype=torch.int64)
+        mine_gathered = (got[gidx >> 5] >> (gidx & 31).to(torch.int32)) & 1          # my samples, read back from the full bitset
+        mine_local = (bits[0][lidx >> 5] >> (lidx & 31).to(torch.int32)) & 1
+        same_local = bool(torch.equal(mine_gathered, mine_local))
+        # every rank holds the same full bitset: compare a checksum of the words
+        chk = got[:words].to(torch.int64).sum().reshape(1)
+        chk_min, chk_max = chk.clone(), chk.clone()
+        dist.all_reduce(chk_min, op=dist.ReduceOp.MIN)
+        dist.all_reduce(chk_max, op=dist.ReduceOp.MAX)
+        bits_set = int(np.unpackbits(got[:words].cpu().numpy().view(np.uint8)).sum())
+        verify = {"my_samples_in_the_full_bitset_equal_float64_scan": same_local,
+                  "full_bitset_identical_on_every_rank": int(chk_min.item()) == int(chk_max.item()),
+                  "bits_set_in_full_bitset": bits_set, "count_equal": members == ref_total == bits_set, "members": ref_total}
+        ok_all = torch.tensor([1 if (same_local and verify["full_bitset_identical_on_every_rank"] and verify["count_equal"]) else 0], device=dev)
+        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+        verify["all_ranks_ok"] = bool(int(ok_all.item()))
+        assert verify["all_ranks_ok"], verify
 
     # ---- this rank's scan alone (no peers, no exchange): the kernel the roofline is about --------------------------------
     k_ms = []
@@ -416,7 +441,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         rv = RolloutEvaluator.from_env(RoadMultipleCarsEnv(), k_star)
         rwin = None
         if window is not None:
-            rwin = PeerWindow(n)
+            rwin = PeerWindow(n, layout=args.layout)
         rtotal = torch.zeros(1, dtype=torch.int64, device=dev)
 
         def rstep():
@@ -531,7 +556,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                          "note": "per GPU: this rank's scan of its shard"},
             "cpu_baseline": cpu,
             "qp_summary": qp_summary,
-            "sharding": {"samples_per_gpu": n_local, "gather": gather_mode, "window_error": window_error,
+            "sharding": {"samples_per_gpu": n_local, "layout": layout, "gather": gather_mode, "window_error": window_error,
                          "scan_alone_ms": stream_ms, "step_overhead_ms": ms_total / args.steps - stream_ms,
                          "verify": verify, "nccl_variant": nccl_variant,
                          "kernel_mode": "fp32 screen + fp64 re-check" if args.mode else "fp64", "members": members},
@@ -552,6 +577,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", type=int, default=1, help="membership kernel: 0 = float64, 1 = float32 screen + float64 re-check")
+    ap.add_argument("--layout", default="cyclic", choices=["cyclic", "contiguous"],
+                    help="how the one sample set is sharded over the ranks (N > 1)")
     ap.add_argument("--staging", default="", help="threads,ring_slots,tiles_per_slot of the scan kernel (tuning)")
     ap.add_argument("--e2e-samples", type=int, default=100_000_000)
     ap.add_argument("--e2e-steps", type=int, default=4)

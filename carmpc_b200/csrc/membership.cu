@@ -40,7 +40,7 @@ struct __align__(16) RowF32 {
 
 // staging geometry of the bulk-async scan: threads per CTA, ring slots per warp, 128-sample tiles per slot
 struct Staging {
-    int threads = 256, stages = 3, tps = 1;
+    int threads = 128, stages = 2, tps = 1;      // measured best of the built geometries on the 10^8 grid
 };
 
 // Device staging of the host-buffer entry points: two slots so that the H2D copy of chunk c+1 overlaps the kernel
@@ -51,6 +51,7 @@ struct HostStage {
     uint32_t* d_bits[2] = {nullptr, nullptr};
     int32_t* d_first[2] = {nullptr, nullptr};
     unsigned long long* d_count = nullptr;
+    unsigned long long* d_work = nullptr;                  // [2][2] work counters of the scan kernel, one pair per slot
     cudaStream_t streams[2] = {nullptr, nullptr};
     bool ready = false;
     int init(bool with_first) {
@@ -61,6 +62,8 @@ struct HostStage {
                 CARMPC_CUDA(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
             }
             CARMPC_CUDA(cudaMalloc(&d_count, sizeof(unsigned long long)));
+            CARMPC_CUDA(cudaMalloc(&d_work, sizeof(unsigned long long) * 4));
+            CARMPC_CUDA(cudaMemset(d_work, 0, sizeof(unsigned long long) * 4));
             ready = true;
         }
         if (with_first && d_first[0] == nullptr)
@@ -75,6 +78,7 @@ struct HostStage {
             if (streams[i]) cudaStreamDestroy(streams[i]);
         }
         cudaFree(d_count);
+        cudaFree(d_work);
     }
 };
 
@@ -87,6 +91,7 @@ struct Polytope : HandleBase {
     std::vector<double> h_rows;      // rows x 5 in device order (host copy, for re-ordering)
     bool tuned = false;              // row order already adapted to a sample set
     Staging staging;                 // geometry of the bulk-async scan (carmpc_scan_staging)
+    unsigned long long* d_work = nullptr;   // [2] work counters of the scan kernel (self-resetting)
     double* d_axes = nullptr;        // grid axes of carmpc_membership_grid (4 x 4096 doubles at most)
     double* h_axes = nullptr;        // pinned staging copy
     ~Polytope() override {
@@ -94,6 +99,7 @@ struct Polytope : HandleBase {
         cudaFree(d_rows32);
         cudaFree(d_axes);
         cudaFreeHost(h_axes);
+        cudaFree(d_work);
     }
 };
 
@@ -106,8 +112,9 @@ struct Rollout : HandleBase {
     std::vector<RowF32> h_rows32;    // host copy (re-ordered by the pilot)
     bool tuned = false;
     Staging staging;
+    unsigned long long* d_work = nullptr;
     HostStage stage;
-    ~Rollout() override { cudaFree(d_data); cudaFree(d_rows32); }
+    ~Rollout() override { cudaFree(d_data); cudaFree(d_rows32); cudaFree(d_work); }
 };
 
 // spread the 8 bits of a byte to every fourth bit position (bit j -> bit 4 j)
@@ -257,23 +264,34 @@ __device__ __forceinline__ void screen32(const RowF32* __restrict__ s_rows32, in
 // partitioned over the GPUs of a box, one destination per rank (the rank's own full bitset and, through NVLink peer
 // mappings, every other rank's), each already pointing at the first word of this shard - the scan kernel itself
 // performs the all-gather, no separate collective.
+// Layout: the k-th 1024-sample group of the scanned arrays is group k * stride of the destination bitsets (stride 1:
+// a contiguous shard; stride = number of ranks: the groups of the sample set are dealt round-robin to the ranks, which
+// balances the load when the cost of a sample depends on where it lies).
 constexpr int kMaxPeers = 8;
 struct BitSink {
     uint32_t* dst[kMaxPeers];
     int n;
+    int64_t stride;
 };
 
 static BitSink single_sink(uint32_t* bits) {
     BitSink s{};
     s.dst[0] = bits;
     s.n = 1;
+    s.stride = 1;
     return s;
 }
 
-static BitSink offset_sink(const BitSink& in, int64_t words) {
+// the sink of the samples that follow `groups` whole local groups
+static BitSink offset_sink(const BitSink& in, int64_t groups) {
     BitSink s = in;
-    for (int d = 0; d < s.n; ++d) s.dst[d] += words;
+    for (int d = 0; d < s.n; ++d) s.dst[d] += groups * in.stride * 32;
     return s;
+}
+
+// destination word of local word wl (32 words per group)
+__device__ __forceinline__ int64_t sink_word(const BitSink& sink, int64_t wl) {
+    return sink.stride == 1 ? wl : ((wl >> 5) * sink.stride << 5) + (wl & 31);
 }
 
 // The 128 decisions of a warp tile (lane t holds samples 4t .. 4t+3) as four words: returns to EVERY lane the word
@@ -300,9 +318,10 @@ __device__ __forceinline__ int store_bits(const BitSink& sink, int64_t warp_base
     if (lane < 4) {
         const int64_t first = warp_base + 32 * lane;
         if (first < n) {
+            const int64_t wg = sink_word(sink, first >> 5);
 #pragma unroll
             for (int d = 0; d < kMaxPeers; ++d)
-                if (d < sink.n) sink.dst[d][first >> 5] = word;
+                if (d < sink.n) sink.dst[d][wg] = word;
         }
     }
     return members;
@@ -435,7 +454,7 @@ __global__ void __launch_bounds__(THREADS)
 membership_tma_kernel(const double* __restrict__ g_rows, const RowF32* __restrict__ g_rows32, const ExactSpec es, int rows_padded,
                       const ScreenConst sc, const double* __restrict__ gx, const double* __restrict__ gy,
                       const double* __restrict__ gp, const double* __restrict__ gv, int64_t n_groups,
-                      const BitSink sink, unsigned long long* __restrict__ count) {
+                      const BitSink sink, unsigned long long* __restrict__ count, unsigned long long* __restrict__ work) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kWarps = THREADS / 32;
     constexpr int kSlot = TPS * kTile;                    // samples per ring slot and array
@@ -458,25 +477,33 @@ membership_tma_kernel(const double* __restrict__ g_rows, const RowF32* __restric
     }
     stage_rows(g_rows, g_rows32, es.len, rows_padded, s_rows, s_rows32);        // ends with __syncthreads()
 
-    const int64_t first = (int64_t)blockIdx.x * kWarps + warp;                   // this warp's groups: first, first + stride, ...
-    const int64_t stride = (int64_t)gridDim.x * kWarps;
-    // slot sequence of this warp: slot j carries tiles [TPS (j % kSlotsPerGroup), ...) of group first + (j / kSlotsPerGroup) stride
-    auto issue = [&](int j) {                                                    // producer: lane 0 of the warp
-        const int64_t group = first + (int64_t)(j / kSlotsPerGroup) * stride;
-        if (group >= n_groups) return;
-        const int64_t sample = group * kGroup + (int64_t)(j % kSlotsPerGroup) * kSlot;
-        const int stage = j % STAGES;
+    // Groups are handed out dynamically (one atomic per 1024 samples): their cost varies a lot (a warp leaves a tile as soon
+    // as every sample is rejected) and, on tensor grids, periodically in the sample index, so a static round-robin leaves
+    // some warps with systematically more work and the kernel with a long tail.
+    // Producer (lane 0): group pg, next slot ps of it, running slot count pj; it is never more than one group ahead of
+    // the consumer (STAGES <= slots per group), so the consumer's next group is always the producer's current one.
+    static_assert(STAGES <= kSlotsPerGroup, "the producer may be at most one group ahead");
+    int64_t pg = 0;
+    int ps = 0, pj = 0;
+    auto advance = [&]() {                                                       // lane 0: issue the next slot of the sequence
+        if (pg >= n_groups) return;
+        const int64_t sample = pg * kGroup + (int64_t)ps * kSlot;
+        const int stage = pj % STAGES;
         mbar_expect_tx(w_bar + stage, 4 * kArrayBytes);
 #pragma unroll
         for (int a = 0; a < 4; ++a)
             bulk_load(w_stage + ((size_t)stage * 4 + a) * kSlot, src[a] + sample, kArrayBytes, w_bar + stage);
+        ++pj;
+        if (++ps == kSlotsPerGroup) { ps = 0; pg = (int64_t)atomicAdd(work, 1ull); }
     };
+    if (lane == 0) pg = (int64_t)atomicAdd(work, 1ull);
+    int64_t group = __shfl_sync(0xffffffffu, pg, 0);
     if (lane == 0)
-        for (int s = 0; s < STAGES; ++s) issue(s);
+        for (int s = 0; s < STAGES; ++s) advance();
 
     int members = 0;
     int j = 0;
-    for (int64_t group = first; group < n_groups; group += stride) {
+    while (group < n_groups) {
         uint32_t acc = 0;                                  // lane l collects word l of the group's 32
 #pragma unroll 1
         for (int sg = 0; sg < kSlotsPerGroup; ++sg, ++j) {
@@ -502,7 +529,7 @@ membership_tma_kernel(const double* __restrict__ g_rows, const RowF32* __restric
                 }
                 if (t == TPS - 1) {
                     __syncwarp();                          // every lane has the slot's last samples in registers: slot is free
-                    if (lane == 0) issue(j + STAGES);
+                    if (lane == 0) advance();
                 }
                 bool in[kNS];
 #pragma unroll
@@ -530,12 +557,22 @@ membership_tma_kernel(const double* __restrict__ g_rows, const RowF32* __restric
                 if ((lane >> 2) == sg * TPS + t) acc = word;
             }
         }
-        const int64_t w0 = group * (kGroup / 32) + lane;
+        const int64_t w0 = group * sink.stride * (kGroup / 32) + lane;
 #pragma unroll
         for (int d = 0; d < kMaxPeers; ++d)
             if (d < sink.n) sink.dst[d][w0] = acc;
+        group = __shfl_sync(0xffffffffu, pg, 0);           // all slots of the finished group were issued: pg is its successor
     }
-    block_count<THREADS>(members, count);
+    block_count<THREADS>(members, count);                  // ends after a __syncthreads(): every warp of the CTA is done
+    // the last CTA to finish re-arms the work counter for the next launch
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(work + 1, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+            work[0] = 0ull;
+            work[1] = 0ull;
+            __threadfence();
+        }
+    }
 }
 
 struct GridDesc {
@@ -643,6 +680,7 @@ membership_grid_kernel(const double* __restrict__ g_rows, const RowF32* __restri
         BitSink sink;
         sink.dst[0] = bits;
         sink.n = 1;
+        sink.stride = 1;
         members += store_bits(sink, warp_base, n, in);
     }
     block_count(members, count);
@@ -704,9 +742,10 @@ rollout_kernel(const double* __restrict__ g_data, int s, int rin, int k_steps, i
         }
         const uint32_t word = __ballot_sync(0xffffffffu, in);
         if ((threadIdx.x & 31) == 0 && i < n) {
+            const int64_t wg = sink_word(sink, i >> 5);
 #pragma unroll
             for (int d = 0; d < kMaxPeers; ++d)
-                if (d < sink.n) sink.dst[d][i >> 5] = word;
+                if (d < sink.n) sink.dst[d][wg] = word;
         }
         if (first_violation != nullptr && valid) first_violation[i] = first;
         if ((threadIdx.x & 31) == 0) members += __popc(word);
@@ -755,7 +794,7 @@ static bool staging_supported(const Staging& g) {
 template <int KIND, int THREADS, int STAGES, int TPS>
 static int launch_tma(const double* d_exact, const RowF32* d_rows32, const ExactSpec& es, int rows_padded, const ScreenConst& sc,
                       const double* x, const double* y, const double* p, const double* v, int64_t n_groups,
-                      const BitSink& sink, unsigned long long* count, size_t smem, cudaStream_t st) {
+                      const BitSink& sink, unsigned long long* count, unsigned long long* work, size_t smem, cudaStream_t st) {
     auto kernel = membership_tma_kernel<1, KIND, THREADS, STAGES, TPS>;
     // the function attribute is per device and the occupancy depends on smem only through the row count, which rarely
     // changes between calls: both are cached per device
@@ -773,7 +812,7 @@ static int launch_tma(const double* d_exact, const RowF32* d_rows32, const Exact
     }
     const int64_t n_units = (n_groups + THREADS / 32 - 1) / (THREADS / 32);
     kernel<<<grid_blocks(n_units, per_sm_cached[dev]), THREADS, smem, st>>>(d_exact, d_rows32, es, rows_padded, sc, x, y, p, v,
-                                                                      n_groups, sink, count);
+                                                                      n_groups, sink, count, work);
     CARMPC_CUDA(cudaGetLastError());
     return CARMPC_OK;
 }
@@ -782,7 +821,8 @@ static int launch_tma(const double* d_exact, const RowF32* d_rows32, const Exact
 template <int KIND>
 static int launch_scan(const double* d_exact, const RowF32* d_rows32, const ExactSpec es, int rows_padded,
                        const ScreenConst sc, const double* x, const double* y, const double* p, const double* v,
-                       int64_t n, BitSink sink, unsigned long long* count, int mode, const Staging& geo, cudaStream_t st) {
+                       int64_t n, BitSink sink, unsigned long long* count, unsigned long long* work, int mode, const Staging& geo,
+                       cudaStream_t st) {
     if (n == 0) return CARMPC_OK;
     const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
                        reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
@@ -795,7 +835,7 @@ static int launch_scan(const double* d_exact, const RowF32* d_rows32, const Exac
         int rc = CARMPC_ERR_UNSUPPORTED;
 #define TMA_CASE(T, S, P)                                                                                              \
         if (geo.threads == T && geo.stages == S && geo.tps == P)                                                           \
-            rc = launch_tma<KIND, T, S, P>(d_exact, d_rows32, es, rows_padded, sc, x, y, p, v, n_groups, sink, count, smem, st)
+            rc = launch_tma<KIND, T, S, P>(d_exact, d_rows32, es, rows_padded, sc, x, y, p, v, n_groups, sink, count, work, smem, st)
         TMA_CASE(256, 3, 1); TMA_CASE(128, 3, 1); TMA_CASE(128, 4, 1); TMA_CASE(128, 2, 2);
         TMA_CASE(128, 3, 2); TMA_CASE(256, 2, 1); TMA_CASE(128, 2, 1); TMA_CASE(256, 2, 2);
 #undef TMA_CASE
@@ -804,7 +844,7 @@ static int launch_scan(const double* d_exact, const RowF32* d_rows32, const Exac
         const int64_t done = n_groups * kGroup;
         if (done == n) return CARMPC_OK;
         x += done; y += done; p += done; v += done; n -= done;
-        sink = offset_sink(sink, done >> 5);
+        sink = offset_sink(sink, n_groups);
     }
     const size_t smem = scan_smem(es.len, rows_padded);
     const int64_t n_chunks = (n + kChunk - 1) / kChunk;
@@ -828,16 +868,17 @@ static int launch_scan(const double* d_exact, const RowF32* d_rows32, const Exac
 }
 
 static int launch_membership(Polytope* P, const double* x, const double* y, const double* p, const double* v,
-                             int64_t n, const BitSink& sink, unsigned long long* count, int mode, cudaStream_t st) {
+                             int64_t n, const BitSink& sink, unsigned long long* count, unsigned long long* work, int mode,
+                             cudaStream_t st) {
     ExactSpec es{};
     es.len = P->rows * 5;
     es.rows = P->rows;
-    return launch_scan<0>(P->d_rows, P->d_rows32, es, pad_rows(P->rows), screen_const(P), x, y, p, v, n, sink, count, mode,
+    return launch_scan<0>(P->d_rows, P->d_rows32, es, pad_rows(P->rows), screen_const(P), x, y, p, v, n, sink, count, work, mode,
                           P->staging, st);
 }
 
 static int launch_rollout(Rollout* R, const double* x, const double* y, const double* p, const double* v, int64_t n,
-                          const BitSink& sink, int32_t* first, unsigned long long* count, cudaStream_t st) {
+                          const BitSink& sink, int32_t* first, unsigned long long* count, unsigned long long* work, cudaStream_t st) {
     if (n == 0) return CARMPC_OK;
     if (first == nullptr && R->d_rows32 != nullptr) {
         // float32 screen over the expanded rows a_r A_k^t, float64 step-by-step rollout for the samples it cannot decide
@@ -846,7 +887,7 @@ static int launch_rollout(Rollout* R, const double* x, const double* y, const do
         es.s = R->s; es.rin = R->rin; es.k_steps = R->k_steps; es.input_mode = R->input_mode;
         ScreenConst sc;
         sc.beta0 = R->beta0; sc.beta1 = R->beta1;
-        return launch_scan<1>(R->d_data, R->d_rows32, es, R->rows_padded, sc, x, y, p, v, n, sink, count, 1, R->staging, st);
+        return launch_scan<1>(R->d_data, R->d_rows32, es, R->rows_padded, sc, x, y, p, v, n, sink, count, work, 1, R->staging, st);
     }
     const size_t smem = sizeof(double) * (20 + 5 * R->s + 5 * R->rin);
     const int64_t n_chunks = (n + kThreads - 1) / kThreads;
@@ -873,7 +914,8 @@ static int host_pipeline(HostStage& S, const double* h_x, const double* h_y, con
         const double* src[4] = {h_x, h_y, h_psi, h_v};
         for (int a = 0; a < 4; ++a)
             CARMPC_CUDA(cudaMemcpyAsync(d + a * chunk, src[a] + s, sizeof(double) * len, cudaMemcpyHostToDevice, st));
-        rc = launch(d, d + chunk, d + 2 * chunk, d + 3 * chunk, len, single_sink(S.d_bits[slot]), S.d_first[slot], S.d_count, st);
+        rc = launch(d, d + chunk, d + 2 * chunk, d + 3 * chunk, len, single_sink(S.d_bits[slot]), S.d_first[slot], S.d_count,
+                    S.d_work + 2 * slot, st);
         if (rc != CARMPC_OK) return rc;
         CARMPC_CUDA(cudaMemcpyAsync(h_bits + (s >> 5), S.d_bits[slot], sizeof(uint32_t) * ((len + 31) / 32),
                                     cudaMemcpyDeviceToHost, st));
@@ -1102,7 +1144,9 @@ int carmpc_polytope_create(const double* h_Ab, int rows, void** handle) {
     h_Ab = sorted.data();
     auto fail = [&](int code) { delete P; return code; };
     if (cudaMalloc(&P->d_rows, sizeof(double) * 5 * (rows > 0 ? rows : 1)) != cudaSuccess ||
-        cudaMalloc(&P->d_rows32, sizeof(RowF32) * r32.size()) != cudaSuccess) {
+        cudaMalloc(&P->d_rows32, sizeof(RowF32) * r32.size()) != cudaSuccess ||
+        cudaMalloc(&P->d_work, sizeof(unsigned long long) * 2) != cudaSuccess ||
+        cudaMemset(P->d_work, 0, sizeof(unsigned long long) * 2) != cudaSuccess) {
         set_error("carmpc_polytope_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(CARMPC_ERR_CUDA);
     }
@@ -1136,7 +1180,7 @@ int carmpc_membership_bitset(void* polytope, const double* d_x, const double* d_
     }
     if (d_count) CARMPC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
     return launch_membership(P, d_x, d_y, d_psi, d_v, n, single_sink(d_bits), reinterpret_cast<unsigned long long*>(d_count),
-                             mode, st);
+                             P->d_work, mode, st);
 }
 
 int carmpc_polytope_tune(void* polytope, const double* d_x, const double* d_y, const double* d_psi, const double* d_v,
@@ -1222,8 +1266,8 @@ int carmpc_membership_bitset_host(void* polytope, const double* h_x, const doubl
     CARMPC_REQUIRE(h_x && h_y && h_psi && h_v && h_bits, "null host pointer");
     return host_pipeline(P->stage, h_x, h_y, h_psi, h_v, n, h_bits, nullptr, h_count,
                          [&](const double* x, const double* y, const double* p, const double* v, int64_t len,
-                             const BitSink& bits, int32_t*, unsigned long long* count, cudaStream_t st) {
-                             return launch_membership(P, x, y, p, v, len, bits, count, mode, st);
+                             const BitSink& bits, int32_t*, unsigned long long* count, unsigned long long* work, cudaStream_t st) {
+                             return launch_membership(P, x, y, p, v, len, bits, count, work, mode, st);
                          });
 }
 
@@ -1248,6 +1292,8 @@ int carmpc_rollout_create(const double* h_Ak, const double* h_Acon, const double
     R->s = s; R->rin = rin; R->k_steps = k_steps; R->input_mode = input_check_mode;
     cudaGetDevice(&R->device);
     if (cudaMalloc(&R->d_data, sizeof(double) * data.size()) != cudaSuccess ||
+        cudaMalloc(&R->d_work, sizeof(unsigned long long) * 2) != cudaSuccess ||
+        cudaMemset(R->d_work, 0, sizeof(unsigned long long) * 2) != cudaSuccess ||
         cudaMemcpy(R->d_data, data.data(), sizeof(double) * data.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
         set_error("carmpc_rollout_create: %s", cudaGetErrorString(cudaGetLastError()));
         delete R;
@@ -1340,7 +1386,7 @@ int carmpc_rollout_bitset(void* rollout, const double* d_x, const double* d_y, c
         if (rc != CARMPC_OK) return rc;
     }
     return launch_rollout(R, d_x, d_y, d_psi, d_v, n, single_sink(d_bits), d_first_violation,
-                          reinterpret_cast<unsigned long long*>(d_count), st);
+                          reinterpret_cast<unsigned long long*>(d_count), R->d_work, st);
 }
 
 int carmpc_rollout_bitset_host(void* rollout, const double* h_x, const double* h_y, const double* h_psi,
@@ -1354,27 +1400,35 @@ int carmpc_rollout_bitset_host(void* rollout, const double* h_x, const double* h
     CARMPC_REQUIRE(h_x && h_y && h_psi && h_v && h_bits, "null host pointer");
     return host_pipeline(R->stage, h_x, h_y, h_psi, h_v, n, h_bits, h_first_violation, h_count,
                          [&](const double* x, const double* y, const double* p, const double* v, int64_t len,
-                             const BitSink& bits, int32_t* first, unsigned long long* count, cudaStream_t st) {
+                             const BitSink& bits, int32_t* first, unsigned long long* count, unsigned long long* work, cudaStream_t st) {
                              return launch_rollout(R, x, y, p, v, len, bits, h_first_violation ? first : nullptr, count,
-                                                   st);
+                                                   work, st);
                          });
 }
 
 // ---- sharded scans: the all-gather of the bitsets is fused into the scan kernel (shard.cuh) ------------------------------
-static int shard_sink(ShardWindow* W, int64_t n_local, int64_t first_sample, BitSink* sink, unsigned long long* step_out) {
+static int shard_sink(ShardWindow* W, int64_t n_local, int64_t first_sample, int64_t group_stride, BitSink* sink,
+                      unsigned long long* step_out) {
     CARMPC_REQUIRE(W->connected, "the shard window is not connected to its peers (carmpc_shard_connect)");
-    CARMPC_REQUIRE(n_local >= 0 && first_sample >= 0, "n_local, first_sample");
+    CARMPC_REQUIRE(n_local >= 0 && first_sample >= 0 && group_stride >= 1, "n_local, first_sample, group_stride");
     CARMPC_REQUIRE(n_local == 0 || (first_sample & 31) == 0, "a shard starts on a whole bitset word");
-    CARMPC_REQUIRE(first_sample + n_local <= W->n_total, "the shard exceeds the sample set of the window");
+    CARMPC_REQUIRE(n_local == 0 || group_stride == 1 || (first_sample & 1023) == 0, "strided shards start on a whole 1024-sample group");
+    if (n_local > 0) {
+        // last sample of the shard in the numbering of the whole set
+        const int64_t last_local = n_local - 1;
+        const int64_t last = first_sample + (last_local >> 10) * group_stride * 1024 + (last_local & 1023);
+        CARMPC_REQUIRE(last < W->n_total, "the shard exceeds the sample set of the window");
+    }
     const unsigned long long step = W->step + 1;
     sink->n = W->world;
+    sink->stride = group_stride;
     for (int r = 0; r < W->world; ++r) sink->dst[r] = W->bits(r, (int)(step & 1ull)) + (first_sample >> 5);
     *step_out = step;
     return CARMPC_OK;
 }
 
 int carmpc_membership_bitset_sharded(void* polytope, void* shard, const double* d_x, const double* d_y, const double* d_psi,
-                                     const double* d_v, int64_t n_local, int64_t first_sample, int mode,
+                                     const double* d_v, int64_t n_local, int64_t first_sample, int64_t group_stride, int mode,
                                      int64_t* d_total_count, void* stream) {
     Polytope* P = check_handle<Polytope>(polytope, kPolytope);
     CARMPC_REQUIRE(P != nullptr, "not a polytope handle");
@@ -1384,7 +1438,7 @@ int carmpc_membership_bitset_sharded(void* polytope, void* shard, const double* 
     CARMPC_REQUIRE(n_local == 0 || (d_x && d_y && d_psi && d_v), "null device pointer");
     BitSink sink{};
     unsigned long long step = 0;
-    int rc = shard_sink(W, n_local, first_sample, &sink, &step);
+    int rc = shard_sink(W, n_local, first_sample, group_stride, &sink, &step);
     if (rc != CARMPC_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (!P->tuned && n_local >= ((int64_t)1 << 20)) {
@@ -1392,7 +1446,7 @@ int carmpc_membership_bitset_sharded(void* polytope, void* shard, const double* 
         if (rc != CARMPC_OK) return rc;
     }
     CARMPC_CUDA(cudaMemsetAsync(W->d_local_count, 0, sizeof(unsigned long long), st));
-    rc = launch_membership(P, d_x, d_y, d_psi, d_v, n_local, sink, W->d_local_count, mode, st);
+    rc = launch_membership(P, d_x, d_y, d_psi, d_v, n_local, sink, W->d_local_count, W->d_local_count + 1, mode, st);
     if (rc != CARMPC_OK) return rc;
     rc = shard_exchange_launch(W, step, d_total_count, st);
     if (rc != CARMPC_OK) return rc;
@@ -1401,8 +1455,8 @@ int carmpc_membership_bitset_sharded(void* polytope, void* shard, const double* 
 }
 
 int carmpc_rollout_bitset_sharded(void* rollout, void* shard, const double* d_x, const double* d_y, const double* d_psi,
-                                  const double* d_v, int64_t n_local, int64_t first_sample, int64_t* d_total_count,
-                                  void* stream) {
+                                  const double* d_v, int64_t n_local, int64_t first_sample, int64_t group_stride,
+                                  int64_t* d_total_count, void* stream) {
     Rollout* R = check_handle<Rollout>(rollout, kRollout);
     CARMPC_REQUIRE(R != nullptr, "not a rollout handle");
     ShardWindow* W = check_handle<ShardWindow>(shard, kShard);
@@ -1410,7 +1464,7 @@ int carmpc_rollout_bitset_sharded(void* rollout, void* shard, const double* d_x,
     CARMPC_REQUIRE(n_local == 0 || (d_x && d_y && d_psi && d_v), "null device pointer");
     BitSink sink{};
     unsigned long long step = 0;
-    int rc = shard_sink(W, n_local, first_sample, &sink, &step);
+    int rc = shard_sink(W, n_local, first_sample, group_stride, &sink, &step);
     if (rc != CARMPC_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (!R->tuned && n_local >= ((int64_t)1 << 20)) {
@@ -1418,7 +1472,7 @@ int carmpc_rollout_bitset_sharded(void* rollout, void* shard, const double* d_x,
         if (rc != CARMPC_OK) return rc;
     }
     CARMPC_CUDA(cudaMemsetAsync(W->d_local_count, 0, sizeof(unsigned long long), st));
-    rc = launch_rollout(R, d_x, d_y, d_psi, d_v, n_local, sink, nullptr, W->d_local_count, st);
+    rc = launch_rollout(R, d_x, d_y, d_psi, d_v, n_local, sink, nullptr, W->d_local_count, W->d_local_count + 1, st);
     if (rc != CARMPC_OK) return rc;
     rc = shard_exchange_launch(W, step, d_total_count, st);
     if (rc != CARMPC_OK) return rc;

@@ -117,7 +117,8 @@ int carmpc_shard_create(int rank, int world, int64_t n_total, void** handle) {
     const int64_t words = (n_total + 31) / 32;
     W->words_pad = (words + 31) / 32 * 32 + 32;
     W->bytes = kShardHeaderBytes + sizeof(uint32_t) * 2 * (size_t)W->words_pad;
-    if (cudaMalloc(&W->base, W->bytes) != cudaSuccess || cudaMalloc(&W->d_local_count, sizeof(unsigned long long)) != cudaSuccess ||
+    if (cudaMalloc(&W->base, W->bytes) != cudaSuccess || cudaMalloc(&W->d_local_count, sizeof(unsigned long long) * 4) != cudaSuccess ||
+        cudaMemset(W->d_local_count, 0, sizeof(unsigned long long) * 4) != cudaSuccess ||
         cudaMemset(W->base, 0, W->bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
         set_error("carmpc_shard_create: %s", cudaGetErrorString(cudaGetLastError()));
         delete W;

@@ -21,7 +21,8 @@ struct ShardWindow : HandleBase {
     bool ipc_opened[kShardMaxWorld] = {false};
     bool connected = false;
     unsigned long long step = 0;                         // completed collective steps (the same on every rank)
-    unsigned long long* d_local_count = nullptr;         // member count of this rank's shard in the current step
+    unsigned long long* d_local_count = nullptr;         // [0] member count of this rank's shard in the current step,
+                                                         // [1..2] work counters of the scan kernel (self-resetting)
     ~ShardWindow() override;
 
     unsigned long long* flags(int r) const { return reinterpret_cast<unsigned long long*>(peer[r]); }

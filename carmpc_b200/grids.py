@@ -43,6 +43,19 @@ def materialise_grid(axes, device="cuda", start: int = 0, stop: int | None = Non
     return out
 
 
+def materialise_grid_at(axes, index):
+    """Four float64 SoA tensors with the grid points (C order) at the flat indices ``index`` (int64 tensor, any device)."""
+    import torch
+    dims = [len(a) for a in axes]
+    stride = grid_size(axes)
+    out = []
+    for a, d in zip(axes, dims):
+        stride //= d
+        ax = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(index.device)
+        out.append(ax[torch.div(index, stride, rounding_mode="floor") % d].contiguous())
+    return out
+
+
 def materialise_grid_host(axes, start: int = 0, stop: int | None = None):
     """numpy version of ``materialise_grid`` (host SoA arrays, used for the end-to-end host path)."""
     dims = [len(a) for a in axes]

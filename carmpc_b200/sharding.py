@@ -115,8 +115,14 @@ class PeerWindow:
     ``all_gather_object``; ``PeerWindow.local_group(n, world)`` builds all windows of a group inside one process
     (several ranks on one or more devices: tests, single-process multi-GPU drivers)."""
 
-    def __init__(self, n_total: int, rank: Optional[int] = None, world: Optional[int] = None, _connect: bool = True):
+    GROUP = 1024        # samples per bitset line (32 words): the unit the scan kernel hands to a warp
+
+    def __init__(self, n_total: int, rank: Optional[int] = None, world: Optional[int] = None, _connect: bool = True,
+                 layout: str = "cyclic"):
         import ctypes
+        if layout not in ("cyclic", "contiguous"):
+            raise ValueError("layout must be 'cyclic' or 'contiguous'")
+        self.layout = layout
         from . import _capi
         self._lib = _capi.load()
         r, w = world_info()
@@ -142,7 +148,7 @@ class PeerWindow:
         _dist().barrier()                      # nobody writes into a window before every rank has mapped it
 
     @classmethod
-    def local_group(cls, n_total: int, world: int, devices=None):
+    def local_group(cls, n_total: int, world: int, devices=None, layout: str = "cyclic"):
         """All ``world`` windows in this process; ``devices[r]`` is the CUDA device index of rank r (default: current)."""
         import ctypes
         import torch
@@ -151,17 +157,50 @@ class PeerWindow:
         for r in range(world):
             if devices is not None:
                 with torch.cuda.device(devices[r]):
-                    wins.append(cls(n_total, rank=r, world=world, _connect=False))
+                    wins.append(cls(n_total, rank=r, world=world, _connect=False, layout=layout))
             else:
-                wins.append(cls(n_total, rank=r, world=world, _connect=False))
+                wins.append(cls(n_total, rank=r, world=world, _connect=False, layout=layout))
         arr = (ctypes.c_void_p * world)(*[w._h for w in wins])
         for w in wins:
             _capi.check(w._lib.carmpc_shard_connect_local(w._h, arr))
         return wins
 
     def shard(self) -> Tuple[int, int]:
-        """[lo, hi) of this rank: whole 1024-sample groups (one 128-byte bitset line per group and destination)."""
-        return shard_range(self.n_total, self.rank, self.world, align=1024)
+        """Contiguous layout: [lo, hi) of this rank, whole 1024-sample groups (one 128-byte bitset line per group and
+        destination)."""
+        if self.layout != "contiguous":
+            raise ValueError("shard() is the contiguous layout; use local_count() / local_index() for the cyclic one")
+        return shard_range(self.n_total, self.rank, self.world, align=self.GROUP)
+
+    def local_count(self) -> int:
+        """Samples this rank evaluates."""
+        if self.layout == "contiguous":
+            lo, hi = self.shard()
+            return hi - lo
+        g = self.GROUP
+        n_groups = -(-self.n_total // g)                     # the last group may be partial
+        mine = max(0, -(-(n_groups - self.rank) // self.world))
+        count = mine * g
+        if mine and (self.rank + (mine - 1) * self.world) == n_groups - 1 and self.n_total % g:
+            count -= g - self.n_total % g
+        return count
+
+    def local_index(self, device="cpu"):
+        """int64 tensor: for every local sample its index in the whole set.  Cyclic layout: the 1024-sample groups of
+        the set are dealt round-robin (group g belongs to rank g % world), so every rank sees the same mix of cheap and
+        expensive regions of a structured sample set."""
+        import torch
+        k = torch.arange(self.local_count(), dtype=torch.int64, device=device)
+        if self.layout == "contiguous":
+            return k + self.shard()[0]
+        g = self.GROUP
+        return (torch.div(k, g, rounding_mode="floor") * self.world + self.rank) * g + k % g
+
+    def _placement(self) -> Tuple[int, int]:
+        """(first_sample, group_stride) of carmpc_*_bitset_sharded."""
+        if self.layout == "contiguous":
+            return self.shard()[0], 1
+        return self.rank * self.GROUP, self.world
 
     def result_bits(self):
         """The full bitset of the last completed step as an int32 CUDA tensor view of the window (valid until the
@@ -196,7 +235,7 @@ class PeerWindow:
 
 def contains_bits_sharded(evaluator, window: "PeerWindow", x, y, psi, v, mode: int = 1, total=None, stream=None):
     """One collective step: membership (``TerminalSetEvaluator``) or rollout form (``RolloutEvaluator``) of this rank's
-    shard ``window.shard()``, bitset words written into every rank's window by the scan kernel itself, member counts
+    shard (``window.local_index()``), bitset words written into every rank's window by the scan kernel itself, member counts
     and completion flags exchanged by a one-warp kernel.  ``total``: int64 CUDA tensor (1,) receiving the global
     member count.  Nothing is synchronised; ``window.result_bits()`` is valid in stream order."""
     import ctypes
@@ -204,19 +243,19 @@ def contains_bits_sharded(evaluator, window: "PeerWindow", x, y, psi, v, mode: i
     from . import _capi
     from .batch import RolloutEvaluator, _check_soa
     n = _check_soa(x, y, psi, v) if x.numel() else 0
-    lo, hi = window.shard()
-    if n != hi - lo:
-        raise ValueError(f"rank {window.rank} owns samples [{lo}, {hi}) of the set, got {n}")
+    if n != window.local_count():
+        raise ValueError(f"rank {window.rank} owns {window.local_count()} samples of the set ({window.layout} layout), got {n}")
+    lo, stride = window._placement()
     if total is None:
         total = torch.empty(1, dtype=torch.int64, device=x.device)
     s = torch.cuda.current_stream() if stream is None else stream
     st = ctypes.c_void_p(s.cuda_stream)
     if isinstance(evaluator, RolloutEvaluator):
         _capi.check(evaluator._lib.carmpc_rollout_bitset_sharded(evaluator._h, window._h, x.data_ptr(), y.data_ptr(),
-                                                                 psi.data_ptr(), v.data_ptr(), n, lo, total.data_ptr(), st))
+                                                                 psi.data_ptr(), v.data_ptr(), n, lo, stride, total.data_ptr(), st))
     else:
         _capi.check(evaluator._lib.carmpc_membership_bitset_sharded(evaluator._h, window._h, x.data_ptr(), y.data_ptr(),
-                                                                    psi.data_ptr(), v.data_ptr(), n, lo, mode,
+                                                                    psi.data_ptr(), v.data_ptr(), n, lo, stride, mode,
                                                                     total.data_ptr(), st))
     return total
 

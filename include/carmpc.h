@@ -106,7 +106,7 @@ int carmpc_rollout_bitset_host(void* rollout, const double* h_x, const double* h
 
 /* Tuning hook for the streaming scans (polytope or rollout handle): staging geometry of the bulk-async kernel -
  * threads per CTA, ring slots per warp, 128-sample tiles per ring slot.  Results never depend on it; combinations the
- * library was not built with return CARMPC_ERR_UNSUPPORTED.  Default 256 / 3 / 1. */
+ * library was not built with return CARMPC_ERR_UNSUPPORTED.  Default 128 / 2 / 1. */
 int carmpc_scan_staging(void* handle, int threads_per_cta, int ring_slots, int tiles_per_slot);
 
 /* ------------------------------------------------------------------------------------------------
@@ -127,15 +127,18 @@ int carmpc_shard_export(void* shard, unsigned char* h_ipc_handle64);
 int carmpc_shard_connect(void* shard, const unsigned char* h_ipc_handles /* world x 64 bytes, rank order */);
 int carmpc_shard_connect_local(void* shard, void* const* peer_shards /* world handles, entry [rank] ignored */);
 
-/* Membership of this rank's shard: samples [first_sample, first_sample + n_local) of the set, first_sample a
- * multiple of 32.  When the step has completed (stream order) the rank's window holds the bitset of ALL n_total
- * samples and *d_total_count (nullable, device int64) the member count over all ranks. */
+/* Membership of this rank's shard.  group_stride = 1: the n_local samples are [first_sample, first_sample + n_local)
+ * of the set, first_sample a multiple of 32 (contiguous shards).  group_stride = s > 1: the k-th 1024-sample group of
+ * the local arrays is group first_sample / 1024 + k s of the set, first_sample a multiple of 1024 (with s = world and
+ * first_sample = 1024 rank the groups are dealt round-robin to the ranks: equal load whatever the cost profile of the
+ * set is; only the last local group may be partial).  When the step has completed (stream order) the rank's window
+ * holds the bitset of ALL n_total samples and *d_total_count (nullable, device int64) the member count over all ranks. */
 int carmpc_membership_bitset_sharded(void* polytope, void* shard, const double* d_x, const double* d_y,
                                      const double* d_psi, const double* d_v, int64_t n_local, int64_t first_sample,
-                                     int mode, int64_t* d_total_count, void* stream);
+                                     int64_t group_stride, int mode, int64_t* d_total_count, void* stream);
 int carmpc_rollout_bitset_sharded(void* rollout, void* shard, const double* d_x, const double* d_y,
                                   const double* d_psi, const double* d_v, int64_t n_local, int64_t first_sample,
-                                  int64_t* d_total_count, void* stream);
+                                  int64_t group_stride, int64_t* d_total_count, void* stream);
 
 /* d_bits: the full bitset (ceil(n_total / 32) words, device memory of this rank) of the last completed step; it stays
  * valid until the second-next sharded call on this window.  h_steps: collective steps done so far. */

@@ -19,8 +19,9 @@ def _samples(torch, n, seed):
     return [(lo[k] + (hi[k] - lo[k]) * u[k]).contiguous() for k in range(4)]
 
 
-@pytest.mark.parametrize("world,n", [(2, 3_000_077), (3, 1_500_000), (8, 9_000_001), (4, 5000), (2, 0)])
-def test_fused_sharded_membership_equals_single_scan(world, n):
+@pytest.mark.parametrize("layout", ["cyclic", "contiguous"])
+@pytest.mark.parametrize("world,n", [(2, 3_000_077), (3, 1_500_000), (8, 9_000_001), (4, 5000), (2, 0), (3, 2048), (4, 1_000_000)])
+def test_fused_sharded_membership_equals_single_scan(world, n, layout):
     import torch
     from carmpc_b200.batch import TerminalSetEvaluator
     from carmpc_b200.sharding import PeerWindow, contains_bits_sharded
@@ -32,21 +33,19 @@ def test_fused_sharded_membership_equals_single_scan(world, n):
         want_bits, want_count = want_bits.clone(), int(want_count.item())
     else:
         want_bits, want_count = torch.empty(0, dtype=torch.int32, device="cuda"), 0
-    wins = PeerWindow.local_group(n, world)
+    wins = PeerWindow.local_group(n, world, layout=layout)
     streams = [torch.cuda.Stream() for _ in range(world)]
     totals = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-    covered = 0
-    for r, w in enumerate(wins):
-        lo, hi = w.shard()
-        assert (lo % 1024 == 0 or lo == n) and lo == covered
-        covered = hi
-    assert covered == n
+    # the ranks' index sets partition the sample set
+    idx = [w.local_index("cuda") for w in wins]
+    allidx = torch.cat(idx)
+    assert allidx.numel() == n and (n == 0 or torch.equal(torch.sort(allidx).values, torch.arange(n, device="cuda")))
+    local = [[t[i].contiguous() for t in (x, y, psi, v)] for i in idx]
     torch.cuda.synchronize()
     for step in range(3):                                   # three steps: both buffer slots, flags keep counting
         for r, w in enumerate(wins):
-            lo, hi = w.shard()
             with torch.cuda.stream(streams[r]):
-                contains_bits_sharded(ev, w, x[lo:hi], y[lo:hi], psi[lo:hi], v[lo:hi], total=totals[r])
+                contains_bits_sharded(ev, w, *local[r], total=totals[r])
         torch.cuda.synchronize()
         for r, w in enumerate(wins):
             w.check()
@@ -68,11 +67,11 @@ def test_fused_sharded_rollout_equals_single_scan():
     wins = PeerWindow.local_group(n, world)
     streams = [torch.cuda.Stream() for _ in range(world)]
     totals = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    local = [[t[w.local_index("cuda")].contiguous() for t in (x, y, psi, v)] for w in wins]
     torch.cuda.synchronize()
     for r, w in enumerate(wins):
-        lo, hi = w.shard()
         with torch.cuda.stream(streams[r]):
-            contains_bits_sharded(rv, w, x[lo:hi], y[lo:hi], psi[lo:hi], v[lo:hi], total=totals[r])
+            contains_bits_sharded(rv, w, *local[r], total=totals[r])
     torch.cuda.synchronize()
     for r, w in enumerate(wins):
         w.check()
@@ -86,7 +85,7 @@ def test_shard_argument_errors():
     from carmpc_b200.sharding import PeerWindow, contains_bits_sharded
     ev = TerminalSetEvaluator(np.load(os.path.join(GOLDEN, "terminal_sets", "RoadMultipleCarsEnv_30_1.5_0_0.npy")))
     x, y, psi, v = _samples(torch, 4096, seed=1)
-    w = PeerWindow(4096, rank=0, world=2, _connect=False)          # never connected to rank 1
+    w = PeerWindow(4096, rank=0, world=2, _connect=False, layout="contiguous")          # never connected to rank 1
     with pytest.raises(CarmpcError, match="not connected"):
         contains_bits_sharded(ev, w, x[:2048], y[:2048], psi[:2048], v[:2048])
     with pytest.raises(ValueError):

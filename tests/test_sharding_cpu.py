@@ -97,3 +97,26 @@ def test_group_aligned_shards_tile_the_sample_set():
             assert covered == n
     lens = [shard_range(10 ** 8, r, 8, align=1024) for r in range(8)]
     assert max(h - l for l, h in lens) - min(h - l for l, h in lens) <= 8 * 1024
+
+
+def test_cyclic_layout_partitions_the_sample_set():
+    """PeerWindow's cyclic layout (group g of 1024 samples belongs to rank g % world): the ranks' index sets partition
+    [0, n), counts match, only the owner of the last group holds a partial one.  Host logic only (no window is created)."""
+    import torch
+    from carmpc_b200.sharding import PeerWindow
+    for n in (0, 1, 1023, 1024, 1025, 5000, 3_000_077, 10 ** 6):
+        for world in (1, 2, 3, 4, 8):
+            parts = []
+            for r in range(world):
+                w = PeerWindow.__new__(PeerWindow)
+                w.n_total, w.rank, w.world, w.layout = n, r, world, "cyclic"
+                idx = w.local_index()
+                assert idx.numel() == w.local_count()
+                assert w._placement() == (r * 1024, world)
+                parts.append(idx)
+            allidx = torch.cat(parts)
+            assert allidx.numel() == n
+            if n:
+                assert torch.equal(torch.sort(allidx).values, torch.arange(n))
+            counts = [p.numel() for p in parts]
+            assert max(counts) - min(counts) <= 1024
