@@ -45,8 +45,9 @@ SIGNATURES = {
     "carmpc_shard_export": (_i32, [_vp, _vp]),
     "carmpc_shard_connect": (_i32, [_vp, _vp]),
     "carmpc_shard_connect_local": (_i32, [_vp, ctypes.POINTER(_vp)]),
-    "carmpc_membership_bitset_sharded": (_i32, [_vp, _vp, _dp, _dp, _dp, _dp, _i64, _i64, _i64, _i32, _vp, _vp]),
-    "carmpc_rollout_bitset_sharded": (_i32, [_vp, _vp, _dp, _dp, _dp, _dp, _i64, _i64, _i64, _vp, _vp]),
+    "carmpc_membership_bitset_sharded": (_i32, [_vp, _vp, _dp, _dp, _dp, _dp, _i64, _i64, _i64, _i32, _vp, _i32, _vp]),
+    "carmpc_rollout_bitset_sharded": (_i32, [_vp, _vp, _dp, _dp, _dp, _dp, _i64, _i64, _i64, _vp, _i32, _vp]),
+    "carmpc_shard_wait": (_i32, [_vp, _vp, _vp]),
     "carmpc_shard_result": (_i32, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_i64)]),
     "carmpc_shard_check": (_i32, [_vp]),
     "carmpc_qp_default_opts": (None, [ctypes.POINTER(QPOpts)]),

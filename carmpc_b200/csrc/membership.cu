@@ -272,13 +272,24 @@ struct BitSink {
     uint32_t* dst[kMaxPeers];
     int n;
     int64_t stride;
+    // double-buffered destinations (peer windows): the buffer of this launch is slot (*step + 1) & 1, slot_words apart.
+    // The step lives in device memory (advanced by the exchange kernel), so the launch arguments of a collective step
+    // never change and the step can be captured in a CUDA graph.  nullptr: single buffer.
+    const unsigned long long* step;
+    int64_t slot_words;
 };
+
+__device__ __forceinline__ int64_t sink_slot_offset(const BitSink& sink) {
+    return sink.step != nullptr ? (int64_t)((*sink.step + 1ull) & 1ull) * sink.slot_words : 0;
+}
 
 static BitSink single_sink(uint32_t* bits) {
     BitSink s{};
     s.dst[0] = bits;
     s.n = 1;
     s.stride = 1;
+    s.step = nullptr;
+    s.slot_words = 0;
     return s;
 }
 
@@ -318,7 +329,7 @@ __device__ __forceinline__ int store_bits(const BitSink& sink, int64_t warp_base
     if (lane < 4) {
         const int64_t first = warp_base + 32 * lane;
         if (first < n) {
-            const int64_t wg = sink_word(sink, first >> 5);
+            const int64_t wg = sink_word(sink, first >> 5) + sink_slot_offset(sink);
 #pragma unroll
             for (int d = 0; d < kMaxPeers; ++d)
                 if (d < sink.n) sink.dst[d][wg] = word;
@@ -503,6 +514,7 @@ membership_tma_kernel(const double* __restrict__ g_rows, const RowF32* __restric
 
     int members = 0;
     int j = 0;
+    const int64_t slot_off = sink_slot_offset(sink);
     while (group < n_groups) {
         uint32_t acc = 0;                                  // lane l collects word l of the group's 32
 #pragma unroll 1
@@ -557,7 +569,7 @@ membership_tma_kernel(const double* __restrict__ g_rows, const RowF32* __restric
                 if ((lane >> 2) == sg * TPS + t) acc = word;
             }
         }
-        const int64_t w0 = group * sink.stride * (kGroup / 32) + lane;
+        const int64_t w0 = slot_off + group * sink.stride * (kGroup / 32) + lane;
 #pragma unroll
         for (int d = 0; d < kMaxPeers; ++d)
             if (d < sink.n) sink.dst[d][w0] = acc;
@@ -681,6 +693,8 @@ membership_grid_kernel(const double* __restrict__ g_rows, const RowF32* __restri
         sink.dst[0] = bits;
         sink.n = 1;
         sink.stride = 1;
+        sink.step = nullptr;
+        sink.slot_words = 0;
         members += store_bits(sink, warp_base, n, in);
     }
     block_count(members, count);
@@ -742,7 +756,7 @@ rollout_kernel(const double* __restrict__ g_data, int s, int rin, int k_steps, i
         }
         const uint32_t word = __ballot_sync(0xffffffffu, in);
         if ((threadIdx.x & 31) == 0 && i < n) {
-            const int64_t wg = sink_word(sink, i >> 5);
+            const int64_t wg = sink_word(sink, i >> 5) + sink_slot_offset(sink);
 #pragma unroll
             for (int d = 0; d < kMaxPeers; ++d)
                 if (d < sink.n) sink.dst[d][wg] = word;
@@ -1422,14 +1436,16 @@ static int shard_sink(ShardWindow* W, int64_t n_local, int64_t first_sample, int
     const unsigned long long step = W->step + 1;
     sink->n = W->world;
     sink->stride = group_stride;
-    for (int r = 0; r < W->world; ++r) sink->dst[r] = W->bits(r, (int)(step & 1ull)) + (first_sample >> 5);
+    sink->step = W->d_local_count + 3;
+    sink->slot_words = W->words_pad;
+    for (int r = 0; r < W->world; ++r) sink->dst[r] = W->bits(r, 0) + (first_sample >> 5);
     *step_out = step;
     return CARMPC_OK;
 }
 
 int carmpc_membership_bitset_sharded(void* polytope, void* shard, const double* d_x, const double* d_y, const double* d_psi,
                                      const double* d_v, int64_t n_local, int64_t first_sample, int64_t group_stride, int mode,
-                                     int64_t* d_total_count, void* stream) {
+                                     int64_t* d_total_count, int defer_wait, void* stream) {
     Polytope* P = check_handle<Polytope>(polytope, kPolytope);
     CARMPC_REQUIRE(P != nullptr, "not a polytope handle");
     ShardWindow* W = check_handle<ShardWindow>(shard, kShard);
@@ -1445,18 +1461,22 @@ int carmpc_membership_bitset_sharded(void* polytope, void* shard, const double* 
         rc = tune_row_order(P, d_x, d_y, d_psi, d_v, n_local, st);
         if (rc != CARMPC_OK) return rc;
     }
-    CARMPC_CUDA(cudaMemsetAsync(W->d_local_count, 0, sizeof(unsigned long long), st));
     rc = launch_membership(P, d_x, d_y, d_psi, d_v, n_local, sink, W->d_local_count, W->d_local_count + 1, mode, st);
     if (rc != CARMPC_OK) return rc;
-    rc = shard_exchange_launch(W, step, d_total_count, st);
+    CARMPC_REQUIRE(!W->pending, "the previous step of this window was published but never waited for (carmpc_shard_wait)");
+    rc = shard_publish_launch(W, st);
     if (rc != CARMPC_OK) return rc;
-    W->step = step;
+    if (!defer_wait) {
+        rc = shard_wait_launch(W, d_total_count, st);
+        if (rc != CARMPC_OK) return rc;
+    }
+    W->step = step;                 // (calls made through this library; graph replays advance only the device counter)
     return CARMPC_OK;
 }
 
 int carmpc_rollout_bitset_sharded(void* rollout, void* shard, const double* d_x, const double* d_y, const double* d_psi,
                                   const double* d_v, int64_t n_local, int64_t first_sample, int64_t group_stride,
-                                  int64_t* d_total_count, void* stream) {
+                                  int64_t* d_total_count, int defer_wait, void* stream) {
     Rollout* R = check_handle<Rollout>(rollout, kRollout);
     CARMPC_REQUIRE(R != nullptr, "not a rollout handle");
     ShardWindow* W = check_handle<ShardWindow>(shard, kShard);
@@ -1471,11 +1491,15 @@ int carmpc_rollout_bitset_sharded(void* rollout, void* shard, const double* d_x,
         rc = tune_rollout_order(R, d_x, d_y, d_psi, d_v, n_local, st);
         if (rc != CARMPC_OK) return rc;
     }
-    CARMPC_CUDA(cudaMemsetAsync(W->d_local_count, 0, sizeof(unsigned long long), st));
     rc = launch_rollout(R, d_x, d_y, d_psi, d_v, n_local, sink, nullptr, W->d_local_count, W->d_local_count + 1, st);
     if (rc != CARMPC_OK) return rc;
-    rc = shard_exchange_launch(W, step, d_total_count, st);
+    CARMPC_REQUIRE(!W->pending, "the previous step of this window was published but never waited for (carmpc_shard_wait)");
+    rc = shard_publish_launch(W, st);
     if (rc != CARMPC_OK) return rc;
+    if (!defer_wait) {
+        rc = shard_wait_launch(W, d_total_count, st);
+        if (rc != CARMPC_OK) return rc;
+    }
     W->step = step;
     return CARMPC_OK;
 }

@@ -3,7 +3,8 @@
 // north_star gathers the membership bitsets of the ranks over NVLink.  Instead of a separate collective after the scan,
 // the scan kernel of every rank stores its bitset words directly into all ranks' windows (peer-mapped device memory:
 // CUDA IPC between the one-process-per-GPU ranks, plain pointers inside one process), 128 bytes per warp store; what is
-// left of the "all-gather" is one flag per rank.  The exchange kernel below is that flag protocol:
+// left of the "all-gather" is one flag per rank.  The two one-warp kernels below are that flag protocol (publish never
+// blocks; wait does):
 //     counts[slot][rank] <- my member count      (relaxed system-scope store into every window)
 //     flags[rank]        <- step                 (release, system scope, after a system fence)
 //     wait until flags[q] >= step for every q    (acquire, system scope, in my own window)
@@ -31,11 +32,10 @@ struct ExchangeArgs {
     long long* peer_counts[kShardMaxWorld];
     const unsigned long long* local_flags;
     const long long* local_counts;
-    const unsigned long long* local_count;
+    unsigned long long* local_count;       // [0] count (re-armed here), [3] completed steps (advanced here)
     int* error_word;
     long long* total;
-    unsigned long long step;
-    int rank, world, slot;
+    int rank, world;
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -52,16 +52,27 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
-__global__ void __launch_bounds__(32) shard_exchange_kernel(const ExchangeArgs a) {
+// publish: my member count, then my flag, into every rank's window (never blocks)
+__global__ void __launch_bounds__(32) shard_publish_kernel(const ExchangeArgs a) {
     const int lane = threadIdx.x;
+    const unsigned long long step = a.local_count[3] + 1ull;
+    const int slot = (int)(step & 1ull);
     if (lane < a.world) {
-        const long long mine = (long long)*a.local_count;
-        asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(a.peer_counts[lane] + a.slot * kShardMaxWorld + a.rank), "l"(mine) : "memory");
+        const long long mine = (long long)a.local_count[0];
+        asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(a.peer_counts[lane] + slot * kShardMaxWorld + a.rank), "l"(mine) : "memory");
         __threadfence_system();
-        st_release_sys(a.peer_flags[lane] + a.rank, a.step);
-        // every rank's flag arrives in this rank's own window
+        st_release_sys(a.peer_flags[lane] + a.rank, step);
+    }
+}
+
+// wait: every rank's flag arrives in this rank's own window; then sum the counts, advance the step, re-arm the count
+__global__ void __launch_bounds__(32) shard_wait_kernel(const ExchangeArgs a) {
+    const int lane = threadIdx.x;
+    const unsigned long long step = a.local_count[3] + 1ull;
+    const int slot = (int)(step & 1ull);
+    if (lane < a.world) {
         const unsigned long long t0 = global_ns();
-        while (ld_acquire_sys(a.local_flags + lane) < a.step) {
+        while (ld_acquire_sys(a.local_flags + lane) < step) {
             if (global_ns() - t0 > 5000000000ull) {          // 5 s: a peer died; fail loudly instead of hanging the GPU
                 atomicExch(a.error_word, 1 + lane);
                 break;
@@ -72,15 +83,19 @@ __global__ void __launch_bounds__(32) shard_exchange_kernel(const ExchangeArgs a
     __syncwarp();
     long long c = 0;
     if (lane < a.world)
-        asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(c) : "l"(a.local_counts + a.slot * kShardMaxWorld + lane) : "memory");
+        asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(c) : "l"(a.local_counts + slot * kShardMaxWorld + lane) : "memory");
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0 && a.total != nullptr) *a.total = c;
+    if (lane == 0) {
+        if (a.total != nullptr) *a.total = c;
+        a.local_count[0] = 0ull;               // re-armed for the next step's scan
+        a.local_count[3] = step;
+    }
 }
 
 }  // namespace
 
-int shard_exchange_launch(ShardWindow* W, unsigned long long step, int64_t* d_total, cudaStream_t st) {
+static ExchangeArgs exchange_args(ShardWindow* W, int64_t* d_total) {
     ExchangeArgs a;
     memset(&a, 0, sizeof(a));
     for (int r = 0; r < W->world; ++r) {
@@ -92,10 +107,21 @@ int shard_exchange_launch(ShardWindow* W, unsigned long long step, int64_t* d_to
     a.local_count = W->d_local_count;
     a.error_word = W->error_word();
     a.total = reinterpret_cast<long long*>(d_total);
-    a.step = step;
-    a.rank = W->rank; a.world = W->world; a.slot = (int)(step & 1ull);
-    shard_exchange_kernel<<<1, 32, 0, st>>>(a);
+    a.rank = W->rank; a.world = W->world;
+    return a;
+}
+
+int shard_publish_launch(ShardWindow* W, cudaStream_t st) {
+    shard_publish_kernel<<<1, 32, 0, st>>>(exchange_args(W, nullptr));
     CARMPC_CUDA(cudaGetLastError());
+    W->pending = true;
+    return CARMPC_OK;
+}
+
+int shard_wait_launch(ShardWindow* W, int64_t* d_total, cudaStream_t st) {
+    shard_wait_kernel<<<1, 32, 0, st>>>(exchange_args(W, d_total));
+    CARMPC_CUDA(cudaGetLastError());
+    W->pending = false;
     return CARMPC_OK;
 }
 
@@ -188,9 +214,19 @@ int carmpc_shard_connect_local(void* shard, void* const* peer_shards) {
 int carmpc_shard_result(void* shard, const uint32_t** d_bits, int64_t* h_steps) {
     ShardWindow* W = check_handle<ShardWindow>(shard, kShard);
     CARMPC_REQUIRE(W != nullptr, "not a shard window");
-    if (d_bits) *d_bits = W->bits(W->rank, (int)(W->step & 1ull));
-    if (h_steps) *h_steps = (int64_t)W->step;
+    // the step counter lives on the device (a captured graph replays steps without passing through this library)
+    unsigned long long step = 0;
+    CARMPC_CUDA(cudaMemcpy(&step, W->d_local_count + 3, sizeof(step), cudaMemcpyDeviceToHost));
+    if (d_bits) *d_bits = W->bits(W->rank, (int)(step & 1ull));
+    if (h_steps) *h_steps = (int64_t)step;
     return CARMPC_OK;
+}
+
+int carmpc_shard_wait(void* shard, int64_t* d_total_count, void* stream) {
+    ShardWindow* W = check_handle<ShardWindow>(shard, kShard);
+    CARMPC_REQUIRE(W != nullptr, "not a shard window");
+    CARMPC_REQUIRE(W->pending, "no published step is waiting for its peers (call a *_sharded function with defer_wait first)");
+    return shard_wait_launch(W, d_total_count, (cudaStream_t)stream);
 }
 
 int carmpc_shard_check(void* shard) {

@@ -20,9 +20,11 @@ struct ShardWindow : HandleBase {
     unsigned char* peer[kShardMaxWorld] = {nullptr};     // every rank's window as mapped here (peer[rank] == base)
     bool ipc_opened[kShardMaxWorld] = {false};
     bool connected = false;
-    unsigned long long step = 0;                         // completed collective steps (the same on every rank)
+    bool pending = false;                                // a step was published and not yet waited for
+    unsigned long long step = 0;                         // collective steps enqueued so far (host mirror of d_local_count[3])
     unsigned long long* d_local_count = nullptr;         // [0] member count of this rank's shard in the current step,
-                                                         // [1..2] work counters of the scan kernel (self-resetting)
+                                                         // [1..2] work counters of the scan kernel (self-resetting),
+                                                         // [3] completed collective steps (advanced by the exchange kernel)
     ~ShardWindow() override;
 
     unsigned long long* flags(int r) const { return reinterpret_cast<unsigned long long*>(peer[r]); }
@@ -33,7 +35,9 @@ struct ShardWindow : HandleBase {
     }
 };
 
-// publish this rank's count + flag for `step` to every rank, wait for every rank's flag, sum the counts
-int shard_exchange_launch(ShardWindow* W, unsigned long long step, int64_t* d_total, cudaStream_t st);
+// publish: this rank's count + flag of the next step into every rank's window (never blocks)
+int shard_publish_launch(ShardWindow* W, cudaStream_t st);
+// wait: for every rank's flag; sum the counts, advance the device-side step, re-arm the local count
+int shard_wait_launch(ShardWindow* W, int64_t* d_total, cudaStream_t st);
 
 }  // namespace carmpc

@@ -233,11 +233,15 @@ class PeerWindow:
             pass
 
 
-def contains_bits_sharded(evaluator, window: "PeerWindow", x, y, psi, v, mode: int = 1, total=None, stream=None):
+def contains_bits_sharded(evaluator, window: "PeerWindow", x, y, psi, v, mode: int = 1, total=None, stream=None,
+                          defer_wait: bool = False):
     """One collective step: membership (``TerminalSetEvaluator``) or rollout form (``RolloutEvaluator``) of this rank's
     shard (``window.local_index()``), bitset words written into every rank's window by the scan kernel itself, member counts
     and completion flags exchanged by a one-warp kernel.  ``total``: int64 CUDA tensor (1,) receiving the global
-    member count.  Nothing is synchronised; ``window.result_bits()`` is valid in stream order."""
+    member count.  Nothing is synchronised; ``window.result_bits()`` is valid in stream order.
+
+    ``defer_wait``: stop after publishing this rank's flag; ``wait_sharded(window, total)`` then enqueues the wait.  Needed
+    when ONE process drives several ranks: enqueue every rank's scan first, then every rank's wait."""
     import ctypes
     import torch
     from . import _capi
@@ -252,11 +256,22 @@ def contains_bits_sharded(evaluator, window: "PeerWindow", x, y, psi, v, mode: i
     st = ctypes.c_void_p(s.cuda_stream)
     if isinstance(evaluator, RolloutEvaluator):
         _capi.check(evaluator._lib.carmpc_rollout_bitset_sharded(evaluator._h, window._h, x.data_ptr(), y.data_ptr(),
-                                                                 psi.data_ptr(), v.data_ptr(), n, lo, stride, total.data_ptr(), st))
+                                                                 psi.data_ptr(), v.data_ptr(), n, lo, stride, total.data_ptr(),
+                                                                 int(defer_wait), st))
     else:
         _capi.check(evaluator._lib.carmpc_membership_bitset_sharded(evaluator._h, window._h, x.data_ptr(), y.data_ptr(),
                                                                     psi.data_ptr(), v.data_ptr(), n, lo, stride, mode,
-                                                                    total.data_ptr(), st))
+                                                                    total.data_ptr(), int(defer_wait), st))
+    return total
+
+
+def wait_sharded(window: "PeerWindow", total, stream=None):
+    """Second half of a collective step started with ``defer_wait=True`` (``carmpc_shard_wait``)."""
+    import ctypes
+    import torch
+    from . import _capi
+    s = torch.cuda.current_stream() if stream is None else stream
+    _capi.check(window._lib.carmpc_shard_wait(window._h, total.data_ptr(), ctypes.c_void_p(s.cuda_stream)))
     return total
 
 

@@ -135,13 +135,21 @@ int carmpc_shard_connect_local(void* shard, void* const* peer_shards /* world ha
  * holds the bitset of ALL n_total samples and *d_total_count (nullable, device int64) the member count over all ranks. */
 int carmpc_membership_bitset_sharded(void* polytope, void* shard, const double* d_x, const double* d_y,
                                      const double* d_psi, const double* d_v, int64_t n_local, int64_t first_sample,
-                                     int64_t group_stride, int mode, int64_t* d_total_count, void* stream);
+                                     int64_t group_stride, int mode, int64_t* d_total_count, int defer_wait, void* stream);
 int carmpc_rollout_bitset_sharded(void* rollout, void* shard, const double* d_x, const double* d_y,
                                   const double* d_psi, const double* d_v, int64_t n_local, int64_t first_sample,
-                                  int64_t group_stride, int64_t* d_total_count, void* stream);
+                                  int64_t group_stride, int64_t* d_total_count, int defer_wait, void* stream);
+/* A collective step is scan (+ stores into every window), publish (count + flag, never blocks) and wait (blocks on the
+ * device until every rank's flag has arrived).  defer_wait = 0: all three are enqueued by the *_sharded call (one
+ * process per GPU).  defer_wait = 1: the call stops after publish and carmpc_shard_wait enqueues the wait - for several
+ * ranks driven by ONE process, which must enqueue every rank's scan + publish before any rank's wait (kernels of
+ * different streams are not guaranteed to run concurrently, so a wait must never sit in front of a peer's publish). */
+int carmpc_shard_wait(void* shard, int64_t* d_total_count, void* stream);
 
 /* d_bits: the full bitset (ceil(n_total / 32) words, device memory of this rank) of the last completed step; it stays
- * valid until the second-next sharded call on this window.  h_steps: collective steps done so far. */
+ * valid until the second-next sharded call on this window.  h_steps: collective steps done so far.  Synchronous (the
+ * step counter lives in device memory: the launch arguments of a collective step never change, so a step can be captured
+ * in a CUDA graph and replayed). */
 int carmpc_shard_result(void* shard, const uint32_t** d_bits, int64_t* h_steps);
 /* Synchronous health check: fails if a peer never published its flag (the exchange kernel gives up after 5 s). */
 int carmpc_shard_check(void* shard);
