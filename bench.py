@@ -331,9 +331,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         for i in range(2):
             step(i)
         barrier()
-    launches = 0
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        barrier()
+        if distributed:
+            # the ranks leave the host barrier tens of microseconds apart, which is a sizeable part of K steps of ~0.1 ms:
+            # one more untimed collective step (its wait kernel is a device-side barrier) lines the GPUs up, and the
+            # start event is enqueued right behind it
+            step(0)
+        launches = 0
         start.record()
         for i in range(args.steps):
             step(i)
@@ -389,6 +395,35 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     s1.record()
     s1.synchronize()
     stream_ms = max_over_ranks(s0.elapsed_time(s1) / args.steps)
+
+    # ---- where a collective step spends its time (graph replays: no host in the loop) -------------------------------------
+    step_parts = None
+    if distributed and window is not None and graph is not None:
+        def replay_ms(fn, reps=100):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            for _ in range(3):
+                g.replay()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                g.replay()
+            b.record()
+            b.synchronize()
+            return max_over_ranks(a.elapsed_time(b) / reps)
+        t_scan = replay_ms(lambda: ev.contains_bits(x, y, psi, v, mode=args.mode, bits=bits[0], count=count))
+        # scan with the stores into every rank's window + publish, no wait (ranks run free): a second window keeps the
+        # protocol state of the timed one untouched
+        w2 = PeerWindow(n, layout=args.layout)
+        t_p2p = replay_ms(lambda: contains_bits_sharded(ev, w2, x, y, psi, v, mode=args.mode, total=total, defer_wait=True))
+        barrier()
+        t_full = replay_ms(lambda: contains_bits_sharded(ev, window, x, y, psi, v, mode=args.mode, total=total))
+        step_parts = {"scan_local_ms": t_scan, "scan_with_peer_stores_and_publish_ms": t_p2p, "full_step_ms": t_full,
+                      "note": "100 CUDA-graph replays each, max over ranks; full step = scan + peer stores + publish + wait for "
+                              "every rank's flag (a device-side barrier per step)"}
+        stream_ms = t_scan
 
     nccl_variant = None
     if distributed and window is not None:
@@ -576,7 +611,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "sharding": {"samples_per_gpu": n_local, "layout": layout, "gather": gather_mode, "window_error": window_error,
                          "step_launch": "CUDA graph replay (scan + exchange kernels captured once)" if graph is not None else "eager",
                          "scan_alone_ms": stream_ms, "step_overhead_ms": ms_total / args.steps - stream_ms,
-                         "verify": verify, "nccl_variant": nccl_variant,
+                         "step_parts": step_parts, "verify": verify, "nccl_variant": nccl_variant,
                          "kernel_mode": "fp32 screen + fp64 re-check" if args.mode else "fp64", "members": members},
             "e2e_grid": e2e_grid,
             "rollout": rollout,

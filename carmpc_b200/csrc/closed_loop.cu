@@ -127,6 +127,8 @@ extern "C" int carmpc_closed_loop(void* qp, int mode, const double* h_A, const d
     if (h_total_iters) *h_total_iters = 0;
     if (runs == 0) return CARMPC_OK;
     CARMPC_REQUIRE(d_x_init && d_final && d_fail_step, "null device pointer");
+    QPBusyGuard guard(q->busy);
+    CARMPC_REQUIRE(guard.acquired, "this QP handle is in use by another call (one call per handle at a time)");
     cudaStream_t st = (cudaStream_t)stream;
     LoopConst K;
     memset(&K, 0, sizeof(K));

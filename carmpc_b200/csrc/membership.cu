@@ -54,20 +54,38 @@ struct HostStage {
     unsigned long long* d_work = nullptr;                  // [2][2] work counters of the scan kernel, one pair per slot
     cudaStream_t streams[2] = {nullptr, nullptr};
     bool ready = false;
-    int init(bool with_first) {
+    int64_t cap = 0, first_cap = 0;                        // samples per slot the buffers are sized for
+    // Slots are sized to the call (a 60,000-point visualise_set grid takes 2 MB, not the 0.55 GB of two full chunks) and
+    // grow on demand up to kChunkSamples; a call that fits one chunk uses one slot.
+    int init(bool with_first, int64_t n) {
         if (!ready) {
-            for (int i = 0; i < 2; ++i) {
-                CARMPC_CUDA(cudaMalloc(&d_coord[i], sizeof(double) * 4 * kChunkSamples));
-                CARMPC_CUDA(cudaMalloc(&d_bits[i], sizeof(uint32_t) * (kChunkSamples / 32)));
-                CARMPC_CUDA(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
-            }
+            for (int i = 0; i < 2; ++i) CARMPC_CUDA(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
             CARMPC_CUDA(cudaMalloc(&d_count, sizeof(unsigned long long)));
             CARMPC_CUDA(cudaMalloc(&d_work, sizeof(unsigned long long) * 4));
             CARMPC_CUDA(cudaMemset(d_work, 0, sizeof(unsigned long long) * 4));
             ready = true;
         }
-        if (with_first && d_first[0] == nullptr)
-            for (int i = 0; i < 2; ++i) CARMPC_CUDA(cudaMalloc(&d_first[i], sizeof(int32_t) * kChunkSamples));
+        const int64_t need = std::min<int64_t>(kChunkSamples, (std::max<int64_t>(n, 1) + 1023) / 1024 * 1024);
+        const int slots = n > kChunkSamples ? 2 : 1;
+        if (need > cap || (slots == 2 && d_coord[1] == nullptr)) {
+            const int64_t sz = std::max(need, cap);
+            for (int i = 0; i < 2; ++i) {
+                cudaFree(d_coord[i]); cudaFree(d_bits[i]); cudaFree(d_first[i]);
+                d_coord[i] = nullptr; d_bits[i] = nullptr; d_first[i] = nullptr;
+            }
+            cap = 0; first_cap = 0;
+            for (int i = 0; i < slots; ++i) {
+                CARMPC_CUDA(cudaMalloc(&d_coord[i], sizeof(double) * 4 * sz));
+                CARMPC_CUDA(cudaMalloc(&d_bits[i], sizeof(uint32_t) * (sz / 32)));
+            }
+            cap = sz;
+        }
+        if (with_first && first_cap < cap) {
+            for (int i = 0; i < 2; ++i) { cudaFree(d_first[i]); d_first[i] = nullptr; }
+            for (int i = 0; i < 2; ++i)
+                if (d_coord[i] != nullptr) CARMPC_CUDA(cudaMalloc(&d_first[i], sizeof(int32_t) * cap));
+            first_cap = cap;
+        }
         return CARMPC_OK;
     }
     ~HostStage() {
@@ -915,9 +933,9 @@ static int launch_rollout(Rollout* R, const double* x, const double* y, const do
 template <class Launch>
 static int host_pipeline(HostStage& S, const double* h_x, const double* h_y, const double* h_psi, const double* h_v,
                          int64_t n, uint32_t* h_bits, int32_t* h_first, int64_t* h_count, Launch launch) {
-    int rc = S.init(h_first != nullptr);
+    int rc = S.init(h_first != nullptr, n);
     if (rc != CARMPC_OK) return rc;
-    const int64_t chunk = HostStage::kChunkSamples;
+    const int64_t chunk = S.cap;                           // = kChunkSamples whenever the call needs more than one chunk
     CARMPC_CUDA(cudaMemsetAsync(S.d_count, 0, sizeof(unsigned long long), S.streams[0]));
     CARMPC_CUDA(cudaStreamSynchronize(S.streams[0]));
     int slot = 0;

@@ -510,6 +510,8 @@ int carmpc_qp_solve_batch(void* qp, const double* d_x0, const double* h_xref, co
     CARMPC_REQUIRE(h_xref != nullptr, "h_xref");
     if (batch == 0) { q->last_total_iters = 0; q->last_launches = 0; return CARMPC_OK; }
     CARMPC_REQUIRE(d_x0 && d_status, "d_x0 and d_status are required");
+    QPBusyGuard guard(q->busy);
+    CARMPC_REQUIRE(guard.acquired, "this QP handle is in use by another call (one call per handle at a time)");
     q->use_records = 0;
     return q->solve(d_x0, batch, h_xref, d_c, nullptr, batch, d_u0, d_objective, d_status, d_iters, d_u_full, d_warm,
                     warm_in, warm_out, (cudaStream_t)stream);
@@ -525,6 +527,8 @@ int carmpc_qp_solve_seeded(void* qp, const double* d_x0, const double* h_xref, c
     if (h_seeded) *h_seeded = 0;
     if (batch == 0) { q->last_total_iters = 0; q->last_launches = 0; return CARMPC_OK; }
     CARMPC_REQUIRE(d_x0 && d_status && d_seed, "d_x0, d_status and d_seed are required");
+    QPBusyGuard guard(q->busy);
+    CARMPC_REQUIRE(guard.acquired, "this QP handle is in use by another call (one call per handle at a time)");
     const int rc = q->solve_seeded(d_x0, batch, h_xref, d_c, d_seed, d_u0, d_objective, d_status, d_iters, d_u_full,
                                    (cudaStream_t)stream);
     if (rc == CARMPC_OK && h_seeded) *h_seeded = q->last_reused;
@@ -539,6 +543,8 @@ int carmpc_qp_solve_host(void* qp, const double* h_x0, const double* h_xref, con
     if (batch == 0) return CARMPC_OK;
     CARMPC_REQUIRE(h_x0 && h_xref && h_status, "null host pointer");
     if (q->host_only) { set_error("carmpc_qp: this handle was created without a CUDA device; there is no CPU solver"); return CARMPC_ERR_CUDA; }
+    QPBusyGuard guard(q->busy);
+    CARMPC_REQUIRE(guard.acquired, "this QP handle is in use by another call (one call per handle at a time)");
     const int n = q->host.n;
     int rc = q->ensure_io(batch, h_u_full != nullptr);
     if (rc != CARMPC_OK) return rc;
@@ -589,6 +595,8 @@ int carmpc_qp_map_host(void* qp, const double* h_axes, const int32_t dims[4], co
     CARMPC_REQUIRE(seen == 15, "axis_to_state must be a permutation of 0..3");
     CARMPC_REQUIRE(n < (int64_t)1 << 31, "grid too large for one call");
     if (h_seeded) *h_seeded = 0;
+    QPBusyGuard guard(q->busy);
+    CARMPC_REQUIRE(guard.acquired, "this QP handle is in use by another call (one call per handle at a time)");
     int rc = q->ensure_io(n, false);
     if (rc != CARMPC_OK) return rc;
     if (q->io_axes == nullptr) CARMPC_CUDA(cudaMalloc(&q->io_axes, sizeof(double) * 4 * 4096));

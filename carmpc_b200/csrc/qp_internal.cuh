@@ -16,6 +16,7 @@
 //                    signs (a KKT certificate), repairs the set a few times, and produces u to ~1e-10.
 #pragma once
 
+#include <atomic>
 #include <vector>
 
 #include "common.cuh"
@@ -206,6 +207,12 @@ int qp_host_setup(int n, int m, int k, const double* H, const double* F, const d
                   const carmpc_qp_opts& opts, QPHost* out);
 
 struct QPHandle;
+struct QPBusyGuard {
+    std::atomic<bool>* flag;
+    bool acquired;
+    explicit QPBusyGuard(std::atomic<bool>& f) : flag(&f) { bool expect = false; acquired = f.compare_exchange_strong(expect, true); }
+    ~QPBusyGuard() { if (acquired) flag->store(false); }
+};
 int admm_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st);
 int polish_launch(QPHandle* q, const PolishBatch& b, cudaStream_t st);
 // infeasible anchors of a seeded map: turn the ADMM dual iterate into an exact Farkas certificate, affine in x0
@@ -267,6 +274,9 @@ struct QPHandle : HandleBase {
     int64_t last_total_iters = 0, last_launches = 0, last_second_pass = 0, last_fallback = 0;
     int sm = 148;
     bool host_only = false;
+    // per-call state lives in the handle (workspace, counters): one call at a time.  A second call entering while one is
+    // in flight (another host thread) is refused instead of corrupting both.
+    std::atomic<bool> busy{false};
     ~QPHandle() override;
     int ensure_workspace(int64_t batch);
     // full solve on device buffers (all pointers device; any output may be null except status)

@@ -42,18 +42,33 @@ def default_seed_block(axes: Sequence[np.ndarray], max_step=(0.8, 0.5, 0.0, 0.0)
 
 
 def feasibility_map(controller, axes: Sequence[np.ndarray], x_ref=None, batch_solver=None, seeded: bool = True,
-                    block=None) -> np.ndarray:
+                    block=None, undecided: str = "raise") -> np.ndarray:
     """Feasibility flag of every point of the tensor grid ``axes`` (C order, x slowest ... v fastest): True where the
     controller's QP is feasible.  Solved on the GPU (no CPU fallback).  ``seeded`` (default) solves only a sub-lattice
     of anchors cold and certifies every other point from its anchor's active set / Farkas certificate
-    (``carmpc_qp_solve_seeded``: same flags, 1.7 - 4.6 x faster on 10^6-point maps)."""
+    (``carmpc_qp_solve_seeded``: same flags, 1.7 - 4.6 x faster on 10^6-point maps).
+
+    Every True is backed by a float64 KKT certificate and every False by a float64 Farkas certificate.  A point the
+    solver could prove neither way (status 2: degenerate states within ~1e-7 of the boundary of the region) is not
+    silently counted as outside: ``undecided`` = "raise" (default, as ``MPC.step`` does for the same status),
+    "outside" or "inside"."""
     from .batch import BatchQP
     bq = batch_solver if batch_solver is not None else BatchQP.from_controller(controller)
     blk = None
     if seeded and bq.opts.polish:
         blk = tuple(int(v) for v in block) if block is not None else default_seed_block(axes)
     res = bq.solve_map_host(axes, block=blk, x_ref=x_ref, want_u0=False, want_objective=False)
-    return res.status == 0
+    flags = res.status == 0
+    n_undecided = int((res.status == 2).sum())
+    if n_undecided:
+        if undecided == "raise":
+            raise RuntimeError(f"feasibility_map: {n_undecided} of {len(flags)} grid points are undecided (QP status 2); "
+                               "pass undecided='outside' or 'inside' to classify them")
+        if undecided == "inside":
+            flags = flags | (res.status == 2)
+        elif undecided != "outside":
+            raise ValueError("undecided must be 'raise', 'outside' or 'inside'")
+    return flags
 
 
 def boundary_layer(flags: np.ndarray, shape: Sequence[int]) -> np.ndarray:
