@@ -1,6 +1,9 @@
 // Error reporting, handle destruction and the device micro-benchmarks of the C ABI.
 #include <stdarg.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace carmpc {
@@ -12,6 +15,45 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_error, sizeof(g_error), fmt, ap);
     va_end(ap);
+}
+
+namespace {
+struct KernelConfigEntry {
+    const void* fn; int device; int threads; size_t smem; int per_sm;
+};
+std::mutex g_kc_mutex;
+std::vector<KernelConfigEntry> g_kc_entries;
+struct KernelAttrEntry { const void* fn; int device; size_t max_smem; };
+std::vector<KernelAttrEntry> g_ka_entries;
+}  // namespace
+
+int kernel_config(const void* fn, int threads, size_t smem, int* per_sm) {
+    int dev = 0;
+    CARMPC_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_kc_mutex);
+    bool attr_ok = false;
+    for (KernelAttrEntry& a : g_ka_entries)
+        if (a.fn == fn && a.device == dev) {
+            if (a.max_smem < smem) {
+                CARMPC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                a.max_smem = smem;
+            }
+            attr_ok = true;
+            break;
+        }
+    if (!attr_ok) {
+        CARMPC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        g_ka_entries.push_back({fn, dev, smem});
+    }
+    if (per_sm == nullptr) return CARMPC_OK;
+    for (const KernelConfigEntry& e : g_kc_entries)
+        if (e.fn == fn && e.device == dev && e.threads == threads && e.smem == smem) { *per_sm = e.per_sm; return CARMPC_OK; }
+    int occ = 0;
+    CARMPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem));
+    if (occ < 1) occ = 1;
+    g_kc_entries.push_back({fn, dev, threads, smem, occ});
+    *per_sm = occ;
+    return CARMPC_OK;
 }
 
 int sm_count() {

@@ -89,9 +89,11 @@ loop_advance_kernel(const LoopConst K, int64_t runs, double* __restrict__ x, dou
 
 // take the QP results of the live runs: new input, or mark the run as failed at this step
 __global__ void __launch_bounds__(256)
-loop_apply_kernel(int64_t runs, int step, const int* __restrict__ live_list, int live, const double* __restrict__ u0,
-                  const int32_t* __restrict__ status, double* __restrict__ u_prev, int32_t* __restrict__ fail_step) {
+loop_apply_kernel(int64_t runs, int step, const int* __restrict__ live_list, int live, const int* __restrict__ live_dev,
+                  const double* __restrict__ u0, const int32_t* __restrict__ status, double* __restrict__ u_prev,
+                  int32_t* __restrict__ fail_step) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (live_dev != nullptr) live = min(live, *live_dev);
     if (q >= live) return;
     const int i = live_list[q];
     if (status[i] == CARMPC_QP_SOLVED) {
@@ -123,6 +125,7 @@ extern "C" int carmpc_closed_loop(void* qp, int mode, const double* h_A, const d
     CARMPC_REQUIRE(h_A && h_B && h_xref, "null model pointer");
     CARMPC_REQUIRE(mode == 0 || (h_C && h_L), "output feedback needs C and L");
     CARMPC_REQUIRE(steps >= 0 && runs >= 0 && runs < (int64_t)1 << 31, "steps / runs");
+    CARMPC_REQUIRE(warm_start >= 0 && warm_start <= 2, "warm_start must be 0, 1 or 2");
     CARMPC_REQUIRE(dt > 0 && l1 > 0, "dt, l1");
     if (h_total_iters) *h_total_iters = 0;
     if (runs == 0) return CARMPC_OK;
@@ -170,6 +173,17 @@ extern "C" int carmpc_closed_loop(void* qp, int mode, const double* h_A, const d
         TRY(cudaMemsetAsync(live_count, 0, sizeof(int), st));
         loop_advance_kernel<<<blocks, 256, 0, st>>>(K, runs, x, xhat, u_prev, d_fail_step, est, live_list, live_count,
                                                     d_traj ? d_traj + (size_t)k * 4 * runs : nullptr);
+        if (warm_valid && warm_start != 2) {
+            // Every later step only enqueues: the number of live runs, of runs whose active set changed, of second-pass and
+            // fallback samples all stay on the device (kernels sized for the upper bound read them there), so the steps
+            // run back to back on the GPU without a host round trip.
+            rc = q->solve_enqueue(est, runs, h_xref, live_list, live_count, runs, u0, status, warm, st);
+            if (rc != CARMPC_OK) { q->defer_total = 0; cleanup(); return rc; }
+            loop_apply_kernel<<<blocks, 256, 0, st>>>(runs, k, live_list, (int)runs, live_count, u0, status, u_prev, d_fail_step);
+            if (d_u_log)
+                TRY(cudaMemcpyAsync(d_u_log + (size_t)k * 2 * runs, u_prev, sizeof(double) * 2 * runs, cudaMemcpyDeviceToDevice, st));
+            continue;
+        }
         int live = 0;
         TRY(cudaMemcpyAsync(&live, live_count, sizeof(int), cudaMemcpyDeviceToHost, st));
         TRY(cudaStreamSynchronize(st));
@@ -179,7 +193,7 @@ extern "C" int carmpc_closed_loop(void* qp, int mode, const double* h_A, const d
                           warm_valid ? 1 : 0, warm ? 1 : 0, st, warm_valid ? 1 : 0);
             if (rc != CARMPC_OK) { q->defer_total = 0; cleanup(); return rc; }
             warm_valid = warm != nullptr;
-            loop_apply_kernel<<<(live + 255) / 256, 256, 0, st>>>(runs, k, live_list, live, u0, status, u_prev, d_fail_step);
+            loop_apply_kernel<<<(live + 255) / 256, 256, 0, st>>>(runs, k, live_list, live, nullptr, u0, status, u_prev, d_fail_step);
         }
         if (d_u_log)      // the input each run will apply at the next plant step (unchanged for stopped runs)
             TRY(cudaMemcpyAsync(d_u_log + (size_t)k * 2 * runs, u_prev, sizeof(double) * 2 * runs, cudaMemcpyDeviceToDevice, st));

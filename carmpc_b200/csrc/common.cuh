@@ -43,6 +43,11 @@ void set_error(const char* fmt, ...);
 
 int sm_count();
 
+// Dynamic shared-memory opt-in and occupancy of a kernel, cached per (function, device, size): both are host-side
+// driver calls of several microseconds, which adds up for pipelines of many small launches (closed-loop steps).
+// per_sm (nullable) receives the resident CTAs per SM.
+int kernel_config(const void* fn, int threads, size_t smem, int* per_sm);
+
 template <class T>
 inline T* check_handle(void* h, HandleKind kind) {
     if (h == nullptr) return nullptr;

@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
     __syncthreads();
 
     const float eps_abs = T.eps_abs * Bq.eps_scale, eps_rel = T.eps_rel * Bq.eps_scale;
+    const int q_count = Bq.count_dev != nullptr ? min(*Bq.count_dev, Bq.count) : Bq.count;
 
     // One ADMM iteration.  CHECK: also accumulate the residual norms and run the infeasibility-certificate product.
     auto iteration = [&](auto check_tag) {
@@ -496,7 +497,7 @@ __global__ void __launch_bounds__(kAdmmThreads * H, 1) admm_kernel(const AdmmTab
             int init = 0;
             if (sm.slot_pos[tid] >= 0) {
                 const int qi = sm.misc[1] + sm.slot_pos[tid];
-                if (qi < Bq.count) {
+                if (qi < q_count) {
                     const int sample = Bq.idx_list ? Bq.idx_list[qi] : qi;
                     double x[4];
 #pragma unroll
@@ -627,11 +628,11 @@ int launch_variant(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
             set_error("admm_launch: matrices of this size class never fit shared memory");
             return CARMPC_ERR_UNSUPPORTED;
         } else {
-            CARMPC_CUDA(cudaFuncSetAttribute(admm_kernel<S, H, GA, GB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            { const int rc = kernel_config(reinterpret_cast<const void*>(admm_kernel<S, H, GA, GB, true>), kAdmmThreads * H, smem, nullptr); if (rc != CARMPC_OK) return rc; }
             admm_kernel<S, H, GA, GB, true><<<blocks, kAdmmThreads * H, smem, st>>>(q->admm, b);
         }
     } else {
-        CARMPC_CUDA(cudaFuncSetAttribute(admm_kernel<S, H, GA, GB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { const int rc = kernel_config(reinterpret_cast<const void*>(admm_kernel<S, H, GA, GB, false>), kAdmmThreads * H, smem, nullptr); if (rc != CARMPC_OK) return rc; }
         admm_kernel<S, H, GA, GB, false><<<blocks, kAdmmThreads * H, smem, st>>>(q->admm, b);
     }
     CARMPC_CUDA(cudaGetLastError());
@@ -646,7 +647,7 @@ int admm_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
     // SM a full tile runs narrower tiles, whose iterations are proportionally shorter.
     const int smax = q->host.samples_per_lane;
     int S = 1;
-    while (S * 2 <= smax && (int64_t)b.count >= (int64_t)32 * (S * 2) * q->sm) S *= 2;
+    while (!b.narrow && S * 2 <= smax && (int64_t)b.count >= (int64_t)32 * (S * 2) * q->sm) S *= 2;
     const int key = q->host.ga_per_warp * 100 + q->host.gb_per_warp * 10 + S;
     switch (key) {
         // n <= 40: 16 warps as two sample-halves of 64 (measured equal to 8 warps x 4 samples per lane, with and without

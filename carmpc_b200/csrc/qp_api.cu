@@ -307,6 +307,69 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
     return CARMPC_OK;
 }
 
+int QPHandle::solve_enqueue(const double* d_x0, int64_t stride, const double* xref, const int* d_idx, const int* d_count,
+                            int64_t max_count, double* d_u0, int32_t* d_status, float* d_warm, cudaStream_t st) {
+    if (host_only) { set_error("carmpc_qp: this handle was created without a CUDA device; there is no CPU solver"); return CARMPC_ERR_CUDA; }
+    if (!host.opts.polish) { set_error("solve_enqueue needs the float64 polish (opts.polish = 1)"); return CARMPC_ERR_INVALID; }
+    int rc = ensure_workspace(stride);
+    if (rc != CARMPC_OK) return rc;
+    CARMPC_CUDA(cudaMemsetAsync(ws_counters, 0, sizeof(int) * 16, st));
+    const int cap = (int)max_count;
+    int* status = d_status;
+
+    PolishBatch pb;
+    memset(&pb, 0, sizeof(pb));
+    pb.x0 = d_x0; pb.stride = stride;
+    for (int c = 0; c < 4; ++c) pb.xref[c] = xref[c];
+    pb.sign = ws_sign; pb.u_admm = ws_u; pb.status = status; pb.u0 = d_u0; pb.polished = ws_polished;
+    pb.rounds = -1; pb.stats = ws_polish_stats; pb.sign_out = ws_sign;
+
+    // 1. the active set certified at the previous step, straight into the float64 polish
+    PolishBatch p0 = pb;
+    p0.idx_list = d_idx; p0.count = cap; p0.count_dev = d_count;
+    p0.rounds = 4; p0.final_pass = 0; p0.n_failed = ws_counters + 5; p0.failed_list = ws_failed0;
+    p0.precheck = 1; p0.Px = admm.Px; p0.Pc = admm.Pc; p0.pre_lo = admm.pre_lo; p0.pre_hi = admm.pre_hi; p0.kpre = admm.kpre;
+    p0.iters_out = ws_iters;
+    rc = polish_launch(this, p0, st);
+    if (rc != CARMPC_OK) return rc;
+
+    // 2. ADMM (warm-started from the previous step's state) for the runs whose set changed, then the polish
+    AdmmBatch ab;
+    memset(&ab, 0, sizeof(ab));
+    ab.x0 = d_x0; ab.stride = stride;
+    for (int c = 0; c < 4; ++c) ab.xref[c] = xref[c];
+    ab.idx_list = ws_failed0; ab.count = cap; ab.count_dev = ws_counters + 5; ab.narrow = 1; ab.next = ws_counters + 0;
+    ab.sign = ws_sign; ab.u_admm = ws_u; ab.status = status; ab.iters = ws_iters;
+    ab.warm = d_warm; ab.warm_in = 1; ab.warm_out = 1;
+    ab.total_iters = ws_total_iters; ab.eps_scale = 1.f; ab.max_iter = host.opts.max_iter;
+    rc = admm_launch(this, ab, st);
+    if (rc != CARMPC_OK) return rc;
+    pb.idx_list = ws_failed0; pb.count = cap; pb.count_dev = ws_counters + 5;
+    pb.n_failed = ws_counters + 1; pb.failed_list = ws_failed; pb.final_pass = 0;
+    rc = polish_launch(this, pb, st);
+    if (rc != CARMPC_OK) return rc;
+    rc = farkas_verify_launch(this, ws_failed0, cap, status, d_warm, d_x0, stride, nullptr, xref, ws_failed, ws_counters + 1, st,
+                              ws_counters + 5);
+    if (rc != CARMPC_OK) return rc;
+
+    // 3. second pass (tighter) for what is still open, then the float64 fallback: all sized on the device, almost always empty
+    ab.idx_list = ws_failed; ab.count_dev = ws_counters + 1; ab.next = ws_counters + 2; ab.eps_scale = 0.01f;
+    ab.iters_accumulate = 1; ab.write_u = 1;
+    rc = admm_launch(this, ab, st);
+    if (rc != CARMPC_OK) return rc;
+    pb.idx_list = ws_failed; pb.count_dev = ws_counters + 1; pb.n_failed = ws_counters + 3; pb.final_pass = 1;
+    rc = polish_launch(this, pb, st);
+    if (rc != CARMPC_OK) return rc;
+    rc = farkas_decide_launch(this, ws_failed, cap, status, d_warm, d_x0, stride, d_u0, nullptr, nullptr, ws_polished, st,
+                              ws_counters + 1);
+    if (rc != CARMPC_OK) return rc;
+    rc = farkas_verify_launch(this, ws_failed, cap, status, d_warm, d_x0, stride, nullptr, xref, ws_overflow, ws_counters + 13, st,
+                              ws_counters + 1);
+    if (rc != CARMPC_OK) return rc;
+    int handled = 0;
+    return exact_fallback(this, pb, ws_failed, cap, d_warm, ws_iters, st, &handled, ws_counters + 1);
+}
+
 int QPHandle::solve_seeded(const double* d_x0, int64_t batch, const double* xref, const double* d_c, const int* d_seed,
                            double* d_u0, double* d_objective, int32_t* d_status, int32_t* d_iters, double* d_u_full,
                            cudaStream_t st) {

@@ -42,14 +42,16 @@ __device__ __forceinline__ double clampd(double w, double lo, double hi) { retur
 
 // samples of `list` that are still unproven after the second pass: out of iterations, "infeasible" without a float64
 // certificate, or "solved" without a KKT certificate
-__global__ void collect_unproven_kernel(const int* __restrict__ list, int count, const int* __restrict__ status,
-                                        const int8_t* __restrict__ polished, int* __restrict__ out, int* __restrict__ n_out) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= count) return;
-    const int s = list[q];
-    const int st = status[s];
-    if (st == CARMPC_QP_MAX_ITER || st == kStatusNeedsMoreAdmm || (st == CARMPC_QP_SOLVED && polished[s] == 0))
-        out[atomicAdd(n_out, 1)] = s;
+__global__ void collect_unproven_kernel(const int* __restrict__ list, int count, const int* __restrict__ count_dev,
+                                        const int* __restrict__ status, const int8_t* __restrict__ polished,
+                                        int* __restrict__ out, int* __restrict__ n_out) {
+    if (count_dev != nullptr) count = min(count, *count_dev);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
+        const int s = list[q];
+        const int st = status[s];
+        if (st == CARMPC_QP_MAX_ITER || st == kStatusNeedsMoreAdmm || (st == CARMPC_QP_SOLVED && polished[s] == 0))
+            out[atomicAdd(n_out, 1)] = s;
+    }
 }
 
 // sum_k M[k * ld + col] * x[k], four independent chains (the tables come from L1 / L2: latency, not throughput)
@@ -167,7 +169,7 @@ __device__ __forceinline__ bool exact_farkas(const PolishTables& T, const ExactW
 // must pass the exact test; a violated u-independent row is a proof by itself.  Unverified samples re-enter the second
 // pass (status kStatusNeedsMoreAdmm, appended to `failed`).
 struct VerifyArgs {
-    const int* list; int count;
+    const int* list; int count; const int* count_dev;
     const double* x0; int64_t stride; const double* cdist; double xref[4];
     const float* warm; int* status;
     const double* Px; const double* Pc; const double* pre_lo; const double* pre_hi; int kpre;
@@ -181,7 +183,8 @@ __global__ void __launch_bounds__(kExactThreads) verify_kernel(const PolishTable
     const int n = T.n, m = T.m, mt = T.mt;
     const ExactWs S(reinterpret_cast<double*>(smem_raw) + (size_t)warp * ExactWs::doubles(n, mt), n, mt);
     const int gw = blockIdx.x * (kExactThreads / 32) + warp, nw = gridDim.x * (kExactThreads / 32);
-    for (int q = gw; q < A.count; q += nw) {
+    const int v_count = A.count_dev != nullptr ? min(*A.count_dev, A.count) : A.count;
+    for (int q = gw; q < v_count; q += nw) {
         const int sample = A.list ? A.list[q] : q;
         if (A.status[sample] != CARMPC_QP_INFEASIBLE) continue;
         double x0[4], dx[4];
@@ -311,20 +314,25 @@ static size_t exact_smem(int n, int mt) { return sizeof(double) * (kExactThreads
 // After the second pass: everything in `d_list` that is still unproven goes through the float64 ADMM; converged samples
 // get one more polish (strict: no certificate -> CARMPC_QP_MAX_ITER).  Returns the number of samples handled.
 int exact_fallback(QPHandle* q, const PolishBatch& pb_final, const int* d_list, int count, float* d_warm, int* d_iters,
-                   cudaStream_t st, int* h_handled) {
+                   cudaStream_t st, int* h_handled, const int* d_count) {
     *h_handled = 0;
     if (count <= 0) return CARMPC_OK;
     int* n_unproven = q->ws_counters + 11;
     CARMPC_CUDA(cudaMemsetAsync(n_unproven, 0, sizeof(int), st));
-    collect_unproven_kernel<<<(count + 255) / 256, 256, 0, st>>>(d_list, count, pb_final.status, q->ws_polished, q->ws_unproven, n_unproven);
+    collect_unproven_kernel<<<std::min((count + 255) / 256, 64), 256, 0, st>>>(d_list, count, d_count, pb_final.status, q->ws_polished,
+                                                                          q->ws_unproven, n_unproven);
     int n = 0;
-    CARMPC_CUDA(cudaMemcpyAsync(&n, n_unproven, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CARMPC_CUDA(cudaStreamSynchronize(st));
-    if (n == 0) return CARMPC_OK;
+    if (d_count == nullptr) {
+        CARMPC_CUDA(cudaMemcpyAsync(&n, n_unproven, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CARMPC_CUDA(cudaStreamSynchronize(st));
+        if (n == 0) return CARMPC_OK;
+    } else {
+        n = std::min(count, 4 * q->sm * 2);        // device-sized: a fixed small grid, the kernels read the count themselves
+    }
     *h_handled = n;
     ExactArgs a;
     memset(&a, 0, sizeof(a));
-    a.list = q->ws_unproven; a.count_dev = n_unproven; a.count_max = n;
+    a.list = q->ws_unproven; a.count_dev = n_unproven; a.count_max = d_count == nullptr ? n : count;
     a.x0 = pb_final.x0; a.stride = pb_final.stride; a.cdist = pb_final.cdist;
     for (int c = 0; c < 4; ++c) a.xref[c] = pb_final.xref[c];
     a.warm = d_warm; a.sign = q->ws_sign; a.status = pb_final.status; a.iters = d_iters;
@@ -335,31 +343,31 @@ int exact_fallback(QPHandle* q, const PolishBatch& pb_final, const int* d_list, 
     const double macs = 2.0 * q->polish.m * nn + (double)nn * nn;
     a.max_iter = (int)std::max(1000.0, std::min(5000.0, 4.0e8 / std::max(1.0, macs)));
     const size_t smem = exact_smem(nn, mt);
-    CARMPC_CUDA(cudaFuncSetAttribute(exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int rc = kernel_config(reinterpret_cast<const void*>(exact_kernel), kExactThreads, smem, nullptr); if (rc != CARMPC_OK) return rc; }
     const int blocks = std::max(1, std::min((n + 3) / 4, q->sm * 2));
     exact_kernel<<<blocks, kExactThreads, smem, st>>>(q->polish, q->exact, a);
     CARMPC_CUDA(cudaGetLastError());
     // one more float64 polish from the float64 active sets; strict: an uncertified sample becomes "undecided"
     PolishBatch pb = pb_final;
-    pb.idx_list = q->ws_unproven; pb.count = n; pb.count_dev = nullptr;
+    pb.idx_list = q->ws_unproven; pb.count = d_count == nullptr ? n : count; pb.count_dev = d_count == nullptr ? nullptr : n_unproven;
     pb.n_failed = q->ws_counters + 12; pb.final_pass = 2; pb.rounds = 40;
     return polish_launch(q, pb, st);
 }
 
 int farkas_verify_launch(QPHandle* q, const int* d_list, int count, int* d_status, const float* d_warm, const double* d_x0,
-                         int64_t stride, const double* d_c, const double* xref, int* d_failed, int* d_n_failed, cudaStream_t st) {
+                         int64_t stride, const double* d_c, const double* xref, int* d_failed, int* d_n_failed, cudaStream_t st,
+                         const int* d_count) {
     if (count <= 0) return CARMPC_OK;
     VerifyArgs a;
     memset(&a, 0, sizeof(a));
-    a.list = d_list; a.count = count; a.x0 = d_x0; a.stride = stride; a.cdist = d_c;
+    a.list = d_list; a.count = count; a.count_dev = d_count; a.x0 = d_x0; a.stride = stride; a.cdist = d_c;
     for (int c = 0; c < 4; ++c) a.xref[c] = xref[c];
     a.warm = d_warm; a.status = d_status;
     a.Px = q->admm.Px; a.Pc = q->admm.Pc; a.pre_lo = q->admm.pre_lo; a.pre_hi = q->admm.pre_hi; a.kpre = q->admm.kpre;
     a.failed = d_failed; a.n_failed = d_n_failed;
     const size_t smem = exact_smem(q->polish.n, q->polish.mt);
-    CARMPC_CUDA(cudaFuncSetAttribute(verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CARMPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, verify_kernel, kExactThreads, smem));
+    { const int rc = kernel_config(reinterpret_cast<const void*>(verify_kernel), kExactThreads, smem, &per_sm); if (rc != CARMPC_OK) return rc; }
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((count + 3) / 4, (int64_t)q->sm * std::max(per_sm, 1)));
     verify_kernel<<<blocks, kExactThreads, smem, st>>>(q->polish, q->exact, a);
     CARMPC_CUDA(cudaGetLastError());

@@ -86,6 +86,8 @@ struct AdmmBatch {
     double xref[4];
     const int* idx_list;     // nullable: sample = idx_list[q]
     int count;               // number of queue entries
+    const int* count_dev;    // nullable: the number of entries lives on the device (count is then an upper bound)
+    int narrow;              // host side: always run the narrowest tile (device-sized batches of unknown, usually small, size)
     int* next;               // global work counter (zeroed before launch)
     int8_t* sign;            // [batch][mt]   +1 upper active, -1 lower active
     float* u_admm;           // [batch][n]    unscaled iterate (fallback when the polish cannot certify)
@@ -225,13 +227,14 @@ int farkas_filter_launch(QPHandle* q, const int* d_list, int count, int* d_statu
 // samples that ran out of ADMM iterations: a valid certificate from their final ADMM state makes them proven infeasible
 int farkas_decide_launch(QPHandle* q, const int* d_list, int count, int* d_status, const float* d_warm, const double* d_x0,
                          int64_t stride, double* d_u0, double* d_objective, double* d_u_full, int8_t* d_polished,
-                         cudaStream_t st);
+                         cudaStream_t st, const int* d_count = nullptr);
 // ADMM verdicts "infeasible" are only accepted with a float64 certificate: the others re-enter the second pass
 int farkas_verify_launch(QPHandle* q, const int* d_list, int count, int* d_status, const float* d_warm, const double* d_x0,
-                         int64_t stride, const double* d_c, const double* xref, int* d_failed, int* d_n_failed, cudaStream_t st);
+                         int64_t stride, const double* d_c, const double* xref, int* d_failed, int* d_n_failed, cudaStream_t st,
+                         const int* d_count = nullptr);
 // float64 fallback for what the second pass could not prove (qp_exact.cu)
 int exact_fallback(QPHandle* q, const PolishBatch& pb_final, const int* d_list, int count, float* d_warm, int* d_iters,
-                   cudaStream_t st, int* h_handled);
+                   cudaStream_t st, int* h_handled, const int* d_count = nullptr);
 size_t admm_smem_bytes(const QPHost& h, int samples_per_lane, bool mats_in_smem);
 
 struct QPHandle : HandleBase {
@@ -284,6 +287,11 @@ struct QPHandle : HandleBase {
               double* d_u0, double* d_objective, int32_t* d_status, int32_t* d_iters, double* d_u_full, float* d_warm,
               int warm_in, int warm_out, cudaStream_t st, int reuse_active_set = 0, const int* d_seed = nullptr,
               int keep_sign = 0);
+    // The same pipeline for a warm-started sequence (closed loop), with every sample count left on the device: the list
+    // d_idx holds *d_count <= max_count entries, the previous step's certified active sets are tried first, and nothing
+    // is read back - the call only enqueues (no host synchronisation), so consecutive steps run back to back on the GPU.
+    int solve_enqueue(const double* d_x0, int64_t stride, const double* xref, const int* d_idx, const int* d_count,
+                      int64_t max_count, double* d_u0, int32_t* d_status, float* d_warm, cudaStream_t st);
     // anchors (seed[i] == i or out of range) cold, then every other sample from its anchor's certified active set
     int solve_seeded(const double* d_x0, int64_t batch, const double* xref, const double* d_c, const int* d_seed,
                      double* d_u0, double* d_objective, int32_t* d_status, int32_t* d_iters, double* d_u_full,

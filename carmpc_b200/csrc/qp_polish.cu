@@ -76,7 +76,16 @@ __device__ __forceinline__ double T_auu(const PolishTables& T, int i, const doub
 
 // 7 CTAs of 4 warps per SM (72 registers, 28.6 KB of shared memory each): measured against 3..10 CTAs per SM with the
 // matching register budgets, fewer warps with more registers (deeper load batching) is slower, more warps no faster.
+// One instantiation per mode, so that the cold launch (10^6 samples) carries none of the seed / record / certificate /
+// pre-check code (round 1: one kernel for all modes, 6,100 SASS instructions, instruction-fetch stalls in the cold launch):
+//   SEEDED   followers of a seeded map (active set and records of an anchor),   PRECHECK  u-independent rows / finiteness
+//   (active-set reuse: closed loop and followers),   RECWRITE  anchors exporting their multiplier map.
+template <bool SEEDED, bool PRECHECK, bool RECWRITE>
 __global__ void __launch_bounds__(kPolishThreads, 7) polish_kernel(const PolishTables T, const PolishBatch B) {
+    const int* const b_seed = SEEDED ? B.seed : nullptr;
+    const bool b_precheck = PRECHECK && B.precheck != 0;
+    const bool b_rec_read = SEEDED && B.rec_read != 0;
+    const bool b_rec_write = RECWRITE && B.rec_write != 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int warps_per_cta = kPolishThreads / 32;
@@ -115,8 +124,8 @@ __global__ void __launch_bounds__(kPolishThreads, 7) polish_kernel(const PolishT
         for (int c = 0; c < 4; ++c) { x0[c] = B.x0[(size_t)c * B.stride + sample]; dx[c] = x0[c] - B.xref[c]; }
         const double cd = B.cdist ? B.cdist[sample] : 0.0;
         // seeded: the guess is the certified set of the sample's anchor (nothing to try when the anchor was infeasible)
-        const int sign_src = B.seed ? B.seed[sample] : sample;
-        const bool seed_ok = !B.seed || B.status[sign_src] == CARMPC_QP_SOLVED;
+        const int sign_src = b_seed ? b_seed[sample] : sample;
+        const bool seed_ok = !b_seed || B.status[sign_src] == CARMPC_QP_SOLVED;
         // everything unconstrained is linear in dx:  u_unc = -H^-1 F dx = Uu dx ,  A u_unc = (A Uu) dx
         for (int j = lane; j < n; j += 32) {
             const double* w = T.Uu + (size_t)j * 4;
@@ -138,7 +147,7 @@ __global__ void __launch_bounds__(kPolishThreads, 7) polish_kernel(const PolishT
         bool certified = false, overflow = false;
         int na = 0;
         int max_rounds = B.rounds < 0 ? kPolishRounds : B.rounds;
-        if (B.precheck) {
+        if (b_precheck) {
             // what the ADMM slot refill checks before it starts a sample: finite state, rows that do not depend on u
             bool pre_ok = isfinite(x0[0]) && isfinite(x0[1]) && isfinite(x0[2]) && isfinite(x0[3]);
             for (int k = 0; k < B.kpre; ++k) {
@@ -150,8 +159,8 @@ __global__ void __launch_bounds__(kPolishThreads, 7) polish_kernel(const PolishT
             // Seeded map: a violated u-independent row is infeasibility by itself; an infeasible anchor may have exported a
             // Farkas certificate y (A'y = 0 exactly, box rows absorb the residual), whose support value is affine in x0:
             // S(x0) = c0 - cx.x0 < 0 proves that THIS state is infeasible as well.
-            bool proven_infeasible = B.seed != nullptr && !pre_ok;
-            if (B.seed && B.rec_read && pre_ok && B.status[sign_src] == CARMPC_QP_INFEASIBLE) {
+            bool proven_infeasible = b_seed != nullptr && !pre_ok;
+            if (b_seed && b_rec_read && pre_ok && B.status[sign_src] == CARMPC_QP_INFEASIBLE) {
                 const int rec = B.rec_of[sign_src];
                 if (rec >= 0 && B.rec_act[(size_t)rec * (kPolishSmallActive + 1)] == -2) {
                     const double* r = B.rec_lam + (size_t)rec * kPolishSmallActive * 5;
@@ -194,7 +203,7 @@ __global__ void __launch_bounds__(kPolishThreads, 7) polish_kernel(const PolishT
         // Seeded from an anchor that exported its multiplier map: on the anchor's critical region lambda is affine in x0
         // (explicit-MPC form), so round 0 needs no factorisation - only the KKT certificate below decides.
         bool lam_ready = false;
-        if (B.rec_read && B.seed && seed_ok && max_rounds > 0 && B.cdist == nullptr) {
+        if (b_rec_read && b_seed && seed_ok && max_rounds > 0 && B.cdist == nullptr) {
             const int rec = B.rec_of[sign_src];
             if (rec >= 0) {
                 const int* ra = B.rec_act + (size_t)rec * (kPolishSmallActive + 1);
@@ -479,7 +488,7 @@ __global__ void __launch_bounds__(kPolishThreads, 7) polish_kernel(const PolishT
         if (B.u_full) for (int j = lane; j < n; j += 32) B.u_full[(size_t)sample * n + j] = u[j];
         // Anchor of a seeded map: export the active rows and the affine multiplier map lambda(x0) = Lam [x0; 1] of this
         // critical region (five more right-hand sides through the factor already in shared memory).
-        if (certified && B.rec_write && B.cdist == nullptr) {
+        if (certified && b_rec_write && B.cdist == nullptr) {
             const int rec = B.rec_of[sample];
             if (rec >= 0 && na <= kPolishSmallActive) {
                 for (int c = 0; c < 5; ++c) {
@@ -514,7 +523,7 @@ __global__ void __launch_bounds__(kPolishThreads, 7) polish_kernel(const PolishT
 //          (barely infeasible states are most of that list, and they are the ones that iterate longest).
 // One warp per sample.
 struct FarkasArgs {
-    const int* list; int count; int mode;
+    const int* list; int count; const int* count_dev; int mode;
     int* status; const float* warm; const double* x0; int64_t stride;
     const double* cdist;                                               // nullable per-sample disturbance
     const int* rec_of; double* rec_lam; int* rec_act;                  // mode 0
@@ -529,7 +538,8 @@ __global__ void __launch_bounds__(128) farkas_kernel(const PolishTables T, const
     const int n = T.n, m = T.m, mt = T.mt;
     double* y = reinterpret_cast<double*>(smem_raw) + (size_t)warp * m;
     const int gw = blockIdx.x * 4 + warp, nw = gridDim.x * 4;
-    for (int q = gw; q < F.count; q += nw) {
+    const int f_count = F.count_dev != nullptr ? min(*F.count_dev, F.count) : F.count;
+    for (int q = gw; q < f_count; q += nw) {
         const int sample = F.list ? F.list[q] : q;
         const int rec = F.mode == 0 ? F.rec_of[sample] : 0;
         const int want = F.mode == 0 ? CARMPC_QP_INFEASIBLE : (F.mode == 1 ? CARMPC_QP_MAX_ITER : kStatusNeedsMoreAdmm);
@@ -620,9 +630,9 @@ int farkas_export_launch(QPHandle* qh, const int* d_anchors, int count, const in
 
 int farkas_decide_launch(QPHandle* qh, const int* d_list, int count, int* d_status, const float* d_warm, const double* d_x0,
                          int64_t stride, double* d_u0, double* d_objective, double* d_u_full, int8_t* d_polished,
-                         cudaStream_t st) {
+                         cudaStream_t st, const int* d_count) {
     FarkasArgs f = {};
-    f.list = d_list; f.count = count; f.mode = 1; f.status = d_status; f.warm = d_warm; f.x0 = d_x0; f.stride = stride;
+    f.list = d_list; f.count = count; f.count_dev = d_count; f.mode = 1; f.status = d_status; f.warm = d_warm; f.x0 = d_x0; f.stride = stride;
     f.u0 = d_u0; f.objective = d_objective; f.u_full = d_u_full; f.polished = d_polished; f.stats = qh->ws_polish_stats;
     return farkas_launch(qh, f, st);
 }
@@ -642,13 +652,16 @@ static int polish_launch_cap(QPHandle* qh, const PolishBatch& b, cudaStream_t st
     constexpr int warps = kPolishThreads / 32;
     const size_t smem = L.per_warp * warps;
     if (smem > (size_t)227 * 1024) { set_error("polish: shared-memory budget exceeded"); return CARMPC_ERR_UNSUPPORTED; }
-    CARMPC_CUDA(cudaFuncSetAttribute(polish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void (*kernel)(const PolishTables, const PolishBatch);
+    if (b.seed != nullptr) kernel = polish_kernel<true, true, false>;
+    else if (b.precheck) kernel = polish_kernel<false, true, false>;
+    else if (b.rec_write) kernel = polish_kernel<false, false, true>;
+    else kernel = polish_kernel<false, false, false>;
     int per_sm = 0;
-    CARMPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, polish_kernel, kPolishThreads, smem));
-    if (per_sm < 1) per_sm = 1;
+    { const int rc = kernel_config(reinterpret_cast<const void*>(kernel), kPolishThreads, smem, &per_sm); if (rc != CARMPC_OK) return rc; }
     const int64_t need = (b.count + warps - 1) / warps;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)qh->sm * per_sm));
-    polish_kernel<<<blocks, kPolishThreads, smem, st>>>(qh->polish, b);
+    kernel<<<blocks, kPolishThreads, smem, st>>>(qh->polish, b);
     CARMPC_CUDA(cudaGetLastError());
     return CARMPC_OK;
 }

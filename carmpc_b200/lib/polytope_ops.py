@@ -62,12 +62,18 @@ def reduce(poly: Polytope, abs_tol: float = ABS_TOL) -> Polytope:
     1. of rows describing the same hyperplane direction (cosine > 1 - abs_tol) keep the tightest;
     2. row k is redundant when  max {a_k x : A x <= b, row k relaxed by 1}  <=  b_k + abs_tol.
     """
+    idx = reduce_indices(poly, abs_tol)
+    return Polytope(poly.A[idx], poly.b[idx])
+
+
+def reduce_indices(poly: Polytope, abs_tol: float = ABS_TOL) -> np.ndarray:
+    """Indices (into ``poly``'s rows, ascending) of the rows ``reduce`` keeps."""
     A, b = poly.A, poly.b
-    finite = b != np.inf
+    finite = np.flatnonzero(b != np.inf)
     A, b = A[finite], b[finite]
     m = len(b)
     if m == 0:
-        return Polytope(A, b, normalize=False)
+        return finite
 
     inv_norm = 1.0 / np.sqrt(np.sum(A * A, axis=1))
     unit = A * inv_norm[:, None]
@@ -87,4 +93,4 @@ def reduce(poly: Polytope, abs_tol: float = ABS_TOL) -> Polytope:
         status, value = _maximise(A[k], A, relaxed)
         if status == 3 or (status == 0 and value - b[k] > abs_tol):
             survivors.append(k)
-    return Polytope(A[survivors], b[survivors])
+    return finite[np.asarray(keep, dtype=np.int64)[survivors]] if survivors else finite[:0]

@@ -264,7 +264,10 @@ int carmpc_qp_polish_stats(void* qp, int64_t* h_hist16);
  *   h_A (4x4), h_B (4x2), h_C (3x4), h_L (4x3) row-major; dt, l1 as in the reference (0.2, 3.5).
  *   d_x_init, d_xhat_init: SoA 4 x runs.  d_final: SoA 4 x runs.  d_fail_step: int32, -1 = none.
  *   d_traj (nullable): steps x 4 x runs float64.  d_u_log (nullable): steps x 2 x runs.
- * A run whose QP is infeasible at step t stops there (the reference raises) and keeps its state. */
+ * A run whose QP is infeasible at step t stops there (the reference raises) and keeps its state.
+ * warm_start: 0 = every QP cold; 1 = the previous step's certified active set / ADMM state is reused and the steps are
+ * only enqueued (every sample count stays on the device, no host synchronisation inside the loop); 2 = the same reuse
+ * with host-sized launches (three count read-backs per step: the round-1 form, kept to time one against the other). */
 int carmpc_closed_loop(void* qp, int mode, const double* h_A, const double* h_B, const double* h_C,
                        const double* h_L, const double* h_xref, double dt, double l1, int steps, int warm_start,
                        const double* d_x_init, const double* d_xhat_init, int64_t runs, double* d_final,
