@@ -60,6 +60,7 @@ SIGNATURES = {
     "carmpc_qp_solve_host": (_i32, [_vp, _dp, _dp, _dp, _i64, _dp, _dp, _vp, _vp, _dp]),
     "carmpc_qp_polish_stats": (_i32, [_vp, ctypes.POINTER(_i64)]),
     "carmpc_qp_last_stats": (_i32, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    "carmpc_qp_tensor_mode": (_i32, [_vp, _i32, ctypes.POINTER(_i64)]),
     "carmpc_closed_loop": (_i32, [_vp, _i32, _dp, _dp, _dp, _dp, _dp, ctypes.c_double, ctypes.c_double, _i32,
                                   _i32, _dp, _dp, _i64, _dp, _vp, _dp, _dp, ctypes.POINTER(_i64), _vp]),
     "carmpc_measure_peak": (_i32, [_i32, ctypes.POINTER(ctypes.c_double)]),

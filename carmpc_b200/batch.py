@@ -283,6 +283,14 @@ class BatchQP(_Handle):
                 "final_polish_uncertified": v[16], "fallback_solved": v[17], "fallback_infeasible": v[18],
                 "fallback_undecided": v[19]}
 
+    def tensor_mode(self, mode: int = -1) -> dict:
+        """Selects (0 / 1) or queries (-1) the ADMM kernel of large first passes (``carmpc_qp_tensor_mode``): 1 = the
+        tcgen05 kernel when the problem has a tensor-core form, 0 = the FFMA tile kernel."""
+        info = (ctypes.c_int64 * 16)()
+        check(self._lib.carmpc_qp_tensor_mode(self._h, int(mode), info))
+        return {"mode": int(info[0]), "available": bool(info[1]), "samples_last_solve": int(info[2]),
+                "matrices_resident": bool(info[3]), "cycles": [int(v) for v in info[4:14]]}
+
     # ---- device tensors ---------------------------------------------------------------------------
     def solve(self, x0, x_ref=None, c=None, want_u_full: bool = False, warm=None, warm_in: bool = False,
               warm_out: bool = False, stream=None, seed=None) -> dict:

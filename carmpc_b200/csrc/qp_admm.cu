@@ -643,6 +643,15 @@ int launch_variant(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
 
 int admm_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
     if (b.count <= 0) return CARMPC_OK;
+    if (admm_tc_usable(q, b)) {
+        q->last_tc_samples += b.count;
+        if (q->tensor_mode != 2) return admm_tc_launch(q, b, st);
+        AdmmBatch bp = b;
+        if (q->ws_prof == nullptr) CARMPC_CUDA(cudaMalloc(&q->ws_prof, sizeof(unsigned long long) * 16));
+        CARMPC_CUDA(cudaMemsetAsync(q->ws_prof, 0, sizeof(unsigned long long) * 16, st));
+        bp.prof = q->ws_prof;
+        return admm_tc_launch(q, bp, st);
+    }
     // Samples per tile: the size class fixes the maximum (registers / shared memory); a batch too small to give every
     // SM a full tile runs narrower tiles, whose iterations are proportionally shorter.
     const int smax = q->host.samples_per_lane;

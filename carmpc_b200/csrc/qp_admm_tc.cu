@@ -1,0 +1,605 @@
+// Tensor-core form of the batched ADMM (same iteration as qp_admm.cu, same role: active-set / infeasibility finder in
+// front of the float64 polish; replaces the cvxpy -> OSQP call of lib/mpc.py:334-335 / :477-478, one QP per state).
+//
+// A CTA owns a tile of 128 samples = the M dimension of tcgen05.mma.cta_group::1.kind::tf32.  Compute thread t (warps
+// 0-3) owns sample slot t = lane t of tensor memory: every per-sample quantity is thread-private (no reductions).
+//   tensor memory   columns [0, mp)        w^ of the general rows (state, written with tcgen05.st)
+//                   columns [mp, 2 mp)     accumulator of product 1 (z^)
+//                   columns [2 mp, +np)    accumulator of products 0 and 2 (x~, Gs' dy)
+//   registers       w of the box rows (np per thread), the sample's constant columns e (16)
+//   shared memory   A-operand ring (chunks of 32 K-columns x 128 samples, TF32 hi image + lo residual image, written by
+//                   the compute threads in the 128-byte swizzled K-major layout), B-operand chunks (resident for small
+//                   problems, else streamed from L2 by cp.async.bulk through a ring), small per-row tables.
+// 3xTF32: every product is issued as A_hi B_hi + A_lo B_hi + A_hi B_lo (float32 accumulate): indistinguishable from the
+// float32 FFMA kernel on this iteration (tests/tf32_study.py), which plain TF32 is not.
+// Roles: warps 0-3 elementwise phases (produce A chunks, consume accumulators), warp 4 lane 0 issues the MMAs, warp 5
+// lane 0 streams B chunks.  The phases of an iteration are pipelined through mbarriers only:
+//   S_B (box rows: x~ -> w_b, X chunks)  ->  product 1  ->  S_G (general rows: z^ -> w^_g, V chunks)  ->  product 0  -> ...
+// with the MMAs of a product consuming the chunks while the phase that produces them is still running.
+#include <math.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "qp_internal.cuh"
+
+namespace carmpc {
+
+namespace {
+
+constexpr int kTcThreads = 192;
+constexpr int kAStageBytes = 128 * 128 * 2;        // hi image + lo image of a 128 x 32 chunk
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    int spins = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!done && ++spins > (1 << 22)) __trap();          // a broken pipeline must fail loudly, not hang the GPU
+    }
+}
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups of 1024 bytes (validated by tools/tc_bench.cu)
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int N) {         // D f32, A / B tf32, both K-major, M = 128
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+// the loaded registers are valid only after the wait: tie them to it so that no use can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+                    "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float clampf(float w, float lo, float hi) { return fminf(fmaxf(w, lo), hi); }
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+// x as three TF32-exact pieces (33 significant bits)
+__device__ __forceinline__ void split3(double x, float& a, float& b, float& c) {
+    a = tf32_hi((float)x);
+    const double r1 = x - (double)a;
+    b = tf32_hi((float)r1);
+    c = tf32_hi((float)(r1 - (double)b));
+}
+
+// cycle counters (tensor mode 2): [0] MMA thread: round total, [1] waiting for A chunks, [2] waiting for B chunks,
+// [3] compute thread 0: waiting for x~ / the certificate product, [4] waiting for z^, [5] waiting for a free A stage,
+// [6] retire / refill, [7] round total, [8] rounds, [9] B stream thread: waiting for a free stage
+__device__ __forceinline__ void mbar_wait_prof(uint64_t* bar, uint32_t parity, unsigned long long* acc) {
+    if (acc == nullptr) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    *acc += (unsigned long long)(clock64() - t0);
+}
+
+struct TcSmem {
+    unsigned char *a_ring, *b_res, *b_ring;
+    float *nwd, *lam, *lb, *ub, *t;
+    uint64_t *a_full, *a_empty, *b_full, *b_empty, *bar_x, *bar_z, *bar_res;
+    uint32_t* tmem_slot;
+};
+
+template <int NP>
+__device__ __forceinline__ TcSmem tc_carve(unsigned char* raw, const TcTables& C) {
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    TcSmem s;
+    s.a_ring = base;
+    s.b_res = s.a_ring + (size_t)C.na_stages * kAStageBytes;
+    s.b_ring = s.b_res + C.resident_bytes;
+    s.nwd = reinterpret_cast<float*>(s.b_ring + (size_t)C.nb_stages * C.b_stage_bytes);
+    s.lam = s.nwd + C.mp;
+    s.lb = s.lam + NP;
+    s.ub = s.lb + NP;
+    s.t = s.ub + NP;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s.t + NP);
+    s.a_full = bars; s.a_empty = bars + 4; s.b_full = bars + 8; s.b_empty = bars + 10;
+    s.bar_x = bars + 12; s.bar_z = bars + 13; s.bar_res = bars + 14;
+    s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    return s;
+}
+
+// The compute threads' view of the A-operand ring: a product's K columns are appended 16 at a time (one tcgen05.ld block);
+// a chunk of 32 columns (or the tail of the product) is published to the MMA warp when complete.
+struct AStream {
+    unsigned char* ring;
+    uint64_t *full, *empty;
+    int na;
+    unsigned chunk;      // chunks published so far (the MMA warp counts the same sequence)
+    unsigned long long* wait_acc;
+    int kpos, kend;
+    uint32_t row_off;    // byte offset of this thread's row inside an image
+    int r7;
+};
+
+__device__ __forceinline__ void a_begin(AStream& A, int kend) { A.kpos = 0; A.kend = kend; }
+
+__device__ __forceinline__ void a_put16(AStream& A, const float (&v)[16], int lane) {
+    const int stage = (int)(A.chunk % (unsigned)A.na);
+    const int half = (A.kpos >> 4) & 1;
+    if (half == 0) mbar_wait_prof(A.empty + stage, ((A.chunk / (unsigned)A.na) & 1u) ^ 1u, A.wait_acc);
+    unsigned char* hi_row = A.ring + (size_t)stage * kAStageBytes + A.row_off;
+    unsigned char* lo_row = hi_row + 128 * 128;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float4 h, l;
+        h.x = tf32_hi(v[4 * q + 0]); h.y = tf32_hi(v[4 * q + 1]); h.z = tf32_hi(v[4 * q + 2]); h.w = tf32_hi(v[4 * q + 3]);
+        l.x = v[4 * q + 0] - h.x; l.y = v[4 * q + 1] - h.y; l.z = v[4 * q + 2] - h.z; l.w = v[4 * q + 3] - h.w;
+        const int piece = ((half << 2) + q) ^ A.r7;
+        *reinterpret_cast<float4*>(hi_row + (piece << 4)) = h;
+        *reinterpret_cast<float4*>(lo_row + (piece << 4)) = l;
+    }
+    A.kpos += 16;
+    if (half == 1 || A.kpos == A.kend) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(A.full + stage);
+        ++A.chunk;
+    }
+}
+
+template <int NP>
+__global__ void __launch_bounds__(kTcThreads, 1) admm_tc_kernel(const AdmmTables T, const TcTables C, const AdmmBatch Bq) {
+    extern __shared__ unsigned char smem_raw[];
+    const TcSmem sm = tc_carve<NP>(smem_raw, C);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mp = C.mp, n = C.n, m = C.m, mt = C.mt;
+    const float alpha = T.alpha;
+
+    // ---- one-time setup ------------------------------------------------------------------------------------------------
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(sm.tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(sm.a_full + i, 4); mbar_init(sm.a_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(sm.b_full + i, 1); mbar_init(sm.b_empty + i, 1); }
+        mbar_init(sm.bar_x, 1); mbar_init(sm.bar_z, 1); mbar_init(sm.bar_res, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (tid < 128) {
+        for (int i = tid; i < mp; i += 128) sm.nwd[i] = C.nwd[i];
+        for (int j = tid; j < NP; j += 128) {
+            sm.lam[j] = C.lam[j]; sm.lb[j] = C.lb[j]; sm.ub[j] = C.ub[j];
+            const double* kf = C.kfv + (size_t)j * 4;
+            sm.t[j] = (float)(-(kf[0] * Bq.xref[0] + kf[1] * Bq.xref[1] + kf[2] * Bq.xref[2] + kf[3] * Bq.xref[3]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *sm.tmem_slot;
+    const uint32_t col_state = tbase, col_z = tbase + (uint32_t)mp, col_x = tbase + (uint32_t)(2 * mp);
+    const int check_every = T.check_every;
+    const int q_count = Bq.count_dev != nullptr ? min(*Bq.count_dev, Bq.count) : Bq.count;
+
+    // role-private pipeline counters (they persist over the rounds)
+    unsigned mma_a = 0, mma_b = 0, tma_b = 0;
+    if (tid == 160 && C.resident) {
+        mbar_expect_tx(sm.bar_res, (uint32_t)C.resident_bytes);
+        for (int o = 0; o < C.resident_bytes; o += 16384)
+            bulk_load(sm.b_res + o, C.img + C.off[0] + o, (uint32_t)min(16384, C.resident_bytes - o), sm.bar_res);
+    }
+    if (tid == 128 && C.resident) { mbar_wait(sm.bar_res, 0); tc_fence_after(); }
+
+    // ---- compute-thread state --------------------------------------------------------------------------------------------
+    float wb[NP];                      // w of the box rows of this thread's sample
+    float ex[16];                      // the sample's constant columns (x0 pieces, 1, disturbance pieces)
+    float x0f[4] = {0.f, 0.f, 0.f, 0.f}, cdf = 0.f;
+    int sample = -1, sstate = kSlotIdle, siter = 0;
+    bool drained = false;
+    unsigned n_x = 0, n_z = 0;         // completed waits on bar_x / bar_z
+    AStream A;
+    A.ring = sm.a_ring; A.full = sm.a_full; A.empty = sm.a_empty; A.na = C.na_stages; A.chunk = 0; A.kpos = 0; A.kend = 0;
+    A.row_off = (uint32_t)((tid >> 3) * 1024 + (tid & 7) * 128); A.r7 = tid & 7;
+    unsigned long long pc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};     // this thread's cycle counters
+    const bool prof = Bq.prof != nullptr && (tid == 0 || tid == 128 || tid == 160);
+    A.wait_acc = prof ? &pc[5] : nullptr;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) wb[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ex[j] = 0.f;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;     // this warp's quarter of tensor memory (compute warps only)
+    const float eps_abs = T.eps_abs * Bq.eps_scale, eps_rel = T.eps_rel * Bq.eps_scale;
+
+    for (;;) {
+        int running = 0;
+        const long long t_round = clock64();
+        if (tid < 128) {
+            // ================= retire a finished sample, take the next one from the queue =================
+            // (tensor-memory loads / stores are warp-collective: every lane executes them, only the owners of a finished /
+            //  fresh slot act on the values)
+            const bool fin = sstate > 0;
+            if (__any_sync(0xffffffffu, fin)) {
+                double xs[4] = {0.0, 0.0, 0.0, 0.0}, cd = 0.0;
+                int8_t* sg = nullptr;
+                float* wo = nullptr;
+                if (fin) {
+                    Bq.status[sample] = sstate == kSlotSolved ? CARMPC_QP_SOLVED : (sstate == kSlotMaxIter ? CARMPC_QP_MAX_ITER : CARMPC_QP_INFEASIBLE);
+                    Bq.iters[sample] = siter + (Bq.iters_accumulate ? Bq.iters[sample] : 0);
+                    atomicAdd(Bq.total_iters, (unsigned long long)siter);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) xs[c] = Bq.x0[(size_t)c * Bq.stride + sample];
+                    if (Bq.cdist) cd = Bq.cdist[sample];
+                    sg = Bq.sign + (size_t)sample * mt;
+                    wo = Bq.warm + (size_t)sample * mt;
+                }
+                for (int g0 = 0; g0 < mp; g0 += 16) {
+                    uint32_t wr[16];
+                    tmem_ld16(col_state + lane_addr + (uint32_t)g0, wr);
+                    tmem_ld_wait(wr);
+                    if (fin) {
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
+                            const int rid = C.row_id[g0 + r];
+                            if (rid < 0) continue;
+                            const float w = __uint_as_float(wr[r]);
+                            sg[rid] = (int8_t)((w > 0.f) - (w < sm.nwd[g0 + r]));
+                            if (Bq.warm_out) {
+                                const double* gx = C.gxs + (size_t)(g0 + r) * 4;
+                                const double h = C.his[g0 + r] - gx[0] * xs[0] - gx[1] * xs[1] - gx[2] * xs[2] - gx[3] * xs[3] - C.gcs[g0 + r] * cd;
+                                wo[rid] = (float)((double)w + h);
+                            }
+                        }
+                    }
+                }
+                if (fin) {
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) {
+                        if (j < n) {
+                            sg[m + j] = (int8_t)((wb[j] > sm.ub[j]) - (wb[j] < sm.lb[j]));
+                            if (Bq.warm_out) wo[m + j] = wb[j];
+                        }
+                    }
+                    sstate = kSlotIdle;
+                }
+            }
+            bool fresh = false;
+            double xs[4] = {0.0, 0.0, 0.0, 0.0}, cd = 0.0;
+            while (sstate == kSlotIdle && !drained) {
+                const int qi = atomicAdd(Bq.next, 1);
+                if (qi >= q_count) { drained = true; break; }
+                sample = Bq.idx_list ? Bq.idx_list[qi] : qi;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) xs[c] = Bq.x0[(size_t)c * Bq.stride + sample];
+                cd = Bq.cdist ? Bq.cdist[sample] : 0.0;
+                bool pre_ok = isfinite(xs[0]) && isfinite(xs[1]) && isfinite(xs[2]) && isfinite(xs[3]);
+                for (int k = 0; k < T.kpre; ++k) {
+                    const double v = T.Px[k * 4 + 0] * xs[0] + T.Px[k * 4 + 1] * xs[1] + T.Px[k * 4 + 2] * xs[2] +
+                                     T.Px[k * 4 + 3] * xs[3] + T.Pc[k] * cd;
+                    pre_ok = pre_ok && v <= T.pre_hi[k] && v >= T.pre_lo[k];
+                }
+                if (!pre_ok) {
+                    // a violated row that does not depend on u: infeasible without iterating (the FFMA kernel books one round)
+                    Bq.status[sample] = CARMPC_QP_INFEASIBLE;
+                    Bq.iters[sample] = check_every + (Bq.iters_accumulate ? Bq.iters[sample] : 0);
+                    atomicAdd(Bq.total_iters, (unsigned long long)check_every);
+                    continue;
+                }
+                fresh = true;
+                siter = 0;
+                sstate = kSlotRunning;
+            }
+            if (__any_sync(0xffffffffu, fresh)) {
+                // state of a new sample: w^ = w - h (cold: w = 0), box rows, constant columns
+                const float* wi = (fresh && Bq.warm_in) ? Bq.warm + (size_t)sample * mt : nullptr;
+                for (int g0 = 0; g0 < mp; g0 += 16) {
+                    uint32_t wr[16];
+                    tmem_ld16(col_state + lane_addr + (uint32_t)g0, wr);
+                    tmem_ld_wait(wr);
+                    if (fresh) {
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
+                            const int rid = C.row_id[g0 + r];
+                            float w = 0.f;
+                            if (rid >= 0) {
+                                const double* gx = C.gxs + (size_t)(g0 + r) * 4;
+                                const double h = C.his[g0 + r] - gx[0] * xs[0] - gx[1] * xs[1] - gx[2] * xs[2] - gx[3] * xs[3] - C.gcs[g0 + r] * cd;
+                                w = (float)((wi ? (double)wi[rid] : 0.0) - h);
+                            }
+                            wr[r] = __float_as_uint(w);
+                        }
+                    }
+                    tmem_st16(col_state + lane_addr + (uint32_t)g0, wr);
+                }
+                tmem_st_wait();
+                if (fresh) {
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) wb[j] = (wi && j < n) ? wi[m + j] : 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { split3(xs[c], ex[3 * c], ex[3 * c + 1], ex[3 * c + 2]); x0f[c] = (float)xs[c]; }
+                    ex[12] = 1.f;
+                    split3(cd, ex[13], ex[14], ex[15]);
+                    cdf = (float)cd;
+                }
+            }
+            running = sstate == kSlotRunning;
+        }
+        if (prof && tid == 0) pc[6] += (unsigned long long)(clock64() - t_round);
+        if (!__syncthreads_or(running)) break;
+        const long long t_work = clock64();
+
+        if (tid < 128) {
+            // ================= elementwise phases of one round (check_every iterations, the last one checked) =================
+            auto put_box_v = [&]() {          // V_b = 2 clip(w_b) - w_b, then the constant columns: the head of product 0's K
+#pragma unroll
+                for (int j0 = 0; j0 < NP; j0 += 16) {
+                    float v[16];
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) { const float w = wb[j0 + r]; v[r] = fmaf(2.f, clampf(w, sm.lb[j0 + r], sm.ub[j0 + r]), -w); }
+                    a_put16(A, v, lane);
+                }
+                a_put16(A, ex, lane);
+            };
+            // round start: every chunk of product 0 from the state
+            a_begin(A, NP + 16 + mp);
+            put_box_v();
+            for (int g0 = 0; g0 < mp; g0 += 16) {
+                uint32_t wr[16];
+                tmem_ld16(col_state + lane_addr + (uint32_t)g0, wr);
+                tmem_ld_wait(wr);
+                float v[16];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) { const float w = __uint_as_float(wr[r]); v[r] = fmaf(2.f, clampf(w, sm.nwd[g0 + r], 0.f), -w); }
+                a_put16(A, v, lane);
+            }
+            float p_res = 0.f, p_nrm = 0.f, p_sup = 0.f, p_abs = 0.f;
+            for (int it = 0; it < check_every; ++it) {
+                const bool check = it == check_every - 1;
+                // ---------------- S_B: box rows (z = lam x~), X chunks of product 1 ----------------
+                mbar_wait_prof(sm.bar_x, n_x & 1u, prof ? &pc[3] : nullptr); ++n_x;
+                tc_fence_after();
+                a_begin(A, NP + 16);
+#pragma unroll
+                for (int j0 = 0; j0 < NP; j0 += 16) {
+                    uint32_t xr[16];
+                    tmem_ld16(col_x + lane_addr + (uint32_t)j0, xr);
+                    tmem_ld_wait(xr);
+                    float x[16];
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        const int j = j0 + r;
+                        x[r] = __uint_as_float(xr[r]) + sm.t[j];
+                        const float lb = sm.lb[j], ub = sm.ub[j];
+                        const float w0 = wb[j], z = sm.lam[j] * x[r];
+                        const float c0 = clampf(w0, lb, ub);
+                        const float w1 = fmaf(alpha, z - c0, w0);
+                        wb[j] = w1;
+                        if (check) {
+                            const float c1 = clampf(w1, lb, ub), einv = C.einv_b[j];
+                            p_res = fmaxf(p_res, fmaxf(fabsf(z - c1), fabsf(c1 - c0)) * einv);
+                            p_nrm = fmaxf(p_nrm, fmaxf(fabsf(z), fabsf(c1)) * einv);
+                        }
+                    }
+                    a_put16(A, x, lane);
+                }
+                a_put16(A, ex, lane);
+                if (!check) { a_begin(A, NP + 16 + mp); put_box_v(); }      // head of the next iteration's product 0
+                else a_begin(A, mp);                                         // dy chunks of the certificate product
+                // ---------------- S_G: general rows (w^ += alpha (z^ - c^)), V chunks of product 0 ----------------
+                mbar_wait_prof(sm.bar_z, n_z & 1u, prof ? &pc[4] : nullptr); ++n_z;
+                tc_fence_after();
+                for (int g0 = 0; g0 < mp; g0 += 16) {
+                    uint32_t zr[16], wr[16];
+                    tmem_ld16(col_z + lane_addr + (uint32_t)g0, zr);
+                    tmem_ld16(col_state + lane_addr + (uint32_t)g0, wr);
+                    tmem_ld_wait(zr);
+                    tmem_ld_wait(wr);
+                    float v[16];
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        const float nwd = sm.nwd[g0 + r];
+                        const float w0 = __uint_as_float(wr[r]), z = __uint_as_float(zr[r]);
+                        const float c0 = clampf(w0, nwd, 0.f);
+                        const float w1 = fmaf(alpha, z - c0, w0);
+                        const float c1 = clampf(w1, nwd, 0.f);
+                        wr[r] = __float_as_uint(w1);
+                        if (!check) {
+                            v[r] = fmaf(2.f, c1, -w1);
+                        } else {
+                            const int i = g0 + r;
+                            const float einv = C.einv_g[i];
+                            const float* gx = C.gxsf + (size_t)i * 4;
+                            const float h = C.hisf[i] - gx[0] * x0f[0] - gx[1] * x0f[1] - gx[2] * x0f[2] - gx[3] * x0f[3] - C.gcsf[i] * cdf;
+                            p_res = fmaxf(p_res, fmaxf(fabsf(z - c1), fabsf(c1 - c0)) * einv);
+                            p_nrm = fmaxf(p_nrm, fmaxf(fabsf(z + h), fabsf(c1 + h)) * einv);
+                            float e = (w1 - c1) - (w0 - c0);
+                            if (nwd == -INFINITY) e = fmaxf(e, 0.f);
+                            v[r] = e;                        // the A operand carries delta-y for the certificate product
+                            const float term = e > 0.f ? h * e : (e < 0.f ? (h + nwd) * e : 0.f);
+                            p_sup += term;
+                            p_abs += fabsf(term);
+                        }
+                    }
+                    tmem_st16(col_state + lane_addr + (uint32_t)g0, wr);
+                    a_put16(A, v, lane);
+                }
+                tmem_st_wait();
+            }
+            // ---------------- certificate: y_b = -(Gs' dy) / lam makes A'y = 0 exactly; infeasible iff the support sum < 0 ----------------
+            mbar_wait_prof(sm.bar_x, n_x & 1u, prof ? &pc[3] : nullptr); ++n_x;
+            tc_fence_after();
+#pragma unroll
+            for (int j0 = 0; j0 < NP; j0 += 16) {
+                uint32_t yr[16];
+                tmem_ld16(col_x + lane_addr + (uint32_t)j0, yr);
+                tmem_ld_wait(yr);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const int j = j0 + r;
+                    const float yb = __uint_as_float(yr[r]) * C.nrl[j];
+                    const float term = yb > 0.f ? sm.ub[j] * yb : (yb < 0.f ? sm.lb[j] * yb : 0.f);
+                    p_sup += term;
+                    p_abs += fabsf(term);
+                }
+            }
+            tc_fence_before();
+            if (sstate == kSlotRunning) {
+                siter += check_every;
+                int ns = kSlotRunning;
+                if (p_abs > 0.f && p_sup <= -T.eps_inf * p_abs) ns = kSlotInfeasible;
+                else if (p_res <= eps_abs + eps_rel * p_nrm) ns = kSlotSolved;
+                else if (siter >= Bq.max_iter || !(p_res == p_res)) ns = kSlotMaxIter;
+                sstate = ns;
+            }
+        } else if (tid == 128) {
+            // ================= MMA issue: the same chunk sequence the compute threads publish =================
+            auto product = [&](int p, uint32_t dcol, bool streamed, uint64_t* done) {
+                const int N = C.ncols[p];
+                const uint32_t idesc = make_idesc(N);
+                const int e_ks = p == 2 ? -1 : NP / 8;              // the two k-steps of the constant columns: their lo image is zero
+                const unsigned char* res_base = sm.b_res + (p == 1 ? (size_t)C.nchunks[0] * C.pair_bytes[0] : 0);
+                for (int c = 0; c < C.nchunks[p]; ++c) {
+                    const int sa = (int)(mma_a % (unsigned)C.na_stages);
+                    mbar_wait_prof(sm.a_full + sa, (mma_a / (unsigned)C.na_stages) & 1u, prof ? &pc[1] : nullptr);
+                    const unsigned char* bsrc;
+                    int sb = 0;
+                    if (streamed) {
+                        sb = (int)(mma_b & 1u);
+                        mbar_wait_prof(sm.b_full + sb, (mma_b >> 1) & 1u, prof ? &pc[2] : nullptr);
+                        bsrc = sm.b_ring + (size_t)sb * C.b_stage_bytes;
+                    } else {
+                        bsrc = res_base + (size_t)c * C.pair_bytes[p];
+                    }
+                    tc_fence_after();
+                    const uint64_t a_hi = desc_sw128(smem_u32(sm.a_ring + (size_t)sa * kAStageBytes));
+                    const uint64_t a_lo = desc_sw128(smem_u32(sm.a_ring + (size_t)sa * kAStageBytes + 128 * 128));
+                    const uint64_t b_hi = desc_sw128(smem_u32(bsrc));
+                    const uint64_t b_lo = desc_sw128(smem_u32(bsrc + (size_t)N * 128));
+                    const int nks = min(4, C.ksteps[p] - 4 * c);
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint64_t o = (uint64_t)(ks * 2);
+                        const int kg = 4 * c + ks;
+                        mma_ss(dcol, a_hi + o, b_hi + o, idesc, (uint32_t)(kg != 0));
+                        if (kg != e_ks && kg != e_ks + 1) mma_ss(dcol, a_lo + o, b_hi + o, idesc, 1u);
+                        mma_ss(dcol, a_hi + o, b_lo + o, idesc, 1u);
+                    }
+                    mma_commit(sm.a_empty + sa);
+                    ++mma_a;
+                    if (streamed) { mma_commit(sm.b_empty + sb); ++mma_b; }
+                }
+                mma_commit(done);
+            };
+            for (int it = 0; it < check_every; ++it) {
+                product(0, col_x, !C.resident, sm.bar_x);
+                product(1, col_z, !C.resident, sm.bar_z);
+            }
+            product(2, col_x, true, sm.bar_x);
+        } else if (tid == 160) {
+            // ================= B-operand stream (L2 -> shared memory ring) =================
+            auto stream = [&](int p) {
+                for (int c = 0; c < C.nchunks[p]; ++c) {
+                    const int sb = (int)(tma_b & 1u);
+                    mbar_wait_prof(sm.b_empty + sb, ((tma_b >> 1) & 1u) ^ 1u, prof ? &pc[9] : nullptr);
+                    const uint32_t bytes = (uint32_t)C.pair_bytes[p];
+                    mbar_expect_tx(sm.b_full + sb, bytes);
+                    const unsigned char* src = C.img + C.off[p] + (size_t)c * bytes;
+                    unsigned char* dst = sm.b_ring + (size_t)sb * C.b_stage_bytes;
+                    for (uint32_t o = 0; o < bytes; o += 16384) bulk_load(dst + o, src + o, min(16384u, bytes - o), sm.b_full + sb);
+                    ++tma_b;
+                }
+            };
+            for (int it = 0; it < check_every; ++it)
+                if (!C.resident) { stream(0); stream(1); }
+            stream(2);
+        }
+        if (prof) {
+            if (tid == 128) pc[0] += (unsigned long long)(clock64() - t_work);
+            if (tid == 0) { pc[7] += (unsigned long long)(clock64() - t_work); ++pc[8]; }
+        }
+        __syncwarp();
+    }
+    if (prof) {
+        if (tid == 128) { atomicAdd(Bq.prof + 0, pc[0]); atomicAdd(Bq.prof + 1, pc[1]); atomicAdd(Bq.prof + 2, pc[2]); }
+        if (tid == 0) for (int i = 3; i <= 8; ++i) atomicAdd(Bq.prof + i, pc[i]);
+        if (tid == 160) atomicAdd(Bq.prof + 9, pc[9]);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase) : "memory");
+}
+
+template <int NP>
+int tc_launch_np(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
+    const size_t smem = (size_t)q->tc.smem_bytes;
+    const int64_t tiles = ((int64_t)b.count + 127) / 128;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, q->sm));
+    { const int rc = kernel_config(reinterpret_cast<const void*>(admm_tc_kernel<NP>), kTcThreads, smem, nullptr); if (rc != CARMPC_OK) return rc; }
+    admm_tc_kernel<NP><<<blocks, kTcThreads, smem, st>>>(q->admm, q->tc, b);
+    CARMPC_CUDA(cudaGetLastError());
+    return CARMPC_OK;
+}
+
+}  // namespace
+
+bool admm_tc_usable(const QPHandle* q, const AdmmBatch& b) {
+    // Large first passes only: the tile is always 128 samples wide, so a batch that cannot give every SM a full tile
+    // (second passes, closed-loop steps) stays on the FFMA kernel's narrow tiles; so does a launch that must export the
+    // raw iterate (write_u: the accumulator that holds x~ is reused by the next product).
+    return q->tensor_mode != 0 && q->tc.ok && !b.narrow && !b.write_u && b.warm != nullptr && b.sign != nullptr &&
+           (int64_t)b.count >= (int64_t)128 * q->sm;
+}
+
+int admm_tc_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
+    switch (q->tc.np) {
+        case 16: return tc_launch_np<16>(q, b, st);
+        case 32: return tc_launch_np<32>(q, b, st);
+        case 48: return tc_launch_np<48>(q, b, st);
+        case 64: return tc_launch_np<64>(q, b, st);
+        case 80: return tc_launch_np<80>(q, b, st);
+    }
+    set_error("admm_tc_launch: no kernel variant for %d variables", q->tc.np);
+    return CARMPC_ERR_UNSUPPORTED;
+}
+
+}  // namespace carmpc

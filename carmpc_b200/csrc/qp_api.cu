@@ -120,7 +120,7 @@ QPHandle::~QPHandle() {
     cudaFree(ws_counters); cudaFree(ws_total_iters); cudaFree(ws_polished); cudaFree(ws_warm); cudaFree(ws_overflow); cudaFree(ws_unproven);
     cudaFree(ws_anchor); cudaFree(ws_follow); cudaFree(ws_rec_of); cudaFree(ws_rec_lam); cudaFree(ws_rec_act); cudaFree(ws_polish_stats);
     cudaFree(io_x0_aos); cudaFree(io_x0); cudaFree(io_c); cudaFree(io_u0); cudaFree(io_u0_aos); cudaFree(io_obj); cudaFree(io_full);
-    cudaFree(io_status); cudaFree(io_iters); cudaFree(io_seed); cudaFree(io_axes);
+    cudaFree(io_status); cudaFree(io_iters); cudaFree(io_seed); cudaFree(io_axes); cudaFree(ws_prof);
 }
 
 int QPHandle::ensure_workspace(int64_t batch) {
@@ -168,6 +168,7 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
     int rc = ensure_workspace(stride);
     if (rc != CARMPC_OK) return rc;
     last_launches = 0;
+    last_tc_samples = 0;
     last_second_pass = 0;
     last_reused = 0;
     last_fallback = 0;
@@ -484,6 +485,21 @@ int carmpc_qp_create(int n, int m, int k, const double* h_H, const double* h_F, 
     UP(Dsc, Dsc); UP(KF, KF); UP(var_id, var_id); UP(segA, segA); UP(segB, segB); UP(Px, Px); UP(Pc, Pc);
     UP(pre_lo, pre_lo); UP(pre_hi, pre_hi);
 #undef UP
+    q->tc = h.tc;
+    if (q->tc.ok) {
+        TcTables& t = q->tc;
+        void* d_img = nullptr;
+        // chunk images are the sources of cp.async.bulk copies: 16-byte granules (cudaMalloc aligns to 256 bytes)
+        if (cudaMalloc(&d_img, h.tc_img.size()) != cudaSuccess) { set_error("cudaMalloc of the tensor-core images failed"); delete q; return CARMPC_ERR_CUDA; }
+        q->allocations.push_back(d_img);
+        if (cudaMemcpy(d_img, h.tc_img.data(), h.tc_img.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("upload of the tensor-core images failed"); delete q; return CARMPC_ERR_CUDA; }
+        t.img = static_cast<const unsigned char*>(d_img);
+#define UPT(vec, field) do { rc = upload(q, h.vec, &t.field); if (rc != CARMPC_OK) { delete q; return rc; } } while (0)
+        UPT(tc_nwd, nwd); UPT(tc_einv_g, einv_g); UPT(tc_hisf, hisf); UPT(tc_gxsf, gxsf); UPT(tc_gcsf, gcsf);
+        UPT(tc_his, his); UPT(tc_gxs, gxs); UPT(tc_gcs, gcs); UPT(tc_row_id, row_id);
+        UPT(tc_lam, lam); UPT(tc_lb, lb); UPT(tc_ub, ub); UPT(tc_einv_b, einv_b); UPT(tc_nrl, nrl); UPT(tc_kfv, kfv);
+#undef UPT
+    }
     PolishTables& p = q->polish;
     p.n = n; p.m = m; p.mt = m + n;
 #define UP(vec, field) do { rc = upload(q, h.vec, &p.field); if (rc != CARMPC_OK) { delete q; return rc; } } while (0)
@@ -554,6 +570,32 @@ int carmpc_qp_get_setup(void* qp, int which, double* h_out, int capacity) {
         case 25: tmp.assign(h.Dsc.begin(), h.Dsc.end()); src = &tmp; break;
         case 26: tmp = {(double)h.geo.n, (double)h.geo.m, (double)h.geo.nA_rows, (double)h.geo.m_phys, (double)h.geo.npad4,
                         (double)h.geo.mv4, (double)h.geo.ktot, (double)h.geo.nGA, (double)h.geo.nGB}; src = &tmp; break;
+        // tensor-core form (qp_admm_tc.cu): geometry, the chunk images as the float32 words they hold, the per-row tables
+        case 30: {
+            const TcTables& t = h.tc;
+            tmp = {(double)t.ok, (double)t.np, (double)t.mp, (double)t.resident, (double)t.na_stages, (double)t.nb_stages,
+                   (double)t.b_stage_bytes, (double)t.smem_bytes};
+            for (int p = 0; p < 3; ++p) { tmp.push_back(t.off[p]); tmp.push_back(t.pair_bytes[p]); tmp.push_back(t.nchunks[p]);
+                                          tmp.push_back(t.ksteps[p]); tmp.push_back(t.ncols[p]); }
+            src = &tmp; break;
+        }
+        case 31: {
+            tmp.resize(h.tc_img.size() / 4);
+            for (size_t i = 0; i < tmp.size(); ++i) { float f; memcpy(&f, h.tc_img.data() + 4 * i, 4); tmp[i] = f; }
+            src = &tmp; break;
+        }
+        case 32: tmp.assign(h.tc_nwd.begin(), h.tc_nwd.end()); src = &tmp; break;
+        case 33: tmp.assign(h.tc_einv_g.begin(), h.tc_einv_g.end()); src = &tmp; break;
+        case 34: src = &h.tc_his; break;
+        case 35: src = &h.tc_gxs; break;
+        case 36: src = &h.tc_gcs; break;
+        case 37: tmp.assign(h.tc_row_id.begin(), h.tc_row_id.end()); src = &tmp; break;
+        case 38: tmp.assign(h.tc_lam.begin(), h.tc_lam.end()); src = &tmp; break;
+        case 39: tmp.assign(h.tc_lb.begin(), h.tc_lb.end()); src = &tmp; break;
+        case 40: tmp.assign(h.tc_ub.begin(), h.tc_ub.end()); src = &tmp; break;
+        case 41: tmp.assign(h.tc_einv_b.begin(), h.tc_einv_b.end()); src = &tmp; break;
+        case 42: tmp.assign(h.tc_nrl.begin(), h.tc_nrl.end()); src = &tmp; break;
+        case 43: src = &h.tc_kfv; break;
         default: set_error("carmpc_qp_get_setup: unknown selector %d", which); return CARMPC_ERR_INVALID;
     }
     const int cnt = (int)src->size();
@@ -698,6 +740,23 @@ int carmpc_qp_polish_stats(void* qp, int64_t* h_hist20) {
     unsigned long long tmp[kPolishStats];
     CARMPC_CUDA(cudaMemcpy(tmp, q->ws_polish_stats, sizeof(tmp), cudaMemcpyDeviceToHost));
     for (int i = 0; i < kPolishStats; ++i) h_hist20[i] = (int64_t)tmp[i];
+    return CARMPC_OK;
+}
+
+int carmpc_qp_tensor_mode(void* qp, int mode, int64_t* h_info) {
+    QPHandle* q = check_handle<QPHandle>(qp, kQP);
+    CARMPC_REQUIRE(q != nullptr, "not a QP handle");
+    CARMPC_REQUIRE(mode <= 2, "mode must be 0, 1, 2 or negative (query)");
+    if (mode >= 0) q->tensor_mode = mode;
+    if (h_info) {
+        for (int i = 0; i < 16; ++i) h_info[i] = 0;
+        h_info[0] = q->tensor_mode; h_info[1] = q->tc.ok; h_info[2] = q->last_tc_samples; h_info[3] = q->tc.resident;
+        if (q->ws_prof != nullptr) {
+            unsigned long long tmp[16];
+            CARMPC_CUDA(cudaMemcpy(tmp, q->ws_prof, sizeof(tmp), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < 12; ++i) h_info[4 + i] = (int64_t)tmp[i];
+        }
+    }
     return CARMPC_OK;
 }
 

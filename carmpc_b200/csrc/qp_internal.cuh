@@ -100,6 +100,42 @@ struct AdmmBatch {
     int max_iter;
     int iters_accumulate;    // second pass: add to the iteration count of the first
     int write_u;             // also write the ADMM iterate (needed when the polish may pass it through)
+    unsigned long long* prof; // nullable (tensor-core kernel, tensor mode 2): cycle counters summed over the CTAs
+};
+
+// Tensor-core form of the ADMM (qp_admm_tc.cu): a tile of 128 samples is the M dimension of tcgen05.mma kind::tf32, the
+// shared matrices are the B operands (K-major, 128-byte swizzle, split into a TF32 "hi" image and a TF32 "lo" residual
+// image for the 3xTF32 products), the ADMM state of the general rows and the accumulators live in tensor memory.
+// Everything is in logical order (live general rows, then variables); pads are inert (zero matrix rows / columns).
+//   product 0   x~ (np)   = [V_b (np) | e (16) | V^_g (mp)] . B0'      K0 = np + 16 + mp
+//   product 1   z^ (mp)   = [x~  (np) | e (16)] . B1'                  K1 = np + 16
+//   product 2   Gs'dy (np) = [dy (mp)] . B2'                           K2 = mp          (certificate, checked iterations)
+// e = per-sample constants as exact TF32 pieces: x0_c as hi / mid / lo (c = 0..3), 1, the disturbance c as hi / mid / lo.
+// General rows are kept shifted by their per-sample upper bound h = his - Gxs x0 - Gcs c (w^ = w - h, z^ = z - h), which
+// makes their clip bounds (-width, 0) sample-independent; the shift enters both products through the e columns.
+struct TcTables {
+    const unsigned char* img;   // chunk images: chunk k of product p at img + off[p] + k * pair_bytes[p] (hi image, then lo)
+    int off[3], pair_bytes[3], nchunks[3], ksteps[3], ncols[3];
+    const float* nwd;           // [mp]   -width (scaled; -inf: one-sided or pad row)
+    const float* einv_g;        // [mp]   1 / Eg (pads 0)
+    const float* hisf;          // [mp]   float copies of his, Gxs, Gcs for the residual norms / support sums (pads 0)
+    const float* gxsf;          // [mp][4]
+    const float* gcsf;          // [mp]
+    const double* his;          // [mp]   (pads 0)
+    const double* gxs;          // [mp][4]
+    const double* gcs;          // [mp]
+    const int* row_id;          // [mp]   logical row, -1 pad
+    const float* lam;           // [np]   Eb D (pads 0)
+    const float* lb;            // [np]   scaled box (pads -inf / +inf)
+    const float* ub;
+    const float* einv_b;        // [np]
+    const float* nrl;           // [np]   -1 / lam (pads 0)
+    const double* kfv;          // [np][4]  x~0 = kfv (x0 - xref)
+    int n, m, mt, np, mp;
+    int resident;               // products 0 and 1 stay in shared memory (loaded once); product 2 always streams
+    int na_stages, nb_stages, b_stage_bytes, resident_bytes;
+    int smem_bytes;
+    int ok;                     // 0: this problem has no tensor-core form (too large for tensor memory / shared memory)
 };
 
 struct PolishTables {
@@ -196,6 +232,12 @@ struct QPHost {
     std::vector<int2> segB;
     // polish (logical order, unscaled)
     std::vector<double> H, Hinv, F, G, Uu, AUu, AH, AHA, Gx, Gc, hi, lo;
+    // tensor-core form (sizes in tc; pointers filled by the handle)
+    TcTables tc;
+    std::vector<unsigned char> tc_img;
+    std::vector<float> tc_nwd, tc_einv_g, tc_hisf, tc_gxsf, tc_gcsf, tc_lam, tc_lb, tc_ub, tc_einv_b, tc_nrl;
+    std::vector<double> tc_his, tc_gxs, tc_gcs, tc_kfv;
+    std::vector<int> tc_row_id;
     int ga_per_warp = 0, gb_per_warp = 0, samples_per_lane = 0;
     bool mats_in_smem = false;
     size_t smem_bytes = 0;
@@ -216,6 +258,9 @@ struct QPBusyGuard {
     ~QPBusyGuard() { if (acquired) flag->store(false); }
 };
 int admm_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st);
+// tcgen05 form of the same iteration (qp_admm_tc.cu); admm_launch picks it for large first passes
+int admm_tc_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st);
+bool admm_tc_usable(const QPHandle* q, const AdmmBatch& b);
 int polish_launch(QPHandle* q, const PolishBatch& b, cudaStream_t st);
 // infeasible anchors of a seeded map: turn the ADMM dual iterate into an exact Farkas certificate, affine in x0
 int farkas_export_launch(QPHandle* q, const int* d_anchors, int count, const int* d_status, const float* d_warm,
@@ -240,6 +285,10 @@ size_t admm_smem_bytes(const QPHost& h, int samples_per_lane, bool mats_in_smem)
 struct QPHandle : HandleBase {
     QPHost host;
     AdmmTables admm;
+    TcTables tc;
+    int tensor_mode = 1;                         // 0: FFMA kernel only; 1: tcgen05 kernel for large first passes
+    int64_t last_tc_samples = 0;                 // samples the tcgen05 kernel took in the last solve
+    unsigned long long* ws_prof = nullptr;       // [16] cycle counters of the tcgen05 kernel (tensor mode 2)
     PolishTables polish;
     ExactTables exact;
     std::vector<void*> allocations;

@@ -442,6 +442,119 @@ int qp_host_setup(int n, int m_in, int kpre, const double* H_in, const double* F
             q.AUu[(size_t)i * 4 + c] = s;
         }
 
+    // ---- tensor-core form (qp_admm_tc.cu): logical order, B operands as swizzled TF32 hi / lo chunk images ---------------------
+    {
+        TcTables& t = q.tc;
+        memset(&t, 0, sizeof(t));
+        const int np = std::max(16, (n + 15) / 16 * 16), mp = std::max(16, (mv + 15) / 16 * 16);
+        t.n = n; t.m = m; t.mt = mt; t.np = np; t.mp = mp;
+        const int K[3] = {np + 16 + mp, np + 16, mp}, N[3] = {np, mp, np};
+        t.ok = mp <= 256 && np <= 256 && 2 * mp + np <= 512;
+        size_t total = 0;
+        for (int p = 0; p < 3; ++p) {
+            t.ncols[p] = N[p]; t.ksteps[p] = K[p] / 8; t.nchunks[p] = (K[p] + 31) / 32;
+            t.pair_bytes[p] = N[p] * 128 * 2;
+            t.off[p] = (int)total;
+            total += (size_t)t.nchunks[p] * t.pair_bytes[p];
+        }
+        const int a_stage = 128 * 128 * 2;
+        const int tables = (4 * mp + 16 * np + 512 + 1023) / 1024 * 1024;
+        const int budget = 227 * 1024 - 1024;                      // the dynamic area is re-aligned to 1024 bytes in the kernel
+        t.resident_bytes = t.nchunks[0] * t.pair_bytes[0] + t.nchunks[1] * t.pair_bytes[1];
+        t.nb_stages = 2;
+        if (2 * a_stage + t.resident_bytes + 2 * t.pair_bytes[2] + tables <= budget) {
+            t.resident = 1;
+            t.b_stage_bytes = t.pair_bytes[2];
+            t.na_stages = 3 * a_stage + t.resident_bytes + 2 * t.pair_bytes[2] + tables <= budget ? 3 : 2;
+            t.smem_bytes = t.na_stages * a_stage + t.resident_bytes + 2 * t.b_stage_bytes + tables + 1024;
+        } else {
+            t.resident = 0;
+            t.resident_bytes = 0;
+            t.b_stage_bytes = std::max(t.pair_bytes[0], std::max(t.pair_bytes[1], t.pair_bytes[2]));
+            t.na_stages = 3 * a_stage + 2 * t.b_stage_bytes + tables <= budget ? 3 : 2;
+            t.smem_bytes = t.na_stages * a_stage + 2 * t.b_stage_bytes + tables + 1024;
+            if (t.smem_bytes > 227 * 1024) t.ok = 0;
+        }
+        if (t.ok) {
+            auto tf32_rn = [](double v) {
+                float f = (float)v;
+                uint32_t u; memcpy(&u, &f, 4);
+                u = (u + 0x1000u) & 0xFFFFE000u;
+                memcpy(&f, &u, 4);
+                return f;
+            };
+            auto sw128 = [](int r, int k) { return (r >> 3) * 1024 + (r & 7) * 128 + (((k >> 2) ^ (r & 7)) << 4) + (k & 3) * 4; };
+            q.tc_img.assign(total, 0);
+            auto put = [&](int p, int r, int k, double v) {
+                if (v == 0.0) return;
+                unsigned char* base = q.tc_img.data() + t.off[p] + (size_t)(k >> 5) * t.pair_bytes[p];
+                const float hi = tf32_rn(v), lo = tf32_rn(v - (double)hi);
+                memcpy(base + sw128(r, k & 31), &hi, 4);
+                memcpy(base + (size_t)N[p] * 128 + sw128(r, k & 31), &lo, 4);
+            };
+            // e columns: x0_c as three pieces (3c .. 3c + 2), the constant 1 (12), the disturbance as three pieces (13 .. 15)
+            auto put_e = [&](int p, int r, int k0, const double* cx, double c1, double cc) {
+                for (int c = 0; c < 4; ++c)
+                    for (int piece = 0; piece < 3; ++piece) put(p, r, k0 + 3 * c + piece, cx[c]);
+                put(p, r, k0 + 12, c1);
+                for (int piece = 0; piece < 3; ++piece) put(p, r, k0 + 13 + piece, cc);
+            };
+            std::vector<double> his(mp, 0.0), gxs((size_t)mp * 4, 0.0), gcs(mp, 0.0);
+            q.tc_nwd.assign(mp, -INFINITY); q.tc_einv_g.assign(mp, 0.f); q.tc_row_id.assign(mp, -1);
+            for (int r = 0; r < mv; ++r) {
+                const int i = rows[r];
+                his[r] = Eg[i] * q.hi[i];
+                for (int c = 0; c < 4; ++c) gxs[(size_t)r * 4 + c] = Eg[i] * q.Gx[(size_t)i * 4 + c];
+                gcs[r] = Eg[i] * q.Gc[i];
+                q.tc_nwd[r] = isinf(q.lo[i]) ? -INFINITY : -(float)(Eg[i] * (q.hi[i] - q.lo[i]));
+                q.tc_einv_g[r] = (float)(1.0 / Eg[i]);
+                q.tc_row_id[r] = i;
+            }
+            q.tc_his = his; q.tc_gxs = gxs; q.tc_gcs = gcs;
+            q.tc_hisf.assign(his.begin(), his.end()); q.tc_gxsf.assign(gxs.begin(), gxs.end()); q.tc_gcsf.assign(gcs.begin(), gcs.end());
+            q.tc_lam.assign(np, 0.f); q.tc_lb.assign(np, -INFINITY); q.tc_ub.assign(np, INFINITY);
+            q.tc_einv_b.assign(np, 0.f); q.tc_nrl.assign(np, 0.f); q.tc_kfv.assign((size_t)np * 4, 0.0);
+            for (int j = 0; j < n; ++j) {
+                q.tc_lam[j] = (float)lam[j];
+                q.tc_lb[j] = isinf(lb_in[j]) ? -INFINITY : (float)(Eb[j] * lb_in[j]);
+                q.tc_ub[j] = isinf(ub_in[j]) ? INFINITY : (float)(Eb[j] * ub_in[j]);
+                q.tc_einv_b[j] = (float)(1.0 / Eb[j]);
+                q.tc_nrl[j] = lam[j] > 0 ? (float)(-1.0 / lam[j]) : 0.f;
+                for (int c = 0; c < 4; ++c) {
+                    double sum = 0;
+                    for (int k = 0; k < n; ++k) sum += q.Kinv[(size_t)j * n + k] * cs * D[k] * q.F[(size_t)k * 4 + c];
+                    q.tc_kfv[(size_t)j * 4 + c] = -sum;
+                }
+            }
+            // product 0: x~ = rho K^-1 [diag(lam) V_b + Gs' (V^_g + h)] + kfv x0 (- kfv xref, added by the kernel)
+            for (int a = 0; a < n; ++a) {
+                double cx[4] = {q.tc_kfv[(size_t)a * 4], q.tc_kfv[(size_t)a * 4 + 1], q.tc_kfv[(size_t)a * 4 + 2], q.tc_kfv[(size_t)a * 4 + 3]};
+                double c1 = 0, cc = 0;
+                for (int j = 0; j < n; ++j)
+                    if (comp[j] == comp[a]) put(0, a, j, rho * q.Kinv[(size_t)a * n + j] * lam[j]);
+                for (int r = 0; r < mv; ++r) {
+                    const int i = rows[r];
+                    if (row_vars[i].empty() || row_comp[i] != comp[a]) continue;
+                    const double pg = rho * KG[(size_t)a * m + i];
+                    put(0, a, np + 16 + r, pg);
+                    for (int c = 0; c < 4; ++c) cx[c] -= pg * gxs[(size_t)r * 4 + c];
+                    c1 += pg * his[r];
+                    cc -= pg * gcs[r];
+                }
+                put_e(0, a, np, cx, c1, cc);
+            }
+            // product 1: z^ = Gs x~ - h ;  product 2: Gs' dy
+            for (int r = 0; r < mv; ++r) {
+                const int i = rows[r];
+                for (int j = 0; j < n; ++j) {
+                    put(1, r, j, q.Gs64[(size_t)i * n + j]);
+                    put(2, j, r, q.Gs64[(size_t)i * n + j]);
+                }
+                put_e(1, r, np, &gxs[(size_t)r * 4], -his[r], gcs[r]);
+            }
+        }
+    }
+
     q.mats_in_smem = GA < 4 && admm_smem_bytes(q, S, true) <= (size_t)226 * 1024;
     q.smem_bytes = admm_smem_bytes(q, S, q.mats_in_smem);
     if (q.smem_bytes > (size_t)227 * 1024) { set_error("carmpc_qp_create: shared-memory budget exceeded"); return CARMPC_ERR_UNSUPPORTED; }

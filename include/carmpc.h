@@ -199,6 +199,9 @@ int carmpc_qp_create(int n, int m, int k, const double* h_H, const double* h_F, 
  *                   padded variables].
  *        10..26 the padded, permuted float32 device images as float64 (P, Gs, Gs', bounds, tiling tables; see
  *        qp_api.cu) - used by the tests to re-run the kernel's arithmetic on the host.
+ *        30..43 the tensor-core form (qp_admm_tc.cu): 30 geometry [has a tensor-core form, padded variables, padded rows,
+ *        matrices resident, A stages, B stages, B stage bytes, shared bytes, then per product: image offset, bytes per
+ *        chunk pair, chunks, k-steps, MMA N], 31 the chunk images as float32 words, 32..43 the per-row tables.
  * Returns the count (written when h_out != NULL).  A handle created on a machine without a CUDA device keeps this
  * view working; its solve calls return CARMPC_ERR_CUDA. */
 int carmpc_qp_get_setup(void* qp, int which, double* h_out, int capacity);
@@ -256,6 +259,19 @@ int carmpc_qp_last_stats(void* qp, int64_t* h_total_iters, int64_t* h_launches);
  * certificate, [14] max_iter samples proven infeasible by the certificate of their own final ADMM state,
  * [15] samples proven infeasible the same way before the second ADMM pass. */
 int carmpc_qp_polish_stats(void* qp, int64_t* h_hist16);
+
+/* Which ADMM kernel large first passes (at least 128 samples per SM) run on: mode 1 (default) = the tcgen05 kernel
+ * (128-sample tiles as the M dimension of kind::tf32 MMAs, 3xTF32 split, state and accumulators in tensor memory) when
+ * the problem has a tensor-core form (up to 256 general rows, 2 rows + variables <= 512 columns of tensor memory:
+ * horizons up to 40 of the shipped environments); mode 0 = the FFMA tile kernel always; mode 2 = mode 1 with cycle
+ * counters (a measuring aid: where the roles of the kernel wait).  mode < 0 only queries.
+ * h_info (nullable, 16 int64): [0] mode, [1] 1 if the problem has a tensor-core form, [2] samples the tcgen05 kernel
+ * took in the last solve, [3] 1 if its matrices stay resident in shared memory (0: streamed from L2 every iteration),
+ * [4..13] mode 2: cycles summed over the CTAs of the last tcgen05 launch - MMA thread: round total, waiting for A
+ * chunks, waiting for B chunks; compute thread 0: waiting for x~, waiting for z^, waiting for a free A stage, retire /
+ * refill, round total, rounds; B stream thread: waiting for a free stage.
+ * Both kernels run the same iteration; the float64 polish certifies the results of either. */
+int carmpc_qp_tensor_mode(void* qp, int mode, int64_t* h_info);
 
 /* ------------------------------------------------------------------------------------------------
  * Monte-Carlo closed loop against the nonlinear bicycle (lib/simulator.py:51-69), in the order of
