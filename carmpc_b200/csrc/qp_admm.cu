@@ -645,7 +645,7 @@ int admm_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
     if (b.count <= 0) return CARMPC_OK;
     if (admm_tc_usable(q, b)) {
         q->last_tc_samples += b.count;
-        if (q->tensor_mode != 2) return admm_tc_launch(q, b, st);
+        if (q->tensor_mode != 3) return admm_tc_launch(q, b, st);
         AdmmBatch bp = b;
         if (q->ws_prof == nullptr) CARMPC_CUDA(cudaMalloc(&q->ws_prof, sizeof(unsigned long long) * 16));
         CARMPC_CUDA(cudaMemsetAsync(q->ws_prof, 0, sizeof(unsigned long long) * 16, st));

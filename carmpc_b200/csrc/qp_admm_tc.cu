@@ -27,7 +27,7 @@ namespace carmpc {
 
 namespace {
 
-constexpr int kTcThreads = 192;
+constexpr int kTcGroups = 3;                       // column groups of four compute warps
 constexpr int kAStageBytes = 128 * 128 * 2;        // hi image + lo image of a 128 x 32 chunk
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -49,9 +49,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
     int spins = 0;
     while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (!done && ++spins > (1 << 22)) __trap();          // a broken pipeline must fail loudly, not hang the GPU
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+        if (!done && ++spins > (1 << 20)) __trap();          // a broken pipeline must fail loudly, not hang the GPU
     }
 }
 
@@ -123,8 +123,14 @@ __device__ __forceinline__ void mbar_wait_prof(uint64_t* bar, uint32_t parity, u
 struct TcSmem {
     unsigned char *a_ring, *b_res, *b_ring;
     float *nwd, *lam, *lb, *ub, *t;
+    double *his, *gxs, *gcs;                   // [mp], [mp][4], [mp]: the per-sample bound h = his - gxs x0 - gcs c
+    double* xs;                                // [5][128]  x0 (4) and the disturbance of each slot's sample
+    int *slot_sample, *slot_state, *slot_iter, *slot_fresh;
+    unsigned *red_res, *red_nrm;
+    float *red_sup, *red_abs;
     uint64_t *a_full, *a_empty, *b_full, *b_empty, *bar_x, *bar_z, *bar_res;
     uint32_t* tmem_slot;
+    unsigned long long* pc;                    // [16] cycle counters of the three profiled threads (tensor mode 2)
 };
 
 template <int NP>
@@ -134,37 +140,59 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* raw, const TcTables& C
     s.a_ring = base;
     s.b_res = s.a_ring + (size_t)C.na_stages * kAStageBytes;
     s.b_ring = s.b_res + C.resident_bytes;
-    s.nwd = reinterpret_cast<float*>(s.b_ring + (size_t)C.nb_stages * C.b_stage_bytes);
+    s.his = reinterpret_cast<double*>(s.b_ring + (size_t)C.nb_stages * C.b_stage_bytes);
+    s.gxs = s.his + C.mp;
+    s.gcs = s.gxs + 4 * C.mp;
+    s.xs = s.gcs + C.mp;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s.xs + 5 * 128);
+    s.a_full = bars; s.a_empty = bars + 4; s.b_full = bars + 8; s.b_empty = bars + 10;
+    s.bar_x = bars + 12; s.bar_z = bars + 13; s.bar_res = bars + 14;
+    s.nwd = reinterpret_cast<float*>(bars + 16);
     s.lam = s.nwd + C.mp;
     s.lb = s.lam + NP;
     s.ub = s.lb + NP;
     s.t = s.ub + NP;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s.t + NP);
-    s.a_full = bars; s.a_empty = bars + 4; s.b_full = bars + 8; s.b_empty = bars + 10;
-    s.bar_x = bars + 12; s.bar_z = bars + 13; s.bar_res = bars + 14;
-    s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    s.slot_sample = reinterpret_cast<int*>(s.t + NP);
+    s.slot_state = s.slot_sample + 128;
+    s.slot_iter = s.slot_state + 128;
+    s.slot_fresh = s.slot_iter + 128;
+    s.red_res = reinterpret_cast<unsigned*>(s.slot_fresh + 128);
+    s.red_nrm = s.red_res + 128;
+    s.red_sup = reinterpret_cast<float*>(s.red_nrm + 128);
+    s.red_abs = s.red_sup + 128;
+    s.tmem_slot = reinterpret_cast<uint32_t*>(s.red_abs + 128);
+    s.pc = reinterpret_cast<unsigned long long*>(s.tmem_slot + 2);
     return s;
 }
 
-// The compute threads' view of the A-operand ring: a product's K columns are appended 16 at a time (one tcgen05.ld block);
-// a chunk of 32 columns (or the tail of the product) is published to the MMA warp when complete.
+__device__ __forceinline__ void atomic_max_pos(unsigned* addr, float v) {      // v >= 0 (NaN maps to a huge value)
+    atomicMax(addr, __float_as_uint(v == v ? v : INFINITY));
+}
+
+// The compute threads' view of the A-operand ring.  A product's K columns are written in blocks of 16 (one tcgen05.ld
+// block) by the column group that owns the block; a chunk of 32 columns is complete after 8 warp arrivals (two blocks x
+// four lane quarters; the lone half chunk at the tail of a product arrives twice).  Every thread derives the chunk
+// sequence arithmetically, the MMA warp counts the same sequence.
 struct AStream {
     unsigned char* ring;
     uint64_t *full, *empty;
     int na;
-    unsigned chunk;      // chunks published so far (the MMA warp counts the same sequence)
-    unsigned long long* wait_acc;
-    int kpos, kend;
+    unsigned base;       // chunks published by the streams before the current one
+    int kend;
     uint32_t row_off;    // byte offset of this thread's row inside an image
     int r7;
+    unsigned long long* wait_acc;
 };
 
-__device__ __forceinline__ void a_begin(AStream& A, int kend) { A.kpos = 0; A.kend = kend; }
+__device__ __forceinline__ void a_begin(AStream& A, int kend) { A.kend = kend; }
+__device__ __forceinline__ void a_end(AStream& A) { A.base += (unsigned)((A.kend + 31) >> 5); }
 
-__device__ __forceinline__ void a_put16(AStream& A, const float (&v)[16], int lane) {
-    const int stage = (int)(A.chunk % (unsigned)A.na);
-    const int half = (A.kpos >> 4) & 1;
-    if (half == 0) mbar_wait_prof(A.empty + stage, ((A.chunk / (unsigned)A.na) & 1u) ^ 1u, A.wait_acc);
+__device__ __forceinline__ void a_put16(const AStream& A, int k0, const float (&v)[16], int lane) {
+    const unsigned chunk = A.base + (unsigned)(k0 >> 5);
+    const unsigned use = A.na == 2 ? chunk >> 1 : chunk / 3u;
+    const int stage = (int)(chunk - use * (unsigned)A.na);
+    const int half = (k0 >> 4) & 1;
+    mbar_wait_prof(A.empty + stage, (use & 1u) ^ 1u, A.wait_acc);
     unsigned char* hi_row = A.ring + (size_t)stage * kAStageBytes + A.row_off;
     unsigned char* lo_row = hi_row + 128 * 128;
 #pragma unroll
@@ -176,42 +204,60 @@ __device__ __forceinline__ void a_put16(AStream& A, const float (&v)[16], int la
         *reinterpret_cast<float4*>(hi_row + (piece << 4)) = h;
         *reinterpret_cast<float4*>(lo_row + (piece << 4)) = l;
     }
-    A.kpos += 16;
-    if (half == 1 || A.kpos == A.kend) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(A.full + stage);
-        ++A.chunk;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+        mbar_arrive(A.full + stage);
+        if (half == 0 && k0 + 16 == A.kend) mbar_arrive(A.full + stage);     // nobody writes the second half
     }
 }
 
-template <int NP>
-__global__ void __launch_bounds__(kTcThreads, 1) admm_tc_kernel(const AdmmTables T, const TcTables C, const AdmmBatch Bq) {
+// G column groups of 4 warps: thread (slot = tid & 127, group = tid >> 7) owns the blocks b = group, group + G, ... of its
+// sample in every phase; warps 4 G and 4 G + 1 issue the MMAs and stream the B chunks.
+template <int NP, int G>
+__global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTables T, const TcTables C, const AdmmBatch Bq) {
+    constexpr int NC = 128 * G;                     // compute threads
+    constexpr int NPB = NP / 16;                    // blocks of box rows
+    constexpr int MAXB = (NPB + G - 1) / G;         // box blocks per thread
+    constexpr int EG = NPB % G;                     // the group that writes the constant columns (the block after the box blocks)
     extern __shared__ unsigned char smem_raw[];
     const TcSmem sm = tc_carve<NP>(smem_raw, C);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slot = tid & 127, cg = tid >> 7;
     const int mp = C.mp, n = C.n, m = C.m, mt = C.mt;
+    const int MPB = mp >> 4;
     const float alpha = T.alpha;
 
     // ---- one-time setup ------------------------------------------------------------------------------------------------
-    if (warp == 4) {
+    if (warp == 4 * G) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(sm.tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(sm.a_full + i, 4); mbar_init(sm.a_empty + i, 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(sm.a_full + i, 8); mbar_init(sm.a_empty + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(sm.b_full + i, 1); mbar_init(sm.b_empty + i, 1); }
         mbar_init(sm.bar_x, 1); mbar_init(sm.bar_z, 1); mbar_init(sm.bar_res, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (tid < 128) {
-        for (int i = tid; i < mp; i += 128) sm.nwd[i] = C.nwd[i];
-        for (int j = tid; j < NP; j += 128) {
+    if (tid < NC) {
+        for (int i = tid; i < mp; i += NC) {
+            sm.nwd[i] = C.nwd[i]; sm.his[i] = C.his[i]; sm.gcs[i] = C.gcs[i];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sm.gxs[i * 4 + c] = C.gxs[(size_t)i * 4 + c];
+        }
+        for (int j = tid; j < NP; j += NC) {
             sm.lam[j] = C.lam[j]; sm.lb[j] = C.lb[j]; sm.ub[j] = C.ub[j];
             const double* kf = C.kfv + (size_t)j * 4;
             sm.t[j] = (float)(-(kf[0] * Bq.xref[0] + kf[1] * Bq.xref[1] + kf[2] * Bq.xref[2] + kf[3] * Bq.xref[3]));
+        }
+        if (tid < 16) sm.pc[tid] = 0;
+        if (tid < 128) {
+            sm.slot_sample[tid] = -1; sm.slot_state[tid] = kSlotIdle; sm.slot_iter[tid] = 0; sm.slot_fresh[tid] = 0;
+            sm.red_res[tid] = 0; sm.red_nrm[tid] = 0; sm.red_sup[tid] = 0.f; sm.red_abs[tid] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) sm.xs[c * 128 + tid] = 0.0;
         }
     }
     tc_fence_before();
@@ -224,56 +270,53 @@ __global__ void __launch_bounds__(kTcThreads, 1) admm_tc_kernel(const AdmmTables
 
     // role-private pipeline counters (they persist over the rounds)
     unsigned mma_a = 0, mma_b = 0, tma_b = 0;
-    if (tid == 160 && C.resident) {
+    if (tid == NC + 32 && C.resident) {
         mbar_expect_tx(sm.bar_res, (uint32_t)C.resident_bytes);
         for (int o = 0; o < C.resident_bytes; o += 16384)
             bulk_load(sm.b_res + o, C.img + C.off[0] + o, (uint32_t)min(16384, C.resident_bytes - o), sm.bar_res);
     }
-    if (tid == 128 && C.resident) { mbar_wait(sm.bar_res, 0); tc_fence_after(); }
+    if (tid == NC && C.resident) { mbar_wait(sm.bar_res, 0); tc_fence_after(); }
 
     // ---- compute-thread state --------------------------------------------------------------------------------------------
-    float wb[NP];                      // w of the box rows of this thread's sample
-    float ex[16];                      // the sample's constant columns (x0 pieces, 1, disturbance pieces)
-    float x0f[4] = {0.f, 0.f, 0.f, 0.f}, cdf = 0.f;
-    int sample = -1, sstate = kSlotIdle, siter = 0;
-    bool drained = false;
+    float wb[MAXB][16];                // w of this thread's box rows: block lb covers variables 16 (lb G + group) ...
+    bool drained = false;              // (group 0) the queue is empty
     unsigned n_x = 0, n_z = 0;         // completed waits on bar_x / bar_z
     AStream A;
-    A.ring = sm.a_ring; A.full = sm.a_full; A.empty = sm.a_empty; A.na = C.na_stages; A.chunk = 0; A.kpos = 0; A.kend = 0;
-    A.row_off = (uint32_t)((tid >> 3) * 1024 + (tid & 7) * 128); A.r7 = tid & 7;
-    unsigned long long pc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};     // this thread's cycle counters
-    const bool prof = Bq.prof != nullptr && (tid == 0 || tid == 128 || tid == 160);
+    A.ring = sm.a_ring; A.full = sm.a_full; A.empty = sm.a_empty; A.na = C.na_stages; A.base = 0; A.kend = 0;
+    A.row_off = (uint32_t)((slot >> 3) * 1024 + (slot & 7) * 128); A.r7 = slot & 7;
+    unsigned long long* const pc = sm.pc;                            // cycle counters (each written by one thread)
+    const bool prof = Bq.prof != nullptr && (tid == 0 || tid == NC || tid == NC + 32);
     A.wait_acc = prof ? &pc[5] : nullptr;
 #pragma unroll
-    for (int j = 0; j < NP; ++j) wb[j] = 0.f;
+    for (int lb = 0; lb < MAXB; ++lb)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) ex[j] = 0.f;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;     // this warp's quarter of tensor memory (compute warps only)
+        for (int r = 0; r < 16; ++r) wb[lb][r] = 0.f;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;     // this warp's quarter of tensor memory
     const float eps_abs = T.eps_abs * Bq.eps_scale, eps_rel = T.eps_rel * Bq.eps_scale;
+    auto sync_compute = [&]() { asm volatile("bar.sync 1, %0;" :: "r"(NC) : "memory"); };
 
     for (;;) {
         int running = 0;
         const long long t_round = clock64();
-        if (tid < 128) {
-            // ================= retire a finished sample, take the next one from the queue =================
+        if (tid < NC) {
+            // ================= retire finished samples, take the next ones from the queue =================
             // (tensor-memory loads / stores are warp-collective: every lane executes them, only the owners of a finished /
             //  fresh slot act on the values)
-            const bool fin = sstate > 0;
+            const bool fin = sm.slot_state[slot] > 0;
+            const int sample_old = sm.slot_sample[slot];
             if (__any_sync(0xffffffffu, fin)) {
                 double xs[4] = {0.0, 0.0, 0.0, 0.0}, cd = 0.0;
                 int8_t* sg = nullptr;
                 float* wo = nullptr;
                 if (fin) {
-                    Bq.status[sample] = sstate == kSlotSolved ? CARMPC_QP_SOLVED : (sstate == kSlotMaxIter ? CARMPC_QP_MAX_ITER : CARMPC_QP_INFEASIBLE);
-                    Bq.iters[sample] = siter + (Bq.iters_accumulate ? Bq.iters[sample] : 0);
-                    atomicAdd(Bq.total_iters, (unsigned long long)siter);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) xs[c] = Bq.x0[(size_t)c * Bq.stride + sample];
-                    if (Bq.cdist) cd = Bq.cdist[sample];
-                    sg = Bq.sign + (size_t)sample * mt;
-                    wo = Bq.warm + (size_t)sample * mt;
+                    for (int c = 0; c < 4; ++c) xs[c] = sm.xs[c * 128 + slot];
+                    cd = sm.xs[4 * 128 + slot];
+                    sg = Bq.sign + (size_t)sample_old * mt;
+                    wo = Bq.warm + (size_t)sample_old * mt;
                 }
-                for (int g0 = 0; g0 < mp; g0 += 16) {
+                for (int b = cg; b < MPB; b += G) {
+                    const int g0 = b << 4;
                     uint32_t wr[16];
                     tmem_ld16(col_state + lane_addr + (uint32_t)g0, wr);
                     tmem_ld_wait(wr);
@@ -285,8 +328,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) admm_tc_kernel(const AdmmTables
                             const float w = __uint_as_float(wr[r]);
                             sg[rid] = (int8_t)((w > 0.f) - (w < sm.nwd[g0 + r]));
                             if (Bq.warm_out) {
-                                const double* gx = C.gxs + (size_t)(g0 + r) * 4;
-                                const double h = C.his[g0 + r] - gx[0] * xs[0] - gx[1] * xs[1] - gx[2] * xs[2] - gx[3] * xs[3] - C.gcs[g0 + r] * cd;
+                                const double* gx = sm.gxs + (g0 + r) * 4;
+                                const double h = sm.his[g0 + r] - gx[0] * xs[0] - gx[1] * xs[1] - gx[2] * xs[2] - gx[3] * xs[3] - sm.gcs[g0 + r] * cd;
                                 wo[rid] = (float)((double)w + h);
                             }
                         }
@@ -294,45 +337,79 @@ __global__ void __launch_bounds__(kTcThreads, 1) admm_tc_kernel(const AdmmTables
                 }
                 if (fin) {
 #pragma unroll
-                    for (int j = 0; j < NP; ++j) {
-                        if (j < n) {
-                            sg[m + j] = (int8_t)((wb[j] > sm.ub[j]) - (wb[j] < sm.lb[j]));
-                            if (Bq.warm_out) wo[m + j] = wb[j];
+                    for (int lb = 0; lb < MAXB; ++lb) {
+                        const int j0 = (lb * G + cg) << 4;
+                        if (j0 < NP) {
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) {
+                                const int j = j0 + r;
+                                if (j < n) {
+                                    sg[m + j] = (int8_t)((wb[lb][r] > sm.ub[j]) - (wb[lb][r] < sm.lb[j]));
+                                    if (Bq.warm_out) wo[m + j] = wb[lb][r];
+                                }
+                            }
                         }
                     }
-                    sstate = kSlotIdle;
                 }
             }
-            bool fresh = false;
-            double xs[4] = {0.0, 0.0, 0.0, 0.0}, cd = 0.0;
-            while (sstate == kSlotIdle && !drained) {
-                const int qi = atomicAdd(Bq.next, 1);
-                if (qi >= q_count) { drained = true; break; }
-                sample = Bq.idx_list ? Bq.idx_list[qi] : qi;
+            sync_compute();                        // every group has read the slot's state and sample
+            if (cg == 0) {
+                int st = sm.slot_state[slot];
+                if (st > 0) {
+                    const int it = sm.slot_iter[slot];
+                    Bq.status[sample_old] = st == kSlotSolved ? CARMPC_QP_SOLVED : (st == kSlotMaxIter ? CARMPC_QP_MAX_ITER : CARMPC_QP_INFEASIBLE);
+                    Bq.iters[sample_old] = it + (Bq.iters_accumulate ? Bq.iters[sample_old] : 0);
+                    atomicAdd(Bq.total_iters, (unsigned long long)it);
+                    st = kSlotIdle;
+                }
+                int fresh = 0;
+                while (st == kSlotIdle && !drained) {
+                    const int qi = atomicAdd(Bq.next, 1);
+                    if (qi >= q_count) { drained = true; break; }
+                    const int sample = Bq.idx_list ? Bq.idx_list[qi] : qi;
+                    double xs[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) xs[c] = Bq.x0[(size_t)c * Bq.stride + sample];
-                cd = Bq.cdist ? Bq.cdist[sample] : 0.0;
-                bool pre_ok = isfinite(xs[0]) && isfinite(xs[1]) && isfinite(xs[2]) && isfinite(xs[3]);
-                for (int k = 0; k < T.kpre; ++k) {
-                    const double v = T.Px[k * 4 + 0] * xs[0] + T.Px[k * 4 + 1] * xs[1] + T.Px[k * 4 + 2] * xs[2] +
-                                     T.Px[k * 4 + 3] * xs[3] + T.Pc[k] * cd;
-                    pre_ok = pre_ok && v <= T.pre_hi[k] && v >= T.pre_lo[k];
+                    for (int c = 0; c < 4; ++c) xs[c] = Bq.x0[(size_t)c * Bq.stride + sample];
+                    const double cd = Bq.cdist ? Bq.cdist[sample] : 0.0;
+                    bool pre_ok = isfinite(xs[0]) && isfinite(xs[1]) && isfinite(xs[2]) && isfinite(xs[3]);
+                    for (int k = 0; k < T.kpre; ++k) {
+                        const double v = T.Px[k * 4 + 0] * xs[0] + T.Px[k * 4 + 1] * xs[1] + T.Px[k * 4 + 2] * xs[2] +
+                                         T.Px[k * 4 + 3] * xs[3] + T.Pc[k] * cd;
+                        pre_ok = pre_ok && v <= T.pre_hi[k] && v >= T.pre_lo[k];
+                    }
+                    if (!pre_ok) {
+                        // a violated row that does not depend on u: infeasible without iterating (the FFMA kernel books one round)
+                        Bq.status[sample] = CARMPC_QP_INFEASIBLE;
+                        Bq.iters[sample] = check_every + (Bq.iters_accumulate ? Bq.iters[sample] : 0);
+                        atomicAdd(Bq.total_iters, (unsigned long long)check_every);
+                        continue;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) sm.xs[c * 128 + slot] = xs[c];
+                    sm.xs[4 * 128 + slot] = cd;
+                    sm.slot_sample[slot] = sample;
+                    sm.slot_iter[slot] = 0;
+                    fresh = 1;
+                    st = kSlotRunning;
                 }
-                if (!pre_ok) {
-                    // a violated row that does not depend on u: infeasible without iterating (the FFMA kernel books one round)
-                    Bq.status[sample] = CARMPC_QP_INFEASIBLE;
-                    Bq.iters[sample] = check_every + (Bq.iters_accumulate ? Bq.iters[sample] : 0);
-                    atomicAdd(Bq.total_iters, (unsigned long long)check_every);
-                    continue;
-                }
-                fresh = true;
-                siter = 0;
-                sstate = kSlotRunning;
+                sm.slot_state[slot] = st;
+                sm.slot_fresh[slot] = fresh;
+                sm.red_res[slot] = 0; sm.red_nrm[slot] = 0; sm.red_sup[slot] = 0.f; sm.red_abs[slot] = 0.f;
             }
+            sync_compute();
+            const bool fresh = sm.slot_fresh[slot] != 0;
             if (__any_sync(0xffffffffu, fresh)) {
-                // state of a new sample: w^ = w - h (cold: w = 0), box rows, constant columns
+                // state of a new sample: w^ = w - h (cold: w = 0), box rows
+                const int sample = sm.slot_sample[slot];
                 const float* wi = (fresh && Bq.warm_in) ? Bq.warm + (size_t)sample * mt : nullptr;
-                for (int g0 = 0; g0 < mp; g0 += 16) {
+                double xs[4] = {0.0, 0.0, 0.0, 0.0}, cd = 0.0;
+                if (fresh) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) xs[c] = sm.xs[c * 128 + slot];
+                    cd = sm.xs[4 * 128 + slot];
+                }
+                for (int b = cg; b < MPB; b += G) {
+                    const int g0 = b << 4;
                     uint32_t wr[16];
                     tmem_ld16(col_state + lane_addr + (uint32_t)g0, wr);
                     tmem_ld_wait(wr);
@@ -342,8 +419,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) admm_tc_kernel(const AdmmTables
                             const int rid = C.row_id[g0 + r];
                             float w = 0.f;
                             if (rid >= 0) {
-                                const double* gx = C.gxs + (size_t)(g0 + r) * 4;
-                                const double h = C.his[g0 + r] - gx[0] * xs[0] - gx[1] * xs[1] - gx[2] * xs[2] - gx[3] * xs[3] - C.gcs[g0 + r] * cd;
+                                const double* gx = sm.gxs + (g0 + r) * 4;
+                                const double h = sm.his[g0 + r] - gx[0] * xs[0] - gx[1] * xs[1] - gx[2] * xs[2] - gx[3] * xs[3] - sm.gcs[g0 + r] * cd;
                                 w = (float)((wi ? (double)wi[rid] : 0.0) - h);
                             }
                             wr[r] = __float_as_uint(w);
@@ -354,44 +431,58 @@ __global__ void __launch_bounds__(kTcThreads, 1) admm_tc_kernel(const AdmmTables
                 tmem_st_wait();
                 if (fresh) {
 #pragma unroll
-                    for (int j = 0; j < NP; ++j) wb[j] = (wi && j < n) ? wi[m + j] : 0.f;
+                    for (int lb = 0; lb < MAXB; ++lb)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) { split3(xs[c], ex[3 * c], ex[3 * c + 1], ex[3 * c + 2]); x0f[c] = (float)xs[c]; }
-                    ex[12] = 1.f;
-                    split3(cd, ex[13], ex[14], ex[15]);
-                    cdf = (float)cd;
+                        for (int r = 0; r < 16; ++r) {
+                            const int j = ((lb * G + cg) << 4) + r;
+                            wb[lb][r] = (wi && j < n) ? wi[m + j] : 0.f;
+                        }
                 }
             }
-            running = sstate == kSlotRunning;
+            running = sm.slot_state[slot] == kSlotRunning;
         }
         if (prof && tid == 0) pc[6] += (unsigned long long)(clock64() - t_round);
         if (!__syncthreads_or(running)) break;
         const long long t_work = clock64();
 
-        if (tid < 128) {
+        if (tid < NC) {
             // ================= elementwise phases of one round (check_every iterations, the last one checked) =================
+            // the constant columns of this slot's sample (x0 pieces, 1, disturbance pieces): exact TF32 values
+            auto put_e = [&](int k0) {
+                float e[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) split3(sm.xs[c * 128 + slot], e[3 * c], e[3 * c + 1], e[3 * c + 2]);
+                e[12] = 1.f;
+                split3(sm.xs[4 * 128 + slot], e[13], e[14], e[15]);
+                a_put16(A, k0, e, lane);
+            };
             auto put_box_v = [&]() {          // V_b = 2 clip(w_b) - w_b, then the constant columns: the head of product 0's K
 #pragma unroll
-                for (int j0 = 0; j0 < NP; j0 += 16) {
-                    float v[16];
+                for (int lb = 0; lb < MAXB; ++lb) {
+                    const int j0 = (lb * G + cg) << 4;
+                    if (j0 < NP) {
+                        float v[16];
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) { const float w = wb[j0 + r]; v[r] = fmaf(2.f, clampf(w, sm.lb[j0 + r], sm.ub[j0 + r]), -w); }
-                    a_put16(A, v, lane);
+                        for (int r = 0; r < 16; ++r) { const float w = wb[lb][r]; v[r] = fmaf(2.f, clampf(w, sm.lb[j0 + r], sm.ub[j0 + r]), -w); }
+                        a_put16(A, j0, v, lane);
+                    }
                 }
-                a_put16(A, ex, lane);
+                if (cg == EG) put_e(NP);
             };
             // round start: every chunk of product 0 from the state
             a_begin(A, NP + 16 + mp);
             put_box_v();
-            for (int g0 = 0; g0 < mp; g0 += 16) {
+            for (int b = cg; b < MPB; b += G) {
+                const int g0 = b << 4;
                 uint32_t wr[16];
                 tmem_ld16(col_state + lane_addr + (uint32_t)g0, wr);
                 tmem_ld_wait(wr);
                 float v[16];
 #pragma unroll
                 for (int r = 0; r < 16; ++r) { const float w = __uint_as_float(wr[r]); v[r] = fmaf(2.f, clampf(w, sm.nwd[g0 + r], 0.f), -w); }
-                a_put16(A, v, lane);
+                a_put16(A, NP + 16 + g0, v, lane);
             }
+            a_end(A);
             float p_res = 0.f, p_nrm = 0.f, p_sup = 0.f, p_abs = 0.f;
             for (int it = 0; it < check_every; ++it) {
                 const bool check = it == check_every - 1;
@@ -400,35 +491,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) admm_tc_kernel(const AdmmTables
                 tc_fence_after();
                 a_begin(A, NP + 16);
 #pragma unroll
-                for (int j0 = 0; j0 < NP; j0 += 16) {
-                    uint32_t xr[16];
-                    tmem_ld16(col_x + lane_addr + (uint32_t)j0, xr);
-                    tmem_ld_wait(xr);
-                    float x[16];
+                for (int lb = 0; lb < MAXB; ++lb) {
+                    const int j0 = (lb * G + cg) << 4;
+                    if (j0 < NP) {
+                        uint32_t xr[16];
+                        tmem_ld16(col_x + lane_addr + (uint32_t)j0, xr);
+                        tmem_ld_wait(xr);
+                        float x[16];
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        const int j = j0 + r;
-                        x[r] = __uint_as_float(xr[r]) + sm.t[j];
-                        const float lb = sm.lb[j], ub = sm.ub[j];
-                        const float w0 = wb[j], z = sm.lam[j] * x[r];
-                        const float c0 = clampf(w0, lb, ub);
-                        const float w1 = fmaf(alpha, z - c0, w0);
-                        wb[j] = w1;
-                        if (check) {
-                            const float c1 = clampf(w1, lb, ub), einv = C.einv_b[j];
-                            p_res = fmaxf(p_res, fmaxf(fabsf(z - c1), fabsf(c1 - c0)) * einv);
-                            p_nrm = fmaxf(p_nrm, fmaxf(fabsf(z), fabsf(c1)) * einv);
+                        for (int r = 0; r < 16; ++r) {
+                            const int j = j0 + r;
+                            x[r] = __uint_as_float(xr[r]) + sm.t[j];
+                            const float lb_ = sm.lb[j], ub_ = sm.ub[j];
+                            const float w0 = wb[lb][r], z = sm.lam[j] * x[r];
+                            const float c0 = clampf(w0, lb_, ub_);
+                            const float w1 = fmaf(alpha, z - c0, w0);
+                            wb[lb][r] = w1;
+                            if (check) {
+                                const float c1 = clampf(w1, lb_, ub_), einv = C.einv_b[j];
+                                p_res = fmaxf(p_res, fmaxf(fabsf(z - c1), fabsf(c1 - c0)) * einv);
+                                p_nrm = fmaxf(p_nrm, fmaxf(fabsf(z), fabsf(c1)) * einv);
+                            }
                         }
+                        a_put16(A, j0, x, lane);
                     }
-                    a_put16(A, x, lane);
                 }
-                a_put16(A, ex, lane);
+                if (cg == EG) put_e(NP);
+                a_end(A);
                 if (!check) { a_begin(A, NP + 16 + mp); put_box_v(); }      // head of the next iteration's product 0
                 else a_begin(A, mp);                                         // dy chunks of the certificate product
+                const int kg0 = check ? 0 : NP + 16;
                 // ---------------- S_G: general rows (w^ += alpha (z^ - c^)), V chunks of product 0 ----------------
                 mbar_wait_prof(sm.bar_z, n_z & 1u, prof ? &pc[4] : nullptr); ++n_z;
                 tc_fence_after();
-                for (int g0 = 0; g0 < mp; g0 += 16) {
+                double xd[4] = {0.0, 0.0, 0.0, 0.0}, cdd = 0.0;
+                if (check) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) xd[c] = sm.xs[c * 128 + slot];
+                    cdd = sm.xs[4 * 128 + slot];
+                }
+                for (int b = cg; b < MPB; b += G) {
+                    const int g0 = b << 4;
                     uint32_t zr[16], wr[16];
                     tmem_ld16(col_z + lane_addr + (uint32_t)g0, zr);
                     tmem_ld16(col_state + lane_addr + (uint32_t)g0, wr);
@@ -448,8 +551,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) admm_tc_kernel(const AdmmTables
                         } else {
                             const int i = g0 + r;
                             const float einv = C.einv_g[i];
-                            const float* gx = C.gxsf + (size_t)i * 4;
-                            const float h = C.hisf[i] - gx[0] * x0f[0] - gx[1] * x0f[1] - gx[2] * x0f[2] - gx[3] * x0f[3] - C.gcsf[i] * cdf;
+                            const double* gx = sm.gxs + i * 4;
+                            const float h = (float)(sm.his[i] - gx[0] * xd[0] - gx[1] * xd[1] - gx[2] * xd[2] - gx[3] * xd[3] - sm.gcs[i] * cdd);
                             p_res = fmaxf(p_res, fmaxf(fabsf(z - c1), fabsf(c1 - c0)) * einv);
                             p_nrm = fmaxf(p_nrm, fmaxf(fabsf(z + h), fabsf(c1 + h)) * einv);
                             float e = (w1 - c1) - (w0 - c0);
@@ -461,37 +564,50 @@ __global__ void __launch_bounds__(kTcThreads, 1) admm_tc_kernel(const AdmmTables
                         }
                     }
                     tmem_st16(col_state + lane_addr + (uint32_t)g0, wr);
-                    a_put16(A, v, lane);
+                    a_put16(A, kg0 + g0, v, lane);
                 }
                 tmem_st_wait();
+                a_end(A);
             }
             // ---------------- certificate: y_b = -(Gs' dy) / lam makes A'y = 0 exactly; infeasible iff the support sum < 0 ----------------
             mbar_wait_prof(sm.bar_x, n_x & 1u, prof ? &pc[3] : nullptr); ++n_x;
             tc_fence_after();
 #pragma unroll
-            for (int j0 = 0; j0 < NP; j0 += 16) {
-                uint32_t yr[16];
-                tmem_ld16(col_x + lane_addr + (uint32_t)j0, yr);
-                tmem_ld_wait(yr);
+            for (int lb = 0; lb < MAXB; ++lb) {
+                const int j0 = (lb * G + cg) << 4;
+                if (j0 < NP) {
+                    uint32_t yr[16];
+                    tmem_ld16(col_x + lane_addr + (uint32_t)j0, yr);
+                    tmem_ld_wait(yr);
 #pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const int j = j0 + r;
-                    const float yb = __uint_as_float(yr[r]) * C.nrl[j];
-                    const float term = yb > 0.f ? sm.ub[j] * yb : (yb < 0.f ? sm.lb[j] * yb : 0.f);
-                    p_sup += term;
-                    p_abs += fabsf(term);
+                    for (int r = 0; r < 16; ++r) {
+                        const int j = j0 + r;
+                        const float yb = __uint_as_float(yr[r]) * C.nrl[j];
+                        const float term = yb > 0.f ? sm.ub[j] * yb : (yb < 0.f ? sm.lb[j] * yb : 0.f);
+                        p_sup += term;
+                        p_abs += fabsf(term);
+                    }
                 }
             }
             tc_fence_before();
-            if (sstate == kSlotRunning) {
-                siter += check_every;
+            atomic_max_pos(sm.red_res + slot, p_res);
+            atomic_max_pos(sm.red_nrm + slot, p_nrm);
+            atomicAdd(sm.red_sup + slot, p_sup);
+            atomicAdd(sm.red_abs + slot, p_abs);
+            sync_compute();
+            if (cg == 0 && sm.slot_state[slot] == kSlotRunning) {
+                const int it = sm.slot_iter[slot] + check_every;
+                sm.slot_iter[slot] = it;
+                const float res = __uint_as_float(sm.red_res[slot]), nrm = __uint_as_float(sm.red_nrm[slot]);
+                const float sup = sm.red_sup[slot], sabs = sm.red_abs[slot];
                 int ns = kSlotRunning;
-                if (p_abs > 0.f && p_sup <= -T.eps_inf * p_abs) ns = kSlotInfeasible;
-                else if (p_res <= eps_abs + eps_rel * p_nrm) ns = kSlotSolved;
-                else if (siter >= Bq.max_iter || !(p_res == p_res)) ns = kSlotMaxIter;
-                sstate = ns;
+                if (sabs > 0.f && sup <= -T.eps_inf * sabs) ns = kSlotInfeasible;
+                else if (res <= eps_abs + eps_rel * nrm) ns = kSlotSolved;
+                else if (it >= Bq.max_iter || !(res == res)) ns = kSlotMaxIter;
+                sm.slot_state[slot] = ns;
             }
-        } else if (tid == 128) {
+            sync_compute();
+        } else if (tid == NC) {
             // ================= MMA issue: the same chunk sequence the compute threads publish =================
             auto product = [&](int p, uint32_t dcol, bool streamed, uint64_t* done) {
                 const int N = C.ncols[p];
@@ -499,29 +615,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) admm_tc_kernel(const AdmmTables
                 const int e_ks = p == 2 ? -1 : NP / 8;              // the two k-steps of the constant columns: their lo image is zero
                 const unsigned char* res_base = sm.b_res + (p == 1 ? (size_t)C.nchunks[0] * C.pair_bytes[0] : 0);
                 for (int c = 0; c < C.nchunks[p]; ++c) {
-                    const int sa = (int)(mma_a % (unsigned)C.na_stages);
-                    mbar_wait_prof(sm.a_full + sa, (mma_a / (unsigned)C.na_stages) & 1u, prof ? &pc[1] : nullptr);
+                    const unsigned use = C.na_stages == 2 ? mma_a >> 1 : mma_a / 3u;
+                    const int sa = (int)(mma_a - use * (unsigned)C.na_stages);
+                    mbar_wait_prof(sm.a_full + sa, use & 1u, prof ? &pc[1] : nullptr);
                     const unsigned char* bsrc;
                     int sb = 0;
                     if (streamed) {
-                        sb = (int)(mma_b & 1u);
-                        mbar_wait_prof(sm.b_full + sb, (mma_b >> 1) & 1u, prof ? &pc[2] : nullptr);
+                        sb = C.nb_stages == 2 ? (int)(mma_b & 1u) : 0;
+                        mbar_wait_prof(sm.b_full + sb, (C.nb_stages == 2 ? mma_b >> 1 : mma_b) & 1u, prof ? &pc[2] : nullptr);
                         bsrc = sm.b_ring + (size_t)sb * C.b_stage_bytes;
                     } else {
                         bsrc = res_base + (size_t)c * C.pair_bytes[p];
                     }
                     tc_fence_after();
                     const uint64_t a_hi = desc_sw128(smem_u32(sm.a_ring + (size_t)sa * kAStageBytes));
-                    const uint64_t a_lo = desc_sw128(smem_u32(sm.a_ring + (size_t)sa * kAStageBytes + 128 * 128));
+                    const uint64_t a_lo = a_hi + (uint64_t)((128 * 128) >> 4);
                     const uint64_t b_hi = desc_sw128(smem_u32(bsrc));
-                    const uint64_t b_lo = desc_sw128(smem_u32(bsrc + (size_t)N * 128));
+                    const uint64_t b_lo = b_hi + (uint64_t)((N * 128) >> 4);
                     const int nks = min(4, C.ksteps[p] - 4 * c);
-                    for (int ks = 0; ks < nks; ++ks) {
-                        const uint64_t o = (uint64_t)(ks * 2);
-                        const int kg = 4 * c + ks;
-                        mma_ss(dcol, a_hi + o, b_hi + o, idesc, (uint32_t)(kg != 0));
-                        if (kg != e_ks && kg != e_ks + 1) mma_ss(dcol, a_lo + o, b_hi + o, idesc, 1u);
-                        mma_ss(dcol, a_hi + o, b_lo + o, idesc, 1u);
+                    const bool e_chunk = 4 * c <= e_ks + 1 && e_ks < 4 * c + 4;       // this chunk holds constant columns
+                    if (!e_chunk && nks == 4) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t o = (uint64_t)(ks * 2);
+                            mma_ss(dcol, a_hi + o, b_hi + o, idesc, (uint32_t)((c | ks) != 0));
+                            mma_ss(dcol, a_lo + o, b_hi + o, idesc, 1u);
+                            mma_ss(dcol, a_hi + o, b_lo + o, idesc, 1u);
+                        }
+                    } else {
+                        for (int ks = 0; ks < nks; ++ks) {
+                            const uint64_t o = (uint64_t)(ks * 2);
+                            const int kg = 4 * c + ks;
+                            mma_ss(dcol, a_hi + o, b_hi + o, idesc, (uint32_t)(kg != 0));
+                            if (kg != e_ks && kg != e_ks + 1) mma_ss(dcol, a_lo + o, b_hi + o, idesc, 1u);
+                            mma_ss(dcol, a_hi + o, b_lo + o, idesc, 1u);
+                        }
                     }
                     mma_commit(sm.a_empty + sa);
                     ++mma_a;
@@ -534,12 +662,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) admm_tc_kernel(const AdmmTables
                 product(1, col_z, !C.resident, sm.bar_z);
             }
             product(2, col_x, true, sm.bar_x);
-        } else if (tid == 160) {
+        } else if (tid == NC + 32) {
             // ================= B-operand stream (L2 -> shared memory ring) =================
             auto stream = [&](int p) {
                 for (int c = 0; c < C.nchunks[p]; ++c) {
-                    const int sb = (int)(tma_b & 1u);
-                    mbar_wait_prof(sm.b_empty + sb, ((tma_b >> 1) & 1u) ^ 1u, prof ? &pc[9] : nullptr);
+                    const int sb = C.nb_stages == 2 ? (int)(tma_b & 1u) : 0;
+                    mbar_wait_prof(sm.b_empty + sb, ((C.nb_stages == 2 ? tma_b >> 1 : tma_b) & 1u) ^ 1u, prof ? &pc[9] : nullptr);
                     const uint32_t bytes = (uint32_t)C.pair_bytes[p];
                     mbar_expect_tx(sm.b_full + sb, bytes);
                     const unsigned char* src = C.img + C.off[p] + (size_t)c * bytes;
@@ -553,29 +681,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) admm_tc_kernel(const AdmmTables
             stream(2);
         }
         if (prof) {
-            if (tid == 128) pc[0] += (unsigned long long)(clock64() - t_work);
+            if (tid == NC) pc[0] += (unsigned long long)(clock64() - t_work);
             if (tid == 0) { pc[7] += (unsigned long long)(clock64() - t_work); ++pc[8]; }
         }
         __syncwarp();
     }
     if (prof) {
-        if (tid == 128) { atomicAdd(Bq.prof + 0, pc[0]); atomicAdd(Bq.prof + 1, pc[1]); atomicAdd(Bq.prof + 2, pc[2]); }
+        if (tid == NC) { atomicAdd(Bq.prof + 0, pc[0]); atomicAdd(Bq.prof + 1, pc[1]); atomicAdd(Bq.prof + 2, pc[2]); }
         if (tid == 0) for (int i = 3; i <= 8; ++i) atomicAdd(Bq.prof + i, pc[i]);
-        if (tid == 160) atomicAdd(Bq.prof + 9, pc[9]);
+        if (tid == NC + 32) atomicAdd(Bq.prof + 9, pc[9]);
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase) : "memory");
+    if (warp == 4 * G) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase) : "memory");
 }
 
-template <int NP>
+template <int NP, int G>
 int tc_launch_np(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
     const size_t smem = (size_t)q->tc.smem_bytes;
     const int64_t tiles = ((int64_t)b.count + 127) / 128;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, q->sm));
-    { const int rc = kernel_config(reinterpret_cast<const void*>(admm_tc_kernel<NP>), kTcThreads, smem, nullptr); if (rc != CARMPC_OK) return rc; }
-    admm_tc_kernel<NP><<<blocks, kTcThreads, smem, st>>>(q->admm, q->tc, b);
+    constexpr int threads = 128 * G + 64;
+    { const int rc = kernel_config(reinterpret_cast<const void*>(admm_tc_kernel<NP, G>), threads, smem, nullptr); if (rc != CARMPC_OK) return rc; }
+    admm_tc_kernel<NP, G><<<blocks, threads, smem, st>>>(q->admm, q->tc, b);
     CARMPC_CUDA(cudaGetLastError());
     return CARMPC_OK;
 }
@@ -586,17 +715,21 @@ bool admm_tc_usable(const QPHandle* q, const AdmmBatch& b) {
     // Large first passes only: the tile is always 128 samples wide, so a batch that cannot give every SM a full tile
     // (second passes, closed-loop steps) stays on the FFMA kernel's narrow tiles; so does a launch that must export the
     // raw iterate (write_u: the accumulator that holds x~ is reused by the next product).
-    return q->tensor_mode != 0 && q->tc.ok && !b.narrow && !b.write_u && b.warm != nullptr && b.sign != nullptr &&
+    // Mode 1 (default) takes it where it measured faster than the FFMA kernel: problems whose matrices the FFMA kernel has
+    // to read through L1 / L2 (horizon 40: 1.75x on the whole solve); with the matrices in shared memory (horizons 10, 20)
+    // the FFMA kernel is 20 % ahead.  Modes 2 / 3 take every problem that has a tensor-core form.
+    const bool wanted = q->tensor_mode >= 2 || (q->tensor_mode == 1 && !q->host.mats_in_smem);
+    return wanted && q->tc.ok && !b.narrow && !b.write_u && b.warm != nullptr && b.sign != nullptr &&
            (int64_t)b.count >= (int64_t)128 * q->sm;
 }
 
 int admm_tc_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
     switch (q->tc.np) {
-        case 16: return tc_launch_np<16>(q, b, st);
-        case 32: return tc_launch_np<32>(q, b, st);
-        case 48: return tc_launch_np<48>(q, b, st);
-        case 64: return tc_launch_np<64>(q, b, st);
-        case 80: return tc_launch_np<80>(q, b, st);
+        case 16: return tc_launch_np<16, kTcGroups>(q, b, st);
+        case 32: return tc_launch_np<32, kTcGroups>(q, b, st);
+        case 48: return tc_launch_np<48, kTcGroups>(q, b, st);
+        case 64: return tc_launch_np<64, kTcGroups>(q, b, st);
+        case 80: return tc_launch_np<80, kTcGroups>(q, b, st);
     }
     set_error("admm_tc_launch: no kernel variant for %d variables", q->tc.np);
     return CARMPC_ERR_UNSUPPORTED;

@@ -746,7 +746,7 @@ int carmpc_qp_polish_stats(void* qp, int64_t* h_hist20) {
 int carmpc_qp_tensor_mode(void* qp, int mode, int64_t* h_info) {
     QPHandle* q = check_handle<QPHandle>(qp, kQP);
     CARMPC_REQUIRE(q != nullptr, "not a QP handle");
-    CARMPC_REQUIRE(mode <= 2, "mode must be 0, 1, 2 or negative (query)");
+    CARMPC_REQUIRE(mode <= 3, "mode must be 0, 1, 2, 3 or negative (query)");
     if (mode >= 0) q->tensor_mode = mode;
     if (h_info) {
         for (int i = 0; i < 16; ++i) h_info[i] = 0;

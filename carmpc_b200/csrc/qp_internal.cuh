@@ -286,7 +286,7 @@ struct QPHandle : HandleBase {
     QPHost host;
     AdmmTables admm;
     TcTables tc;
-    int tensor_mode = 1;                         // 0: FFMA kernel only; 1: tcgen05 kernel for large first passes
+    int tensor_mode = 1;                         // 0: FFMA kernel only; 1: tcgen05 kernel where it is faster; 2: wherever possible; 3: 2 + cycle counters
     int64_t last_tc_samples = 0;                 // samples the tcgen05 kernel took in the last solve
     unsigned long long* ws_prof = nullptr;       // [16] cycle counters of the tcgen05 kernel (tensor mode 2)
     PolishTables polish;

@@ -458,15 +458,20 @@ int qp_host_setup(int n, int m_in, int kpre, const double* H_in, const double* F
             total += (size_t)t.nchunks[p] * t.pair_bytes[p];
         }
         const int a_stage = 128 * 128 * 2;
-        const int tables = (4 * mp + 16 * np + 512 + 1023) / 1024 * 1024;
+        // tables, per-slot state and barriers behind the rings (tc_carve in qp_admm_tc.cu): 4 mp + 16 np floats, 6 mp doubles,
+        // 5 x 128 doubles, 8 x 128 words, 16 barriers
+        const int tables = (4 * mp + 16 * np + 48 * mp + 40 * 128 + 32 * 128 + 8 * 16 + 8 + 8 * 16 + 64 + 1023) / 1024 * 1024;
         const int budget = 227 * 1024 - 1024;                      // the dynamic area is re-aligned to 1024 bytes in the kernel
         t.resident_bytes = t.nchunks[0] * t.pair_bytes[0] + t.nchunks[1] * t.pair_bytes[1];
         t.nb_stages = 2;
-        if (2 * a_stage + t.resident_bytes + 2 * t.pair_bytes[2] + tables <= budget) {
+        if (2 * a_stage + t.resident_bytes + t.pair_bytes[2] + tables <= budget) {
+            // small problems: the matrices of products 0 and 1 stay in shared memory; the certificate product (once per
+            // round) streams through one or two stages
             t.resident = 1;
             t.b_stage_bytes = t.pair_bytes[2];
-            t.na_stages = 3 * a_stage + t.resident_bytes + 2 * t.pair_bytes[2] + tables <= budget ? 3 : 2;
-            t.smem_bytes = t.na_stages * a_stage + t.resident_bytes + 2 * t.b_stage_bytes + tables + 1024;
+            t.nb_stages = 2 * a_stage + t.resident_bytes + 2 * t.pair_bytes[2] + tables <= budget ? 2 : 1;
+            t.na_stages = 3 * a_stage + t.resident_bytes + t.nb_stages * t.pair_bytes[2] + tables <= budget ? 3 : 2;
+            t.smem_bytes = t.na_stages * a_stage + t.resident_bytes + t.nb_stages * t.b_stage_bytes + tables + 1024;
         } else {
             t.resident = 0;
             t.resident_bytes = 0;

@@ -23,7 +23,7 @@ else:
 bq = BatchQP.from_controller(_controller("RoadOneCarEnv", [29.9, 1.5, 0, 0], N))
 print("tensor form:", bq.tensor_mode())
 res = {}
-for mode in (0, 1):
+for mode in (0, 2):
     bq.tensor_mode(mode)
     for r in range(reps):
         torch.cuda.synchronize()
@@ -39,7 +39,7 @@ for mode in (0, 1):
               f"tc samples {info['samples_last_solve']}", flush=True)
     res[mode] = {k: v.clone() for k, v in out.items() if torch.is_tensor(v)}
     print("   polish:", bq.polish_stats()["certified_after_rounds"], "handed back", bq.polish_stats()["handed_to_admm"], flush=True)
-bq.tensor_mode(2)
+bq.tensor_mode(3)
 bq.solve(x0)
 info = bq.tensor_mode()
 cyc = info["cycles"]
@@ -48,9 +48,9 @@ names = ["mma: round total", "mma: wait A", "mma: wait B", "cmp: wait x~", "cmp:
 rounds = max(cyc[8], 1)
 print("cycle counters per round (one round = check_every iterations of a 128-sample tile):")
 for nm, v in zip(names, cyc):
-    print(f"   {nm:22s} {v / rounds:12.0f}")
+    print(f"   {nm:22s} {(v if nm == 'rounds' else v / rounds):12.0f}")
 bq.tensor_mode(1)
-a, b = res[0], res[1]
+a, b = res[0], res[2]
 same = (a["status"] == b["status"])
 print("status equal:", same.float().mean().item(), "differences:", (~same).sum().item())
 ok = (a["status"] == 0) & (b["status"] == 0)
