@@ -270,6 +270,13 @@ def run_qp_bench(args, rank, world, dev, barrier):
             ms_n = max_over_ranks(ms_n)
             it_n = sum_over_ranks(it_n)
             tl = bN.tiling()
+            tinfo = bN.tensor_mode()
+            on_tensor = tinfo["samples_last_solve"] > 0
+            ffma_ms = None
+            if on_tensor:                      # the same solve on the FFMA tile kernel, for the comparison the default rests on
+                bN.tensor_mode(0)
+                ffma_ms = max_over_ranks(_time_solves(bN, x0, 2, 1, torch, gather, barrier)[0])
+                bN.tensor_mode(1)
             seeded_n = None
             if not args.skip_seeded and full_grid:
                 from carmpc_b200.grids import lattice_seeds
@@ -290,7 +297,11 @@ def run_qp_bench(args, rank, world, dev, barrier):
                              "feasible_frac": float((o["status"] == 0).float().mean().item()),
                              "max_iter_count": int((o["status"] == 2).sum().item()),
                              "executed_tflops": it_n * tl["flop_per_iter"] / (ms_n * 1e-3) / 1e12,
-                             "samples_per_lane": tl["samples_per_lane"], "matrices_in_smem": tl["matrices_in_smem"]}
+                             "samples_per_lane": tl["samples_per_lane"], "matrices_in_smem": tl["matrices_in_smem"],
+                             "admm_kernel": "tcgen05 kind::tf32, 3xTF32 split, 128-sample tiles" if on_tensor else "ffma tile kernel",
+                             "tensor_form_available": tinfo["available"], "ffma_kernel_ms": ffma_ms}
+            if on_tensor:       # dense multiply-adds the tensor pipe executes: three TF32 products per float32 product
+                sweep[str(N)]["tensor_dense_tflops"] = 3 * it_n * tl["flop_per_iter_dense"] / (ms_n * 1e-3) / 1e12
         res["horizon_sweep"] = sweep
 
     return res

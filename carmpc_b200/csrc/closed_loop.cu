@@ -30,9 +30,11 @@ __global__ void __launch_bounds__(256)
 loop_advance_kernel(const LoopConst K, int64_t runs, double* __restrict__ x, double* __restrict__ xhat,
                     const double* __restrict__ u_prev, const int32_t* __restrict__ fail_step,
                     double* __restrict__ est, int* __restrict__ live_list, int* __restrict__ live_count,
-                    double* __restrict__ traj_step) {
+                    double* __restrict__ traj_step, const int* __restrict__ step_dev) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= runs) return;
+    // replayed steps (CUDA graph) read the step number on the device: traj_step is then the base of the trajectory
+    if (traj_step != nullptr && step_dev != nullptr) traj_step += (size_t)*step_dev * 4 * runs;
     double s[4], u[2];
 #pragma unroll
     for (int c = 0; c < 4; ++c) s[c] = x[c * runs + i];
@@ -91,9 +93,10 @@ loop_advance_kernel(const LoopConst K, int64_t runs, double* __restrict__ x, dou
 __global__ void __launch_bounds__(256)
 loop_apply_kernel(int64_t runs, int step, const int* __restrict__ live_list, int live, const int* __restrict__ live_dev,
                   const double* __restrict__ u0, const int32_t* __restrict__ status, double* __restrict__ u_prev,
-                  int32_t* __restrict__ fail_step) {
+                  int32_t* __restrict__ fail_step, const int* __restrict__ step_dev) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (live_dev != nullptr) live = min(live, *live_dev);
+    if (step_dev != nullptr) step = *step_dev;
     if (q >= live) return;
     const int i = live_list[q];
     if (status[i] == CARMPC_QP_SOLVED) {
@@ -103,6 +106,16 @@ loop_apply_kernel(int64_t runs, int step, const int* __restrict__ live_list, int
         fail_step[i] = step;
     }
 }
+
+// replayed steps: the input log of this step, then the step number moves on (one thread, after everything that read it)
+__global__ void __launch_bounds__(256)
+loop_log_kernel(int64_t runs, const double* __restrict__ u_prev, double* __restrict__ u_log, const int* __restrict__ step_dev) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * runs) return;
+    u_log[(size_t)*step_dev * 2 * runs + i] = u_prev[i];
+}
+__global__ void loop_next_kernel(int* step_dev) { *step_dev += 1; }
+__global__ void loop_set_kernel(int* step_dev, int v) { *step_dev = v; }
 
 __global__ void fill_i32(int32_t* p, int64_t n, int32_t v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,7 +145,14 @@ extern "C" int carmpc_closed_loop(void* qp, int mode, const double* h_A, const d
     CARMPC_REQUIRE(d_x_init && d_final && d_fail_step, "null device pointer");
     QPBusyGuard guard(q->busy);
     CARMPC_REQUIRE(guard.acquired, "this QP handle is in use by another call (one call per handle at a time)");
-    cudaStream_t st = (cudaStream_t)stream;
+    // The loop runs on its own (capturable) stream, ordered after the caller's stream by an event and joined at the end by
+    // the final synchronisation: the legacy default stream cannot be captured into a graph.
+    cudaStream_t user_st = (cudaStream_t)stream, st = nullptr;
+    cudaEvent_t ev = nullptr;
+    bool graph_ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    if (graph_ok) graph_ok = cudaEventRecord(ev, user_st) == cudaSuccess && cudaStreamWaitEvent(st, ev, 0) == cudaSuccess;
+    if (!graph_ok) { cudaGetLastError(); if (st) cudaStreamDestroy(st); st = user_st; }
     LoopConst K;
     memset(&K, 0, sizeof(K));
     memcpy(K.A, h_A, sizeof(K.A));
@@ -147,7 +167,8 @@ extern "C" int carmpc_closed_loop(void* qp, int mode, const double* h_A, const d
     int *live_list = nullptr, *live_count = nullptr;
     float* warm = nullptr;
     int rc = CARMPC_OK;
-    auto cleanup = [&]() { q->defer_total = 0; cudaFree(xhat); cudaFree(est); cudaFree(u_prev); cudaFree(u0); cudaFree(status); cudaFree(live_list); cudaFree(live_count); cudaFree(warm); };
+    auto cleanup = [&]() { if (st != user_st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); } if (ev) cudaEventDestroy(ev);
+                           q->defer_total = 0; cudaFree(xhat); cudaFree(est); cudaFree(u_prev); cudaFree(u0); cudaFree(status); cudaFree(live_list); cudaFree(live_count); cudaFree(warm); };
 #define TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(e__)); cleanup(); return CARMPC_ERR_CUDA; } } while (0)
     TRY(cudaMalloc(&xhat, sizeof(double) * 4 * runs));
     TRY(cudaMalloc(&est, sizeof(double) * 4 * runs));
@@ -155,7 +176,7 @@ extern "C" int carmpc_closed_loop(void* qp, int mode, const double* h_A, const d
     TRY(cudaMalloc(&u0, sizeof(double) * 2 * runs));
     TRY(cudaMalloc(&status, sizeof(int32_t) * runs));
     TRY(cudaMalloc(&live_list, sizeof(int) * runs));
-    TRY(cudaMalloc(&live_count, sizeof(int)));
+    TRY(cudaMalloc(&live_count, sizeof(int) * 2));      // [0] live runs of the step, [1] step number of replayed steps
     if (warm_start) TRY(cudaMalloc(&warm, sizeof(float) * (size_t)mt * runs));
     if (x != d_x_init) TRY(cudaMemcpyAsync(x, d_x_init, sizeof(double) * 4 * runs, cudaMemcpyDeviceToDevice, st));
     TRY(cudaMemcpyAsync(xhat, d_xhat_init ? d_xhat_init : d_x_init, sizeof(double) * 4 * runs, cudaMemcpyDeviceToDevice, st));
@@ -169,21 +190,57 @@ extern "C" int carmpc_closed_loop(void* qp, int mode, const double* h_A, const d
     if (rc != CARMPC_OK) { cleanup(); return rc; }
     TRY(cudaMemsetAsync(q->ws_total_iters, 0, sizeof(unsigned long long), st));
     q->defer_total = 1;
-    for (int k = 0; k < steps; ++k) {
-        TRY(cudaMemsetAsync(live_count, 0, sizeof(int), st));
+    // One enqueue-only step (every count stays on the device).  step_dev == nullptr: the step number k comes from the host.
+    auto enqueue_step = [&](int k, const int* step_dev) -> int {
+        cudaError_t e = cudaMemsetAsync(live_count, 0, sizeof(int), st);
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return CARMPC_ERR_CUDA; }
         loop_advance_kernel<<<blocks, 256, 0, st>>>(K, runs, x, xhat, u_prev, d_fail_step, est, live_list, live_count,
-                                                    d_traj ? d_traj + (size_t)k * 4 * runs : nullptr);
+                                                    d_traj ? (step_dev ? d_traj : d_traj + (size_t)k * 4 * runs) : nullptr, step_dev);
+        const int rc2 = q->solve_enqueue(est, runs, h_xref, live_list, live_count, runs, u0, status, warm, st);
+        if (rc2 != CARMPC_OK) return rc2;
+        loop_apply_kernel<<<blocks, 256, 0, st>>>(runs, k, live_list, (int)runs, live_count, u0, status, u_prev, d_fail_step, step_dev);
+        if (d_u_log) {
+            if (step_dev) {
+                loop_log_kernel<<<(int)((2 * runs + 255) / 256), 256, 0, st>>>(runs, u_prev, d_u_log, step_dev);
+            } else {
+                e = cudaMemcpyAsync(d_u_log + (size_t)k * 2 * runs, u_prev, sizeof(double) * 2 * runs, cudaMemcpyDeviceToDevice, st);
+                if (e != cudaSuccess) { set_error("cudaMemcpyAsync: %s", cudaGetErrorString(e)); return CARMPC_ERR_CUDA; }
+            }
+        }
+        if (step_dev) loop_next_kernel<<<1, 1, 0, st>>>(live_count + 1);
+        return CARMPC_OK;
+    };
+    for (int k = 0; k < steps; ++k) {
         if (warm_valid && warm_start != 2) {
             // Every later step only enqueues: the number of live runs, of runs whose active set changed, of second-pass and
             // fallback samples all stay on the device (kernels sized for the upper bound read them there), so the steps
-            // run back to back on the GPU without a host round trip.
-            rc = q->solve_enqueue(est, runs, h_xref, live_list, live_count, runs, u0, status, warm, st);
-            if (rc != CARMPC_OK) { q->defer_total = 0; cleanup(); return rc; }
-            loop_apply_kernel<<<blocks, 256, 0, st>>>(runs, k, live_list, (int)runs, live_count, u0, status, u_prev, d_fail_step);
-            if (d_u_log)
-                TRY(cudaMemcpyAsync(d_u_log + (size_t)k * 2 * runs, u_prev, sizeof(double) * 2 * runs, cudaMemcpyDeviceToDevice, st));
-            continue;
+            // run back to back on the GPU without a host round trip.  The first such step is launched kernel by kernel
+            // (it also fills the kernel-attribute caches); the remaining ones are ONE captured CUDA graph replayed with
+            // the step number on the device, so that a slow host (thousands of small launches otherwise) cannot stretch
+            // the loop.
+            if (!graph_ok || k + 2 >= steps || k < 2) {
+                rc = enqueue_step(k, nullptr);
+                if (rc != CARMPC_OK) { q->defer_total = 0; cleanup(); return rc; }
+                continue;
+            }
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            loop_set_kernel<<<1, 1, 0, st>>>(live_count + 1, k);
+            TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue_step(k, live_count + 1);
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc == CARMPC_OK && ce != cudaSuccess) { set_error("cudaStreamEndCapture: %s", cudaGetErrorString(ce)); rc = CARMPC_ERR_CUDA; }
+            if (rc == CARMPC_OK && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { set_error("cudaGraphInstantiate failed"); rc = CARMPC_ERR_CUDA; }
+            for (; rc == CARMPC_OK && k < steps; ++k)
+                if (cudaGraphLaunch(exec, st) != cudaSuccess) { set_error("cudaGraphLaunch failed"); rc = CARMPC_ERR_CUDA; }
+            if (exec) cudaGraphExecDestroy(exec);
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != CARMPC_OK) { cudaGetLastError(); q->defer_total = 0; cleanup(); return rc; }
+            break;
         }
+        TRY(cudaMemsetAsync(live_count, 0, sizeof(int), st));
+        loop_advance_kernel<<<blocks, 256, 0, st>>>(K, runs, x, xhat, u_prev, d_fail_step, est, live_list, live_count,
+                                                    d_traj ? d_traj + (size_t)k * 4 * runs : nullptr, nullptr);
         int live = 0;
         TRY(cudaMemcpyAsync(&live, live_count, sizeof(int), cudaMemcpyDeviceToHost, st));
         TRY(cudaStreamSynchronize(st));
@@ -193,7 +250,7 @@ extern "C" int carmpc_closed_loop(void* qp, int mode, const double* h_A, const d
                           warm_valid ? 1 : 0, warm ? 1 : 0, st, warm_valid ? 1 : 0);
             if (rc != CARMPC_OK) { q->defer_total = 0; cleanup(); return rc; }
             warm_valid = warm != nullptr;
-            loop_apply_kernel<<<(live + 255) / 256, 256, 0, st>>>(runs, k, live_list, live, nullptr, u0, status, u_prev, d_fail_step);
+            loop_apply_kernel<<<(live + 255) / 256, 256, 0, st>>>(runs, k, live_list, live, nullptr, u0, status, u_prev, d_fail_step, nullptr);
         }
         if (d_u_log)      // the input each run will apply at the next plant step (unchanged for stopped runs)
             TRY(cudaMemcpyAsync(d_u_log + (size_t)k * 2 * runs, u_prev, sizeof(double) * 2 * runs, cudaMemcpyDeviceToDevice, st));

@@ -75,6 +75,13 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a, uint64_t b, 
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
+// one lane of a converged warp (the lane that issues the warp's tcgen05.mma / cp.async.bulk instructions)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\tselp.u32 %0, 1, 0, px;\n\t}"
+                 : "=r"(pred) : "r"(0xffffffffu));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -99,6 +106,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// 16 consecutive entries of a shared-memory table with four 128-bit loads (a broadcast 4-byte load costs the same
+// shared-memory wavefront as a broadcast 16-byte load, and the kernel is short of shared-memory bandwidth)
+__device__ __forceinline__ void lds16(const float* p, float (&v)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(p + 4 * q);
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+}
 __device__ __forceinline__ float clampf(float w, float lo, float hi) { return fminf(fmaxf(w, lo), hi); }
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
@@ -223,7 +239,8 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
     constexpr int EG = NPB % G;                     // the group that writes the constant columns (the block after the box blocks)
     extern __shared__ unsigned char smem_raw[];
     const TcSmem sm = tc_carve<NP>(smem_raw, C);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);        // provably warp-uniform: the roles below branch on it
     const int slot = tid & 127, cg = tid >> 7;
     const int mp = C.mp, n = C.n, m = C.m, mt = C.mt;
     const int MPB = mp >> 4;
@@ -270,12 +287,12 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
 
     // role-private pipeline counters (they persist over the rounds)
     unsigned mma_a = 0, mma_b = 0, tma_b = 0;
-    if (tid == NC + 32 && C.resident) {
+    if (warp == 4 * G + 1 && C.resident && elect_one()) {
         mbar_expect_tx(sm.bar_res, (uint32_t)C.resident_bytes);
         for (int o = 0; o < C.resident_bytes; o += 16384)
             bulk_load(sm.b_res + o, C.img + C.off[0] + o, (uint32_t)min(16384, C.resident_bytes - o), sm.bar_res);
     }
-    if (tid == NC && C.resident) { mbar_wait(sm.bar_res, 0); tc_fence_after(); }
+    if (warp == 4 * G && C.resident) { mbar_wait(sm.bar_res, 0); tc_fence_after(); }
 
     // ---- compute-thread state --------------------------------------------------------------------------------------------
     float wb[MAXB][16];                // w of this thread's box rows: block lb covers variables 16 (lb G + group) ...
@@ -285,7 +302,8 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
     A.ring = sm.a_ring; A.full = sm.a_full; A.empty = sm.a_empty; A.na = C.na_stages; A.base = 0; A.kend = 0;
     A.row_off = (uint32_t)((slot >> 3) * 1024 + (slot & 7) * 128); A.r7 = slot & 7;
     unsigned long long* const pc = sm.pc;                            // cycle counters (each written by one thread)
-    const bool prof = Bq.prof != nullptr && (tid == 0 || tid == NC || tid == NC + 32);
+    const bool prof_on = Bq.prof != nullptr;
+    const bool prof = prof_on && tid == 0;
     A.wait_acc = prof ? &pc[5] : nullptr;
 #pragma unroll
     for (int lb = 0; lb < MAXB; ++lb)
@@ -298,7 +316,7 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
     for (;;) {
         int running = 0;
         const long long t_round = clock64();
-        if (tid < NC) {
+        if (warp < 4 * G) {
             // ================= retire finished samples, take the next ones from the queue =================
             // (tensor-memory loads / stores are warp-collective: every lane executes them, only the owners of a finished /
             //  fresh slot act on the values)
@@ -445,7 +463,7 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
         if (!__syncthreads_or(running)) break;
         const long long t_work = clock64();
 
-        if (tid < NC) {
+        if (warp < 4 * G) {
             // ================= elementwise phases of one round (check_every iterations, the last one checked) =================
             // the constant columns of this slot's sample (x0 pieces, 1, disturbance pieces): exact TF32 values
             auto put_e = [&](int k0) {
@@ -461,9 +479,10 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
                 for (int lb = 0; lb < MAXB; ++lb) {
                     const int j0 = (lb * G + cg) << 4;
                     if (j0 < NP) {
-                        float v[16];
+                        float v[16], tl[16], tu[16];
+                        lds16(sm.lb + j0, tl); lds16(sm.ub + j0, tu);
 #pragma unroll
-                        for (int r = 0; r < 16; ++r) { const float w = wb[lb][r]; v[r] = fmaf(2.f, clampf(w, sm.lb[j0 + r], sm.ub[j0 + r]), -w); }
+                        for (int r = 0; r < 16; ++r) { const float w = wb[lb][r]; v[r] = fmaf(2.f, clampf(w, tl[r], tu[r]), -w); }
                         a_put16(A, j0, v, lane);
                     }
                 }
@@ -477,9 +496,10 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
                 uint32_t wr[16];
                 tmem_ld16(col_state + lane_addr + (uint32_t)g0, wr);
                 tmem_ld_wait(wr);
-                float v[16];
+                float v[16], tn[16];
+                lds16(sm.nwd + g0, tn);
 #pragma unroll
-                for (int r = 0; r < 16; ++r) { const float w = __uint_as_float(wr[r]); v[r] = fmaf(2.f, clampf(w, sm.nwd[g0 + r], 0.f), -w); }
+                for (int r = 0; r < 16; ++r) { const float w = __uint_as_float(wr[r]); v[r] = fmaf(2.f, clampf(w, tn[r], 0.f), -w); }
                 a_put16(A, NP + 16 + g0, v, lane);
             }
             a_end(A);
@@ -499,18 +519,27 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
                         tmem_ld_wait(xr);
                         float x[16];
 #pragma unroll
-                        for (int r = 0; r < 16; ++r) {
-                            const int j = j0 + r;
-                            x[r] = __uint_as_float(xr[r]) + sm.t[j];
-                            const float lb_ = sm.lb[j], ub_ = sm.ub[j];
-                            const float w0 = wb[lb][r], z = sm.lam[j] * x[r];
-                            const float c0 = clampf(w0, lb_, ub_);
-                            const float w1 = fmaf(alpha, z - c0, w0);
-                            wb[lb][r] = w1;
-                            if (check) {
-                                const float c1 = clampf(w1, lb_, ub_), einv = C.einv_b[j];
-                                p_res = fmaxf(p_res, fmaxf(fabsf(z - c1), fabsf(c1 - c0)) * einv);
-                                p_nrm = fmaxf(p_nrm, fmaxf(fabsf(z), fabsf(c1)) * einv);
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(sm.t + j0 + 4 * q);
+                            const float4 l4 = *reinterpret_cast<const float4*>(sm.lb + j0 + 4 * q);
+                            const float4 u4 = *reinterpret_cast<const float4*>(sm.ub + j0 + 4 * q);
+                            const float4 m4 = *reinterpret_cast<const float4*>(sm.lam + j0 + 4 * q);
+                            const float tt[4] = {t4.x, t4.y, t4.z, t4.w}, tl[4] = {l4.x, l4.y, l4.z, l4.w};
+                            const float tu[4] = {u4.x, u4.y, u4.z, u4.w}, tm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                            for (int rr = 0; rr < 4; ++rr) {
+                                const int r = 4 * q + rr, j = j0 + r;
+                                x[r] = __uint_as_float(xr[r]) + tt[rr];
+                                const float lb_ = tl[rr], ub_ = tu[rr];
+                                const float w0 = wb[lb][r], z = tm[rr] * x[r];
+                                const float c0 = clampf(w0, lb_, ub_);
+                                const float w1 = fmaf(alpha, z - c0, w0);
+                                wb[lb][r] = w1;
+                                if (check) {
+                                    const float c1 = clampf(w1, lb_, ub_), einv = C.einv_b[j];
+                                    p_res = fmaxf(p_res, fmaxf(fabsf(z - c1), fabsf(c1 - c0)) * einv);
+                                    p_nrm = fmaxf(p_nrm, fmaxf(fabsf(z), fabsf(c1)) * einv);
+                                }
                             }
                         }
                         a_put16(A, j0, x, lane);
@@ -537,10 +566,11 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
                     tmem_ld16(col_state + lane_addr + (uint32_t)g0, wr);
                     tmem_ld_wait(zr);
                     tmem_ld_wait(wr);
-                    float v[16];
+                    float v[16], tn[16];
+                    lds16(sm.nwd + g0, tn);
 #pragma unroll
                     for (int r = 0; r < 16; ++r) {
-                        const float nwd = sm.nwd[g0 + r];
+                        const float nwd = tn[r];
                         const float w0 = __uint_as_float(wr[r]), z = __uint_as_float(zr[r]);
                         const float c0 = clampf(w0, nwd, 0.f);
                         const float w1 = fmaf(alpha, z - c0, w0);
@@ -607,8 +637,13 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
                 sm.slot_state[slot] = ns;
             }
             sync_compute();
-        } else if (tid == NC) {
+        } else if (warp == 4 * G) {
             // ================= MMA issue: the same chunk sequence the compute threads publish =================
+            // The whole warp runs the control flow (waits, counters, descriptors stay warp-uniform, so they live in uniform
+            // registers); one elected lane issues the tcgen05 instructions.
+            const bool leader = elect_one();
+            unsigned long long* const pa = (prof_on && leader) ? &pc[1] : nullptr;
+            unsigned long long* const pb = (prof_on && leader) ? &pc[2] : nullptr;
             auto product = [&](int p, uint32_t dcol, bool streamed, uint64_t* done) {
                 const int N = C.ncols[p];
                 const uint32_t idesc = make_idesc(N);
@@ -617,12 +652,12 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
                 for (int c = 0; c < C.nchunks[p]; ++c) {
                     const unsigned use = C.na_stages == 2 ? mma_a >> 1 : mma_a / 3u;
                     const int sa = (int)(mma_a - use * (unsigned)C.na_stages);
-                    mbar_wait_prof(sm.a_full + sa, use & 1u, prof ? &pc[1] : nullptr);
+                    mbar_wait_prof(sm.a_full + sa, use & 1u, pa);
                     const unsigned char* bsrc;
                     int sb = 0;
                     if (streamed) {
                         sb = C.nb_stages == 2 ? (int)(mma_b & 1u) : 0;
-                        mbar_wait_prof(sm.b_full + sb, (C.nb_stages == 2 ? mma_b >> 1 : mma_b) & 1u, prof ? &pc[2] : nullptr);
+                        mbar_wait_prof(sm.b_full + sb, (C.nb_stages == 2 ? mma_b >> 1 : mma_b) & 1u, pb);
                         bsrc = sm.b_ring + (size_t)sb * C.b_stage_bytes;
                     } else {
                         bsrc = res_base + (size_t)c * C.pair_bytes[p];
@@ -634,45 +669,56 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
                     const uint64_t b_lo = b_hi + (uint64_t)((N * 128) >> 4);
                     const int nks = min(4, C.ksteps[p] - 4 * c);
                     const bool e_chunk = 4 * c <= e_ks + 1 && e_ks < 4 * c + 4;       // this chunk holds constant columns
-                    if (!e_chunk && nks == 4) {
+                    if (leader) {
+                        if (!e_chunk && nks == 4) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t o = (uint64_t)(ks * 2);
-                            mma_ss(dcol, a_hi + o, b_hi + o, idesc, (uint32_t)((c | ks) != 0));
-                            mma_ss(dcol, a_lo + o, b_hi + o, idesc, 1u);
-                            mma_ss(dcol, a_hi + o, b_lo + o, idesc, 1u);
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t o = (uint64_t)(ks * 2);
+                                mma_ss(dcol, a_hi + o, b_hi + o, idesc, (uint32_t)((c | ks) != 0));
+                                mma_ss(dcol, a_lo + o, b_hi + o, idesc, 1u);
+                                mma_ss(dcol, a_hi + o, b_lo + o, idesc, 1u);
+                            }
+                        } else {
+                            for (int ks = 0; ks < nks; ++ks) {
+                                const uint64_t o = (uint64_t)(ks * 2);
+                                const int kg = 4 * c + ks;
+                                mma_ss(dcol, a_hi + o, b_hi + o, idesc, (uint32_t)(kg != 0));
+                                if (kg != e_ks && kg != e_ks + 1) mma_ss(dcol, a_lo + o, b_hi + o, idesc, 1u);
+                                mma_ss(dcol, a_hi + o, b_lo + o, idesc, 1u);
+                            }
                         }
-                    } else {
-                        for (int ks = 0; ks < nks; ++ks) {
-                            const uint64_t o = (uint64_t)(ks * 2);
-                            const int kg = 4 * c + ks;
-                            mma_ss(dcol, a_hi + o, b_hi + o, idesc, (uint32_t)(kg != 0));
-                            if (kg != e_ks && kg != e_ks + 1) mma_ss(dcol, a_lo + o, b_hi + o, idesc, 1u);
-                            mma_ss(dcol, a_hi + o, b_lo + o, idesc, 1u);
-                        }
+                        mma_commit(sm.a_empty + sa);
+                        if (streamed) mma_commit(sm.b_empty + sb);
                     }
-                    mma_commit(sm.a_empty + sa);
+                    __syncwarp();
                     ++mma_a;
-                    if (streamed) { mma_commit(sm.b_empty + sb); ++mma_b; }
+                    if (streamed) ++mma_b;
                 }
-                mma_commit(done);
+                if (leader) mma_commit(done);
+                __syncwarp();
             };
             for (int it = 0; it < check_every; ++it) {
                 product(0, col_x, !C.resident, sm.bar_x);
                 product(1, col_z, !C.resident, sm.bar_z);
             }
             product(2, col_x, true, sm.bar_x);
-        } else if (tid == NC + 32) {
+            if (prof_on && leader) pc[0] += (unsigned long long)(clock64() - t_work);
+        } else {
             // ================= B-operand stream (L2 -> shared memory ring) =================
+            const bool leader = elect_one();
+            unsigned long long* const pw = (prof_on && leader) ? &pc[9] : nullptr;
             auto stream = [&](int p) {
                 for (int c = 0; c < C.nchunks[p]; ++c) {
                     const int sb = C.nb_stages == 2 ? (int)(tma_b & 1u) : 0;
-                    mbar_wait_prof(sm.b_empty + sb, ((C.nb_stages == 2 ? tma_b >> 1 : tma_b) & 1u) ^ 1u, prof ? &pc[9] : nullptr);
-                    const uint32_t bytes = (uint32_t)C.pair_bytes[p];
-                    mbar_expect_tx(sm.b_full + sb, bytes);
-                    const unsigned char* src = C.img + C.off[p] + (size_t)c * bytes;
-                    unsigned char* dst = sm.b_ring + (size_t)sb * C.b_stage_bytes;
-                    for (uint32_t o = 0; o < bytes; o += 16384) bulk_load(dst + o, src + o, min(16384u, bytes - o), sm.b_full + sb);
+                    mbar_wait_prof(sm.b_empty + sb, ((C.nb_stages == 2 ? tma_b >> 1 : tma_b) & 1u) ^ 1u, pw);
+                    if (leader) {
+                        const uint32_t bytes = (uint32_t)C.pair_bytes[p];
+                        mbar_expect_tx(sm.b_full + sb, bytes);
+                        const unsigned char* src = C.img + C.off[p] + (size_t)c * bytes;
+                        unsigned char* dst = sm.b_ring + (size_t)sb * C.b_stage_bytes;
+                        for (uint32_t o = 0; o < bytes; o += 16384) bulk_load(dst + o, src + o, min(16384u, bytes - o), sm.b_full + sb);
+                    }
+                    __syncwarp();
                     ++tma_b;
                 }
             };
@@ -680,17 +726,11 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
                 if (!C.resident) { stream(0); stream(1); }
             stream(2);
         }
-        if (prof) {
-            if (tid == NC) pc[0] += (unsigned long long)(clock64() - t_work);
-            if (tid == 0) { pc[7] += (unsigned long long)(clock64() - t_work); ++pc[8]; }
-        }
+        if (prof) { pc[7] += (unsigned long long)(clock64() - t_work); ++pc[8]; }
         __syncwarp();
     }
-    if (prof) {
-        if (tid == NC) { atomicAdd(Bq.prof + 0, pc[0]); atomicAdd(Bq.prof + 1, pc[1]); atomicAdd(Bq.prof + 2, pc[2]); }
-        if (tid == 0) for (int i = 3; i <= 8; ++i) atomicAdd(Bq.prof + i, pc[i]);
-        if (tid == NC + 32) atomicAdd(Bq.prof + 9, pc[9]);
-    }
+    __syncthreads();
+    if (prof_on && tid < 10) atomicAdd(Bq.prof + tid, pc[tid]);
 
     tc_fence_before();
     __syncthreads();

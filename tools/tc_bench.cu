@@ -130,6 +130,65 @@ __global__ void __launch_bounds__(128, 1) tc_bench_kernel(const float* __restric
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase) : "memory");
 }
 
+// Chunked issue, as the ADMM kernel does it: `per` MMAs, then `ncommit` tcgen05.commit to scratch barriers, repeated `chunks`
+// times; drain = 1 additionally waits for each chunk's completion before issuing the next (the latency of one hand-off).
+__global__ void __launch_bounds__(128, 1) tc_chunk_kernel(int N, int per, int ncommit, int chunks, int drain, long long* cycles) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) uint64_t bars[4];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + 4 * 128 * 128;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < (4 * 128 * 128 + 4 * 256 * 128) / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 0.f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t idesc = make_idesc(128, N);
+    if (tid == 0) {
+        const long long t0 = clock64();
+        uint32_t phase = 0;
+        for (int c = 0; c < chunks; ++c) {
+            const uint64_t ad = desc_sw128(smem_u32(sA + (size_t)(c & 3) * 128 * 128));
+            const uint64_t bd = desc_sw128(smem_u32(sB + (size_t)(c & 3) * N * 128));
+            for (int i = 0; i < per; ++i) mma_ss(tbase, ad + (uint64_t)((i & 3) * 2), bd + (uint64_t)((i & 3) * 2), idesc, (uint32_t)(c | i));
+            for (int k = 0; k < ncommit; ++k) mma_commit(smem_u32(&bars[drain ? 0 : 1 + k]));
+            if (drain) { mbar_wait(smem_u32(&bars[0]), phase); phase ^= 1; asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+        }
+        mma_commit(smem_u32(&bars[3]));
+        mbar_wait(smem_u32(&bars[3]), 0);
+        cycles[blockIdx.x] = clock64() - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase) : "memory");
+}
+
+static void run_chunks(int N, int per, int ncommit, int drain) {
+    const int chunks = 256;
+    long long* dc; CK(cudaMalloc(&dc, 8));
+    const size_t smem = 4 * 128 * 128 + 4 * 256 * 128 + 1024;
+    CK(cudaFuncSetAttribute(tc_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_chunk_kernel<<<1, 128, smem>>>(N, per, ncommit, chunks, drain, dc);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    long long c = 0;
+    CK(cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost));
+    printf("chunked issue N=%3d: %2d MMAs + %d commits per chunk%s: %7.0f cycles per chunk, %6.1f per MMA\n", N, per, ncommit,
+           drain ? " + wait for completion" : "", (double)c / chunks, (double)c / chunks / per);
+    cudaFree(dc);
+}
+
 static float trunc_tf32(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
 
 static int run(int N, int KB, int rounds, int blocks, double clock_ghz) {
@@ -181,6 +240,9 @@ int main() {
     for (int N : Ns) bad += run(N, 4, 64, prop.multiProcessorCount, ghz);
     bad += run(160, 2, 4, 1, ghz);                                      // a short sequence (32 MMAs): latency-dominated, what round 1 timed
     bad += run(48, 4, 1, 1, ghz);
+    for (int N : {48, 80, 192}) {
+        run_chunks(N, 12, 0, 0); run_chunks(N, 12, 1, 0); run_chunks(N, 12, 2, 0); run_chunks(N, 12, 1, 1); run_chunks(N, 4, 1, 1);
+    }
     printf(bad ? "TC BENCH FAILED (%d)\n" : "TC BENCH OK\n", bad);
     return bad != 0;
 }
