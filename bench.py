@@ -539,7 +539,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         ach = n_local * BYTES_PER_SAMPLE / (rk_ms * 1e-3) / 1e9
         rollout = {"metric": "rollout-form terminal-set samples/s", "value": n / (r_ms * 1e-3), "unit": "samples/s",
                    "ms_per_step": r_ms, "steps": args.rollout_steps, "k_steps": k_star, "state_rows": s_rows, "input_rows": r_in,
-                   "screen_rows": s_rows * (k_star + 1) + r_in, "members": r_members, "members_hrep": members,
+                   "expanded_rows": s_rows * (k_star + 1) + r_in, "screen_rows": rv.screen_rows or rv.expanded_rows,
+                   "screen_note": "the float32 screen holds the irredundant subset of the expanded rows (dual certificates for the "
+                                  "dropped ones, verified by the library); band samples go to the float64 step-by-step rollout",
+                   "members": r_members, "members_hrep": members,
                    "float64_kernel_ms": exact_ms,
                    "float64_kernel_note": "rollout_kernel, also writes the first violated step (4 B/sample)",
                    "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

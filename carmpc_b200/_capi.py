@@ -40,6 +40,8 @@ SIGNATURES = {
     "carmpc_rollout_create": (_i32, [_dp, _dp, _dp, _i32, _dp, _dp, _i32, _dp, _i32, _i32, ctypes.POINTER(_vp)]),
     "carmpc_rollout_bitset": (_i32, [_vp, _dp, _dp, _dp, _dp, _i64, _vp, _vp, _vp, _vp]),
     "carmpc_rollout_bitset_host": (_i32, [_vp, _dp, _dp, _dp, _dp, _i64, _vp, _vp, ctypes.POINTER(_i64)]),
+    "carmpc_rollout_get_rows": (_i32, [_vp, _dp, _i32]),
+    "carmpc_rollout_reduce_screen": (_i32, [_vp, ctypes.POINTER(ctypes.c_int32), _i32, ctypes.POINTER(ctypes.c_int32), _dp, _i32]),
     "carmpc_scan_staging": (_i32, [_vp, _i32, _i32, _i32]),
     "carmpc_shard_create": (_i32, [_i32, _i32, _i64, ctypes.POINTER(_vp)]),
     "carmpc_shard_export": (_i32, [_vp, _vp]),

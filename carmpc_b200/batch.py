@@ -153,7 +153,8 @@ class RolloutEvaluator(_Handle, _ScanTuning):
     """Sampled form of the terminal set: e(0) = p - goal, e(t+1) = A_k e(t); state rows for t = 0..k_steps, input
     rows at t = 0 only (``input_every_step=False``, what the reference's construction does) or at every step."""
 
-    def __init__(self, A_k, A_con, b_con, A_in, b_in, goal, k_steps: int, input_every_step: bool = False):
+    def __init__(self, A_k, A_con, b_con, A_in, b_in, goal, k_steps: int, input_every_step: bool = False,
+                 reduce_screen: bool = True):
         super().__init__()
         self.A_k, self.A_con, self.b_con = _f64(A_k), _f64(A_con).reshape(-1, 4), _f64(b_con).ravel()
         self.A_in, self.b_in, self.goal = _f64(A_in).reshape(-1, 4), _f64(b_in).ravel(), _f64(goal).ravel()
@@ -162,6 +163,66 @@ class RolloutEvaluator(_Handle, _ScanTuning):
                                               len(self.b_con), _capi.ptr(self.A_in), _capi.ptr(self.b_in),
                                               len(self.b_in), _capi.ptr(self.goal), self.k_steps,
                                               1 if input_every_step else 0, ctypes.byref(self._h)))
+        self.screen_rows = self.expanded_rows = 0
+        if reduce_screen:
+            self._reduce_screen()
+
+    def expanded(self) -> np.ndarray:
+        """The expanded rows ``g = a_r A_k^t`` of the float32 screen as the library built them: (rows, 5) = g, b'."""
+        n = self._lib.carmpc_rollout_get_rows(self._h, None, 0)
+        if n <= 0:
+            return np.zeros((0, 5))
+        rows = np.zeros((n, 5))
+        check(min(0, self._lib.carmpc_rollout_get_rows(self._h, _capi.ptr(rows), rows.size)))
+        return rows
+
+    @staticmethod
+    def irredundant_rows(rows: np.ndarray, abs_tol: float = 1e-9, n_dual: int = 4):
+        """For expanded rows (m, 5) = g, b': the indices kept (ascending), and for every other row a redundancy certificate
+        over kept rows - (m, n_dual) row indices and weights >= 0 with ``g_d = sum w_k g_k`` and ``sum w_k b_k <= b_d`` (the
+        dual solution of ``max g_d . p`` over the kept rows; a vertex solution has at most four non-zero weights in R^4).
+        Rows without a clean certificate are kept."""
+        from scipy.optimize import linprog
+        from .lib import polytope_ops as pc
+        G, b = rows[:, :4], rows[:, 4]
+        kept = set(int(i) for i in pc.reduce_indices(pc.Polytope(G, b, normalize=False), abs_tol))
+        idx = np.zeros((len(rows), n_dual), dtype=np.int32)
+        w = np.zeros((len(rows), n_dual))
+        for _ in range(3):                                   # a dropped row without a clean certificate is kept instead
+            order = np.array(sorted(kept), dtype=np.int64)
+            again = False
+            for d in range(len(rows)):
+                if d in kept:
+                    continue
+                res = linprog(b[order], A_eq=G[order].T, b_eq=G[d], bounds=[(0, None)] * len(order), method="highs")
+                lam = res.x if res.status == 0 else None
+                nz = np.flatnonzero(lam > 1e-12) if lam is not None else np.zeros(0, dtype=np.int64)
+                if lam is None or len(nz) == 0 or len(nz) > n_dual or res.fun - b[d] > 1e-6:
+                    kept.add(d)
+                    again = True
+                    continue
+                idx[d] = order[nz[0]]
+                w[d] = 0.0
+                idx[d, :len(nz)] = order[nz]
+                w[d, :len(nz)] = lam[nz]
+            if not again:
+                break
+        return np.array(sorted(kept), dtype=np.int32), idx, w
+
+    def _reduce_screen(self) -> None:
+        """Keeps only the irredundant expanded rows in the float32 screen (the operation ``lib/terminal_set.py:203`` applies
+        to the same set) and hands the library one certificate per dropped row; the library verifies them and widens its
+        acceptance band by what they leave open (``carmpc_rollout_reduce_screen``)."""
+        rows = self.expanded()
+        self.expanded_rows = self.screen_rows = len(rows)
+        if len(rows) < 24 or not np.all(np.isfinite(rows)):
+            return
+        order, idx, w = self.irredundant_rows(rows)
+        if len(order) >= len(rows):
+            return
+        check(self._lib.carmpc_rollout_reduce_screen(self._h, order.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), len(order),
+                                                     idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _capi.ptr(w), idx.shape[1]))
+        self.screen_rows = len(order)
 
     @classmethod
     def from_env(cls, env, k_steps: int, input_every_step: bool = False) -> "RolloutEvaluator":

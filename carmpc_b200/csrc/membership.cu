@@ -127,6 +127,8 @@ struct Rollout : HandleBase {
     RowF32* d_rows32 = nullptr;      // float32 screen: expanded rows a_r A_k^t in absolute coordinates (null: exact kernel only)
     int rows_padded = 0, rows32 = 0;
     float beta0 = 0.f, beta1 = 0.f;
+    float in0 = 0.f, in1 = 0.f;      // acceptance band (= beta unless the screen was reduced to the irredundant rows)
+    std::vector<double> h_rows64;    // every expanded row as built: [rows][5] = g (4), b' (absolute coordinates)
     std::vector<RowF32> h_rows32;    // host copy (re-ordered by the pilot)
     bool tuned = false;
     Staging staging;
@@ -145,7 +147,9 @@ __device__ __forceinline__ uint32_t spread8x4(uint32_t v) {
 }
 
 struct ScreenConst {         // float32 error-bound constants of the polytope
-    float beta0, beta1;
+    float beta0, beta1;      // a sample is surely outside when its smallest margin is below -(beta0 + beta1 |p|_1)
+    float in0, in1;          // ... and surely inside when it is above in0 + in1 |p|_1 (= the beta pair, unless the screen only
+                             // holds the irredundant rows of the set: then the dropped rows' certificates widen it)
 };
 
 constexpr int kExit64 = 4;       // rows between "whole warp already outside" votes, float64 path
@@ -234,13 +238,14 @@ __device__ __forceinline__ void decide_exact(const double* __restrict__ s_rows, 
 __device__ __forceinline__ void screen32(const RowF32* __restrict__ s_rows32, int rows_padded, const ScreenConst sc,
                                          const float (&xf)[kNS], const float (&yf)[kNS], const float (&pf)[kNS],
                                          const float (&vf)[kNS], bool (&in)[kNS], bool (&amb)[kNS]) {
-    float nbeta[kNS], mmin[kNS];
+    float nbeta[kNS], ibeta[kNS], mmin[kNS];
 #pragma unroll
     for (int k = 0; k < kNS; ++k) {
         // |x| + |y| + |psi| + |v| >= max |coordinate|, and (unlike fmaxf) it propagates NaN / inf into the bound,
         // which then fails both "surely in" and "surely out": such samples are decided by the float64 chain
         const float psum = (fabsf(xf[k]) + fabsf(yf[k])) + (fabsf(pf[k]) + fabsf(vf[k]));
         nbeta[k] = -fmaf(sc.beta1, psum, sc.beta0);
+        ibeta[k] = fmaf(sc.in1, psum, sc.in0);
         mmin[k] = in[k] ? INFINITY : -INFINITY;              // padding lanes count as "already outside"
     }
     // samples in pairs: the four fmas of a row run as FFMA2 (same IEEE result per sample as fmaf, half the issue slots)
@@ -272,7 +277,7 @@ __device__ __forceinline__ void screen32(const RowF32* __restrict__ s_rows32, in
     }
 #pragma unroll
     for (int k = 0; k < kNS; ++k) {
-        const bool sure_in = mmin[k] > -nbeta[k], sure_out = mmin[k] < nbeta[k];
+        const bool sure_in = mmin[k] > ibeta[k], sure_out = mmin[k] < nbeta[k];
         amb[k] = in[k] && !sure_in && !sure_out;
         in[k] = in[k] && sure_in;
     }
@@ -806,6 +811,8 @@ static ScreenConst screen_const(const Polytope* P) {
     ScreenConst sc;
     sc.beta0 = P->beta0;
     sc.beta1 = P->beta1;
+    sc.in0 = P->beta0;
+    sc.in1 = P->beta1;
     return sc;
 }
 
@@ -918,7 +925,7 @@ static int launch_rollout(Rollout* R, const double* x, const double* y, const do
         es.len = 20 + 5 * R->s + 5 * R->rin;
         es.s = R->s; es.rin = R->rin; es.k_steps = R->k_steps; es.input_mode = R->input_mode;
         ScreenConst sc;
-        sc.beta0 = R->beta0; sc.beta1 = R->beta1;
+        sc.beta0 = R->beta0; sc.beta1 = R->beta1; sc.in0 = R->in0; sc.in1 = R->in1;
         return launch_scan<1>(R->d_data, R->d_rows32, es, R->rows_padded, sc, x, y, p, v, n, sink, count, work, 1, R->staging, st);
     }
     const size_t smem = sizeof(double) * (20 + 5 * R->s + 5 * R->rin);
@@ -1362,6 +1369,8 @@ int carmpc_rollout_create(const double* h_Ak, const double* h_Acon, const double
             q.na0 = (float)-g[0]; q.na1 = (float)-g[1]; q.na2 = (float)-g[2]; q.na3 = (float)-g[3];
             q.b = (float)bp;
             q.pad0 = q.pad1 = q.pad2 = 0.f;
+            for (int j = 0; j < 4; ++j) R->h_rows64.push_back((double)g[j]);
+            R->h_rows64.push_back(b == INFINITY ? INFINITY : (double)bp);
             finite = finite && std::isfinite(q.na0) && std::isfinite(q.na1) && std::isfinite(q.na2) && std::isfinite(q.na3) && !std::isnan(q.b);
             if (b == INFINITY) q.b = INFINITY;
             r32[w++] = q;
@@ -1388,6 +1397,8 @@ int carmpc_rollout_create(const double* h_Ak, const double* h_Acon, const double
         if (finite && std::isfinite((double)b0) && std::isfinite((double)b1) && (double)b0 < 1e30 && (double)b1 < 1e30) {
             R->beta0 = nextafterf((float)b0, INFINITY);
             R->beta1 = nextafterf((float)b1, INFINITY);
+            R->in0 = R->beta0;
+            R->in1 = R->beta1;
             R->rows_padded = (int)r32.size();
             R->rows32 = (int)total_rows;
             R->h_rows32 = r32;
@@ -1400,6 +1411,90 @@ int carmpc_rollout_create(const double* h_Ak, const double* h_Acon, const double
         }
     }
     *handle = R;
+    return CARMPC_OK;
+}
+
+int carmpc_rollout_get_rows(void* rollout, double* h_rows, int capacity) {
+    Rollout* R = check_handle<Rollout>(rollout, kRollout);
+    CARMPC_REQUIRE(R != nullptr, "not a rollout handle");
+    const int cnt = (int)R->h_rows64.size();
+    if (h_rows) {
+        CARMPC_REQUIRE(capacity >= cnt, "capacity too small");
+        memcpy(h_rows, R->h_rows64.data(), sizeof(double) * cnt);
+    }
+    return R->d_rows32 != nullptr ? cnt / 5 : 0;
+}
+
+int carmpc_rollout_reduce_screen(void* rollout, const int32_t* h_kept, int n_kept, const int32_t* h_dual_idx,
+                                 const double* h_dual_w, int n_dual) {
+    Rollout* R = check_handle<Rollout>(rollout, kRollout);
+    CARMPC_REQUIRE(R != nullptr, "not a rollout handle");
+    CARMPC_REQUIRE(R->d_rows32 != nullptr, "this rollout has no float32 screen");
+    const int rows = (int)R->h_rows64.size() / 5;
+    CARMPC_REQUIRE(h_kept && n_kept >= 1 && n_kept <= rows, "kept rows");
+    CARMPC_REQUIRE(n_kept == rows || (h_dual_idx && h_dual_w && n_dual >= 1 && n_dual <= 16), "dual certificates");
+    std::vector<char> kept(rows, 0);
+    for (int i = 0; i < n_kept; ++i) {
+        CARMPC_REQUIRE(h_kept[i] >= 0 && h_kept[i] < rows && !kept[h_kept[i]], "kept row index out of range or repeated");
+        kept[h_kept[i]] = 1;
+    }
+    // Every dropped row d needs a certificate lambda >= 0 over kept rows with  g_d ~ sum lambda_k g_k  and
+    // sum lambda_k b_k <~ b_d : then, with M_r(p) = b_r - g_r . p,
+    //     M_d >= sum lambda_k M_k - tol_d - rho_d |p|_1 ,   tol_d = (sum lambda_k b_k - b_d)+ ,  rho_d = |g_d - sum lambda_k g_k|_inf
+    // so a sample whose smallest float32 margin over the KEPT rows exceeds
+    //     beta(p) max(1, 1 / L) + (tol + rho |p|_1) / L ,    L = min_d sum lambda_k
+    // clears the float64 band of every dropped row as well.  The certificates are only CHECKED here (in long double, against
+    // the rows this handle built), wherever they come from; what they do not prove widens the band or is refused.
+    long double lam_min = INFINITY, tol_max = 0, rho_max = 0;
+    const double* G = R->h_rows64.data();
+    for (int d = 0; d < rows; ++d) {
+        if (kept[d]) continue;
+        if (G[5 * d + 4] == INFINITY) continue;                 // a row without a bound constrains nothing
+        long double sum = 0, bsum = 0, acc[4] = {0, 0, 0, 0};
+        for (int j = 0; j < n_dual; ++j) {
+            const int k = h_dual_idx[(size_t)d * n_dual + j];
+            const long double w = h_dual_w[(size_t)d * n_dual + j];
+            if (w == 0) continue;
+            CARMPC_REQUIRE(k >= 0 && k < rows && kept[k] && w > 0 && std::isfinite((double)w) && G[5 * k + 4] != INFINITY,
+                           "a certificate must combine kept rows with non-negative weights");
+            sum += w;
+            bsum += w * (long double)G[5 * k + 4];
+            for (int c = 0; c < 4; ++c) acc[c] += w * (long double)G[5 * k + c];
+        }
+        CARMPC_REQUIRE(sum > 1e-9L, "empty certificate for a dropped row");
+        long double rho = 0;
+        for (int c = 0; c < 4; ++c) rho = std::max(rho, fabsl((long double)G[5 * d + c] - acc[c]));
+        lam_min = std::min(lam_min, sum);
+        tol_max = std::max(tol_max, bsum - (long double)G[5 * d + 4]);
+        rho_max = std::max(rho_max, rho);
+    }
+    long double in0 = R->beta0, in1 = R->beta1;
+    if (lam_min != INFINITY) {
+        const long double scale = std::max(1.0L, 1.0L / lam_min);
+        in0 = (long double)R->beta0 * scale + tol_max / lam_min;
+        in1 = (long double)R->beta1 * scale + rho_max / lam_min;
+    }
+    CARMPC_REQUIRE(std::isfinite((double)in0) && std::isfinite((double)in1) && (double)in0 < 1e-2 && (double)in1 < 1e-2,
+                   "the certificates leave an acceptance band wider than 1e-2: screen not reduced");
+    std::vector<RowF32> r32(pad_rows(n_kept));
+    for (RowF32& q : r32) { q.na0 = q.na1 = q.na2 = q.na3 = 0.f; q.b = INFINITY; q.pad0 = q.pad1 = q.pad2 = 0.f; }
+    for (int i = 0; i < n_kept; ++i) {
+        const double* g = G + 5 * (size_t)h_kept[i];
+        RowF32 q;
+        q.na0 = (float)-g[0]; q.na1 = (float)-g[1]; q.na2 = (float)-g[2]; q.na3 = (float)-g[3];
+        q.b = g[4] == INFINITY ? INFINITY : (float)g[4];
+        q.pad0 = q.pad1 = q.pad2 = 0.f;
+        r32[i] = q;
+    }
+    CARMPC_REQUIRE(r32.size() <= R->h_rows32.size(), "internal: the reduced screen cannot be larger than the full one");
+    CARMPC_CUDA(cudaDeviceSynchronize());
+    CARMPC_CUDA(cudaMemcpy(R->d_rows32, r32.data(), sizeof(RowF32) * r32.size(), cudaMemcpyHostToDevice));
+    R->h_rows32 = r32;
+    R->rows_padded = (int)r32.size();
+    R->rows32 = n_kept;
+    R->in0 = nextafterf((float)in0, INFINITY);
+    R->in1 = nextafterf((float)in1, INFINITY);
+    R->tuned = false;
     return CARMPC_OK;
 }
 

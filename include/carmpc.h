@@ -94,6 +94,19 @@ int carmpc_rollout_create(const double* h_Ak, const double* h_Acon, const double
                           const double* h_Ain, const double* h_bin, int rin, const double* h_goal,
                           int k_steps, int input_check_mode, void** handle);
 
+/* The float32 screen of a rollout handle evaluates the EXPANDED rows g = a_r A_k^t (k_steps + 1 copies of the state rows,
+ * 140 rows for the shipped sets), most of which are redundant (the reference reduces the same set to ~42 rows,
+ * lib/terminal_set.py:203).  carmpc_rollout_get_rows returns the expanded rows as this handle built them (row-major
+ * [rows][5] = g (4), b' in absolute coordinates; returns the row count, 0 if the handle has no screen; h_rows may be
+ * NULL).  carmpc_rollout_reduce_screen keeps only rows h_kept for the screen; every other row d needs a redundancy
+ * certificate: n_dual (row index, weight >= 0) pairs over kept rows with  g_d = sum w_k g_k  and  sum w_k b_k <= b_d
+ * (the dual solution of  max g_d . p  over the kept rows).  The library only CHECKS the certificates (in long double,
+ * against its own rows) and widens the screen's acceptance band by what they leave open; samples inside the band are
+ * decided by the float64 step-by-step rollout as before, so results never depend on the reduction. */
+int carmpc_rollout_get_rows(void* rollout, double* h_rows, int capacity);
+int carmpc_rollout_reduce_screen(void* rollout, const int32_t* h_kept, int n_kept, const int32_t* h_dual_idx,
+                                 const double* h_dual_w, int n_dual);
+
 /* d_first_violation (nullable): int32 per sample, first step t at which a row is violated, -1 if none. */
 int carmpc_rollout_bitset(void* rollout, const double* d_x, const double* d_y, const double* d_psi,
                           const double* d_v, int64_t n, uint32_t* d_bits, int32_t* d_first_violation,

@@ -346,3 +346,38 @@ def test_implicit_grid_equals_explicit_points_on_ragged_grids(torch_cuda, dims):
     bits2, count2 = ev.contains_grid_bits([axes[k] for k in perm], axis_to_state=perm)
     got2 = unpack_bits(_bits_np(bits2), n).reshape([dims[k] for k in perm])
     np.testing.assert_array_equal(np.transpose(got2, np.argsort(perm)).ravel(), want)
+
+
+def test_reduced_rollout_screen_gives_the_full_screens_bits(torch_cuda):
+    """The float32 screen keeps only the irredundant expanded rows (42 of 140 for RoadMultipleCarsEnv); decisions are those
+    of the full screen and of the exact kernel, and certificates that do not hold are refused."""
+    import ctypes
+    from carmpc_b200 import _capi
+    from carmpc_b200.batch import RolloutEvaluator, CarmpcError
+    env = make_env("RoadMultipleCarsEnv", [30, 1.5, 0, 0])
+    k = K_STAR["RoadMultipleCarsEnv"]
+    red, full = RolloutEvaluator.from_env(env, k), RolloutEvaluator.from_env(env, k)
+    full2 = RolloutEvaluator(full.A_k, full.A_con, full.b_con, full.A_in, full.b_in, full.goal, k, reduce_screen=False)
+    assert red.expanded_rows == 140 and red.screen_rows <= 48 and full2.screen_rows == 0
+    rng = np.random.default_rng(3)
+    n = 2_000_000 + 37
+    g = np.array(env.goal, dtype=float)
+    p = g + rng.uniform(-1, 1, size=(n, 4)) * np.array([8.0, 2.5, 0.45, 3.0])
+    dev = _dev(torch_cuda, *p.T)
+    b_red, c_red = red.contains_bits(*dev)
+    b_full, c_full = full2.contains_bits(*dev)
+    b_exact, c_exact, _ = full2.contains_bits(*dev, want_first_violation=True)
+    assert int(c_red.item()) == int(c_full.item()) == int(c_exact.item()) > 1000
+    np.testing.assert_array_equal(_bits_np(b_red), _bits_np(b_full))
+    np.testing.assert_array_equal(_bits_np(b_red), _bits_np(b_exact))
+    # a certificate that does not reproduce the dropped row is refused and leaves the handle as it was
+    rows = full2.expanded()
+    kept, idx, w = RolloutEvaluator.irredundant_rows(rows)
+    bad = w.copy()
+    bad[bad > 0] *= 0.5
+    lib = _capi.load()
+    rc = lib.carmpc_rollout_reduce_screen(full2._h, kept.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), len(kept),
+                                          idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _capi.ptr(bad), idx.shape[1])
+    assert rc != 0
+    b_again, c_again = full2.contains_bits(*dev)
+    np.testing.assert_array_equal(_bits_np(b_again), _bits_np(b_full))
