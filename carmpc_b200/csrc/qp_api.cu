@@ -116,7 +116,7 @@ int QPHandle::ensure_io(int64_t batch, bool want_full) {
 
 QPHandle::~QPHandle() {
     for (void* p : allocations) cudaFree(p);
-    cudaFree(ws_sign); cudaFree(ws_u); cudaFree(ws_status); cudaFree(ws_iters); cudaFree(ws_failed); cudaFree(ws_failed0);
+    cudaFree(ws_sign); cudaFree(ws_u); cudaFree(ws_status); cudaFree(ws_iters); cudaFree(ws_failed); cudaFree(ws_failed0); cudaFree(ws_rest);
     cudaFree(ws_counters); cudaFree(ws_total_iters); cudaFree(ws_polished); cudaFree(ws_warm); cudaFree(ws_overflow); cudaFree(ws_unproven);
     cudaFree(ws_anchor); cudaFree(ws_follow); cudaFree(ws_rec_of); cudaFree(ws_rec_lam); cudaFree(ws_rec_act); cudaFree(ws_polish_stats);
     cudaFree(io_x0_aos); cudaFree(io_x0); cudaFree(io_c); cudaFree(io_u0); cudaFree(io_u0_aos); cudaFree(io_obj); cudaFree(io_full);
@@ -136,6 +136,7 @@ int QPHandle::ensure_workspace(int64_t batch) {
     cudaFree(ws_overflow); ws_overflow = nullptr;
     cudaFree(ws_unproven); ws_unproven = nullptr;
     cudaFree(ws_failed0); ws_failed0 = nullptr;
+    cudaFree(ws_rest); ws_rest = nullptr;
     cudaFree(ws_anchor); ws_anchor = nullptr;
     cudaFree(ws_follow); ws_follow = nullptr;
     cudaFree(ws_rec_of); ws_rec_of = nullptr;
@@ -149,6 +150,7 @@ int QPHandle::ensure_workspace(int64_t batch) {
     CARMPC_CUDA(cudaMalloc(&ws_overflow, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_unproven, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_failed0, sizeof(int) * (size_t)batch));
+    CARMPC_CUDA(cudaMalloc(&ws_rest, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_anchor, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_follow, sizeof(int) * (size_t)batch));
     CARMPC_CUDA(cudaMalloc(&ws_rec_of, sizeof(int) * (size_t)batch));
@@ -198,6 +200,20 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
     // Active-set reuse (closed loop): consecutive QPs of a run mostly share their active set, so the set certified at
     // the previous step (kept in the workspace, same sample indexing) goes through the float64 polish first; only the
     // samples it does not certify (set changed, or infeasible now) run ADMM iterations.
+    // The empty active set first (polish_unconstrained_kernel): where the unconstrained minimiser satisfies every row it is
+    // the optimum - certified in float64 by one thread, no iteration, no factorisation.  Closed-loop runs near their goal
+    // live there; on the config-3 grid it settles 8.6 % of the states.  The rest (listed on the device) goes on.
+    const int* d_count = nullptr;                        // device-side count of the list the pipeline below works on
+    if (host.opts.polish) {
+        PolishBatch pu = pb;
+        pu.sign_out = ws_sign; pu.iters_out = iters;
+        rc = polish_unconstrained_launch(this, pu, ws_rest, ws_counters + 6, st);
+        if (rc != CARMPC_OK) return rc;
+        ++last_launches;
+        d_idx = ws_rest;
+        d_count = ws_counters + 6;
+        pb.idx_list = d_idx; pb.count_dev = d_count;
+    }
     if (reuse_active_set && host.opts.polish) {
         PolishBatch p0 = pb;
         p0.rounds = 4; p0.final_pass = 0; p0.n_failed = ws_counters + 5; p0.failed_list = ws_failed0;
@@ -207,21 +223,24 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
         rc = polish_launch(this, p0, st);
         if (rc != CARMPC_OK) return rc;
         ++last_launches;
-        int n_failed0 = 0;
+        int n_failed0 = 0, n_rest = 0;
         CARMPC_CUDA(cudaMemcpyAsync(&n_failed0, ws_counters + 5, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CARMPC_CUDA(cudaMemcpyAsync(&n_rest, ws_counters + 6, sizeof(int), cudaMemcpyDeviceToHost, st));
         CARMPC_CUDA(cudaStreamSynchronize(st));
         last_reused = count - n_failed0;
+        (void)n_rest;
         if (n_failed0 == 0) { last_total_iters = 0; return CARMPC_OK; }        // (deferred totals: nothing was added)
         d_idx = ws_failed0;
         count = n_failed0;
-        pb.idx_list = d_idx; pb.count = (int)count;
+        d_count = nullptr;
+        pb.idx_list = d_idx; pb.count = (int)count; pb.count_dev = nullptr;
     }
 
     AdmmBatch ab;
     memset(&ab, 0, sizeof(ab));
     ab.x0 = d_x0; ab.stride = stride; ab.cdist = d_c;
     for (int c = 0; c < 4; ++c) ab.xref[c] = xref[c];
-    ab.idx_list = d_idx; ab.count = (int)count; ab.next = ws_counters + 0;
+    ab.idx_list = d_idx; ab.count = (int)count; ab.count_dev = d_count; ab.next = ws_counters + 0;
     ab.sign = ws_sign; ab.u_admm = ws_u; ab.status = status; ab.iters = iters;
     // the ADMM state of every sample is kept (caller's buffer or the workspace): the second pass resumes from it
     ab.warm = d_warm ? d_warm : ws_warm; ab.warm_in = d_warm ? warm_in : 0; ab.warm_out = 1;
@@ -247,7 +266,7 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
     if (host.opts.polish) {
         // "infeasible" verdicts of the float32 ADMM are accepted only with a float64 Farkas certificate of their final
         // dual iterate (or a violated u-independent row); the others join the list of the second pass
-        rc = farkas_verify_launch(this, d_idx, (int)count, status, ab.warm, d_x0, stride, d_c, xref, ws_failed, ws_counters + 1, st);
+        rc = farkas_verify_launch(this, d_idx, (int)count, status, ab.warm, d_x0, stride, d_c, xref, ws_failed, ws_counters + 1, st, d_count);
         if (rc != CARMPC_OK) return rc;
         ++last_launches;
         CARMPC_CUDA(cudaMemcpyAsync(&n_failed, ws_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -270,12 +289,12 @@ int QPHandle::solve(const double* d_x0, int64_t stride, const double* xref, cons
     if (n_failed > 0) {
         // second pass on the samples whose active set the polish could not certify: tighter ADMM, then accept
         last_second_pass = n_failed;
-        ab.idx_list = second_list; ab.count = n_failed; ab.next = ws_counters + 2; ab.eps_scale = 0.01f;
+        ab.idx_list = second_list; ab.count = n_failed; ab.count_dev = nullptr; ab.next = ws_counters + 2; ab.eps_scale = 0.01f;
         ab.max_iter = host.opts.max_iter;
         ab.warm_in = 1; ab.iters_accumulate = 1; ab.write_u = 1;
         rc = admm_launch(this, ab, st);
         if (rc != CARMPC_OK) return rc;
-        pb.idx_list = second_list; pb.count = n_failed; pb.n_failed = ws_counters + 3; pb.final_pass = 1;
+        pb.idx_list = second_list; pb.count = n_failed; pb.count_dev = nullptr; pb.n_failed = ws_counters + 3; pb.final_pass = 1;
         rc = polish_launch(this, pb, st);
         if (rc != CARMPC_OK) return rc;
         // whoever is still at "max_iter" is almost always barely infeasible: the dual iterate of its final ADMM state,
@@ -325,9 +344,14 @@ int QPHandle::solve_enqueue(const double* d_x0, int64_t stride, const double* xr
     pb.sign = ws_sign; pb.u_admm = ws_u; pb.status = status; pb.u0 = d_u0; pb.polished = ws_polished;
     pb.rounds = -1; pb.stats = ws_polish_stats; pb.sign_out = ws_sign;
 
+    // 0. the empty active set (runs near their goal: the unconstrained minimiser is feasible), one thread per run
+    PolishBatch pu = pb;
+    pu.idx_list = d_idx; pu.count = cap; pu.count_dev = d_count; pu.iters_out = ws_iters;
+    rc = polish_unconstrained_launch(this, pu, ws_rest, ws_counters + 6, st);
+    if (rc != CARMPC_OK) return rc;
     // 1. the active set certified at the previous step, straight into the float64 polish
     PolishBatch p0 = pb;
-    p0.idx_list = d_idx; p0.count = cap; p0.count_dev = d_count;
+    p0.idx_list = ws_rest; p0.count = cap; p0.count_dev = ws_counters + 6;
     p0.rounds = 4; p0.final_pass = 0; p0.n_failed = ws_counters + 5; p0.failed_list = ws_failed0;
     p0.precheck = 1; p0.Px = admm.Px; p0.Pc = admm.Pc; p0.pre_lo = admm.pre_lo; p0.pre_hi = admm.pre_hi; p0.kpre = admm.kpre;
     p0.iters_out = ws_iters;

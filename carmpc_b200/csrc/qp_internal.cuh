@@ -262,6 +262,8 @@ int admm_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st);
 int admm_tc_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st);
 bool admm_tc_usable(const QPHandle* q, const AdmmBatch& b);
 int polish_launch(QPHandle* q, const PolishBatch& b, cudaStream_t st);
+// the empty active set tried first (one thread per sample); samples it does not settle are appended to d_rest
+int polish_unconstrained_launch(QPHandle* q, const PolishBatch& b, int* d_rest, int* d_n_rest, cudaStream_t st);
 // infeasible anchors of a seeded map: turn the ADMM dual iterate into an exact Farkas certificate, affine in x0
 int farkas_export_launch(QPHandle* q, const int* d_anchors, int count, const int* d_status, const float* d_warm,
                          const double* d_x0, int64_t stride, cudaStream_t st);
@@ -300,6 +302,7 @@ struct QPHandle : HandleBase {
     int* ws_iters = nullptr;
     int* ws_failed = nullptr;
     int* ws_failed0 = nullptr;                   // samples whose reused active set did not certify
+    int* ws_rest = nullptr;                      // samples the empty active set does not settle
     int* ws_anchor = nullptr;                    // seeded solve: samples solved cold (anchors) / from a seed (followers)
     int* ws_follow = nullptr;
     int* ws_rec_of = nullptr;                    // [batch] record index of an anchor
