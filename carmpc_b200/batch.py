@@ -350,7 +350,7 @@ class BatchQP(_Handle):
         info = (ctypes.c_int64 * 16)()
         check(self._lib.carmpc_qp_tensor_mode(self._h, int(mode), info))
         return {"mode": int(info[0]), "available": bool(info[1]), "samples_last_solve": int(info[2]),
-                "matrices_resident": bool(info[3]), "cycles": [int(v) for v in info[4:14]]}
+                "matrices_resident": bool(info[3]), "cycles": [int(v) for v in info[4:16]]}
 
     # ---- device tensors ---------------------------------------------------------------------------
     def solve(self, x0, x_ref=None, c=None, want_u_full: bool = False, warm=None, warm_in: bool = False,

@@ -220,9 +220,12 @@ __device__ __forceinline__ void a_put16(const AStream& A, int k0, const float (&
         *reinterpret_cast<float4*>(hi_row + (piece << 4)) = h;
         *reinterpret_cast<float4*>(lo_row + (piece << 4)) = l;
     }
+    const long long tf0 = A.wait_acc ? clock64() : 0;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
+    if (A.wait_acc) A.wait_acc[5] += (unsigned long long)(clock64() - tf0);          // [10]: the proxy fence
     __syncwarp();
+    if (A.wait_acc) { A.wait_acc[6] += (unsigned long long)(clock64() - tf0); ++A.wait_acc[7]; }   // [11]: fence + warp sync, [12]: chunks written
     if (lane == 0) {
         mbar_arrive(A.full + stage);
         if (half == 0 && k0 + 16 == A.kend) mbar_arrive(A.full + stage);     // nobody writes the second half
@@ -281,7 +284,10 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *sm.tmem_slot;
-    const uint32_t col_state = tbase, col_z = tbase + (uint32_t)mp, col_x = tbase + (uint32_t)(2 * mp);
+    // merged: every accumulator is 2 N wide - columns [0, N) hold A_hi B_hi + A_lo B_hi, columns [N, 2 N) hold A_hi B_lo
+    const bool merged = C.merged != 0;
+    const uint32_t col_state = tbase, col_z = tbase + (uint32_t)mp, col_x = col_z + (uint32_t)(merged ? 2 * mp : mp);
+    const uint32_t col_z2 = col_z + (uint32_t)mp, col_x2 = col_x + (uint32_t)NP;
     const int check_every = T.check_every;
     const int q_count = Bq.count_dev != nullptr ? min(*Bq.count_dev, Bq.count) : Bq.count;
 
@@ -516,7 +522,16 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
                     if (j0 < NP) {
                         uint32_t xr[16];
                         tmem_ld16(col_x + lane_addr + (uint32_t)j0, xr);
-                        tmem_ld_wait(xr);
+                        if (merged) {
+                            uint32_t x2[16];
+                            tmem_ld16(col_x2 + lane_addr + (uint32_t)j0, x2);
+                            tmem_ld_wait(xr);
+                            tmem_ld_wait(x2);
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) xr[r] = __float_as_uint(__uint_as_float(xr[r]) + __uint_as_float(x2[r]));
+                        } else {
+                            tmem_ld_wait(xr);
+                        }
                         float x[16];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -563,6 +578,13 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
                     const int g0 = b << 4;
                     uint32_t zr[16], wr[16];
                     tmem_ld16(col_z + lane_addr + (uint32_t)g0, zr);
+                    if (merged) {
+                        tmem_ld16(col_z2 + lane_addr + (uint32_t)g0, wr);
+                        tmem_ld_wait(zr);
+                        tmem_ld_wait(wr);
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) zr[r] = __float_as_uint(__uint_as_float(zr[r]) + __uint_as_float(wr[r]));
+                    }
                     tmem_ld16(col_state + lane_addr + (uint32_t)g0, wr);
                     tmem_ld_wait(zr);
                     tmem_ld_wait(wr);
@@ -608,7 +630,16 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
                 if (j0 < NP) {
                     uint32_t yr[16];
                     tmem_ld16(col_x + lane_addr + (uint32_t)j0, yr);
-                    tmem_ld_wait(yr);
+                    if (merged) {
+                        uint32_t y2[16];
+                        tmem_ld16(col_x2 + lane_addr + (uint32_t)j0, y2);
+                        tmem_ld_wait(yr);
+                        tmem_ld_wait(y2);
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) yr[r] = __float_as_uint(__uint_as_float(yr[r]) + __uint_as_float(y2[r]));
+                    } else {
+                        tmem_ld_wait(yr);
+                    }
 #pragma unroll
                     for (int r = 0; r < 16; ++r) {
                         const int j = j0 + r;
@@ -646,7 +677,7 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
             unsigned long long* const pb = (prof_on && leader) ? &pc[2] : nullptr;
             auto product = [&](int p, uint32_t dcol, bool streamed, uint64_t* done) {
                 const int N = C.ncols[p];
-                const uint32_t idesc = make_idesc(N);
+                const uint32_t idesc = make_idesc(N), idesc2 = make_idesc(2 * N);
                 const int e_ks = p == 2 ? -1 : NP / 8;              // the two k-steps of the constant columns: their lo image is zero
                 const unsigned char* res_base = sm.b_res + (p == 1 ? (size_t)C.nchunks[0] * C.pair_bytes[0] : 0);
                 for (int c = 0; c < C.nchunks[p]; ++c) {
@@ -670,7 +701,15 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
                     const int nks = min(4, C.ksteps[p] - 4 * c);
                     const bool e_chunk = 4 * c <= e_ks + 1 && e_ks < 4 * c + 4;       // this chunk holds constant columns
                     if (leader) {
-                        if (!e_chunk && nks == 4) {
+                        if (merged) {
+                            // A_hi x [B_hi; B_lo] (the lo image follows the hi image: one operand of 2 N rows), then A_lo x B_hi
+                            for (int ks = 0; ks < nks; ++ks) {
+                                const uint64_t o = (uint64_t)(ks * 2);
+                                const int kg = 4 * c + ks;
+                                mma_ss(dcol, a_hi + o, b_hi + o, idesc2, (uint32_t)(kg != 0));
+                                if (kg != e_ks && kg != e_ks + 1) mma_ss(dcol, a_lo + o, b_hi + o, idesc, 1u);
+                            }
+                        } else if (!e_chunk && nks == 4) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 const uint64_t o = (uint64_t)(ks * 2);
@@ -730,7 +769,7 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
         __syncwarp();
     }
     __syncthreads();
-    if (prof_on && tid < 10) atomicAdd(Bq.prof + tid, pc[tid]);
+    if (prof_on && tid < 13) atomicAdd(Bq.prof + tid, pc[tid]);
 
     tc_fence_before();
     __syncthreads();

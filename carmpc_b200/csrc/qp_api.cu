@@ -779,6 +779,7 @@ int carmpc_qp_tensor_mode(void* qp, int mode, int64_t* h_info) {
             unsigned long long tmp[16];
             CARMPC_CUDA(cudaMemcpy(tmp, q->ws_prof, sizeof(tmp), cudaMemcpyDeviceToHost));
             for (int i = 0; i < 12; ++i) h_info[4 + i] = (int64_t)tmp[i];
+            // (h_info has 16 slots: counters 0..11)
         }
     }
     return CARMPC_OK;

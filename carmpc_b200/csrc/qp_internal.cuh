@@ -133,6 +133,8 @@ struct TcTables {
     const double* kfv;          // [np][4]  x~0 = kfv (x0 - xref)
     int n, m, mt, np, mp;
     int resident;               // products 0 and 1 stay in shared memory (loaded once); product 2 always streams
+    int merged;                 // B_hi and B_lo are consumed as ONE operand of 2 N rows (A_hi fetched once per k-step: two
+                                // MMAs instead of three); needs 2 N accumulator columns per product: 3 mp + 2 np <= 512
     int na_stages, nb_stages, b_stage_bytes, resident_bytes;
     int smem_bytes;
     int ok;                     // 0: this problem has no tensor-core form (too large for tensor memory / shared memory)

@@ -450,6 +450,7 @@ int qp_host_setup(int n, int m_in, int kpre, const double* H_in, const double* F
         t.n = n; t.m = m; t.mt = mt; t.np = np; t.mp = mp;
         const int K[3] = {np + 16 + mp, np + 16, mp}, N[3] = {np, mp, np};
         t.ok = mp <= 256 && np <= 256 && 2 * mp + np <= 512;
+        t.merged = 3 * mp + 2 * np <= 512 && 2 * mp <= 256;
         size_t total = 0;
         for (int p = 0; p < 3; ++p) {
             t.ncols[p] = N[p]; t.ksteps[p] = K[p] / 8; t.nchunks[p] = (K[p] + 31) / 32;

@@ -44,7 +44,7 @@ bq.solve(x0)
 info = bq.tensor_mode()
 cyc = info["cycles"]
 names = ["mma: round total", "mma: wait A", "mma: wait B", "cmp: wait x~", "cmp: wait z^", "cmp: wait A stage", "cmp: retire/refill",
-         "cmp: round total", "rounds", "tma: wait stage"]
+         "cmp: round total", "rounds", "tma: wait stage", "cmp: proxy fence", "cmp: fence + syncwarp"]
 rounds = max(cyc[8], 1)
 print("cycle counters per round (one round = check_every iterations of a 128-sample tile):")
 for nm, v in zip(names, cyc):
