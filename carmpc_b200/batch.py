@@ -349,7 +349,7 @@ class BatchQP(_Handle):
         tcgen05 kernel when the problem has a tensor-core form, 0 = the FFMA tile kernel."""
         info = (ctypes.c_int64 * 16)()
         check(self._lib.carmpc_qp_tensor_mode(self._h, int(mode), info))
-        return {"mode": int(info[0]), "available": bool(info[1]), "samples_last_solve": int(info[2]),
+        return {"mode": int(info[0]), "available": bool(info[1]), "parts": int(info[1]), "samples_last_solve": int(info[2]),
                 "matrices_resident": bool(info[3]), "cycles": [int(v) for v in info[4:16]]}
 
     # ---- device tensors ---------------------------------------------------------------------------

@@ -366,10 +366,10 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
                         if (j0 < NP) {
 #pragma unroll
                             for (int r = 0; r < 16; ++r) {
-                                const int j = j0 + r;
-                                if (j < n) {
-                                    sg[m + j] = (int8_t)((wb[lb][r] > sm.ub[j]) - (wb[lb][r] < sm.lb[j]));
-                                    if (Bq.warm_out) wo[m + j] = wb[lb][r];
+                                const int j = j0 + r, vj = C.var_id[j];
+                                if (vj >= 0) {
+                                    sg[m + vj] = (int8_t)((wb[lb][r] > sm.ub[j]) - (wb[lb][r] < sm.lb[j]));
+                                    if (Bq.warm_out) wo[m + vj] = wb[lb][r];
                                 }
                             }
                         }
@@ -381,9 +381,21 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
                 int st = sm.slot_state[slot];
                 if (st > 0) {
                     const int it = sm.slot_iter[slot];
-                    Bq.status[sample_old] = st == kSlotSolved ? CARMPC_QP_SOLVED : (st == kSlotMaxIter ? CARMPC_QP_MAX_ITER : CARMPC_QP_INFEASIBLE);
-                    Bq.iters[sample_old] = it + (Bq.iters_accumulate ? Bq.iters[sample_old] : 0);
-                    atomicAdd(Bq.total_iters, (unsigned long long)it);
+                    int verdict = st == kSlotSolved ? CARMPC_QP_SOLVED : (st == kSlotMaxIter ? CARMPC_QP_MAX_ITER : CARMPC_QP_INFEASIBLE);
+                    if (Bq.combine) {
+                        // a later chain of a split problem: infeasible if any chain is, solved only if every chain is; the
+                        // sample's iteration count is the longest chain's
+                        const int before = Bq.status[sample_old], it_before = Bq.iters[sample_old];
+                        if (before == CARMPC_QP_INFEASIBLE || verdict == CARMPC_QP_INFEASIBLE) verdict = CARMPC_QP_INFEASIBLE;
+                        else if (before != CARMPC_QP_SOLVED || verdict != CARMPC_QP_SOLVED) verdict = CARMPC_QP_MAX_ITER;
+                        Bq.status[sample_old] = verdict;
+                        Bq.iters[sample_old] = max(it, it_before);
+                        if (it > it_before) atomicAdd(Bq.total_iters, (unsigned long long)(it - it_before));
+                    } else {
+                        Bq.status[sample_old] = verdict;
+                        Bq.iters[sample_old] = it + (Bq.iters_accumulate ? Bq.iters[sample_old] : 0);
+                        atomicAdd(Bq.total_iters, (unsigned long long)it);
+                    }
                     st = kSlotIdle;
                 }
                 int fresh = 0;
@@ -403,9 +415,11 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
                     }
                     if (!pre_ok) {
                         // a violated row that does not depend on u: infeasible without iterating (the FFMA kernel books one round)
-                        Bq.status[sample] = CARMPC_QP_INFEASIBLE;
-                        Bq.iters[sample] = check_every + (Bq.iters_accumulate ? Bq.iters[sample] : 0);
-                        atomicAdd(Bq.total_iters, (unsigned long long)check_every);
+                        if (!Bq.combine) {
+                            Bq.status[sample] = CARMPC_QP_INFEASIBLE;
+                            Bq.iters[sample] = check_every + (Bq.iters_accumulate ? Bq.iters[sample] : 0);
+                            atomicAdd(Bq.total_iters, (unsigned long long)check_every);
+                        }
                         continue;
                     }
 #pragma unroll
@@ -459,7 +473,8 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
 #pragma unroll
                         for (int r = 0; r < 16; ++r) {
                             const int j = ((lb * G + cg) << 4) + r;
-                            wb[lb][r] = (wi && j < n) ? wi[m + j] : 0.f;
+                            const int vj = (wi && j < NP) ? C.var_id[j] : -1;
+                            wb[lb][r] = vj >= 0 ? wi[m + vj] : 0.f;
                         }
                 }
             }
@@ -777,13 +792,13 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
 }
 
 template <int NP, int G>
-int tc_launch_np(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
-    const size_t smem = (size_t)q->tc.smem_bytes;
+int tc_launch_np(QPHandle* q, const TcTables& part, const AdmmBatch& b, cudaStream_t st) {
+    const size_t smem = (size_t)part.smem_bytes;
     const int64_t tiles = ((int64_t)b.count + 127) / 128;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, q->sm));
     constexpr int threads = 128 * G + 64;
     { const int rc = kernel_config(reinterpret_cast<const void*>(admm_tc_kernel<NP, G>), threads, smem, nullptr); if (rc != CARMPC_OK) return rc; }
-    admm_tc_kernel<NP, G><<<blocks, threads, smem, st>>>(q->admm, q->tc, b);
+    admm_tc_kernel<NP, G><<<blocks, threads, smem, st>>>(q->admm, part, b);
     CARMPC_CUDA(cudaGetLastError());
     return CARMPC_OK;
 }
@@ -798,20 +813,30 @@ bool admm_tc_usable(const QPHandle* q, const AdmmBatch& b) {
     // to read through L1 / L2 (horizon 40: 1.75x on the whole solve); with the matrices in shared memory (horizons 10, 20)
     // the FFMA kernel is 20 % ahead.  Modes 2 / 3 take every problem that has a tensor-core form.
     const bool wanted = q->tensor_mode >= 2 || (q->tensor_mode == 1 && !q->host.mats_in_smem);
-    return wanted && q->tc.ok && !b.narrow && !b.write_u && b.warm != nullptr && b.sign != nullptr &&
+    return wanted && !q->tc_parts.empty() && !b.narrow && !b.write_u && b.warm != nullptr && b.sign != nullptr &&
            (int64_t)b.count >= (int64_t)128 * q->sm;
 }
 
-int admm_tc_launch(QPHandle* q, const AdmmBatch& b, cudaStream_t st) {
-    switch (q->tc.np) {
-        case 16: return tc_launch_np<16, kTcGroups>(q, b, st);
-        case 32: return tc_launch_np<32, kTcGroups>(q, b, st);
-        case 48: return tc_launch_np<48, kTcGroups>(q, b, st);
-        case 64: return tc_launch_np<64, kTcGroups>(q, b, st);
-        case 80: return tc_launch_np<80, kTcGroups>(q, b, st);
+int admm_tc_launch(QPHandle* q, const AdmmBatch& b_in, cudaStream_t st) {
+    // one pass per part: the whole problem, or the independent chains one after the other (same samples, disjoint rows and
+    // variables; the later passes merge their verdicts into the earlier ones')
+    for (size_t k = 0; k < q->tc_parts.size(); ++k) {
+        const TcTables& part = q->tc_parts[k];
+        AdmmBatch b = b_in;
+        b.combine = k > 0 ? 1 : 0;
+        if (k > 0) CARMPC_CUDA(cudaMemsetAsync(b.next, 0, sizeof(int), st));
+        int rc = CARMPC_ERR_UNSUPPORTED;
+        switch (part.np) {
+            case 16: rc = tc_launch_np<16, kTcGroups>(q, part, b, st); break;
+            case 32: rc = tc_launch_np<32, kTcGroups>(q, part, b, st); break;
+            case 48: rc = tc_launch_np<48, kTcGroups>(q, part, b, st); break;
+            case 64: rc = tc_launch_np<64, kTcGroups>(q, part, b, st); break;
+            case 80: rc = tc_launch_np<80, kTcGroups>(q, part, b, st); break;
+            default: set_error("admm_tc_launch: no kernel variant for %d variables", part.np);
+        }
+        if (rc != CARMPC_OK) return rc;
     }
-    set_error("admm_tc_launch: no kernel variant for %d variables", q->tc.np);
-    return CARMPC_ERR_UNSUPPORTED;
+    return CARMPC_OK;
 }
 
 }  // namespace carmpc

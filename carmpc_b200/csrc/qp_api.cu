@@ -510,19 +510,23 @@ int carmpc_qp_create(int n, int m, int k, const double* h_H, const double* h_F, 
     UP(pre_lo, pre_lo); UP(pre_hi, pre_hi);
 #undef UP
     q->tc = h.tc;
-    if (q->tc.ok) {
-        TcTables& t = q->tc;
-        void* d_img = nullptr;
-        // chunk images are the sources of cp.async.bulk copies: 16-byte granules (cudaMalloc aligns to 256 bytes)
-        if (cudaMalloc(&d_img, h.tc_img.size()) != cudaSuccess) { set_error("cudaMalloc of the tensor-core images failed"); delete q; return CARMPC_ERR_CUDA; }
-        q->allocations.push_back(d_img);
-        if (cudaMemcpy(d_img, h.tc_img.data(), h.tc_img.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("upload of the tensor-core images failed"); delete q; return CARMPC_ERR_CUDA; }
-        t.img = static_cast<const unsigned char*>(d_img);
-#define UPT(vec, field) do { rc = upload(q, h.vec, &t.field); if (rc != CARMPC_OK) { delete q; return rc; } } while (0)
-        UPT(tc_nwd, nwd); UPT(tc_einv_g, einv_g); UPT(tc_hisf, hisf); UPT(tc_gxsf, gxsf); UPT(tc_gcsf, gcsf);
-        UPT(tc_his, his); UPT(tc_gxs, gxs); UPT(tc_gcs, gcs); UPT(tc_row_id, row_id);
-        UPT(tc_lam, lam); UPT(tc_lb, lb); UPT(tc_ub, ub); UPT(tc_einv_b, einv_b); UPT(tc_nrl, nrl); UPT(tc_kfv, kfv);
+    if (h.tc.ok || h.tc_parts.size() > 1) {
+        for (const TcPart& part : h.tc_parts) {
+            TcTables t = part.t;
+            void* d_img = nullptr;
+            // chunk images are the sources of cp.async.bulk copies: 16-byte granules (cudaMalloc aligns to 256 bytes)
+            if (cudaMalloc(&d_img, part.img.size()) != cudaSuccess) { set_error("cudaMalloc of the tensor-core images failed"); delete q; return CARMPC_ERR_CUDA; }
+            q->allocations.push_back(d_img);
+            if (cudaMemcpy(d_img, part.img.data(), part.img.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("upload of the tensor-core images failed"); delete q; return CARMPC_ERR_CUDA; }
+            t.img = static_cast<const unsigned char*>(d_img);
+#define UPT(vec, field) do { rc = upload(q, part.vec, &t.field); if (rc != CARMPC_OK) { delete q; return rc; } } while (0)
+            UPT(nwd, nwd); UPT(einv_g, einv_g); UPT(hisf, hisf); UPT(gxsf, gxsf); UPT(gcsf, gcsf);
+            UPT(his, his); UPT(gxs, gxs); UPT(gcs, gcs); UPT(row_id, row_id);
+            UPT(lam, lam); UPT(lb, lb); UPT(ub, ub); UPT(einv_b, einv_b); UPT(nrl, nrl); UPT(kfv, kfv); UPT(var_id, var_id);
 #undef UPT
+            q->tc_parts.push_back(t);
+        }
+        q->tc = q->tc_parts[0];
     }
     PolishTables& p = q->polish;
     p.n = n; p.m = m; p.mt = m + n;
@@ -604,22 +608,23 @@ int carmpc_qp_get_setup(void* qp, int which, double* h_out, int capacity) {
             src = &tmp; break;
         }
         case 31: {
-            tmp.resize(h.tc_img.size() / 4);
-            for (size_t i = 0; i < tmp.size(); ++i) { float f; memcpy(&f, h.tc_img.data() + 4 * i, 4); tmp[i] = f; }
+            const std::vector<unsigned char>& img = h.tc_parts[0].img;
+            tmp.resize(img.size() / 4);
+            for (size_t i = 0; i < tmp.size(); ++i) { float f; memcpy(&f, img.data() + 4 * i, 4); tmp[i] = f; }
             src = &tmp; break;
         }
-        case 32: tmp.assign(h.tc_nwd.begin(), h.tc_nwd.end()); src = &tmp; break;
-        case 33: tmp.assign(h.tc_einv_g.begin(), h.tc_einv_g.end()); src = &tmp; break;
-        case 34: src = &h.tc_his; break;
-        case 35: src = &h.tc_gxs; break;
-        case 36: src = &h.tc_gcs; break;
-        case 37: tmp.assign(h.tc_row_id.begin(), h.tc_row_id.end()); src = &tmp; break;
-        case 38: tmp.assign(h.tc_lam.begin(), h.tc_lam.end()); src = &tmp; break;
-        case 39: tmp.assign(h.tc_lb.begin(), h.tc_lb.end()); src = &tmp; break;
-        case 40: tmp.assign(h.tc_ub.begin(), h.tc_ub.end()); src = &tmp; break;
-        case 41: tmp.assign(h.tc_einv_b.begin(), h.tc_einv_b.end()); src = &tmp; break;
-        case 42: tmp.assign(h.tc_nrl.begin(), h.tc_nrl.end()); src = &tmp; break;
-        case 43: src = &h.tc_kfv; break;
+        case 32: tmp.assign(h.tc_parts[0].nwd.begin(), h.tc_parts[0].nwd.end()); src = &tmp; break;
+        case 33: tmp.assign(h.tc_parts[0].einv_g.begin(), h.tc_parts[0].einv_g.end()); src = &tmp; break;
+        case 34: src = &h.tc_parts[0].his; break;
+        case 35: src = &h.tc_parts[0].gxs; break;
+        case 36: src = &h.tc_parts[0].gcs; break;
+        case 37: tmp.assign(h.tc_parts[0].row_id.begin(), h.tc_parts[0].row_id.end()); src = &tmp; break;
+        case 38: tmp.assign(h.tc_parts[0].lam.begin(), h.tc_parts[0].lam.end()); src = &tmp; break;
+        case 39: tmp.assign(h.tc_parts[0].lb.begin(), h.tc_parts[0].lb.end()); src = &tmp; break;
+        case 40: tmp.assign(h.tc_parts[0].ub.begin(), h.tc_parts[0].ub.end()); src = &tmp; break;
+        case 41: tmp.assign(h.tc_parts[0].einv_b.begin(), h.tc_parts[0].einv_b.end()); src = &tmp; break;
+        case 42: tmp.assign(h.tc_parts[0].nrl.begin(), h.tc_parts[0].nrl.end()); src = &tmp; break;
+        case 43: src = &h.tc_parts[0].kfv; break;
         default: set_error("carmpc_qp_get_setup: unknown selector %d", which); return CARMPC_ERR_INVALID;
     }
     const int cnt = (int)src->size();
@@ -774,7 +779,8 @@ int carmpc_qp_tensor_mode(void* qp, int mode, int64_t* h_info) {
     if (mode >= 0) q->tensor_mode = mode;
     if (h_info) {
         for (int i = 0; i < 16; ++i) h_info[i] = 0;
-        h_info[0] = q->tensor_mode; h_info[1] = q->tc.ok; h_info[2] = q->last_tc_samples; h_info[3] = q->tc.resident;
+        h_info[0] = q->tensor_mode; h_info[1] = q->tc_parts.empty() ? 0 : (int64_t)q->tc_parts.size();
+        h_info[2] = q->last_tc_samples; h_info[3] = q->tc.resident;
         if (q->ws_prof != nullptr) {
             unsigned long long tmp[16];
             CARMPC_CUDA(cudaMemcpy(tmp, q->ws_prof, sizeof(tmp), cudaMemcpyDeviceToHost));

@@ -100,6 +100,8 @@ struct AdmmBatch {
     int max_iter;
     int iters_accumulate;    // second pass: add to the iteration count of the first
     int write_u;             // also write the ADMM iterate (needed when the polish may pass it through)
+    int combine;             // tensor-core kernel, second and later chains of a split problem: merge status / iterations
+                             // with what the earlier chains wrote (infeasible if any chain is, solved if all are)
     unsigned long long* prof; // nullable (tensor-core kernel, tensor mode 2): cycle counters summed over the CTAs
 };
 
@@ -131,6 +133,7 @@ struct TcTables {
     const float* einv_b;        // [np]
     const float* nrl;           // [np]   -1 / lam (pads 0)
     const double* kfv;          // [np][4]  x~0 = kfv (x0 - xref)
+    const int* var_id;          // [np]   logical variable, -1 pad
     int n, m, mt, np, mp;
     int resident;               // products 0 and 1 stay in shared memory (loaded once); product 2 always streams
     int merged;                 // B_hi and B_lo are consumed as ONE operand of 2 N rows (A_hi fetched once per k-step: two
@@ -138,6 +141,15 @@ struct TcTables {
     int na_stages, nb_stages, b_stage_bytes, resident_bytes;
     int smem_bytes;
     int ok;                     // 0: this problem has no tensor-core form (too large for tensor memory / shared memory)
+};
+
+// host images of one part of the tensor-core form (the whole problem, or one independent chain of it)
+struct TcPart {
+    TcTables t;
+    std::vector<unsigned char> img;
+    std::vector<float> nwd, einv_g, hisf, gxsf, gcsf, lam, lb, ub, einv_b, nrl;
+    std::vector<double> his, gxs, gcs, kfv;
+    std::vector<int> row_id, var_id;
 };
 
 struct PolishTables {
@@ -234,12 +246,9 @@ struct QPHost {
     std::vector<int2> segB;
     // polish (logical order, unscaled)
     std::vector<double> H, Hinv, F, G, Uu, AUu, AH, AHA, Gx, Gc, hi, lo;
-    // tensor-core form (sizes in tc; pointers filled by the handle)
-    TcTables tc;
-    std::vector<unsigned char> tc_img;
-    std::vector<float> tc_nwd, tc_einv_g, tc_hisf, tc_gxsf, tc_gcsf, tc_lam, tc_lb, tc_ub, tc_einv_b, tc_nrl;
-    std::vector<double> tc_his, tc_gxs, tc_gcs, tc_kfv;
-    std::vector<int> tc_row_id;
+    // tensor-core form: one part for the whole problem, or one per independent chain (sizes in t; pointers filled by the handle)
+    TcTables tc;                     // = tc_parts[0].t
+    std::vector<TcPart> tc_parts;
     int ga_per_warp = 0, gb_per_warp = 0, samples_per_lane = 0;
     bool mats_in_smem = false;
     size_t smem_bytes = 0;
@@ -289,7 +298,8 @@ size_t admm_smem_bytes(const QPHost& h, int samples_per_lane, bool mats_in_smem)
 struct QPHandle : HandleBase {
     QPHost host;
     AdmmTables admm;
-    TcTables tc;
+    TcTables tc;                                 // = tc_parts[0]
+    std::vector<TcTables> tc_parts;              // device tables of every part (one, or one per independent chain)
     int tensor_mode = 1;                         // 0: FFMA kernel only; 1: tcgen05 kernel where it is faster; 2: wherever possible; 3: 2 + cycle counters
     int64_t last_tc_samples = 0;                 // samples the tcgen05 kernel took in the last solve
     unsigned long long* ws_prof = nullptr;       // [16] cycle counters of the tcgen05 kernel (tensor mode 2)

@@ -443,10 +443,14 @@ int qp_host_setup(int n, int m_in, int kpre, const double* H_in, const double* F
         }
 
     // ---- tensor-core form (qp_admm_tc.cu): logical order, B operands as swizzled TF32 hi / lo chunk images ---------------------
-    {
-        TcTables& t = q.tc;
+    // One part for the whole problem when it fits tensor memory; else (horizon 80) one part per independent chain of the
+    // variable graph - K is block diagonal over the chains, so the ADMM iteration of the whole problem IS the chains'
+    // iterations side by side, and each chain is a horizon-40-sized problem.
+    auto build_part = [&](const std::vector<int>& vars, const std::vector<int>& prows, TcPart& P) {
+        TcTables& t = P.t;
         memset(&t, 0, sizeof(t));
-        const int np = std::max(16, (n + 15) / 16 * 16), mp = std::max(16, (mv + 15) / 16 * 16);
+        const int nv = (int)vars.size(), nr = (int)prows.size();
+        const int np = std::max(16, (nv + 15) / 16 * 16), mp = std::max(16, (nr + 15) / 16 * 16);
         t.n = n; t.m = m; t.mt = mt; t.np = np; t.mp = mp;
         const int K[3] = {np + 16 + mp, np + 16, mp}, N[3] = {np, mp, np};
         t.ok = mp <= 256 && np <= 256 && 2 * mp + np <= 512;
@@ -481,84 +485,109 @@ int qp_host_setup(int n, int m_in, int kpre, const double* H_in, const double* F
             t.smem_bytes = t.na_stages * a_stage + 2 * t.b_stage_bytes + tables + 1024;
             if (t.smem_bytes > 227 * 1024) t.ok = 0;
         }
-        if (t.ok) {
-            auto tf32_rn = [](double v) {
-                float f = (float)v;
-                uint32_t u; memcpy(&u, &f, 4);
-                u = (u + 0x1000u) & 0xFFFFE000u;
-                memcpy(&f, &u, 4);
-                return f;
-            };
-            auto sw128 = [](int r, int k) { return (r >> 3) * 1024 + (r & 7) * 128 + (((k >> 2) ^ (r & 7)) << 4) + (k & 3) * 4; };
-            q.tc_img.assign(total, 0);
-            auto put = [&](int p, int r, int k, double v) {
-                if (v == 0.0) return;
-                unsigned char* base = q.tc_img.data() + t.off[p] + (size_t)(k >> 5) * t.pair_bytes[p];
-                const float hi = tf32_rn(v), lo = tf32_rn(v - (double)hi);
-                memcpy(base + sw128(r, k & 31), &hi, 4);
-                memcpy(base + (size_t)N[p] * 128 + sw128(r, k & 31), &lo, 4);
-            };
-            // e columns: x0_c as three pieces (3c .. 3c + 2), the constant 1 (12), the disturbance as three pieces (13 .. 15)
-            auto put_e = [&](int p, int r, int k0, const double* cx, double c1, double cc) {
-                for (int c = 0; c < 4; ++c)
-                    for (int piece = 0; piece < 3; ++piece) put(p, r, k0 + 3 * c + piece, cx[c]);
-                put(p, r, k0 + 12, c1);
-                for (int piece = 0; piece < 3; ++piece) put(p, r, k0 + 13 + piece, cc);
-            };
-            std::vector<double> his(mp, 0.0), gxs((size_t)mp * 4, 0.0), gcs(mp, 0.0);
-            q.tc_nwd.assign(mp, -INFINITY); q.tc_einv_g.assign(mp, 0.f); q.tc_row_id.assign(mp, -1);
-            for (int r = 0; r < mv; ++r) {
-                const int i = rows[r];
-                his[r] = Eg[i] * q.hi[i];
-                for (int c = 0; c < 4; ++c) gxs[(size_t)r * 4 + c] = Eg[i] * q.Gx[(size_t)i * 4 + c];
-                gcs[r] = Eg[i] * q.Gc[i];
-                q.tc_nwd[r] = isinf(q.lo[i]) ? -INFINITY : -(float)(Eg[i] * (q.hi[i] - q.lo[i]));
-                q.tc_einv_g[r] = (float)(1.0 / Eg[i]);
-                q.tc_row_id[r] = i;
-            }
-            q.tc_his = his; q.tc_gxs = gxs; q.tc_gcs = gcs;
-            q.tc_hisf.assign(his.begin(), his.end()); q.tc_gxsf.assign(gxs.begin(), gxs.end()); q.tc_gcsf.assign(gcs.begin(), gcs.end());
-            q.tc_lam.assign(np, 0.f); q.tc_lb.assign(np, -INFINITY); q.tc_ub.assign(np, INFINITY);
-            q.tc_einv_b.assign(np, 0.f); q.tc_nrl.assign(np, 0.f); q.tc_kfv.assign((size_t)np * 4, 0.0);
-            for (int j = 0; j < n; ++j) {
-                q.tc_lam[j] = (float)lam[j];
-                q.tc_lb[j] = isinf(lb_in[j]) ? -INFINITY : (float)(Eb[j] * lb_in[j]);
-                q.tc_ub[j] = isinf(ub_in[j]) ? INFINITY : (float)(Eb[j] * ub_in[j]);
-                q.tc_einv_b[j] = (float)(1.0 / Eb[j]);
-                q.tc_nrl[j] = lam[j] > 0 ? (float)(-1.0 / lam[j]) : 0.f;
-                for (int c = 0; c < 4; ++c) {
-                    double sum = 0;
-                    for (int k = 0; k < n; ++k) sum += q.Kinv[(size_t)j * n + k] * cs * D[k] * q.F[(size_t)k * 4 + c];
-                    q.tc_kfv[(size_t)j * 4 + c] = -sum;
-                }
-            }
-            // product 0: x~ = rho K^-1 [diag(lam) V_b + Gs' (V^_g + h)] + kfv x0 (- kfv xref, added by the kernel)
-            for (int a = 0; a < n; ++a) {
-                double cx[4] = {q.tc_kfv[(size_t)a * 4], q.tc_kfv[(size_t)a * 4 + 1], q.tc_kfv[(size_t)a * 4 + 2], q.tc_kfv[(size_t)a * 4 + 3]};
-                double c1 = 0, cc = 0;
-                for (int j = 0; j < n; ++j)
-                    if (comp[j] == comp[a]) put(0, a, j, rho * q.Kinv[(size_t)a * n + j] * lam[j]);
-                for (int r = 0; r < mv; ++r) {
-                    const int i = rows[r];
-                    if (row_vars[i].empty() || row_comp[i] != comp[a]) continue;
-                    const double pg = rho * KG[(size_t)a * m + i];
-                    put(0, a, np + 16 + r, pg);
-                    for (int c = 0; c < 4; ++c) cx[c] -= pg * gxs[(size_t)r * 4 + c];
-                    c1 += pg * his[r];
-                    cc -= pg * gcs[r];
-                }
-                put_e(0, a, np, cx, c1, cc);
-            }
-            // product 1: z^ = Gs x~ - h ;  product 2: Gs' dy
-            for (int r = 0; r < mv; ++r) {
-                const int i = rows[r];
-                for (int j = 0; j < n; ++j) {
-                    put(1, r, j, q.Gs64[(size_t)i * n + j]);
-                    put(2, j, r, q.Gs64[(size_t)i * n + j]);
-                }
-                put_e(1, r, np, &gxs[(size_t)r * 4], -his[r], gcs[r]);
+        if (!t.ok) return;
+        auto tf32_rn = [](double v) {
+            float f = (float)v;
+            uint32_t u; memcpy(&u, &f, 4);
+            u = (u + 0x1000u) & 0xFFFFE000u;
+            memcpy(&f, &u, 4);
+            return f;
+        };
+        auto sw128 = [](int r, int k) { return (r >> 3) * 1024 + (r & 7) * 128 + (((k >> 2) ^ (r & 7)) << 4) + (k & 3) * 4; };
+        P.img.assign(total, 0);
+        auto put = [&](int p, int r, int k, double v) {
+            if (v == 0.0) return;
+            unsigned char* base = P.img.data() + t.off[p] + (size_t)(k >> 5) * t.pair_bytes[p];
+            const float hi = tf32_rn(v), lo = tf32_rn(v - (double)hi);
+            memcpy(base + sw128(r, k & 31), &hi, 4);
+            memcpy(base + (size_t)N[p] * 128 + sw128(r, k & 31), &lo, 4);
+        };
+        // e columns: x0_c as three pieces (3c .. 3c + 2), the constant 1 (12), the disturbance as three pieces (13 .. 15)
+        auto put_e = [&](int p, int r, int k0, const double* cx, double c1, double cc) {
+            for (int c = 0; c < 4; ++c)
+                for (int piece = 0; piece < 3; ++piece) put(p, r, k0 + 3 * c + piece, cx[c]);
+            put(p, r, k0 + 12, c1);
+            for (int piece = 0; piece < 3; ++piece) put(p, r, k0 + 13 + piece, cc);
+        };
+        std::vector<double> his(mp, 0.0), gxs((size_t)mp * 4, 0.0), gcs(mp, 0.0);
+        P.nwd.assign(mp, -INFINITY); P.einv_g.assign(mp, 0.f); P.row_id.assign(mp, -1);
+        for (int r = 0; r < nr; ++r) {
+            const int i = prows[r];
+            his[r] = Eg[i] * q.hi[i];
+            for (int c = 0; c < 4; ++c) gxs[(size_t)r * 4 + c] = Eg[i] * q.Gx[(size_t)i * 4 + c];
+            gcs[r] = Eg[i] * q.Gc[i];
+            P.nwd[r] = isinf(q.lo[i]) ? -INFINITY : -(float)(Eg[i] * (q.hi[i] - q.lo[i]));
+            P.einv_g[r] = (float)(1.0 / Eg[i]);
+            P.row_id[r] = i;
+        }
+        P.his = his; P.gxs = gxs; P.gcs = gcs;
+        P.hisf.assign(his.begin(), his.end()); P.gxsf.assign(gxs.begin(), gxs.end()); P.gcsf.assign(gcs.begin(), gcs.end());
+        P.lam.assign(np, 0.f); P.lb.assign(np, -INFINITY); P.ub.assign(np, INFINITY);
+        P.einv_b.assign(np, 0.f); P.nrl.assign(np, 0.f); P.kfv.assign((size_t)np * 4, 0.0);
+        P.var_id.assign(np, -1);
+        for (int a = 0; a < nv; ++a) {
+            const int j = vars[a];
+            P.var_id[a] = j;
+            P.lam[a] = (float)lam[j];
+            P.lb[a] = isinf(lb_in[j]) ? -INFINITY : (float)(Eb[j] * lb_in[j]);
+            P.ub[a] = isinf(ub_in[j]) ? INFINITY : (float)(Eb[j] * ub_in[j]);
+            P.einv_b[a] = (float)(1.0 / Eb[j]);
+            P.nrl[a] = lam[j] > 0 ? (float)(-1.0 / lam[j]) : 0.f;
+            for (int c = 0; c < 4; ++c) {
+                double sum = 0;
+                for (int k = 0; k < n; ++k) sum += q.Kinv[(size_t)j * n + k] * cs * D[k] * q.F[(size_t)k * 4 + c];
+                P.kfv[(size_t)a * 4 + c] = -sum;
             }
         }
+        // product 0: x~ = rho K^-1 [diag(lam) V_b + Gs' (V^_g + h)] + kfv x0 (- kfv xref, added by the kernel)
+        for (int a = 0; a < nv; ++a) {
+            const int ja = vars[a];
+            double cx[4] = {P.kfv[(size_t)a * 4], P.kfv[(size_t)a * 4 + 1], P.kfv[(size_t)a * 4 + 2], P.kfv[(size_t)a * 4 + 3]};
+            double c1 = 0, cc = 0;
+            for (int b2 = 0; b2 < nv; ++b2) {
+                const int j = vars[b2];
+                if (comp[j] == comp[ja]) put(0, a, b2, rho * q.Kinv[(size_t)ja * n + j] * lam[j]);
+            }
+            for (int r = 0; r < nr; ++r) {
+                const int i = prows[r];
+                if (row_vars[i].empty() || row_comp[i] != comp[ja]) continue;
+                const double pg = rho * KG[(size_t)ja * m + i];
+                put(0, a, np + 16 + r, pg);
+                for (int c = 0; c < 4; ++c) cx[c] -= pg * gxs[(size_t)r * 4 + c];
+                c1 += pg * his[r];
+                cc -= pg * gcs[r];
+            }
+            put_e(0, a, np, cx, c1, cc);
+        }
+        // product 1: z^ = Gs x~ - h ;  product 2: Gs' dy
+        for (int r = 0; r < nr; ++r) {
+            const int i = prows[r];
+            for (int a = 0; a < nv; ++a) {
+                put(1, r, a, q.Gs64[(size_t)i * n + vars[a]]);
+                put(2, a, r, q.Gs64[(size_t)i * n + vars[a]]);
+            }
+            put_e(1, r, np, &gxs[(size_t)r * 4], -his[r], gcs[r]);
+        }
+    };
+    {
+        q.tc_parts.clear();
+        std::vector<int> all_vars(n);
+        std::iota(all_vars.begin(), all_vars.end(), 0);
+        q.tc_parts.emplace_back();
+        build_part(all_vars, rows, q.tc_parts[0]);
+        if (!q.tc_parts[0].t.ok && ncomp >= 2) {
+            std::vector<TcPart> parts(ncomp);
+            bool all_ok = true;
+            for (int c = 0; c < ncomp && all_ok; ++c) {
+                std::vector<int> cv, cr;
+                for (int j = 0; j < n; ++j) if (comp[j] == c) cv.push_back(j);
+                for (int i : rows) if ((row_vars[i].empty() ? 0 : row_comp[i]) == c) cr.push_back(i);
+                build_part(cv, cr, parts[c]);
+                all_ok = parts[c].t.ok != 0;
+            }
+            if (all_ok) q.tc_parts.swap(parts);
+        }
+        q.tc = q.tc_parts[0].t;
     }
 
     q.mats_in_smem = GA < 4 && admm_smem_bytes(q, S, true) <= (size_t)226 * 1024;

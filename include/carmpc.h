@@ -277,12 +277,15 @@ int carmpc_qp_polish_stats(void* qp, int64_t* h_hist16);
  *   mode 0  the FFMA tile kernel always;
  *   mode 1  (default) the tcgen05 kernel where it measured faster: problems whose matrices the FFMA kernel cannot keep in
  *           shared memory (horizon 40 of the shipped environments);
- *   mode 2  the tcgen05 kernel whenever the problem has a tensor-core form (up to 256 general rows and
- *           2 rows + variables <= 512 columns of tensor memory: horizons up to 40);
+ *   mode 2  the tcgen05 kernel whenever the problem has a tensor-core form: up to 256 general rows and
+ *           2 rows + variables <= 512 columns of tensor memory (horizons up to 40), or - larger problems - the same for
+ *           every independent chain of the variable graph (horizon 80 of RoadEnv / RoadOneCarEnv: the acceleration and
+ *           steering chains are solved as two passes of the kernel and their verdicts merged);
  *   mode 3  mode 2 with cycle counters (a measuring aid: where the roles of the kernel wait);   mode < 0 only queries.
  * The tcgen05 kernel: 128-sample tiles as the M dimension of kind::tf32 MMAs, 3xTF32 split, state and accumulators in
  * tensor memory.  Both kernels run the same iteration; the float64 polish certifies the results of either.
- * h_info (nullable, 16 int64): [0] mode, [1] 1 if the problem has a tensor-core form, [2] samples the tcgen05 kernel
+ * h_info (nullable, 16 int64): [0] mode, [1] number of tensor-core parts (0: no tensor-core form, 1: the whole problem,
+ * > 1: one pass per independent chain), [2] samples the tcgen05 kernel
  * took in the last solve, [3] 1 if its matrices stay resident in shared memory (0: streamed from L2 every iteration),
  * [4..13] mode 3: cycles summed over the CTAs of the last tcgen05 launch - MMA thread: round total, waiting for A
  * chunks, waiting for B chunks; compute thread 0: waiting for x~, waiting for z^, waiting for a free A stage, retire /

@@ -17,11 +17,12 @@ def _random_config_states(torch, n, seed):
 
 @pytest.mark.parametrize("env_name,N,n_states", [("RoadOneCarEnv", 10, 40_000), ("RoadOneCarEnv", 20, 60_000),
                                                  ("RoadOneCarEnv", 40, 40_000), ("RoadMultipleCarsEnv", 20, 30_000),
-                                                 ("RoadEnv", 40, 30_000)])
+                                                 ("RoadEnv", 40, 30_000), ("RoadOneCarEnv", 80, 30_000), ("RoadEnv", 80, 25_000)])
 def test_tensor_kernel_gives_the_ffma_kernels_results(torch_cuda, env_name, N, n_states):
     torch = torch_cuda
     c, bq, oq = _setup(env_name, N)
     assert bq.tensor_mode()["available"]
+    assert bq.tensor_mode()["parts"] == (2 if N == 80 else 1)      # horizon 80: one pass per independent chain
     x0 = _random_config_states(torch, n_states, seed=N)
     bq.tensor_mode(0)
     a = {k: v.clone() for k, v in bq.solve(x0, want_u_full=True).items() if torch.is_tensor(v)}

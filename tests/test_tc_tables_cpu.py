@@ -33,9 +33,15 @@ def test_tensor_form_reproduces_ffma_iterates(env_name, goal, N):
         assert (sign == sign2).all(1).mean() >= 0.97
 
 
-def test_horizon_80_has_no_tensor_form():
+def test_horizon_80_splits_into_its_independent_chains():
+    """346 general rows do not fit tensor memory (state + accumulators exceed 512 columns), but K is block diagonal over the
+    acceleration and steering chains of RoadOneCarEnv: each chain is a horizon-40-sized part.  RoadMultipleCarsEnv couples
+    the chains (its terminal / car rows mix x and y): no tensor-core form at horizon 80."""
     from carmpc_b200.batch import BatchQP
-    c = make_controller(make_env("RoadOneCarEnv", [29.9, 1.5, 0, 0]), 80)
-    bq = BatchQP.from_controller(c)
-    assert not TcTables(bq).ok        # 346 general rows: state + accumulators exceed the 512 columns of tensor memory
-    assert bq.tensor_mode()["available"] is False
+    bq = BatchQP.from_controller(make_controller(make_env("RoadOneCarEnv", [29.9, 1.5, 0, 0]), 80))
+    part0 = TcTables(bq)                               # the library exports the first part
+    assert part0.ok and part0.np_ == 80 and part0.mp <= 192 and 2 * part0.mp + part0.np_ <= 512
+    live = part0.row_id[part0.row_id >= 0]
+    assert 80 < len(live) < bq.pq.m                    # a strict subset of the rows: one chain
+    bq2 = BatchQP.from_controller(make_controller(make_env("RoadMultipleCarsEnv", [30, 1.5, 0, 0]), 80))
+    assert not TcTables(bq2).ok
