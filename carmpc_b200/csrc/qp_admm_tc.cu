@@ -1,21 +1,28 @@
 // Tensor-core form of the batched ADMM (same iteration as qp_admm.cu, same role: active-set / infeasibility finder in
 // front of the float64 polish; replaces the cvxpy -> OSQP call of lib/mpc.py:334-335 / :477-478, one QP per state).
 //
-// A CTA owns a tile of 128 samples = the M dimension of tcgen05.mma.cta_group::1.kind::tf32.  Compute thread t (warps
-// 0-3) owns sample slot t = lane t of tensor memory: every per-sample quantity is thread-private (no reductions).
-//   tensor memory   columns [0, mp)        w^ of the general rows (state, written with tcgen05.st)
-//                   columns [mp, 2 mp)     accumulator of product 1 (z^)
-//                   columns [2 mp, +np)    accumulator of products 0 and 2 (x~, Gs' dy)
-//   registers       w of the box rows (np per thread), the sample's constant columns e (16)
+// A CTA owns a tile of 128 samples = the M dimension of tcgen05.mma.cta_group::1.kind::tf32.  Compute thread (slot, group)
+// - 4 G compute warps, G column groups - owns lane `slot` of tensor memory and the 16-column blocks b = group, group + G, ...
+// of its sample in every phase, so per-sample quantities are private to G threads (combined through shared memory once
+// per round, at the convergence check).
+//   tensor memory   columns [0, mp)            w^ of the general rows (state, written with tcgen05.st)
+//                   next mp (2 mp) columns     accumulator of product 1 (z^)
+//                   next np (2 np) columns     accumulator of products 0 and 2 (x~, Gs' dy)
+//   registers       w of the box rows (16 per owned block)
 //   shared memory   A-operand ring (chunks of 32 K-columns x 128 samples, TF32 hi image + lo residual image, written by
 //                   the compute threads in the 128-byte swizzled K-major layout), B-operand chunks (resident for small
-//                   problems, else streamed from L2 by cp.async.bulk through a ring), small per-row tables.
+//                   problems, else streamed from L2 by cp.async.bulk through a ring), per-row tables, per-slot state.
 // 3xTF32: every product is issued as A_hi B_hi + A_lo B_hi + A_hi B_lo (float32 accumulate): indistinguishable from the
-// float32 FFMA kernel on this iteration (tests/tf32_study.py), which plain TF32 is not.
-// Roles: warps 0-3 elementwise phases (produce A chunks, consume accumulators), warp 4 lane 0 issues the MMAs, warp 5
-// lane 0 streams B chunks.  The phases of an iteration are pipelined through mbarriers only:
+// float32 FFMA kernel on this iteration (tests/tf32_study.py), which plain TF32 is not.  Where tensor memory allows
+// (TcTables::merged) B_hi and B_lo are consumed as one operand of 2 N rows (their chunk images are adjacent), i.e. two MMAs
+// per k-step, and the two accumulator halves are added when they are read.
+// Roles: the compute warps run the elementwise phases (produce A chunks, consume accumulators); warp 4 G issues the MMAs and
+// warp 4 G + 1 streams B chunks - both run their control flow warp-uniformly and one elected lane issues, so descriptors
+// live in uniform registers.  The phases of an iteration are pipelined through mbarriers only:
 //   S_B (box rows: x~ -> w_b, X chunks)  ->  product 1  ->  S_G (general rows: z^ -> w^_g, V chunks)  ->  product 0  -> ...
 // with the MMAs of a product consuming the chunks while the phase that produces them is still running.
+// A problem too large for tensor memory whose variable graph splits into independent chains (horizon 80) is solved as one
+// pass of this kernel per chain (TcTables per part; AdmmBatch::combine merges the verdicts).
 #include <math.h>
 #include <stdint.h>
 
@@ -245,7 +252,7 @@ __global__ void __launch_bounds__(128 * G + 64, 1) admm_tc_kernel(const AdmmTabl
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);        // provably warp-uniform: the roles below branch on it
     const int slot = tid & 127, cg = tid >> 7;
-    const int mp = C.mp, n = C.n, m = C.m, mt = C.mt;
+    const int mp = C.mp, m = C.m, mt = C.mt;
     const int MPB = mp >> 4;
     const float alpha = T.alpha;
 
