@@ -89,3 +89,43 @@ def test_tensor_kernel_with_disturbance_and_warm_start(torch_cuda):
         again = bq.solve(x0, warm=warm.clone(), warm_in=True, warm_out=True)
         assert (again["status"] != first["status"]).sum().item() <= 3
         assert bq.last_stats()[0] <= 0.6 * it_cold
+
+
+@pytest.mark.parametrize("N", [20, 40, 80])
+def test_tensor_kernel_disturbance_columns_and_bad_states(torch_cuda, N):
+    """MPCOutputFBWithDisturbance has a non-zero Gc (the per-sample disturbance shifts the constraint bounds): the constant
+    columns of the tcgen05 kernel (x0 pieces, 1, disturbance pieces - per chain at horizon 80) must reproduce the FFMA
+    kernel's results; non-finite states are flagged infeasible by both and do not disturb their tile neighbours."""
+    torch = torch_cuda
+    from conftest import make_env, make_controller
+    from carmpc_b200.batch import BatchQP
+    ctl = make_controller(make_env("RoadEnv"), N, cls="MPCOutputFBWithDisturbance", init_state=[20, 0.5, 0, 2])
+    bq = BatchQP.from_controller(ctl)
+    assert bq.tensor_mode()["parts"] == (2 if N == 80 else 1)
+    n = 24_000
+    g = torch.Generator(device="cpu").manual_seed(N)
+    x_ref = torch.tensor([30.0, 1.5, 0.0, 0.0], dtype=torch.float64)
+    spread = torch.tensor([12.0, 1.2, 0.2, 2.0], dtype=torch.float64)
+    x0 = (x_ref[:, None] + (torch.rand((4, n), generator=g, dtype=torch.float64) * 2 - 1) * spread[:, None]).cuda().contiguous()
+    cd = ((torch.rand(n, generator=g, dtype=torch.float64) - 0.5) * 0.04).cuda()
+    x0[0, 5] = float("nan"); x0[1, 130] = float("inf"); x0[3, 4097] = -float("inf"); x0[2, 20_000] = 1e300
+    outs = {}
+    for mode in (0, 2):
+        bq.tensor_mode(mode)
+        outs[mode] = {k: v.clone() for k, v in bq.solve(x0, x_ref=x_ref.numpy(), c=cd).items() if torch.is_tensor(v)}
+        assert bq.tensor_mode()["samples_last_solve"] == (n if mode else 0)
+    sa, sb = outs[0]["status"], outs[2]["status"]
+    # (with a disturbance there is no float64 Farkas kernel: barely infeasible states can stay "undecided" (2) in one
+    #  kernel and be flagged in the other - never solved in one and infeasible in the other)
+    diff = sa != sb
+    assert diff.sum().item() <= n // 1000 and bool(((sa[diff] == 2) | (sb[diff] == 2)).all())
+    for i in (5, 130, 4097, 20_000):
+        assert sb[i].item() == 1
+    ok = (sa == 0) & (sb == 0)
+    assert ok.sum().item() > n // 10
+    assert (outs[0]["u0"] - outs[2]["u0"])[:, ok].abs().max().item() <= 1e-7
+    # the disturbance matters on this batch: solving without it changes the answers
+    bq.tensor_mode(2)
+    plain = bq.solve(x0, x_ref=x_ref.numpy())
+    both = ok & (plain["status"] == 0)
+    assert (plain["u0"] - outs[2]["u0"])[:, both].abs().max().item() > 1e-4
