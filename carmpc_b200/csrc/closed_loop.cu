@@ -226,7 +226,14 @@ extern "C" int carmpc_closed_loop(void* qp, int mode, const double* h_A, const d
             cudaGraph_t graph = nullptr;
             cudaGraphExec_t exec = nullptr;
             loop_set_kernel<<<1, 1, 0, st>>>(live_count + 1, k);
-            TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                // no capture possible here (e.g. the caller is capturing itself): launch the steps one by one
+                cudaGetLastError();
+                graph_ok = false;
+                rc = enqueue_step(k, nullptr);
+                if (rc != CARMPC_OK) { q->defer_total = 0; cleanup(); return rc; }
+                continue;
+            }
             rc = enqueue_step(k, live_count + 1);
             cudaError_t ce = cudaStreamEndCapture(st, &graph);
             if (rc == CARMPC_OK && ce != cudaSuccess) { set_error("cudaStreamEndCapture: %s", cudaGetErrorString(ce)); rc = CARMPC_ERR_CUDA; }
