@@ -289,7 +289,8 @@ int carmpc_qp_polish_stats(void* qp, int64_t* h_hist16);
  * took in the last solve, [3] 1 if its matrices stay resident in shared memory (0: streamed from L2 every iteration),
  * [4..13] mode 3: cycles summed over the CTAs of the last tcgen05 launch - MMA thread: round total, waiting for A
  * chunks, waiting for B chunks; compute thread 0: waiting for x~, waiting for z^, waiting for a free A stage, retire /
- * refill, round total, rounds; B stream thread: waiting for a free stage. */
+ * refill, round total, rounds; B stream thread: waiting for a free stage; [14], [15] compute thread 0: cycles in the
+ * generic-to-async proxy fence of its A-chunk writes, and in fence + warp synchronisation. */
 int carmpc_qp_tensor_mode(void* qp, int mode, int64_t* h_info);
 
 /* ------------------------------------------------------------------------------------------------
