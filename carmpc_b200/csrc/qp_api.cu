@@ -459,7 +459,7 @@ extern "C" {
 void carmpc_qp_default_opts(carmpc_qp_opts* o) {
     if (!o) return;
     o->rho = 0.0; o->alpha = 1.8; o->eps_abs = 3e-3; o->eps_rel = 3e-3; o->eps_prim_inf = 1e-4;
-    o->max_iter = 4000; o->check_every = 10; o->scaling_iters = 15; o->polish = 1;
+    o->max_iter = 4000; o->check_every = 0; o->scaling_iters = 15; o->polish = 1;
 }
 
 int carmpc_qp_create(int n, int m, int k, const double* h_H, const double* h_F, const double* h_G, const double* h_Gx,
@@ -482,6 +482,10 @@ int carmpc_qp_create(int n, int m, int k, const double* h_H, const double* h_F, 
         o.rho = 320.0 / ((double)n * n);
         o.rho = o.rho > 0.4 ? 0.4 : (o.rho < 0.02 ? 0.02 : o.rho);
     }
+    // automatic cadence of the convergence checks: a check costs about two plain iterations whatever the problem size, so
+    // small problems (cheap iterations) check less often (measured on the config-3 grid: horizon 10 is 8 % faster with 14
+    // than with 10, horizon 20 is best at 10)
+    if (o.check_every <= 0) o.check_every = n <= 20 ? 14 : 10;
     CARMPC_REQUIRE(o.alpha > 0 && o.alpha < 2, "0 < alpha < 2");
     CARMPC_REQUIRE(o.check_every >= 1 && o.max_iter >= o.check_every, "check_every >= 1, max_iter >= check_every");
     CARMPC_REQUIRE(o.scaling_iters >= 0 && o.scaling_iters <= 100, "scaling_iters");

@@ -188,7 +188,8 @@ typedef struct carmpc_qp_opts {
     double eps_rel;        /*   the float64 polish, not this tolerance, sets the final accuracy)     */
     double eps_prim_inf;   /* primal infeasibility certificate tolerance (default 1e-4)              */
     int32_t max_iter;      /* per sample (default 4000)                                              */
-    int32_t check_every;   /* residual / certificate test cadence in iterations (default 10)         */
+    int32_t check_every;   /* residual / certificate test cadence in iterations; <= 0 (default): 14  */
+                           /*   for n <= 20 variables, else 10                                       */
     int32_t scaling_iters; /* Ruiz equilibration passes on the host (default 15; 0 = none)           */
     int32_t polish;        /* 1 (default): float64 active-set polish with a KKT check after the      */
                            /*   float32 ADMM; 0: return the raw ADMM iterate                         */
