@@ -301,7 +301,13 @@ def run_qp_bench(args, rank, world, dev, barrier):
                              "admm_kernel": "tcgen05 kind::tf32, 3xTF32 split, 128-sample tiles" if on_tensor else "ffma tile kernel",
                              "tensor_form_available": tinfo["available"], "ffma_kernel_ms": ffma_ms}
             if on_tensor:       # dense multiply-adds the tensor pipe executes: three TF32 products per float32 product
-                sweep[str(N)]["tensor_dense_tflops"] = 3 * it_n * tl["flop_per_iter_dense"] / (ms_n * 1e-3) / 1e12
+                tf = 3 * it_n * tl["flop_per_iter_dense"] / (ms_n * 1e-3) / 1e12
+                sweep[str(N)]["tensor_dense_tflops"] = tf
+                sweep[str(N)]["tensor_roofline"] = {
+                    "bound": "tensor", "achieved": tf, "peak": 1188.0 * world, "unit": "TFLOP/s", "frac": tf / (1188.0 * world),
+                    "peak_source": "measured: sustained tcgen05.mma kind::tf32, 148 SMs (tools/tc_bench.cu, profiles/r02_tc_bench.txt)",
+                    "note": "whole solve (ADMM + polish) time; the kernel is bound by the shared-memory port that feeds the K = 8 "
+                            "MMAs, not by the tensor pipe (DESIGN.md section 4)"}
         res["horizon_sweep"] = sweep
 
     return res
